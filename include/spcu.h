@@ -1,0 +1,286 @@
+/*
+ * spcu.h — C-ABI of the B200 path-tracing backend for SimplePath ("CudaIntegrator").
+ *
+ * This is the drop-in boundary: plain C structs, pointers and sizes; no C++ / torch types.
+ * The host side (simplepath_b200/host/, C++ against the reference's own headers) flattens an
+ * `sp::Scene` (reference base/Scene.h:47-106) into `spcu_flat_scene` and calls these entry points
+ * from `sp::CudaIntegrator`, the new subclass of `sp::Integrator`
+ * (reference Integrators/Integrator.h:32-52).  Every entry point cites what it replaces.
+ *
+ * Conventions
+ *  - all functions return SPCU_OK (0) or a negative error code; spcu_last_error() gives text.
+ *  - "host" pointers are ordinary CPU memory; "device" pointers live on the context's GPU.
+ *  - IDs are *reference order* IDs: geometry prims = the top-level unbounded list of
+ *    Scene::m_accelerator_geometry in list order, followed by the BVH leaves' primitives in the
+ *    reference's left-to-right depth-first order (shapes/BVHAccelerator.h:62-77,
+ *    shapes/ListAccelerator.h:50-62).  Lights likewise over Scene::m_accelerator_lights.
+ */
+#ifndef SPCU_H
+#define SPCU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPCU_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define SPCU_OK 0
+#define SPCU_ERR_INVALID (-1)   /* bad argument / malformed scene                              */
+#define SPCU_ERR_CUDA (-2)      /* CUDA runtime error (no CPU fallback exists)                 */
+#define SPCU_ERR_NO_SCENE (-3)  /* call needs spcu_upload_scene first                          */
+#define SPCU_ERR_LIMIT (-4)     /* scene exceeds a compiled-in limit (stack depth, bxdfs, ...) */
+
+/* ---- primitive / light / material kinds -------------------------------------------------- */
+#define SPCU_PRIM_TRIANGLE 0u /* shapes/Triangle.h:69-246 (vertices pre-transformed to world) */
+#define SPCU_PRIM_SPHERE 1u   /* shapes/Sphere.h:13-150   (unit sphere in object space)       */
+#define SPCU_PRIM_PLANE 2u    /* shapes/Plane.h:12-100    (y = 0 in object space, unbounded)  */
+
+#define SPCU_LIGHT_SPHERE 0u    /* Lights/Light.h:336-388 SphereLight                */
+#define SPCU_LIGHT_ENV_CONST 1u /* Lights/Light.h:120-177 EnvironmentLight           */
+#define SPCU_LIGHT_ENV_IBL 2u   /* Lights/Light.h:179-334 ImageBasedEnvironmentLight */
+
+#define SPCU_BXDF_LAMBERT 0u    /* materials/Material.h:313-350 */
+#define SPCU_BXDF_MICROFACET 1u /* materials/Material.h:386-454 + BeckmannDistribution :213-267 */
+#define SPCU_BXDF_SPECULAR 2u   /* materials/Material.h:352-383 */
+
+#define SPCU_MAT_ONE_SAMPLE 0u /* materials/Material.h:533-718 OneSampleMaterial */
+#define SPCU_MAT_CLEARCOAT 1u  /* materials/Material.h:723-806 ClearcoatMaterial */
+
+#define SPCU_MAX_BXDFS 4u      /* per OneSampleMaterial (the .sp parser creates at most 2) */
+#define SPCU_MAX_COAT_DEPTH 4u /* nesting of clearcoat-over-clearcoat                      */
+#define SPCU_MAX_BVH_DEPTH 96u /* traversal stack capacity                                 */
+
+/* ---- integrators (reference Integrators/Integrator.h:18-28) ------------------------------- */
+#define SPCU_INTEGRATOR_ITERATIVE_RRNEE 0u   /* Integrator.cpp:550-635 (north star)  */
+#define SPCU_INTEGRATOR_BRUTE_FORCE_RR 1u    /* Integrator.cpp:211-266               */
+#define SPCU_INTEGRATOR_DIRECT_LIGHTING 2u   /* Integrator.cpp:277-312               */
+
+/* ---- rays and hits ------------------------------------------------------------------------ */
+/* One query: sp::Ray (math/Ray.h:21-49) + sp::RayLimits (math/Ray.h:13-19). 32 bytes. */
+typedef struct spcu_ray {
+    float ox, oy, oz, t_min;
+    float dx, dy, dz, t_max;
+} spcu_ray;
+
+/* Result of a closest-hit query. id = -1 and t = the query's t_max when nothing was hit. */
+typedef struct spcu_hit {
+    int32_t id;
+    float   t;
+} spcu_hit;
+
+/* ---- flattened acceleration structure ------------------------------------------------------ */
+/*
+ * One internal node of shapes/BVHAccelerator.h (NodeInternal :36-93): the bounds of BOTH children
+ * (the reference tests a child's own bounds before descending, :67 / :84) and their links.
+ *   box = { lo0.x lo0.y lo0.z hi0.x | hi0.y hi0.z lo1.x lo1.y | lo1.z hi1.x hi1.y hi1.z }
+ *   child[k] >= 0 : index of an internal node
+ *   child[k] <  0 : leaf; first primitive = ~child[k], number of primitives = count[k] & 0x7fffffff,
+ *                   bit 31 of count[k] set when the leaf holds a non-triangle primitive
+ * 64 bytes = four 16-byte vector loads, one cache-line half.
+ */
+typedef struct spcu_bvh_node {
+    float    box[12];
+    int32_t  child[2];
+    uint32_t count[2];
+} spcu_bvh_node;
+
+#define SPCU_LEAF_COUNT_MASK 0x7fffffffu
+#define SPCU_LEAF_MIXED_FLAG 0x80000000u
+
+/*
+ * Intersection data of one primitive, 48 bytes (three 16-byte loads).
+ *   triangle     : p0.xyz _ | p1.xyz _ | p2.xyz _           (world space, Triangle.h:99-101)
+ *   sphere/plane : world_to_object, column major + affine:
+ *                  c0.x c0.y c0.z c1.x | c1.y c1.z c2.x c2.y | c2.z a.x a.y a.z
+ */
+typedef struct spcu_prim_geom {
+    float v[12];
+} spcu_prim_geom;
+
+/*
+ * Shading data of one primitive, 48 bytes, read once per accepted closest hit.
+ *   triangle     : n0.xyz _ | n1.xyz _ | n2.xyz _           (Triangle.h:148-155)
+ *   sphere/plane : normal matrix inverse(object_to_world.linear).transposed(), column major:
+ *                  c0.xyz _ | c1.xyz _ | c2.xyz _            (math/LinearSpace3x3.h:163-167)
+ */
+typedef struct spcu_prim_shade {
+    float v[12];
+} spcu_prim_shade;
+
+/* meta word of a primitive: bits 0-1 kind (SPCU_PRIM_*), bits 2-31 material index */
+#define SPCU_META_KIND(m) ((m) & 3u)
+#define SPCU_META_MATERIAL(m) ((m) >> 2)
+#define SPCU_MAKE_META(kind, material) (((uint32_t)(material) << 2) | ((uint32_t)(kind) & 3u))
+
+/* One accelerator = reference ListAccelerator [unbounded..., BVHAccelerator(bounded)]
+ * built by internal::create_acceleration_structure (base/Scene.h:27-45). */
+typedef struct spcu_accel {
+    uint32_t n_prims;     /* unbounded + bounded                                            */
+    uint32_t n_unbounded; /* prims [0, n_unbounded) are scanned linearly first              */
+    uint32_t n_nodes;     /* internal nodes                                                 */
+    int32_t  root;        /* >= 0 internal node; < 0 leaf with first prim ~root             */
+    uint32_t root_count;  /* leaf root: count (+ mixed flag); the root's own bounds are never
+                             tested (BVHAccelerator.h:132-148)                              */
+    uint32_t max_depth;   /* deepest internal-node nesting, for the traversal stack         */
+    const spcu_bvh_node* nodes; /* [n_nodes]                                                */
+} spcu_accel;
+
+/* ---- materials ----------------------------------------------------------------------------- */
+typedef struct spcu_bxdf {
+    uint32_t kind;           /* SPCU_BXDF_*                                                     */
+    float    r[3];           /* Lambert: albedo/pi (m_albedo, Material.h:317); microfacet/specular: m_r */
+    float    alpha_x;        /* BeckmannDistribution::m_alpha_x (after roughness_to_alpha)      */
+    float    alpha_y;
+    float    ior;            /* MicrofacetReflection::m_ior                                     */
+    uint32_t sample_visible; /* MicrofacetDistribution::m_sample_visible_area                   */
+} spcu_bxdf;
+
+typedef struct spcu_material {
+    uint32_t kind;        /* SPCU_MAT_*                                     */
+    uint32_t n_bxdfs;     /* one-sample: number of BxDFs                    */
+    uint32_t first_bxdf;  /* one-sample: index into bxdfs[]                 */
+    uint32_t base;        /* clearcoat: index of the base material          */
+    float    ior;         /* clearcoat: m_ior                               */
+    float    specular[3]; /* clearcoat: m_specular_color                    */
+} spcu_material;
+
+/* ---- lights -------------------------------------------------------------------------------- */
+typedef struct spcu_light {
+    uint32_t kind; /* SPCU_LIGHT_* */
+    float    radiance[3];
+    /* sphere light: Sphere::m_object_to_world and inverse (12 floats each, layout of spcu_prim_geom)
+     * and the normal matrix (9 floats, column major) */
+    float world_to_object[12];
+    float object_to_world[12];
+    float normal_xf[9];
+    /* image based light: m_light_to_world linear and inverse (column major 3x3) */
+    float    light_to_world[9];
+    float    world_to_light[9];
+    uint32_t img_w, img_h; /* radiance image (after modify_image), row major RGB in float_pool */
+    uint32_t nu, nv;       /* Distribution2D resolution (= 2*img_w, 2*img_h)                   */
+    float    marg_integral;
+    uint32_t _pad;
+    uint64_t img_off;       /* [img_h][img_w][3]                                                */
+    uint64_t cond_func_off; /* [nv][nu]      Distribution1D::m_function of each conditional     */
+    uint64_t cond_cdf_off;  /* [nv][nu+1]    Distribution1D::m_cdf (reference-built, incl. its
+                               shifted normalisation, math/Distribution1D.h:42-43)              */
+    uint64_t cond_int_off;  /* [nv]          m_function_integral of each conditional            */
+    uint64_t marg_func_off; /* [nv]                                                             */
+    uint64_t marg_cdf_off;  /* [nv+1]                                                           */
+} spcu_light;
+
+/* ---- whole scene --------------------------------------------------------------------------- */
+typedef struct spcu_flat_scene {
+    uint32_t abi_version; /* SPCU_ABI_VERSION */
+    /* render parameters: Scene::{image_width,image_height,russian_roulette_depth,max_depth} */
+    uint32_t width, height;
+    uint32_t rr_depth, max_depth;
+    /* PerspectiveCamera m_transform (Cameras/Camera.h:99-129): col0 col1 col2 affine, xyz each */
+    float camera[12];
+
+    /* geometry (Scene::m_accelerator_geometry) */
+    spcu_accel             geom;
+    const spcu_prim_geom*  geom_prims; /* [geom.n_prims] */
+    const spcu_prim_shade* geom_shade; /* [geom.n_prims] */
+    const uint32_t*        geom_meta;  /* [geom.n_prims] */
+
+    /* lights (Scene::m_accelerator_lights); "prims" of this accelerator are lights[] entries */
+    spcu_accel        lights_accel;
+    uint32_t          n_lights;
+    uint32_t          _pad0;
+    const spcu_light* lights;      /* [n_lights] in accelerator (ID) order                     */
+    const uint32_t*   light_order; /* [n_lights] Scene::m_lights (for_each_light) order → ID   */
+
+    uint32_t             n_materials;
+    uint32_t             n_bxdfs;
+    const spcu_material* materials;
+    const spcu_bxdf*     bxdfs;
+
+    uint64_t     n_pool; /* floats */
+    const float* float_pool;
+} spcu_flat_scene;
+
+/* ---- work partition and render outputs ------------------------------------------------------ */
+/*
+ * What one GPU renders.  The unit is the reference's 8x8 tile (base/Tile.h:12, TileScheduler.h:66-82,
+ * row major over tiles).  This rank renders tiles t with  t % tile_stride == tile_offset  and, for
+ * each of their pixels, samples [sample_begin, sample_end) of spp_total.
+ */
+typedef struct spcu_partition {
+    uint32_t tile_offset;
+    uint32_t tile_stride;
+    uint32_t sample_begin;
+    uint32_t sample_end;
+    uint32_t spp_total; /* jitter table length; samples are indexed globally */
+    uint32_t integrator; /* SPCU_INTEGRATOR_* */
+    uint64_t seed;
+} spcu_partition;
+
+/* Per-stage device counters of one render call. */
+typedef struct spcu_stats {
+    uint64_t paths;               /* camera samples started                                       */
+    uint64_t rays_closest;        /* Scene::intersect queries (geometry accelerator)              */
+    uint64_t rays_any;            /* Scene::intersect_p queries (geometry half)                   */
+    uint64_t rays_lights;         /* Scene::intersect_lights queries (lights accelerator)         */
+    uint64_t nodes_visited;       /* internal nodes fetched by geometry queries                   */
+    uint64_t prims_tested;        /* triangle tests by geometry queries                           */
+    uint64_t xf_prims_tested;     /* sphere / plane tests by geometry queries                     */
+    uint64_t shade_calls;         /* Material::sample/eval/pdf evaluations                        */
+    uint64_t kernel_launches;     /* kernels launched by this call                                */
+    float    device_ms;           /* CUDA-event time of the wavefront loop                        */
+    float    trace_ms;            /* ... of which extend/any-hit traversal kernels                */
+    float    shade_ms;            /* ... of which shading / NEE kernels                           */
+    float    _pad;
+} spcu_stats;
+
+typedef struct spcu_ctx spcu_ctx;
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+
+/* Create / destroy a context bound to one CUDA device.  Replaces nothing in the reference (it has no
+ * device); owned by CudaIntegrator's constructor / destructor. */
+int  spcu_create(int device, spcu_ctx** out);
+void spcu_destroy(spcu_ctx* ctx);
+const char* spcu_last_error(const spcu_ctx* ctx); /* ctx may be NULL: last creation error */
+int  spcu_abi_version(void);
+
+/* Copy a flattened scene (host pointers) to the device.  Replaces the in-memory object graph handed to
+ * Integrator::integrate (Scene&, base/Scene.h:47-106).  jitter = spp x 2 floats from
+ * RSequenceSampler::get_next_2D (math/Sampler.h:158-162, main.cpp:67-71,96). */
+int spcu_upload_scene(spcu_ctx* ctx, const spcu_flat_scene* scene, const float* jitter, uint32_t spp);
+
+/* Scene::intersect (base/Scene.h:74-77) over a batch: closest geometry hit, reference order, exact
+ * arithmetic.  rays/hits are host pointers. */
+int spcu_trace_closest(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits);
+/* Scene::intersect_p (base/Scene.h:79-82): geometry OR lights accelerator any-hit. out[i] = 0/1. */
+int spcu_trace_any(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, uint8_t* out);
+/* Scene::intersect_lights (base/Scene.h:69-72): closest light (ID order of lights[]) and distance. */
+int spcu_trace_lights(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits);
+/* Same three queries through the ordered ("fast") traversal used by the renderer's extend stage. */
+int spcu_trace_closest_fast(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits);
+
+/* Camera::generate_ray for (pixel, sample) pairs (Cameras/Camera.h:119-129 + main.cpp:96-98):
+ * rays[i] for pixel index pix[i] (= y*width+x) and sample index smp[i]. host pointers. */
+int spcu_generate_rays(spcu_ctx* ctx, const uint32_t* pix, const uint32_t* smp, uint64_t n, spcu_ray* rays);
+
+/* render_thread + Integrator::integrate over a partition (main.cpp:77-107, Integrator.cpp:550-635):
+ * rgb_sum[(y*w+x)*3+c] += sum over this partition's samples of L; lum_sumsq[y*w+x] += sum of
+ * luminance(L)^2 (may be NULL).  Host buffers, full image size, accumulated into (caller zeroes). */
+int spcu_render(spcu_ctx* ctx, const spcu_partition* part, float* rgb_sum, float* lum_sumsq,
+                spcu_stats* stats);
+/* Same, accumulating into DEVICE buffers (so the caller can reduce them across GPUs with NCCL before
+ * the single device→host copy).  stream = cudaStream_t as void*, NULL for the default stream. */
+int spcu_render_device(spcu_ctx* ctx, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq,
+                       spcu_stats* stats, void* stream);
+
+/* Upper bound of paths kept in flight per wavefront batch (0 = default). */
+int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPCU_H */

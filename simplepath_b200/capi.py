@@ -1,0 +1,246 @@
+"""ctypes mirror of include/spcu.h and loader of the CUDA backend `libspcu.so`.
+
+There is no CPU fallback: if the shared library (built by `__graft_entry__.build()` /
+`make -C simplepath_b200/csrc`) is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "csrc" / "libspcu.so"
+
+ABI_VERSION = 1
+INTEGRATORS = {"iterative_rrnee": 0, "brute_force_iterative_rr": 1, "direct_lighting": 2}
+
+
+class Ray(C.Structure):
+    _fields_ = [("ox", C.c_float), ("oy", C.c_float), ("oz", C.c_float), ("t_min", C.c_float),
+                ("dx", C.c_float), ("dy", C.c_float), ("dz", C.c_float), ("t_max", C.c_float)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("id", C.c_int32), ("t", C.c_float)]
+
+
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("t_min", "<f4"), ("d", "<f4", 3), ("t_max", "<f4")])
+HIT_DTYPE = np.dtype([("id", "<i4"), ("t", "<f4")])
+NODE_DTYPE = np.dtype([("box", "<f4", 12), ("child", "<i4", 2), ("count", "<u4", 2)])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 8 and NODE_DTYPE.itemsize == 64
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("box", C.c_float * 12), ("child", C.c_int32 * 2), ("count", C.c_uint32 * 2)]
+
+
+class PrimGeom(C.Structure):
+    _fields_ = [("v", C.c_float * 12)]
+
+
+class PrimShade(C.Structure):
+    _fields_ = [("v", C.c_float * 12)]
+
+
+class Accel(C.Structure):
+    _fields_ = [("n_prims", C.c_uint32), ("n_unbounded", C.c_uint32), ("n_nodes", C.c_uint32),
+                ("root", C.c_int32), ("root_count", C.c_uint32), ("max_depth", C.c_uint32),
+                ("nodes", C.POINTER(BvhNode))]
+
+
+class Bxdf(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("r", C.c_float * 3), ("alpha_x", C.c_float), ("alpha_y", C.c_float),
+                ("ior", C.c_float), ("sample_visible", C.c_uint32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("n_bxdfs", C.c_uint32), ("first_bxdf", C.c_uint32), ("base", C.c_uint32),
+                ("ior", C.c_float), ("specular", C.c_float * 3)]
+
+
+class Light(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("radiance", C.c_float * 3),
+                ("world_to_object", C.c_float * 12), ("object_to_world", C.c_float * 12), ("normal_xf", C.c_float * 9),
+                ("light_to_world", C.c_float * 9), ("world_to_light", C.c_float * 9),
+                ("img_w", C.c_uint32), ("img_h", C.c_uint32), ("nu", C.c_uint32), ("nv", C.c_uint32),
+                ("marg_integral", C.c_float), ("_pad", C.c_uint32),
+                ("img_off", C.c_uint64), ("cond_func_off", C.c_uint64), ("cond_cdf_off", C.c_uint64),
+                ("cond_int_off", C.c_uint64), ("marg_func_off", C.c_uint64), ("marg_cdf_off", C.c_uint64)]
+
+
+class FlatScene(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("rr_depth", C.c_uint32), ("max_depth", C.c_uint32), ("camera", C.c_float * 12),
+                ("geom", Accel), ("geom_prims", C.POINTER(PrimGeom)), ("geom_shade", C.POINTER(PrimShade)),
+                ("geom_meta", C.POINTER(C.c_uint32)),
+                ("lights_accel", Accel), ("n_lights", C.c_uint32), ("_pad0", C.c_uint32),
+                ("lights", C.POINTER(Light)), ("light_order", C.POINTER(C.c_uint32)),
+                ("n_materials", C.c_uint32), ("n_bxdfs", C.c_uint32),
+                ("materials", C.POINTER(Material)), ("bxdfs", C.POINTER(Bxdf)),
+                ("n_pool", C.c_uint64), ("float_pool", C.POINTER(C.c_float))]
+
+
+class Partition(C.Structure):
+    _fields_ = [("tile_offset", C.c_uint32), ("tile_stride", C.c_uint32), ("sample_begin", C.c_uint32),
+                ("sample_end", C.c_uint32), ("spp_total", C.c_uint32), ("integrator", C.c_uint32),
+                ("seed", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_any", C.c_uint64),
+                ("rays_lights", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("xf_prims_tested", C.c_uint64), ("shade_calls", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("device_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("_pad", C.c_float)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
+
+
+EXPORTS = [
+    "spcu_create", "spcu_destroy", "spcu_last_error", "spcu_abi_version", "spcu_upload_scene",
+    "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
+    "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size",
+]
+
+
+class SpcuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(path: Path | str | None = None) -> C.CDLL:
+    """dlopen libspcu.so and declare prototypes.  Raises if the library is absent (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise SpcuError(f"CUDA backend {p} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                        "There is no CPU fallback.")
+    lib = C.CDLL(str(p))
+    vp = C.c_void_p
+    lib.spcu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.spcu_create.restype = C.c_int
+    lib.spcu_destroy.argtypes = [vp]
+    lib.spcu_destroy.restype = None
+    lib.spcu_last_error.argtypes = [vp]
+    lib.spcu_last_error.restype = C.c_char_p
+    lib.spcu_abi_version.argtypes = []
+    lib.spcu_abi_version.restype = C.c_int
+    lib.spcu_upload_scene.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(C.c_float), C.c_uint32]
+    lib.spcu_upload_scene.restype = C.c_int
+    for fn in (lib.spcu_trace_closest, lib.spcu_trace_lights, lib.spcu_trace_closest_fast):
+        fn.argtypes = [vp, vp, C.c_uint64, vp]
+        fn.restype = C.c_int
+    lib.spcu_trace_any.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.spcu_trace_any.restype = C.c_int
+    lib.spcu_generate_rays.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    lib.spcu_generate_rays.restype = C.c_int
+    lib.spcu_render.argtypes = [vp, C.POINTER(Partition), vp, vp, C.POINTER(Stats)]
+    lib.spcu_render.restype = C.c_int
+    lib.spcu_render_device.argtypes = [vp, C.POINTER(Partition), vp, vp, C.POINTER(Stats), vp]
+    lib.spcu_render_device.restype = C.c_int
+    lib.spcu_set_wavefront_size.argtypes = [vp, C.c_uint64]
+    lib.spcu_set_wavefront_size.restype = C.c_int
+    if lib.spcu_abi_version() != ABI_VERSION:
+        raise SpcuError("libspcu.so ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One CUDA device context (spcu_ctx).  Mirrors what sp::CudaIntegrator owns on the C++ side."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.spcu_create(device, C.byref(h))
+        if rc != 0:
+            raise SpcuError(f"spcu_create({device}) failed: {self.lib.spcu_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+        self._scene_keepalive = None
+        self.width = self.height = 0
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.spcu_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise SpcuError(f"{what} failed ({rc}): {self.lib.spcu_last_error(self.h).decode()}")
+
+    def upload_scene(self, flat: "C.POINTER(FlatScene) | FlatScene", jitter: np.ndarray, keepalive=None) -> None:
+        jitter = np.ascontiguousarray(jitter, dtype=np.float32).reshape(-1, 2)
+        fp = flat if isinstance(flat, C.POINTER(FlatScene)) else C.pointer(flat)
+        self._check(self.lib.spcu_upload_scene(self.h, fp, jitter.ctypes.data_as(C.POINTER(C.c_float)),
+                                               jitter.shape[0]), "spcu_upload_scene")
+        self.width, self.height = fp.contents.width, fp.contents.height
+        self.spp = jitter.shape[0]
+        self._scene_keepalive = keepalive
+
+    def _trace(self, fn, rays: np.ndarray, what: str) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        self._check(fn(self.h, _ptr(rays), rays.shape[0], _ptr(hits)), what)
+        return hits
+
+    def trace_closest(self, rays):
+        return self._trace(self.lib.spcu_trace_closest, rays, "spcu_trace_closest")
+
+    def trace_closest_fast(self, rays):
+        return self._trace(self.lib.spcu_trace_closest_fast, rays, "spcu_trace_closest_fast")
+
+    def trace_lights(self, rays):
+        return self._trace(self.lib.spcu_trace_lights, rays, "spcu_trace_lights")
+
+    def trace_any(self, rays) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.empty(rays.shape[0], dtype=np.uint8)
+        self._check(self.lib.spcu_trace_any(self.h, _ptr(rays), rays.shape[0], _ptr(out)), "spcu_trace_any")
+        return out
+
+    def generate_rays(self, pix, smp) -> np.ndarray:
+        pix = np.ascontiguousarray(pix, dtype=np.uint32)
+        smp = np.ascontiguousarray(smp, dtype=np.uint32)
+        rays = np.empty(pix.shape[0], dtype=RAY_DTYPE)
+        self._check(self.lib.spcu_generate_rays(self.h, _ptr(pix), _ptr(smp), pix.shape[0], _ptr(rays)),
+                    "spcu_generate_rays")
+        return rays
+
+    def partition(self, spp: int | None = None, integrator: str = "iterative_rrnee", rank: int = 0, world: int = 1,
+                  sample_begin: int = 0, sample_end: int | None = None, seed: int = 0) -> Partition:
+        spp = self.spp if spp is None else spp
+        return Partition(rank, world, sample_begin, spp if sample_end is None else sample_end, spp,
+                         INTEGRATORS[integrator], seed)
+
+    def render(self, part: Partition, want_sumsq: bool = True):
+        """Host-buffer render: returns (rgb_sum [H,W,3], lum_sumsq [H,W] | None, stats dict)."""
+        rgb = np.zeros((self.height, self.width, 3), dtype=np.float32)
+        sq = np.zeros((self.height, self.width), dtype=np.float32) if want_sumsq else None
+        st = Stats()
+        self._check(self.lib.spcu_render(self.h, C.byref(part), _ptr(rgb), _ptr(sq) if want_sumsq else None,
+                                         C.byref(st)), "spcu_render")
+        return rgb, sq, st.as_dict()
+
+    def render_device(self, part: Partition, d_rgb_sum: int, d_lum_sumsq: int | None, stream: int | None = None) -> dict:
+        st = Stats()
+        self._check(self.lib.spcu_render_device(self.h, C.byref(part), C.c_void_p(d_rgb_sum),
+                                                C.c_void_p(d_lum_sumsq) if d_lum_sumsq else None, C.byref(st),
+                                                C.c_void_p(stream) if stream else None), "spcu_render_device")
+        return st.as_dict()
+
+    def set_wavefront_size(self, n: int) -> None:
+        self._check(self.lib.spcu_set_wavefront_size(self.h, n), "spcu_set_wavefront_size")

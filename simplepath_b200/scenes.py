@@ -1,0 +1,356 @@
+"""Deterministic scene / asset generators for the BASELINE.json configs.
+
+None of the reference's five configured scenes runs as shipped: the PLY/STL/PFM assets
+are not in the repository, `example_scene.sp` uses block types the parser rejects
+(base/FileParser.cpp:871-873) and `scenes/elf.sp:11` has commas the vector reader cannot parse.  This module
+writes `.sp` files the *stock* reference parser accepts, with
+
+  * geometry / materials / lights / cameras copied in meaning from the reference scenes
+    (scenes/material_spheres.sp:15-88, scenes/bunny.sp, scenes/elf.sp, scenes/lucy.sp, example_scene.sp),
+  * procedural binary little-endian PLY meshes with the named triangle counts (closed-form displacement of a
+    sphere, no RNG) in exactly the dialect base/PlyReader.cpp:326-531 reads,
+  * a synthetic lat-long PFM environment map (analytic sky + one bright lobe) for Image/Image.cpp:78-119.
+
+Everything is a pure function of its arguments, so a GPU box regenerates identical bytes.
+CLI:  python -m simplepath_b200.scenes [--out DIR] [names...]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import struct
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+DEFAULT_OUT = REPO / "scenes" / "_gen"
+
+BUNNY_TRIS = 69_451        # bun_zipper.ply (public Stanford figure)
+LUCY_TRIS = 28_055_742     # lucy.ply (public Stanford figure)
+ELF_TRIS = 750_000         # stand-in for stl_files/elf/nude-body.stl (count not published; stated in reports)
+
+
+# --------------------------------------------------------------------------------------------------
+# assets
+# --------------------------------------------------------------------------------------------------
+def _grid_for(n_tris: int) -> tuple[int, int]:
+    """Smallest near-square (nu, nv) with 2*nu*nv >= n_tris."""
+    nv = int(np.floor(np.sqrt(n_tris / 2.0)))
+    nu = nv
+    while 2 * nu * nv < n_tris:
+        nu += 1
+    return nu, nv
+
+
+def bumpy_sphere(n_tris: int, lo, hi) -> tuple[np.ndarray, np.ndarray]:
+    """Displaced sphere with exactly n_tris triangles, fitted to the box [lo, hi].
+
+    Latitude runs over (eps, pi-eps) so no triangle is degenerate (the reader drops zero-area faces,
+    base/PlyReader.cpp:489-493); the face list of the full grid is truncated to n_tris."""
+    nu, nv = _grid_for(n_tris)
+    eps = 0.02
+    theta = np.linspace(eps, np.pi - eps, nv + 1, dtype=np.float64)[:, None]      # rows
+    phi = (np.arange(nu, dtype=np.float64) * (2.0 * np.pi / nu))[None, :]          # columns (wrapping)
+    r = (1.0 + 0.18 * np.sin(3.0 * theta) * np.sin(5.0 * phi)
+         + 0.07 * np.sin(13.0 * theta + 0.5) * np.sin(17.0 * phi + 1.0)
+         + 0.02 * np.sin(41.0 * theta) * np.cos(37.0 * phi))
+    x = r * np.sin(theta) * np.cos(phi)
+    y = r * np.cos(theta) * np.ones_like(phi)
+    z = r * np.sin(theta) * np.sin(phi)
+    v = np.stack([x, y, z], axis=-1).reshape(-1, 3)
+    vmin, vmax = v.min(0), v.max(0)
+    lo = np.asarray(lo, np.float64)
+    hi = np.asarray(hi, np.float64)
+    v = (v - vmin) / (vmax - vmin) * (hi - lo) + lo
+
+    i = np.arange(nv, dtype=np.int64)[:, None]
+    j = np.arange(nu, dtype=np.int64)[None, :]
+    a = i * nu + j
+    b = i * nu + (j + 1) % nu
+    c = (i + 1) * nu + j
+    d = (i + 1) * nu + (j + 1) % nu
+    # counter-clockwise seen from outside (y up, theta from +y)
+    t0 = np.stack([a, b, c], axis=-1)
+    t1 = np.stack([b, d, c], axis=-1)
+    faces = np.stack([t0, t1], axis=2).reshape(-1, 3)[:n_tris]
+    assert faces.shape[0] == n_tris
+    return v.astype("<f4"), faces.astype("<i4")
+
+
+def write_ply(path: Path, verts: np.ndarray, faces: np.ndarray) -> None:
+    header = (
+        "ply\n"
+        "format binary_little_endian 1.0\n"
+        f"element vertex {len(verts)}\n"
+        "property float x\nproperty float y\nproperty float z\n"
+        f"element face {len(faces)}\n"
+        "property list uchar int vertex_indices\n"
+        "end_header\n"
+    ).encode("ascii")
+    rec = np.empty(len(faces), dtype=[("n", "u1"), ("i", "<i4", (3,))])
+    rec["n"] = 3
+    rec["i"] = faces
+    tmp = path.with_suffix(path.suffix + ".tmp")
+    with open(tmp, "wb") as f:
+        f.write(header)
+        f.write(np.ascontiguousarray(verts, dtype="<f4").tobytes())
+        f.write(rec.tobytes())
+    os.replace(tmp, path)
+
+
+def sky_image(w: int, h: int) -> np.ndarray:
+    """[h, w, 3] radiance, row 0 = top of the lat-long map (theta = 0)."""
+    v = (np.arange(h, dtype=np.float64) + 0.5)[:, None] / h        # theta / pi
+    u = (np.arange(w, dtype=np.float64) + 0.5)[None, :] / w        # phi / 2pi
+    up = np.clip(1.0 - 2.0 * v, -1.0, 1.0)                         # cos(theta)-ish
+    horizon = np.exp(-8.0 * np.abs(up))
+    base_r = 0.15 + 0.35 * horizon + 0.10 * np.maximum(up, 0.0)
+    base_g = 0.20 + 0.40 * horizon + 0.25 * np.maximum(up, 0.0)
+    base_b = 0.35 + 0.45 * horizon + 0.60 * np.maximum(up, 0.0)
+    ground = (up < 0.0) * 0.6
+    lobe = 60.0 * np.exp(-((u - 0.30) ** 2 / (2 * 0.012 ** 2) + (v - 0.28) ** 2 / (2 * 0.02 ** 2)))
+    img = np.stack([
+        base_r * (1.0 - ground) + 0.08 * ground + lobe * 1.00 + 0.0 * u,
+        base_g * (1.0 - ground) + 0.07 * ground + lobe * 0.90 + 0.0 * u,
+        base_b * (1.0 - ground) + 0.06 * ground + lobe * 0.70 + 0.0 * u,
+    ], axis=-1)
+    return img.astype("<f4")
+
+
+def write_pfm(path: Path, img: np.ndarray) -> None:
+    """Image(x, y) = img[y, x]; the file stores rows j = ny-1 .. 0 (Image/Image.cpp:40-55)."""
+    h, w, _ = img.shape
+    tmp = path.with_suffix(path.suffix + ".tmp")
+    with open(tmp, "wb") as f:
+        f.write(f"PF\n{w} {h}\n-1\n".encode("ascii"))
+        f.write(np.ascontiguousarray(img[::-1], dtype="<f4").tobytes())
+    os.replace(tmp, path)
+
+
+def read_pfm(path: Path) -> np.ndarray:
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"PF"
+        w, h = map(int, f.readline().split())
+        f.readline()
+        data = np.frombuffer(f.read(w * h * 12), dtype="<f4").reshape(h, w, 3)
+    return data[::-1].copy()
+
+
+# --------------------------------------------------------------------------------------------------
+# .sp text
+# --------------------------------------------------------------------------------------------------
+_MATERIALS_SPHERES = """\
+material_lambertian {
+    name: "material_lambertian"
+    diffuse: 0.1 0.8 0.8
+}
+
+material_lambertian {
+    name: "material_lambertian_base"
+    diffuse: 0.1 0.2 0.8
+}
+
+material_glossy {
+    name: "material_glossy_base"
+    diffuse: 0.8 0.2 0.8
+    ior: 1.8
+    roughness: 0.25
+}
+
+material_glossy {
+    name: "material_glossy"
+    diffuse: 0.8 0.2 0.2
+    ior: 1.8
+    roughness: 0.75
+}
+
+material_glossy {
+    name: "material_glossy_plane"
+    diffuse: 0.6 0.6 0.6
+    ior: 1.8
+    roughness: 0.01
+}
+
+material_clearcoat {
+    name: "material_lambertian_clearcoat"
+    base: "material_lambertian_base"
+    ior: 1.5
+    color: 1.0 0.8 0.8
+}
+
+material_clearcoat {
+    name: "material_glossy_clearcoat"
+    base: "material_glossy_base"
+    ior: 1.3
+    color: 1.0 1.0 1.0
+}
+"""
+
+_MATERIALS_STATUE = """\
+material_glossy {
+    name: "material_glossy_base"
+    diffuse: 0.7 0.7 0.7
+    ior: 1.3
+    roughness: 0.75
+}
+
+material_glossy {
+    name: "material_glossy_plane"
+    diffuse: 0.4 0.1 0.1
+    ior: 1.8
+    roughness: 0.01
+}
+
+material_clearcoat {
+    name: "material_glossy_clearcoat"
+    base: "material_glossy_base"
+    ior: 1.5
+    color: 1.0 1.0 1.0
+}
+"""
+
+
+def _head(w: int, h: int, extra: str = "") -> str:
+    return f"version: 1\n\nscene_parameters {{\n    output_file_name: \"image.pfm\"\n    width: {w}\n    height: {h}\n{extra}}}\n\n"
+
+
+def sp_material_spheres(w: int, h: int, env: str) -> str:
+    """scenes/material_spheres.sp:15-88 verbatim; env = 'const' or a PFM path (scenes/material_spheres.sp:90-95)."""
+    light = ("environment_light {\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 1.0 1.0 1.0\n}\n" if env == "const" else
+             f"environment_light {{\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 1.0 1.0 1.0\n    max_radiance: 100\n    image: \"{env}\"\n}}\n")
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: 0.0 0.0 10.0\n    look_at: 0.0 0.0 0.0\n    fov: 45\n}\n\n" +
+            _MATERIALS_SPHERES + "\n" +
+            "sphere {\n    translate: 0.0 3.0 0.0\n    material: \"material_glossy_clearcoat\"\n}\n\n"
+            "sphere {\n    translate: 0.0 1.0 0.0\n    material: \"material_lambertian_clearcoat\"\n}\n\n"
+            "sphere {\n    translate: 0.0 -1.0 0.0\n    material: \"material_lambertian\"\n}\n\n"
+            "sphere {\n    translate: 0.0 -3.0 0.0\n    material: \"material_glossy\"\n}\n\n"
+            "plane {\n    material: \"material_glossy_plane\"\n    rotate: 1 0 0 90\n    translate: 0.0 0.0 -1.0\n}\n\n" +
+            light)
+
+
+def sp_example_scene(w: int, h: int) -> str:
+    """Parseable restatement of example_scene.sp: clearcoat(ior 1.3) over Lambert (0.1,0.2,0.8)
+    sphere scaled 10 at (10,0.5,0) rotated 45 deg about y; y=0 plane; sphere light; constant environment."""
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: 0.0 2.0 5.0\n    look_at: 0.0 1.0 0.0\n    fov: 45\n}\n\n"
+            "material_lambertian {\n    name: \"base\"\n    diffuse: 0.1 0.2 0.8\n}\n\n"
+            "material_clearcoat {\n    name: \"material0\"\n    base: \"base\"\n    ior: 1.3\n}\n\n"
+            "sphere {\n    translate: 10.0 0.5 0.0\n    rotate: 0.0 1.0 0.0 45.0\n    scale: 10.0 10.0 10.0\n    material: \"material0\"\n}\n\n"
+            "plane {\n    material: \"base\"\n}\n\n"
+            "sphere_light {\n    translate: 10.0 15.0 0.0\n    radiance: 10.0 10.0 15.0\n}\n\n"
+            "environment_light {\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 1.0 1.0 1.3\n}\n")
+
+
+def sp_bunny(w: int, h: int, ply: str) -> str:
+    """scenes/bunny.sp with the PLY path replaced."""
+    meshes = ""
+    for tx, mat in ((2.25, "material_glossy_clearcoat"), (0.75, "material_lambertian_clearcoat"),
+                    (-0.75, "material_lambertian"), (-2.25, "material_glossy")):
+        meshes += (f"mesh {{\n    file: \"{ply}\"\n    translate: {tx} 0.0 0.0\n    scale: 10.0 10.0 10.0\n"
+                   f"    material: \"{mat}\"\n}}\n\n")
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: 0.0 2.0 5.0\n    look_at: -0.25 1.0 0.0\n    fov: 45\n}\n\n" +
+            _MATERIALS_SPHERES + "\n" + meshes +
+            "plane {\n    material: \"material_glossy_plane\"\n    translate: 0.0 0.329874 0.0\n}\n\n"
+            "sphere_light {\n    translate: 0.0 3.0 0.0\n    scale: 0.5 0.5 0.5\n    radiance: 10.0 10.0 10.0\n}\n")
+
+
+def sp_elf(w: int, h: int, ply: str) -> str:
+    """scenes/elf.sp with the commas of :11 removed and the STL replaced by a procedural PLY."""
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: -1.79536 -0.0338669 130.0\n    look_at: -1.79536 -0.0338669 13.8378\n    fov: 45\n}\n\n" +
+            _MATERIALS_STATUE + "\n" +
+            f"mesh {{\n    file: \"{ply}\"\n    material: \"material_glossy_clearcoat\"\n}}\n\n"
+            "plane {\n    material: \"material_glossy_plane\"\n    translate: 0.0 -42.7188 0.0\n}\n\n"
+            "environment_light {\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 0.75 0.75 0.75\n}\n")
+
+
+def sp_lucy(w: int, h: int, ply: str) -> str:
+    """scenes/lucy.sp with the PLY path replaced."""
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: 690.756 500.0 -2000.0\n    look_at: 690.756 200.0 192.627\n    fov: 45\n}\n\n" +
+            _MATERIALS_STATUE + "\n" +
+            f"mesh {{\n    file: \"{ply}\"\n    rotate: 1.0 0.0 0.0 -90.0\n    material: \"material_glossy_clearcoat\"\n}}\n\n"
+            "plane {\n    material: \"material_glossy_plane\"\n    translate: 0.0 -605.893 0.0\n}\n\n"
+            "environment_light {\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 1.0 1.0 1.3\n}\n")
+
+
+# Stanford-bunny object-space bounds (public figures; consistent with the plane at y = 0.329874 after x10).
+BUNNY_LO, BUNNY_HI = (-0.0947, 0.0329874, -0.0619), (0.0610, 0.1873, 0.0588)
+# elf: stands on the plane at y = -42.7188, centred on the camera axis x = -1.795, z ~ 13.8
+ELF_LO, ELF_HI = (-22.0, -42.7188, -4.0), (18.4, 42.6, 31.7)
+# lucy is modelled z-up and rotated -90 deg about x by the scene; after rotation it should stand on
+# y = -605.893 around (690.8, *, 192.6).  Object space: (x, y, z) -> world (x, z, -y).
+LUCY_LO, LUCY_HI = (290.0, -420.0, -605.893), (1090.0, 35.0, 994.0)
+
+
+# name -> (width, height, spp, builder)
+def _specs():
+    return {
+        # BASELINE.json configs
+        "c1_material_spheres": (256, 256, 16, lambda o: sp_material_spheres(256, 256, _pfm(o, 1024, 512))),
+        "c1_material_spheres_const": (256, 256, 16, lambda o: sp_material_spheres(256, 256, "const")),
+        "c2_example_scene": (1920, 1080, 64, lambda o: sp_example_scene(1920, 1080)),
+        "c3_bunny": (1920, 1080, 256, lambda o: sp_bunny(1920, 1080, _ply(o, "bunny", BUNNY_TRIS, BUNNY_LO, BUNNY_HI))),
+        "c4_elf": (1920, 1080, 256, lambda o: sp_elf(1920, 1080, _ply(o, "elf", ELF_TRIS, ELF_LO, ELF_HI))),
+        "c5_lucy": (3840, 2160, 256, lambda o: sp_lucy(3840, 2160, _ply(o, "lucy", LUCY_TRIS, LUCY_LO, LUCY_HI))),
+        # reduced sizes of the same scenes for parity tests (oracle finishes in seconds)
+        "t_spheres_const": (96, 96, 8, lambda o: sp_material_spheres(96, 96, "const")),
+        "t_spheres_ibl": (96, 96, 8, lambda o: sp_material_spheres(96, 96, _pfm(o, 128, 64))),
+        "t_example": (160, 90, 8, lambda o: sp_example_scene(160, 90)),
+        "t_bunny": (160, 90, 4, lambda o: sp_bunny(160, 90, _ply(o, "bunny_small", 5_001, BUNNY_LO, BUNNY_HI))),
+        "t_bunny_full": (480, 270, 4, lambda o: sp_bunny(480, 270, _ply(o, "bunny", BUNNY_TRIS, BUNNY_LO, BUNNY_HI))),
+        "t_elf": (120, 90, 4, lambda o: sp_elf(120, 90, _ply(o, "elf_small", 20_000, ELF_LO, ELF_HI))),
+        "t_lucy": (128, 72, 4, lambda o: sp_lucy(128, 72, _ply(o, "lucy_small", 40_002, LUCY_LO, LUCY_HI))),
+    }
+
+
+def _ply(out: Path, stem: str, n_tris: int, lo, hi) -> str:
+    path = out / f"{stem}_{n_tris}.ply"
+    if not path.exists():
+        v, f = bumpy_sphere(n_tris, lo, hi)
+        write_ply(path, v, f)
+    return path.name
+
+
+def _pfm(out: Path, w: int, h: int) -> str:
+    path = out / f"sky_{w}x{h}.pfm"
+    if not path.exists():
+        write_pfm(path, sky_image(w, h))
+    return path.name
+
+
+def names() -> list[str]:
+    return list(_specs().keys())
+
+
+def info(name: str) -> tuple[int, int, int]:
+    w, h, spp, _ = _specs()[name]
+    return w, h, spp
+
+
+def ensure(name: str, out: Path | str = DEFAULT_OUT) -> Path:
+    """Write <out>/<name>.sp (and the assets it references, beside it) if missing; return its path."""
+    out = Path(out)
+    out.mkdir(parents=True, exist_ok=True)
+    w, h, spp, build = _specs()[name]
+    path = out / f"{name}.sp"
+    text = build(out)
+    if not path.exists() or path.read_text() != text:
+        path.write_text(text)
+    return path
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("--out", default=str(DEFAULT_OUT))
+    ap.add_argument("names", nargs="*", default=[n for n in names() if n != "c5_lucy"])
+    args = ap.parse_args()
+    for n in args.names:
+        print(ensure(n, args.out))
+
+
+if __name__ == "__main__":
+    main()

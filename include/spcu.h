@@ -280,6 +280,22 @@ int spcu_render_device(spcu_ctx* ctx, const spcu_partition* part, float* d_rgb_s
 /* Upper bound of paths kept in flight per wavefront batch (0 = default). */
 int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 
+/* Instrumentation switches (all default 0 = off; they never change results).
+ *   SPCU_OPT_COUNT_NODES : spcu_stats.{nodes_visited,prims_tested,xf_prims_tested} are counted (per-thread
+ *                          counters in the traversal loops; off in timed runs).
+ *   SPCU_OPT_STAGE_TIMING: spcu_stats.{trace_ms,shade_ms} are measured with one CUDA-event pair per launch. */
+#define SPCU_OPT_COUNT_NODES 0u
+#define SPCU_OPT_STAGE_TIMING 1u
+#define SPCU_OPT_COUNT_ 2u
+int spcu_set_option(spcu_ctx* ctx, uint32_t option, uint32_t value);
+
+/* Bytes of scene data resident on the device after spcu_upload_scene (what one upload copies host->device). */
+uint64_t spcu_scene_bytes(const spcu_ctx* ctx);
+
+/* spcu_trace_closest plus the traversal work it did, summed over the batch: counters = { internal nodes visited,
+ * triangle tests, sphere/plane tests } — the N_node / N_tri / N_xf of the byte model in DESIGN.md. */
+int spcu_trace_closest_counted(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits, uint64_t counters[3]);
+
 #ifdef __cplusplus
 }
 #endif

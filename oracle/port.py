@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE — ctypes access to oracle/libsp_oracle.so, the plain-C restatement of the hot path."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from simplepath_b200.capi import FlatScene, HIT_DTYPE, RAY_DTYPE, Light, Partition, Stats
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "libsp_oracle.so"
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        l = C.CDLL(str(LIB))
+        vp, fsp = C.c_void_p, C.POINTER(FlatScene)
+        l.spo_trace_closest.argtypes = [fsp, vp, C.c_uint64, vp, vp]
+        l.spo_trace_any.argtypes = [fsp, vp, C.c_uint64, vp]
+        l.spo_trace_lights.argtypes = [fsp, vp, C.c_uint64, vp]
+        l.spo_generate_rays.argtypes = [fsp, vp, vp, vp, C.c_uint64, vp]
+        l.spo_hit_records.argtypes = [fsp, vp, C.c_uint64, vp, vp]
+        for fn in (l.spo_trace_closest, l.spo_trace_any, l.spo_trace_lights, l.spo_generate_rays, l.spo_hit_records):
+            fn.restype = None
+        _lib = l
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def trace_closest(flat, rays, counters=False):
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+    cnt = np.zeros(3, dtype=np.uint64)
+    lib().spo_trace_closest(flat, _p(rays), rays.shape[0], _p(hits), _p(cnt) if counters else None)
+    return (hits, cnt) if counters else hits
+
+
+def trace_any(flat, rays):
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    out = np.empty(rays.shape[0], dtype=np.uint8)
+    lib().spo_trace_any(flat, _p(rays), rays.shape[0], _p(out))
+    return out
+
+
+def trace_lights(flat, rays):
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+    lib().spo_trace_lights(flat, _p(rays), rays.shape[0], _p(hits))
+    return hits
+
+
+def generate_rays(flat, jitter, pix, smp):
+    jitter = np.ascontiguousarray(jitter, dtype=np.float32)
+    pix = np.ascontiguousarray(pix, dtype=np.uint32)
+    smp = np.ascontiguousarray(smp, dtype=np.uint32)
+    rays = np.empty(pix.shape[0], dtype=RAY_DTYPE)
+    lib().spo_generate_rays(flat, _p(jitter), _p(pix), _p(smp), pix.shape[0], _p(rays))
+    return rays
+
+
+def hit_records(flat, rays):
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    out = np.empty((rays.shape[0], 6), dtype=np.float32)
+    mat = np.empty(rays.shape[0], dtype=np.int32)
+    lib().spo_hit_records(flat, _p(rays), rays.shape[0], _p(out), _p(mat))
+    return out, mat

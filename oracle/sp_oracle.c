@@ -1,0 +1,502 @@
+/*
+ * TEST INFRASTRUCTURE — see sp_oracle.h.  Plain-C restatement of the reference's hot path over the flattened
+ * scene.  Compiled with -ffp-contract=off -mfma: the ONLY fused multiply-adds are the explicit fmaf() calls
+ * that restate the reference's madd/msub (math/Math.h:137-162 == std::fma under -mavx2), which is the
+ * arithmetic contract the canonical reference build (oracle/_ref/libsp_ref.so) follows.
+ *
+ * Each function cites the reference lines it restates.
+ */
+#include "sp_oracle.h"
+
+#include <float.h>
+#include <immintrin.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SP_PI 3.14159265358979323846f /* std::numbers::pi_v<float> */
+#define SP_INV_PI 0.318309886183790671538f
+#define K_RAY_EPSILON 0.001f /* math/Ray.h:11 */
+#define K_INFINITE FLT_MAX    /* base/Constants.h:16 */
+
+typedef struct { float x, y, z; } v3;
+
+static inline v3 V(float x, float y, float z) { v3 r = { x, y, z }; return r; }
+
+/* ===================================================================================================
+ * Vector kernel (math/Vector3.h, math/Math.h)
+ * =================================================================================================== */
+
+/* dot = _mm_dp_ps(a, b, 0x7F) (math/Vector3.h:742-746): three rounded products, summed (x+y)+(z+0). */
+static inline float dot3(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + 0.0f); }
+
+/* rsqrt (math/Math.h:205-227): hardware estimate + one Newton step, same operation order. */
+static inline float sp_rsqrt(float x)
+{
+    const __m128 a = _mm_set_ss(x);
+    __m128       r = _mm_rsqrt_ss(a);
+    const __m128 c = _mm_add_ss(_mm_mul_ss(_mm_set_ss(1.5f), r),
+                                _mm_mul_ss(_mm_mul_ss(_mm_mul_ss(a, _mm_set_ss(-0.5f)), r), _mm_mul_ss(r, r)));
+    return _mm_cvtss_f32(c);
+}
+
+/* normalize (math/Vector3.h:797-805) */
+static inline v3 normalize3(v3 a)
+{
+    const float s = sp_rsqrt(dot3(a, a));
+    return V(a.x * s, a.y * s, a.z * s);
+}
+
+static inline v3 add3(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 sub3(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 scale3(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static inline v3 neg3(v3 a) { return V(-a.x, -a.y, -a.z); }
+
+/* AffineSpace::operator()(Point3) (math/AffineSpace.h:79-86): fma chain per component.  m = 12 floats c0 c1 c2 a. */
+static inline v3 xf_point(const float* m, v3 p)
+{
+    return V(fmaf(p.x, m[0], fmaf(p.y, m[3], fmaf(p.z, m[6], m[9]))),
+             fmaf(p.x, m[1], fmaf(p.y, m[4], fmaf(p.z, m[7], m[10]))),
+             fmaf(p.x, m[2], fmaf(p.y, m[5], fmaf(p.z, m[8], m[11]))));
+}
+
+/* LinearSpace3x3::operator()(Vector3) (math/LinearSpace3x3.h:153-161): m = 9 floats c0 c1 c2 */
+static inline v3 xf_vector(const float* m, v3 v)
+{
+    return V(fmaf(v.x, m[0], fmaf(v.y, m[3], v.z * m[6])),
+             fmaf(v.x, m[1], fmaf(v.y, m[4], v.z * m[7])),
+             fmaf(v.x, m[2], fmaf(v.y, m[5], v.z * m[8])));
+}
+
+/* get_ray_offset (math/Ray.h:51-85) */
+static inline float ray_offset_cos(float cos_d) { return cos_d == 0.0f ? K_RAY_EPSILON : K_RAY_EPSILON / cos_d; }
+static inline float ray_offset(v3 n, v3 d) { return ray_offset_cos(fabsf(dot3(n, d))); }
+
+/* ===================================================================================================
+ * Intersection (math/BBox.h, shapes/*.h)
+ * =================================================================================================== */
+typedef struct {
+    v3    o, d;
+    float t_min, t_max;
+} ray_t;
+
+/* sp::intersect_p(BBox, Ray, RayLimits) (math/BBox.h:122-146).  std::max(a,b) = (a<b)?b:a and
+ * std::min(a,b) = (b<a)?b:a: a NaN t_near REPLACES t0.  Do not use fmaxf/fminf here. */
+static inline int slab(const float* lo, const float* hi, const ray_t* r, float t_min, float t_max)
+{
+    const float o[3] = { r->o.x, r->o.y, r->o.z };
+    const float d[3] = { r->d.x, r->d.y, r->d.z };
+    float       t0 = t_min, t1 = t_max;
+    for (int i = 0; i < 3; ++i) {
+        const float inv    = 1.0f / d[i];
+        float       t_near = (lo[i] - o[i]) * inv;
+        float       t_far  = (hi[i] - o[i]) * inv;
+        if (t_near > t_far) {
+            const float tmp = t_near;
+            t_near          = t_far;
+            t_far           = tmp;
+        }
+        t0 = (t_near < t0) ? t0 : t_near; /* std::max(t_near, t0) */
+        t1 = (t1 < t_far) ? t1 : t_far;   /* std::min(t_far, t1)  */
+        if (t0 > t1) {
+            return 0;
+        }
+    }
+    return 1;
+}
+
+/* Triangle::intersect_impl (shapes/Triangle.h:97-146).  Returns 1 and *t, *beta, *gamma on a hit. */
+static inline int tri_hit(const float* g, const ray_t* r, float t_min, float t_max, float* t_out, float* b_out, float* c_out)
+{
+    const float A = g[0] - g[4], B = g[1] - g[5], C = g[2] - g[6];
+    const float D = g[0] - g[8], E = g[1] - g[9], F = g[2] - g[10];
+    const float G = r->d.x, H = r->d.y, I = r->d.z;
+    const float J = g[0] - r->o.x, K = g[1] - r->o.y, L = g[2] - r->o.z;
+
+    const float EIHF = fmaf(E, I, -(H * F));
+    const float GFDI = fmaf(G, F, -(D * I));
+    const float DHEG = fmaf(D, H, -(E * G));
+
+    const float denom = fmaf(A, EIHF, fmaf(B, GFDI, C * DHEG));
+    if (denom == 0) {
+        return 0;
+    }
+    const float beta = fmaf(J, EIHF, fmaf(K, GFDI, L * DHEG)) / denom;
+    if (beta <= 0.0f || beta >= 1.0f) {
+        return 0;
+    }
+    const float AKJB = fmaf(A, K, -(J * B));
+    const float JCAL = fmaf(J, C, -(A * L));
+    const float BLKC = fmaf(B, L, -(K * C));
+
+    const float gamma = fmaf(I, AKJB, fmaf(H, JCAL, G * BLKC)) / denom;
+    if (gamma <= 0.0f || beta + gamma >= 1.0f) {
+        return 0;
+    }
+    const float t = -fmaf(F, AKJB, fmaf(E, JCAL, D * BLKC)) / denom;
+    if (t < t_min || t > t_max) {
+        return 0;
+    }
+    *t_out = t;
+    *b_out = beta;
+    *c_out = gamma;
+    return 1;
+}
+
+/* Sphere::intersect_impl (shapes/Sphere.h:77-109): m = world_to_object (12 floats).  Local o, d are returned
+ * for the normal computation. */
+static inline int sphere_hit(const float* m, const ray_t* r, float t_min, float t_max, float* t_out, v3* lo, v3* ld)
+{
+    const v3    o = xf_point(m, r->o);
+    const v3    d = xf_vector(m, r->d);
+    const float a = dot3(d, d);
+    const float b = 2.0f * dot3(d, o);
+    const float c = dot3(o, o) - 1.0f; /* k_radius * k_radius */
+    float       disc = b * b - 4.0f * a * c;
+    if (disc > 0.0f) {
+        disc    = sqrtf(disc);
+        float t = (-b - disc) / (2.0f * a);
+        if (t < t_min) {
+            t = (-b + disc) / (2.0f * a);
+        }
+        if (t < t_min || t > t_max) {
+            return 0;
+        }
+        *t_out = t;
+        if (lo) {
+            *lo = o;
+            *ld = d;
+        }
+        return 1;
+    }
+    return 0;
+}
+
+/* Plane::intersect_impl (shapes/Plane.h:21-71) */
+static inline int plane_hit(const float* m, const ray_t* r, float t_min, float t_max, float* t_out)
+{
+    const v3 d = xf_vector(m, r->d);
+    if (d.y == 0.0f) {
+        return 0;
+    }
+    const v3    o = xf_point(m, r->o);
+    const float t = -o.y / d.y;
+    if (t < t_min || t > t_max) {
+        return 0;
+    }
+    *t_out = t;
+    return 1;
+}
+
+typedef struct {
+    int32_t id;
+    float   t;
+    float   beta, gamma; /* triangle barycentrics of the accepted hit */
+} closest_t;
+
+/* GeometricPrimitive::intersect via ListAccelerator::intersect_impl's accept rule (shapes/ListAccelerator.h:50-62):
+ * a hit replaces the result and shrinks t_max, so an equal-t later primitive wins. */
+static inline void geom_prim(const spcu_flat_scene* s, uint32_t id, const ray_t* r, float* t_max, closest_t* c, spo_counters* cnt)
+{
+    const float*   g    = s->geom_prims[id].v;
+    const uint32_t kind = SPCU_META_KIND(s->geom_meta[id]);
+    float          t, b = 0.0f, gm = 0.0f;
+    int            hit;
+    if (kind == SPCU_PRIM_TRIANGLE) {
+        if (cnt) ++cnt->tris;
+        hit = tri_hit(g, r, r->t_min, *t_max, &t, &b, &gm);
+    } else if (kind == SPCU_PRIM_SPHERE) {
+        if (cnt) ++cnt->xf;
+        hit = sphere_hit(g, r, r->t_min, *t_max, &t, NULL, NULL);
+    } else {
+        if (cnt) ++cnt->xf;
+        hit = plane_hit(g, r, r->t_min, *t_max, &t);
+    }
+    if (hit) {
+        *t_max   = t;
+        c->id    = (int32_t)id;
+        c->t     = t;
+        c->beta  = b;
+        c->gamma = gm;
+    }
+}
+
+static inline int geom_prim_any(const spcu_flat_scene* s, uint32_t id, const ray_t* r)
+{
+    const float*   g    = s->geom_prims[id].v;
+    const uint32_t kind = SPCU_META_KIND(s->geom_meta[id]);
+    float          t, b, gm;
+    if (kind == SPCU_PRIM_TRIANGLE) return tri_hit(g, r, r->t_min, r->t_max, &t, &b, &gm);
+    if (kind == SPCU_PRIM_SPHERE) return sphere_hit(g, r, r->t_min, r->t_max, &t, NULL, NULL);
+    return plane_hit(g, r, r->t_min, r->t_max, &t);
+}
+
+/* NodeInternal::intersect / NodeLeaf::intersect (shapes/BVHAccelerator.h:62-77,110-113): children left then right,
+ * each child's own bounds tested against the CURRENT limits; the root's bounds are never tested (:138-142). */
+static void geom_node(const spcu_flat_scene* s, int32_t link, uint32_t count, const ray_t* r, float* t_max, closest_t* c, spo_counters* cnt)
+{
+    if (link < 0) {
+        const uint32_t first = (uint32_t)~link, n = count & SPCU_LEAF_COUNT_MASK;
+        for (uint32_t i = 0; i < n; ++i) {
+            geom_prim(s, first + i, r, t_max, c, cnt);
+        }
+        return;
+    }
+    const spcu_bvh_node* node = &s->geom.nodes[link];
+    if (cnt) ++cnt->nodes;
+    for (int k = 0; k < 2; ++k) {
+        if (slab(node->box + 6 * k, node->box + 6 * k + 3, r, r->t_min, *t_max)) {
+            geom_node(s, node->child[k], node->count[k], r, t_max, c, cnt);
+        }
+    }
+}
+
+static int geom_node_any(const spcu_flat_scene* s, int32_t link, uint32_t count, const ray_t* r)
+{
+    if (link < 0) {
+        const uint32_t first = (uint32_t)~link, n = count & SPCU_LEAF_COUNT_MASK;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (geom_prim_any(s, first + i, r)) return 1;
+        }
+        return 0;
+    }
+    const spcu_bvh_node* node = &s->geom.nodes[link];
+    for (int k = 0; k < 2; ++k) {
+        if (slab(node->box + 6 * k, node->box + 6 * k + 3, r, r->t_min, r->t_max) &&
+            geom_node_any(s, node->child[k], node->count[k], r)) {
+            return 1;
+        }
+    }
+    return 0;
+}
+
+/* Scene::intersect -> ListAccelerator [unbounded..., BVH] (base/Scene.h:74-77, shapes/ListAccelerator.h:50-62) */
+static closest_t scene_intersect(const spcu_flat_scene* s, const ray_t* r, spo_counters* cnt)
+{
+    closest_t c     = { -1, r->t_max, 0.0f, 0.0f };
+    float     t_max = r->t_max;
+    for (uint32_t i = 0; i < s->geom.n_unbounded; ++i) {
+        geom_prim(s, i, r, &t_max, &c, cnt);
+    }
+    geom_node(s, s->geom.root, s->geom.root_count, r, &t_max, &c, cnt);
+    return c;
+}
+
+/* ---- lights accelerator ------------------------------------------------------------------------ */
+/* Light::intersect_lights_impl: SphereLight (Lights/Light.h:354-361), EnvironmentLight (:135-141),
+ * ImageBasedEnvironmentLight (:196-209) */
+static inline int light_hit(const spcu_light* l, const ray_t* r, float t_min, float t_max, float* t_out)
+{
+    if (l->kind == SPCU_LIGHT_SPHERE) {
+        return sphere_hit(l->world_to_object, r, t_min, t_max, t_out, NULL, NULL);
+    }
+    if (t_max < K_INFINITE) {
+        return 0;
+    }
+    *t_out = K_INFINITE;
+    return 1;
+}
+
+static inline int light_hit_any(const spcu_light* l, const ray_t* r)
+{
+    float t;
+    if (l->kind == SPCU_LIGHT_SPHERE) { /* SphereLight::intersect_p_impl :363-366 */
+        return sphere_hit(l->world_to_object, r, r->t_min, r->t_max, &t, NULL, NULL);
+    }
+    return 0; /* environment lights never occlude (:143-146, :211-214) */
+}
+
+static void lights_node(const spcu_flat_scene* s, int32_t link, uint32_t count, const ray_t* r, float* t_max, closest_t* c)
+{
+    if (link < 0) {
+        const uint32_t first = (uint32_t)~link, n = count & SPCU_LEAF_COUNT_MASK;
+        for (uint32_t i = 0; i < n; ++i) {
+            float t;
+            if (light_hit(&s->lights[first + i], r, r->t_min, *t_max, &t)) {
+                *t_max = t;
+                c->id  = (int32_t)(first + i);
+                c->t   = t;
+            }
+        }
+        return;
+    }
+    const spcu_bvh_node* node = &s->lights_accel.nodes[link];
+    for (int k = 0; k < 2; ++k) {
+        if (slab(node->box + 6 * k, node->box + 6 * k + 3, r, r->t_min, *t_max)) {
+            lights_node(s, node->child[k], node->count[k], r, t_max, c);
+        }
+    }
+}
+
+static int lights_node_any(const spcu_flat_scene* s, int32_t link, uint32_t count, const ray_t* r)
+{
+    if (link < 0) {
+        const uint32_t first = (uint32_t)~link, n = count & SPCU_LEAF_COUNT_MASK;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (light_hit_any(&s->lights[first + i], r)) return 1;
+        }
+        return 0;
+    }
+    const spcu_bvh_node* node = &s->lights_accel.nodes[link];
+    for (int k = 0; k < 2; ++k) {
+        if (slab(node->box + 6 * k, node->box + 6 * k + 3, r, r->t_min, r->t_max) &&
+            lights_node_any(s, node->child[k], node->count[k], r)) {
+            return 1;
+        }
+    }
+    return 0;
+}
+
+/* Scene::intersect_lights (base/Scene.h:69-72) */
+static closest_t scene_intersect_lights(const spcu_flat_scene* s, const ray_t* r)
+{
+    closest_t c     = { -1, r->t_max, 0.0f, 0.0f };
+    float     t_max = r->t_max;
+    for (uint32_t i = 0; i < s->lights_accel.n_unbounded; ++i) {
+        float t;
+        if (light_hit(&s->lights[i], r, r->t_min, t_max, &t)) {
+            t_max = t;
+            c.id  = (int32_t)i;
+            c.t   = t;
+        }
+    }
+    lights_node(s, s->lights_accel.root, s->lights_accel.root_count, r, &t_max, &c);
+    return c;
+}
+
+/* Scene::intersect_p (base/Scene.h:79-82): geometry || lights */
+static int scene_intersect_p(const spcu_flat_scene* s, const ray_t* r)
+{
+    for (uint32_t i = 0; i < s->geom.n_unbounded; ++i) {
+        if (geom_prim_any(s, i, r)) return 1;
+    }
+    if (geom_node_any(s, s->geom.root, s->geom.root_count, r)) return 1;
+    for (uint32_t i = 0; i < s->lights_accel.n_unbounded; ++i) {
+        if (light_hit_any(&s->lights[i], r)) return 1;
+    }
+    return lights_node_any(s, s->lights_accel.root, s->lights_accel.root_count, r);
+}
+
+static inline ray_t load_ray(const spcu_ray* q)
+{
+    ray_t r = { V(q->ox, q->oy, q->oz), V(q->dx, q->dy, q->dz), q->t_min, q->t_max };
+    return r;
+}
+
+/* ---- Intersection record (shapes/Intersection.h:17-23) ------------------------------------------ */
+typedef struct {
+    float    t;
+    v3       normal, point;
+    uint32_t material;
+} isect_t;
+
+/* Triangle.h:148-160, Sphere.h:99-104, Plane.h:65-70 */
+static isect_t make_isect(const spcu_flat_scene* s, const ray_t* r, const closest_t* c)
+{
+    isect_t        is;
+    const uint32_t meta = s->geom_meta[c->id];
+    const float*   sh   = s->geom_shade[c->id].v;
+    is.t                = c->t;
+    is.material         = SPCU_META_MATERIAL(meta);
+    /* Ray::operator() (math/Ray.h:30-34): origin + direction * d */
+    is.point = add3(r->o, scale3(r->d, c->t));
+    if (SPCU_META_KIND(meta) == SPCU_PRIM_TRIANGLE) {
+        const float alpha = 1.0f - c->beta - c->gamma;
+        const v3    n     = V(fmaf(alpha, sh[0], fmaf(c->beta, sh[4], c->gamma * sh[8])),
+                              fmaf(alpha, sh[1], fmaf(c->beta, sh[5], c->gamma * sh[9])),
+                              fmaf(alpha, sh[2], fmaf(c->beta, sh[6], c->gamma * sh[10])));
+        is.normal         = normalize3(n);
+    } else if (SPCU_META_KIND(meta) == SPCU_PRIM_SPHERE) {
+        const float* m = s->geom_prims[c->id].v;
+        const v3     o = xf_point(m, r->o);
+        const v3     d = xf_vector(m, r->d);
+        /* madd(t, d, o) / k_radius */
+        const v3 n = V(fmaf(c->t, d.x, o.x) / 1.0f, fmaf(c->t, d.y, o.y) / 1.0f, fmaf(c->t, d.z, o.z) / 1.0f);
+        const v3 w = V(fmaf(n.x, sh[0], fmaf(n.y, sh[4], n.z * sh[8])),
+                       fmaf(n.x, sh[1], fmaf(n.y, sh[5], n.z * sh[9])),
+                       fmaf(n.x, sh[2], fmaf(n.y, sh[6], n.z * sh[10])));
+        is.normal  = normalize3(w);
+    } else {
+        /* get_object_to_world()(Normal3{0,1,0}) — NOT normalised (Plane.h:66) */
+        is.normal = V(fmaf(0.0f, sh[0], fmaf(1.0f, sh[4], 0.0f * sh[8])),
+                      fmaf(0.0f, sh[1], fmaf(1.0f, sh[5], 0.0f * sh[9])),
+                      fmaf(0.0f, sh[2], fmaf(1.0f, sh[6], 0.0f * sh[10])));
+    }
+    return is;
+}
+
+/* ===================================================================================================
+ * Public batch entry points
+ * =================================================================================================== */
+void spo_trace_closest(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, spcu_hit* hits, spo_counters* cnt)
+{
+    spo_counters local = { 0, 0, 0 };
+    for (uint64_t i = 0; i < n; ++i) {
+        const ray_t     r = load_ray(&rays[i]);
+        const closest_t c = scene_intersect(s, &r, cnt ? &local : NULL);
+        hits[i].id        = c.id;
+        hits[i].t         = c.t;
+    }
+    if (cnt) *cnt = local;
+}
+
+void spo_trace_any(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, uint8_t* out)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const ray_t r = load_ray(&rays[i]);
+        out[i]        = (uint8_t)scene_intersect_p(s, &r);
+    }
+}
+
+void spo_trace_lights(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, spcu_hit* hits)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const ray_t     r = load_ray(&rays[i]);
+        const closest_t c = scene_intersect_lights(s, &r);
+        hits[i].id        = c.id;
+        hits[i].t         = c.t;
+    }
+}
+
+/* PerspectiveCamera::generate_ray_impl (Cameras/Camera.h:119-129): normalize(px*col0 + py*col1 + col2) */
+static ray_t camera_ray(const spcu_flat_scene* s, float px, float py)
+{
+    const float* m = s->camera;
+    const v3     d = V((px * m[0] + py * m[3]) + m[6], (px * m[1] + py * m[4]) + m[7], (px * m[2] + py * m[5]) + m[8]);
+    ray_t        r = { V(m[9], m[10], m[11]), normalize3(d), K_RAY_EPSILON, K_INFINITE };
+    return r;
+}
+
+void spo_generate_rays(const spcu_flat_scene* s, const float* jitter, const uint32_t* pix, const uint32_t* smp,
+                       uint64_t n, spcu_ray* rays)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t x = pix[i] % s->width, y = pix[i] / s->width;
+        /* main.cpp:97: p.x + sample.x with p.x an int */
+        const ray_t r = camera_ray(s, (float)(int)x + jitter[2 * smp[i]], (float)(int)y + jitter[2 * smp[i] + 1]);
+        const spcu_ray q = { r.o.x, r.o.y, r.o.z, r.t_min, r.d.x, r.d.y, r.d.z, r.t_max };
+        rays[i]          = q;
+    }
+}
+
+void spo_hit_records(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, float* normal_point, int32_t* material)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const ray_t     r = load_ray(&rays[i]);
+        const closest_t c = scene_intersect(s, &r, NULL);
+        float*          o = normal_point + 6 * i;
+        memset(o, 0, 6 * sizeof(float));
+        if (material) material[i] = -1;
+        if (c.id >= 0) {
+            const isect_t is = make_isect(s, &r, &c);
+            o[0] = is.normal.x; o[1] = is.normal.y; o[2] = is.normal.z;
+            o[3] = is.point.x;  o[4] = is.point.y;  o[5] = is.point.z;
+            if (material) material[i] = (int32_t)is.material;
+        }
+    }
+}
+
+#include "sp_oracle_shade.inc"

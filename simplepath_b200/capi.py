@@ -101,8 +101,10 @@ class Stats(C.Structure):
 EXPORTS = [
     "spcu_create", "spcu_destroy", "spcu_last_error", "spcu_abi_version", "spcu_upload_scene",
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
-    "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size",
+    "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
+    "spcu_scene_bytes", "spcu_trace_closest_counted",
 ]
+OPT_COUNT_NODES, OPT_STAGE_TIMING = 0, 1
 
 
 class SpcuError(RuntimeError):
@@ -146,6 +148,12 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_render_device.restype = C.c_int
     lib.spcu_set_wavefront_size.argtypes = [vp, C.c_uint64]
     lib.spcu_set_wavefront_size.restype = C.c_int
+    lib.spcu_set_option.argtypes = [vp, C.c_uint32, C.c_uint32]
+    lib.spcu_set_option.restype = C.c_int
+    lib.spcu_scene_bytes.argtypes = [vp]
+    lib.spcu_scene_bytes.restype = C.c_uint64
+    lib.spcu_trace_closest_counted.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    lib.spcu_trace_closest_counted.restype = C.c_int
     if lib.spcu_abi_version() != ABI_VERSION:
         raise SpcuError("libspcu.so ABI version mismatch")
     if path is None:
@@ -199,6 +207,21 @@ class Context:
 
     def trace_closest(self, rays):
         return self._trace(self.lib.spcu_trace_closest, rays, "spcu_trace_closest")
+
+    def trace_closest_counted(self, rays):
+        """(hits, [internal nodes visited, triangle tests, sphere/plane tests])"""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        cnt = np.zeros(3, dtype=np.uint64)
+        self._check(self.lib.spcu_trace_closest_counted(self.h, _ptr(rays), rays.shape[0], _ptr(hits), _ptr(cnt)),
+                    "spcu_trace_closest_counted")
+        return hits, cnt
+
+    def set_option(self, option: int, value: int) -> None:
+        self._check(self.lib.spcu_set_option(self.h, option, value), "spcu_set_option")
+
+    def scene_bytes(self) -> int:
+        return int(self.lib.spcu_scene_bytes(self.h))
 
     def trace_closest_fast(self, rays):
         return self._trace(self.lib.spcu_trace_closest_fast, rays, "spcu_trace_closest_fast")

@@ -1,0 +1,106 @@
+// Private to the backend's host code: the context behind the opaque spcu_ctx handle and error plumbing.
+#pragma once
+
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace spcu {
+
+struct DevBuf
+{
+    void*  p     = nullptr;
+    size_t bytes = 0;
+
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) {
+            return cudaSuccess;
+        }
+        if (p) {
+            cudaFree(p);
+            p     = nullptr;
+            bytes = 0;
+        }
+        const cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) {
+            bytes = n;
+        }
+        return e;
+    }
+
+    void release()
+    {
+        if (p) {
+            cudaFree(p);
+        }
+        p     = nullptr;
+        bytes = 0;
+    }
+
+    template <typename T>
+    T* as() const
+    {
+        return static_cast<T*>(p);
+    }
+};
+
+constexpr int      kNumQueues      = 5;        // cur, next, live, shadow, mis
+constexpr int      kMaxQueueCounts = 4096;     // device queue-length words zeroed once per batch
+constexpr uint64_t kBatchRays      = 1u << 22; // rays per chunk of the batch query entry points
+
+} // namespace spcu
+
+struct spcu_ctx
+{
+    int          device = 0;
+    std::string  err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    int          sm_count = 148;
+
+    // scene
+    bool         have_scene = false;
+    spcu::DScene ds{};
+    spcu::DevBuf geom_nodes, geom_prims, geom_shade, geom_meta, light_nodes, lights, light_order, materials, bxdfs, pool,
+        jitter;
+    uint64_t scene_bytes = 0;
+
+    // batch-query scratch
+    spcu::DevBuf q_rays, q_out, q_aux, q_cnt;
+
+    // wavefront
+    uint64_t                  wavefront_size = 0; // 0 = default
+    spcu::DWave               wave{};
+    std::vector<spcu::DevBuf> wave_bufs;
+    spcu::DevBuf              queues[spcu::kNumQueues];
+    spcu::DevBuf              queue_counts; // uint32[kMaxQueueCounts]
+    spcu::DevBuf              counters;     // unsigned long long[kNumCounters] followed by TraceCounters
+    spcu::DevBuf              pix_list;
+    uint32_t                  pix_list_offset = ~0u, pix_list_stride = 0, pix_list_n = 0;
+    spcu::DevBuf              host_rgb, host_sq; // device accumulators of the host-buffer entry point
+
+    uint32_t                 options[SPCU_OPT_COUNT_] = {};
+    std::vector<cudaEvent_t> stage_events; // pairs, when SPCU_OPT_STAGE_TIMING is on
+    std::vector<int>         stage_kinds;
+};
+
+namespace spcu {
+
+int fail(spcu_ctx* c, int code, const char* fmt, ...);
+int need_scene(spcu_ctx* c);
+
+#define CK(ctx, call)                                                                                                     \
+    do {                                                                                                                  \
+        const cudaError_t e_ = (call);                                                                                    \
+        if (e_ != cudaSuccess) {                                                                                          \
+            return spcu::fail((ctx), SPCU_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                                 \
+    } while (0)
+
+} // namespace spcu

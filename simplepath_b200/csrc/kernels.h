@@ -1,0 +1,71 @@
+// Host-callable launchers of the backend's kernels.  Each .cu translation unit defines its own kernels (no
+// relocatable device code); the C-ABI layer (spcu_api.cu) only sees these functions.
+#pragma once
+
+#include "device_scene.h"
+
+namespace spcu {
+
+// ---- trace_kernels.cu (compiled with --fmad=false; exact, reference-order traversal) ---------------------------
+void launch_trace_closest(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, TraceCounters* d_cnt,
+                          cudaStream_t st);
+void launch_trace_any(const DScene& s, const spcu_ray* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t st);
+void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, cudaStream_t st);
+
+// Wavefront stages that traverse.  `queue` holds path slots; n_queue is read on the device (no host sync).
+// extend: Scene::intersect_lights then Scene::intersect for every queued path (Integrator.cpp:558-563).
+void launch_extend(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
+                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st);
+// shadow: Scene::intersect_p of the light-sample visibility ray (Integrator.cpp:503).
+void launch_shadow(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
+                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st);
+// mis: Scene::intersect_lights then, on a light hit, Scene::intersect_p of the BSDF-sampled ray (Integrator.cpp:531-532).
+void launch_mis_trace(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
+                      unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st);
+
+// ---- shade_kernels.cu ------------------------------------------------------------------------------------------
+struct RenderParams
+{
+    uint64_t seed;
+    uint32_t integrator;
+    uint32_t depth;       // current path depth
+    uint32_t light_index; // index into light_order of the light handled by the NEE stages
+};
+
+void launch_generate_rays(const DScene& s, const uint32_t* d_pix, const uint32_t* d_smp, uint64_t n, spcu_ray* d_rays,
+                          cudaStream_t st);
+// raygen: fills slots [0, n) from (pixel list, sample range) and the initial queue (main.cpp:90-98).
+void launch_raygen(const DScene& s, const DWave& w, const uint32_t* d_pix_list, uint32_t pix_begin, uint32_t n_pix,
+                   uint32_t sample_begin, uint32_t n_samples, uint32_t* queue, uint32_t* d_n_queue,
+                   unsigned long long* d_counters, cudaStream_t st);
+// shade: hit/miss handling + primary BSDF sample S0 (Integrator.cpp:558-572,627-632).  Surviving paths go to q_out.
+void launch_shade(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in, const uint32_t* d_n_in,
+                  uint32_t max_n, uint32_t* q_out, uint32_t* d_n_out, unsigned long long* d_counters, cudaStream_t st);
+// nee_light: Light::sample for light p.light_index; paths with a usable sample go to q_shadow (Integrator.cpp:497-501).
+void launch_nee_light(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in, const uint32_t* d_n_in,
+                      uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow, unsigned long long* d_counters,
+                      cudaStream_t st);
+// nee_bsdf: light-strategy contribution, second BSDF sample, Light::pdf; paths needing the BSDF-strategy ray go to
+// q_mis (Integrator.cpp:508-530).
+void launch_nee_bsdf(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
+                     const uint32_t* d_n_shadow, uint32_t max_n, uint32_t* q_mis, uint32_t* d_n_mis,
+                     unsigned long long* d_counters, cudaStream_t st);
+// nee_mis_accumulate: BSDF-strategy contribution after the mis trace (Integrator.cpp:531-535).
+void launch_nee_mis_accumulate(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_mis,
+                               const uint32_t* d_n_mis, uint32_t max_n, cudaStream_t st);
+// direct: DirectLightingIntegrator's per-light term after the shadow trace (Integrator.cpp:296-306).
+void launch_direct_accumulate(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
+                              const uint32_t* d_n_shadow, uint32_t max_n, unsigned long long* d_counters, cudaStream_t st);
+// advance: throughput update, Russian roulette, next segment (Integrator.cpp:601-626); survivors go to q_out.
+void launch_advance(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in, const uint32_t* d_n_in,
+                    uint32_t max_n, uint32_t* q_out, uint32_t* d_n_out, cudaStream_t st);
+// resolve: per pixel, add this batch's samples in sample order to the accumulators (main.cpp:100).
+void launch_resolve(const DWave& w, const uint32_t* d_pix_list, uint32_t pix_begin, uint32_t n_pix, uint32_t n_samples,
+                    float* d_rgb_sum, float* d_lum_sumsq, cudaStream_t st);
+// pixel list of one rank: tiles t with t % stride == offset, 8x8 tiles row major (TileScheduler.h:66-82)
+uint32_t    count_partition_pixels(uint32_t width, uint32_t height, uint32_t tile_offset, uint32_t tile_stride);
+// d_tile_prefix_scratch: one uint32 per owned tile.  Synchronises the stream.
+cudaError_t build_pixel_list(uint32_t width, uint32_t height, uint32_t tile_offset, uint32_t tile_stride,
+                             uint32_t* d_pix_list, uint32_t* d_tile_prefix_scratch, cudaStream_t st);
+
+} // namespace spcu

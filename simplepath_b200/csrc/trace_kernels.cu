@@ -1,0 +1,246 @@
+// Traversal kernels of the backend: the batch queries behind spcu_trace_* (parity tests) and the three wavefront
+// stages that traverse (extend, shadow, mis).  All of them walk the flattened accelerators in REFERENCE ORDER with
+// the reference's exact arithmetic (trace.cuh); this TU is compiled with --fmad=false.
+//
+// Launch shape: one thread per ray, kTraceBlock threads per CTA, grid = ceil(n / kTraceBlock).  The traversal stack's
+// first kStackShared levels live in shared memory ([level][thread], conflict free), the rest spills to local memory.
+#include "kernels.h"
+#include "trace.cuh"
+
+namespace spcu {
+namespace {
+
+__device__ __forceinline__ Ray load_ray(const spcu_ray* rays, uint64_t i, float& t_max)
+{
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 0);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1);
+    t_max          = b.w;
+    return Ray{ a.x, a.y, a.z, b.x, b.y, b.z, a.w };
+}
+
+// Warp-aggregated add of per-thread counters: one atomic per warp and counter.
+__device__ __forceinline__ void flush_counters(const TraceCounters& local, TraceCounters* global)
+{
+    unsigned long long n = local.nodes, t = local.tris, x = local.xf;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n += __shfl_down_sync(0xffffffffu, n, off);
+        t += __shfl_down_sync(0xffffffffu, t, off);
+        x += __shfl_down_sync(0xffffffffu, x, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n) atomicAdd(&global->nodes, n);
+        if (t) atomicAdd(&global->tris, t);
+        if (x) atomicAdd(&global->xf, x);
+    }
+}
+
+__device__ __forceinline__ void warp_count(unsigned long long* counter, bool pred)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if ((threadIdx.x & 31) == 0 && m) {
+        atomicAdd(counter, static_cast<unsigned long long>(__popc(m)));
+    }
+}
+
+// ---- batch queries -----------------------------------------------------------------------------------------------
+template <bool kCount>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ DScene s, const spcu_ray* rays,
+                                                               uint64_t n, spcu_hit* hits, TraceCounters* cnt)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint64_t     i = static_cast<uint64_t>(blockIdx.x) * kTraceBlock + threadIdx.x;
+    TraceCounters      local{ 0, 0, 0 };
+    if (i < n) {
+        float           t_max, beta, gamma;
+        const Ray       r = load_ray(rays, i, t_max);
+        const GeomPrims gp{ s.geom_prims, s.geom_meta };
+        const int32_t   id = closest_hit<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local);
+        hits[i]            = spcu_hit{ id, t_max };
+    }
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+__global__ void __launch_bounds__(kTraceBlock) k_trace_any(const __grid_constant__ DScene s, const spcu_ray* rays, uint64_t n,
+                                                           uint8_t* out)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint64_t     i = static_cast<uint64_t>(blockIdx.x) * kTraceBlock + threadIdx.x;
+    if (i < n) {
+        float     t_max;
+        const Ray r = load_ray(rays, i, t_max);
+        out[i]      = scene_any_hit<false>(s, r, t_max, stack + threadIdx.x, nullptr) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kTraceBlock) k_trace_lights(const __grid_constant__ DScene s, const spcu_ray* rays,
+                                                              uint64_t n, spcu_hit* hits)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint64_t     i = static_cast<uint64_t>(blockIdx.x) * kTraceBlock + threadIdx.x;
+    if (i < n) {
+        float            t_max, beta, gamma;
+        const Ray        r = load_ray(rays, i, t_max);
+        const LightPrims lp{ s.lights };
+        const int32_t    id = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack + threadIdx.x, nullptr);
+        hits[i]             = spcu_hit{ id, t_max };
+    }
+}
+
+// ---- wavefront stages ----------------------------------------------------------------------------------------------
+// extend: Integrator.cpp:558-563.  intersect_lights first; a light hit shrinks t_max for the geometry query.
+template <bool kCount>
+__global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                        const uint32_t* queue, const uint32_t* n_queue,
+                                                        unsigned long long* counters, TraceCounters* cnt)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint32_t     i      = blockIdx.x * kTraceBlock + threadIdx.x;
+    const bool         active = i < *n_queue;
+    TraceCounters      local{ 0, 0, 0 };
+    if (active) {
+        const uint32_t slot = queue[i];
+        const float4   o    = w.ray_o[slot];
+        const float4   d    = w.ray_d[slot];
+        const Ray      r{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
+        float          t_max = d.w, beta, gamma;
+
+        const LightPrims lp{ s.lights };
+        const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack + threadIdx.x, nullptr);
+        w.light_hit[slot]   = make_int2(li, __float_as_int(t_max));
+
+        const GeomPrims gp{ s.geom_prims, s.geom_meta };
+        const int32_t   gi = closest_hit<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local);
+        w.hit[slot]        = HitRec{ gi, t_max, beta, gamma };
+    }
+    warp_count(counters + kCntRaysClosest, active);
+    warp_count(counters + kCntRaysLights, active);
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+// shadow: Integrator.cpp:503 — Scene::intersect_p of the light sample's visibility ray.
+template <bool kCount>
+__global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                        const uint32_t* queue, const uint32_t* n_queue,
+                                                        unsigned long long* counters, TraceCounters* cnt)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint32_t     i      = blockIdx.x * kTraceBlock + threadIdx.x;
+    const bool         active = i < *n_queue;
+    TraceCounters      local{ 0, 0, 0 };
+    if (active) {
+        const uint32_t slot = queue[i];
+        const float4   p    = w.isect_p[slot];
+        const float4   d    = w.sh_d[slot];
+        const Ray      r{ p.x, p.y, p.z, d.x, d.y, d.z, w.sh_tmin[slot] };
+        w.occluded[slot] = scene_any_hit<kCount>(s, r, d.w, stack + threadIdx.x, &local) ? 1 : 0;
+    }
+    warp_count(counters + kCntRaysAny, active);
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+// mis: Integrator.cpp:527-532 — intersect_lights of the BSDF-sampled ray and, when it reaches a light, intersect_p
+// with the SAME limits (t_max stays FLT_MAX: a sphere light therefore occludes itself, as in the reference).
+template <bool kCount>
+__global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                           const uint32_t* queue, const uint32_t* n_queue,
+                                                           unsigned long long* counters, TraceCounters* cnt)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint32_t     i      = blockIdx.x * kTraceBlock + threadIdx.x;
+    const bool         active = i < *n_queue;
+    TraceCounters      local{ 0, 0, 0 };
+    bool               traced_any = false;
+    if (active) {
+        const uint32_t slot = queue[i];
+        const float4   p    = w.isect_p[slot];
+        const float4   d    = w.mis_d[slot];
+        const Ray      r{ p.x, p.y, p.z, d.x, d.y, d.z, d.w };
+        float          t_max = kInfinite, beta, gamma;
+
+        const LightPrims lp{ s.lights };
+        const int32_t    li  = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack + threadIdx.x, nullptr);
+        int              occ = 0;
+        if (li >= 0) {
+            traced_any = true;
+            occ        = scene_any_hit<kCount>(s, r, kInfinite, stack + threadIdx.x, &local) ? 1 : 0;
+        }
+        w.mis_hit[slot] = make_int2(li, occ);
+    }
+    warp_count(counters + kCntRaysLights, active);
+    warp_count(counters + kCntRaysAny, traced_any);
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+inline unsigned grid_for(uint64_t n)
+{
+    return static_cast<unsigned>((n + kTraceBlock - 1) / kTraceBlock);
+}
+
+} // namespace
+
+void launch_trace_closest(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, TraceCounters* d_cnt,
+                          cudaStream_t st)
+{
+    if (n == 0) return;
+    if (d_cnt) {
+        k_trace_closest<true><<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits, d_cnt);
+    } else {
+        k_trace_closest<false><<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits, nullptr);
+    }
+}
+
+void launch_trace_any(const DScene& s, const spcu_ray* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t st)
+{
+    if (n == 0) return;
+    k_trace_any<<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_out);
+}
+
+void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, cudaStream_t st)
+{
+    if (n == 0) return;
+    k_trace_lights<<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits);
+}
+
+void launch_extend(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
+                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st)
+{
+    if (max_n == 0) return;
+    if (d_cnt) {
+        k_extend<true><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, d_cnt);
+    } else {
+        k_extend<false><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, nullptr);
+    }
+}
+
+void launch_shadow(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
+                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st)
+{
+    if (max_n == 0) return;
+    if (d_cnt) {
+        k_shadow<true><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, d_cnt);
+    } else {
+        k_shadow<false><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, nullptr);
+    }
+}
+
+void launch_mis_trace(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
+                      unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st)
+{
+    if (max_n == 0) return;
+    if (d_cnt) {
+        k_mis_trace<true><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, d_cnt);
+    } else {
+        k_mis_trace<false><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, nullptr);
+    }
+}
+
+} // namespace spcu

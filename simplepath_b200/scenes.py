@@ -304,6 +304,12 @@ def _specs():
         "t_bunny_full": (480, 270, 4, lambda o: sp_bunny(480, 270, _ply(o, "bunny", BUNNY_TRIS, BUNNY_LO, BUNNY_HI))),
         "t_elf": (120, 90, 4, lambda o: sp_elf(120, 90, _ply(o, "elf_small", 20_000, ELF_LO, ELF_HI))),
         "t_lucy": (128, 72, 4, lambda o: sp_lucy(128, 72, _ply(o, "lucy_small", 40_002, LUCY_LO, LUCY_HI))),
+        # tiny versions whose flattened form is committed under tests/golden/ (tests/golden/make_golden.py)
+        "g_spheres": (32, 32, 4, lambda o: sp_material_spheres(32, 32, "const")),
+        "g_spheres_ibl": (32, 32, 4, lambda o: sp_material_spheres(32, 32, _pfm(o, 32, 16))),
+        "g_example": (48, 27, 4, lambda o: sp_example_scene(48, 27)),
+        "g_bunny": (48, 27, 4, lambda o: sp_bunny(48, 27, _ply(o, "bunny_tiny", 420, BUNNY_LO, BUNNY_HI))),
+        "g_elf": (32, 24, 4, lambda o: sp_elf(32, 24, _ply(o, "elf_tiny", 1_500, ELF_LO, ELF_HI))),
     }
 
 

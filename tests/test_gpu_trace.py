@@ -1,0 +1,103 @@
+"""Parity of the CUDA traversal kernels, through the C-ABI, with the oracle and the golden vectors of the reference:
+primitive IDs bit-exact, distances 0 ulp (identical operation sequence), any-hit flags and light hits identical,
+traversal counters identical (same topology walked in the same order)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names
+from simplepath_b200.capi import RAY_DTYPE, HIT_DTYPE
+from simplepath_b200.flat import FlatSceneData
+import raybatches
+
+pytestmark = pytest.mark.gpu
+BATCHES = ["camera", "random", "segments", "axis", "grazing"]
+
+
+def ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+@pytest.fixture(scope="module", params=golden_names())
+def scene(request, ctx):
+    flat = FlatSceneData.load(GOLDEN / f"{request.param}.flat.npz")
+    vec = np.load(GOLDEN / f"{request.param}.vectors.npz")
+    ctx.upload_scene(flat.pointer(), vec["jitter"], keepalive=flat)
+    return request.param, flat, vec
+
+
+@pytest.mark.parametrize("batch", BATCHES)
+def test_golden_batches(ctx, scene, batch):
+    name, flat, vec = scene
+    rays = np.ascontiguousarray(vec[f"{batch}.rays"]).view(RAY_DTYPE).reshape(-1)
+    hits, cnt = ctx.trace_closest_counted(rays)
+    mism = int((hits["id"] != vec[f"{batch}.closest_id"]).sum())
+    assert mism == 0, f"{name}/{batch}: {mism} primitive-ID mismatches vs the reference"
+    assert ulp_diff(hits["t"], vec[f"{batch}.closest_t"]).max() == 0
+    assert np.array_equal(cnt, vec[f"{batch}.counters"])
+    assert np.array_equal(ctx.trace_any(rays), vec[f"{batch}.any"])
+    lh = ctx.trace_lights(rays)
+    assert np.array_equal(lh["id"], vec[f"{batch}.lights_id"])
+    assert ulp_diff(lh["t"], vec[f"{batch}.lights_t"]).max() == 0
+
+
+def test_camera_rays(ctx, scene):
+    """Directions differ from the reference only through normalize() (SSE rsqrt estimate + Newton step there, correctly
+    rounded rsqrt here): stated tolerance 4 ulp per component; origins and limits bitwise."""
+    name, flat, vec = scene
+    want = np.ascontiguousarray(vec["camera.rays"]).view(RAY_DTYPE).reshape(-1)
+    got = ctx.generate_rays(vec["cam_pix"], vec["cam_smp"])
+    assert got["o"].tobytes() == want["o"].tobytes()
+    assert got["t_min"].tobytes() == want["t_min"].tobytes() and got["t_max"].tobytes() == want["t_max"].tobytes()
+    assert ulp_diff(got["d"].reshape(-1), want["d"].reshape(-1)).max() <= 4
+
+
+def test_empty_and_ragged_batches(ctx, scene):
+    name, flat, vec = scene
+    empty = np.empty(0, dtype=RAY_DTYPE)
+    assert ctx.trace_closest(empty).shape == (0,)
+    assert ctx.trace_any(empty).shape == (0,)
+    rays = np.ascontiguousarray(vec["random.rays"]).view(RAY_DTYPE).reshape(-1)
+    for n in (1, 31, 33, 127, 129):
+        got = ctx.trace_closest(rays[:n])
+        assert np.array_equal(got["id"], vec["random.closest_id"][:n])
+
+
+def test_degenerate_limits(ctx, scene, oracle_port):
+    """t_max below t_min, zero-length windows and t_max = 0: nothing may be hit, result t echoes the query's t_max."""
+    name, flat, vec = scene
+    rays = np.ascontiguousarray(vec["random.rays"]).view(RAY_DTYPE).reshape(-1)[:512].copy()
+    rays["t_min"] = 5.0
+    rays["t_max"] = 1.0
+    got = ctx.trace_closest(rays)
+    want = oracle_port.trace_closest(flat.pointer(), rays)
+    assert np.array_equal(got["id"], want["id"]) and got["t"].tobytes() == want["t"].tobytes()
+    assert (got["id"] == -1).all()
+
+
+@pytest.mark.parametrize("n_each", [1 << 16])
+def test_large_fresh_batches_vs_oracle(ctx, scene, oracle_port, n_each):
+    """Fresh seeds at a size the oracle still finishes in seconds."""
+    name, flat, vec = scene
+    for bname, rays in raybatches.all_batches(flat, n_each).items():
+        rays = rays.copy()
+        got = ctx.trace_closest(rays)
+        want = oracle_port.trace_closest(flat.pointer(), rays)
+        assert int((got["id"] != want["id"]).sum()) == 0, f"{name}/{bname}"
+        assert got["t"].tobytes() == want["t"].tobytes()
+        assert np.array_equal(ctx.trace_any(rays), oracle_port.trace_any(flat.pointer(), rays))
+        gl, wl = ctx.trace_lights(rays), oracle_port.trace_lights(flat.pointer(), rays)
+        assert np.array_equal(gl["id"], wl["id"]) and gl["t"].tobytes() == wl["t"].tobytes()
+
+
+def test_errors_are_reported(ctx):
+    from simplepath_b200 import capi
+    fresh = capi.Context(0)
+    try:
+        with pytest.raises(capi.SpcuError):
+            fresh.trace_closest(np.zeros(4, dtype=RAY_DTYPE))  # no scene uploaded
+    finally:
+        fresh.close()

@@ -70,3 +70,29 @@ def hit_records(flat, rays):
     mat = np.empty(rays.shape[0], dtype=np.int32)
     lib().spo_hit_records(flat, _p(rays), rays.shape[0], _p(out), _p(mat))
     return out, mat
+
+
+def render(flat, jitter, part: Partition, threads: int = 0, want_sumsq: bool = True):
+    """spo_render over a partition: (rgb_sum [H,W,3], lum_sumsq [H,W] | None, stats dict)."""
+    import os
+    l = lib()
+    l.spo_render.argtypes = [C.POINTER(FlatScene), C.c_void_p, C.POINTER(Partition), C.c_void_p, C.c_void_p,
+                             C.POINTER(Stats), C.c_int]
+    l.spo_render.restype = None
+    fs = flat.contents if isinstance(flat, C.POINTER(FlatScene)) else flat
+    jitter = np.ascontiguousarray(jitter, dtype=np.float32)
+    rgb = np.zeros((fs.height, fs.width, 3), dtype=np.float32)
+    sq = np.zeros((fs.height, fs.width), dtype=np.float32) if want_sumsq else None
+    st = Stats()
+    l.spo_render(flat, _p(jitter), C.byref(part), _p(rgb), _p(sq) if want_sumsq else None, C.byref(st),
+                 threads or (os.cpu_count() or 1))
+    return rgb, sq, st.as_dict()
+
+
+def rng4(seed: int, pixel: int, sample: int, ctr: int) -> np.ndarray:
+    l = lib()
+    l.spo_rng4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    l.spo_rng4.restype = None
+    out = np.zeros(4, dtype=np.float32)
+    l.spo_rng4(seed, pixel, sample, ctr, _p(out))
+    return out

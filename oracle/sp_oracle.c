@@ -224,12 +224,16 @@ static inline void geom_prim(const spcu_flat_scene* s, uint32_t id, const ray_t*
     }
 }
 
-static inline int geom_prim_any(const spcu_flat_scene* s, uint32_t id, const ray_t* r)
+static inline int geom_prim_any(const spcu_flat_scene* s, uint32_t id, const ray_t* r, spo_counters* cnt)
 {
     const float*   g    = s->geom_prims[id].v;
     const uint32_t kind = SPCU_META_KIND(s->geom_meta[id]);
     float          t, b, gm;
-    if (kind == SPCU_PRIM_TRIANGLE) return tri_hit(g, r, r->t_min, r->t_max, &t, &b, &gm);
+    if (kind == SPCU_PRIM_TRIANGLE) {
+        if (cnt) ++cnt->tris;
+        return tri_hit(g, r, r->t_min, r->t_max, &t, &b, &gm);
+    }
+    if (cnt) ++cnt->xf;
     if (kind == SPCU_PRIM_SPHERE) return sphere_hit(g, r, r->t_min, r->t_max, &t, NULL, NULL);
     return plane_hit(g, r, r->t_min, r->t_max, &t);
 }
@@ -254,19 +258,20 @@ static void geom_node(const spcu_flat_scene* s, int32_t link, uint32_t count, co
     }
 }
 
-static int geom_node_any(const spcu_flat_scene* s, int32_t link, uint32_t count, const ray_t* r)
+static int geom_node_any(const spcu_flat_scene* s, int32_t link, uint32_t count, const ray_t* r, spo_counters* cnt)
 {
     if (link < 0) {
         const uint32_t first = (uint32_t)~link, n = count & SPCU_LEAF_COUNT_MASK;
         for (uint32_t i = 0; i < n; ++i) {
-            if (geom_prim_any(s, first + i, r)) return 1;
+            if (geom_prim_any(s, first + i, r, cnt)) return 1;
         }
         return 0;
     }
     const spcu_bvh_node* node = &s->geom.nodes[link];
+    if (cnt) ++cnt->nodes;
     for (int k = 0; k < 2; ++k) {
         if (slab(node->box + 6 * k, node->box + 6 * k + 3, r, r->t_min, r->t_max) &&
-            geom_node_any(s, node->child[k], node->count[k], r)) {
+            geom_node_any(s, node->child[k], node->count[k], r, cnt)) {
             return 1;
         }
     }
@@ -368,12 +373,12 @@ static closest_t scene_intersect_lights(const spcu_flat_scene* s, const ray_t* r
 }
 
 /* Scene::intersect_p (base/Scene.h:79-82): geometry || lights */
-static int scene_intersect_p(const spcu_flat_scene* s, const ray_t* r)
+static int scene_intersect_p(const spcu_flat_scene* s, const ray_t* r, spo_counters* cnt)
 {
     for (uint32_t i = 0; i < s->geom.n_unbounded; ++i) {
-        if (geom_prim_any(s, i, r)) return 1;
+        if (geom_prim_any(s, i, r, cnt)) return 1;
     }
-    if (geom_node_any(s, s->geom.root, s->geom.root_count, r)) return 1;
+    if (geom_node_any(s, s->geom.root, s->geom.root_count, r, cnt)) return 1;
     for (uint32_t i = 0; i < s->lights_accel.n_unbounded; ++i) {
         if (light_hit_any(&s->lights[i], r)) return 1;
     }
@@ -447,7 +452,7 @@ void spo_trace_any(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, u
 {
     for (uint64_t i = 0; i < n; ++i) {
         const ray_t r = load_ray(&rays[i]);
-        out[i]        = (uint8_t)scene_intersect_p(s, &r);
+        out[i]        = (uint8_t)scene_intersect_p(s, &r, NULL);
     }
 }
 

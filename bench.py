@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: whole-frame renders of the BASELINE.json workload through the CUDA backend.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CudaIntegrator path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU implementation, same workload
+
+A *step* is one frame: `spp` samples for every pixel of the workload's image on every rank.  At N = 1 the workload is
+BASELINE.json configs[1] (example_scene, 1920x1080, 64 spp).  With N ranks the sample range is partitioned (rank r
+renders global samples [r*spp, (r+1)*spp) of N*spp, scene replicated, RNG keyed by the global sample index) and the
+per-pixel accumulators are summed to rank 0 with NCCL inside the timed region: per-GPU work is fixed ("weak").
+
+value   = Mpaths/s, device-timed (CUDA events, max over ranks), scene resident in HBM, accumulators on the device
+e2e     = the same metric through the host-buffer C-ABI call a plugin makes (spcu_upload_scene + spcu_render):
+          flattened scene copied host->device and accumulators copied device->host inside the timed region
+roofline= the kernel with the largest share of the timed region, algorithmic bytes (DESIGN.md "byte model") over its
+          mean CUDA-event duration, against MEASURED_PEAKS.json
+cpu_baseline = the reference binary (oracle/_ref/SimplePath) on this box's host cores on a bounded sample of the workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name -> (scene name in simplepath_b200.scenes, spp)
+    "example_scene_1080p_64spp": ("c2_example_scene", 64),
+    "material_spheres_256_16spp": ("c1_material_spheres_const", 16),
+    "bunny_1080p_256spp": ("c3_bunny", 256),
+    "elf_1080p_256spp": ("c4_elf", 256),
+}
+DEFAULT_WORKLOAD = "example_scene_1080p_64spp"
+INTEGRATOR = "iterative_rrnee"
+
+# ---- byte model: algorithmic bytes per item of each wavefront stage, excluding traversal ---------------
+STAGE_BYTES = {
+    "raygen": 84, "extend": 60, "shade": 196, "nee_light": 92, "shadow": 41, "nee_bsdf": 177, "mis_trace": 44,
+    "nee_mis_accumulate": 116, "direct_accumulate": 113, "advance": 152, "resolve": 28,
+}
+NODE_BYTES, TRI_BYTES, XF_BYTES = 64, 48, 96
+
+
+def peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =====================================================================================================================
+def run_cuda(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from simplepath_b200 import capi, host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene_name, spp = WORKLOADS[args.workload]
+    spp = args.spp or spp
+    flat = host.workload(scene_name)
+    w, h = flat.width, flat.height
+    spp_total = spp * world
+    jitter = host.jitter(spp_total)
+    ctx = capi.Context(local_rank)
+    ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
+    part = ctx.partition(spp=spp_total, integrator=INTEGRATOR, sample_begin=rank * spp, sample_end=(rank + 1) * spp,
+                         seed=args.seed)
+
+    rgb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    sq = torch.zeros((h, w), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step(want_stats: bool):
+        rgb.zero_(); sq.zero_()
+        st = ctx.render_device(part, rgb.data_ptr(), sq.data_ptr(), stream.cuda_stream, want_stats=want_stats)
+        if world > 1:
+            dist.reduce(rgb, dst=0); dist.reduce(sq, dst=0)
+        return st
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also: one counting pass for the byte model's N_node / N_tri / N_xf) --------------------------------
+    ctx.set_option(capi.OPT_COUNT_NODES, 1)
+    counted = step(True)
+    ctx.set_option(capi.OPT_COUNT_NODES, 0)
+    for _ in range(max(args.warmup - 1, 2)):
+        step(False)
+    barrier()
+
+    # ---- timed region: K steps, device-timed ----------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_option(capi.OPT_STAGE_TIMING, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms: dict[str, float] = {}
+    stage_launches: dict[str, int] = {}
+    stage_items: dict[str, int] = {}
+    last = None
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        last = step(True)   # stats readback = one small D2H per step; it is part of the step
+        for s in ctx.stage_times():
+            stage_ms[s["name"]] = stage_ms.get(s["name"], 0.0) + s["ms"]
+            stage_launches[s["name"]] = stage_launches.get(s["name"], 0) + s["launches"]
+            stage_items[s["name"]] = stage_items.get(s["name"], 0) + s["items"]
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.set_option(capi.OPT_STAGE_TIMING, 0)
+
+    counts = torch.tensor([last["paths"], last["rays_closest"], last["rays_any"], last["rays_lights"],
+                           last["kernel_launches"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(counts)
+    paths, rays_closest, rays_any, rays_lights, launches = (float(x) for x in counts.tolist())
+
+    # ---- end to end through the host-buffer C-ABI (what sp::CudaIntegrator::render_frame does) -------------------
+    h_rgb = np.zeros((h, w, 3), dtype=np.float32)
+    h_sq = np.zeros((h, w), dtype=np.float32)
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        h_rgb.fill(0.0); h_sq.fill(0.0)
+        ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
+        ctx.render(part, into=(h_rgb, h_sq))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    scene_bytes = ctx.scene_bytes()
+    acc_bytes = h_rgb.nbytes + h_sq.nbytes
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
+    peak, peak_src = peaks()
+    dominant = max(stage_ms, key=stage_ms.get)
+    n_launch = max(stage_launches[dominant], 1)
+    items = stage_items[dominant]
+    bytes_total = items * STAGE_BYTES[dominant]
+    trav = {"extend", "shadow", "mis_trace"}
+    geom_queries = counted["rays_closest"] + counted["rays_any"]
+    per_query = ((counted["nodes_visited"] * NODE_BYTES + counted["prims_tested"] * TRI_BYTES +
+                  counted["xf_prims_tested"] * XF_BYTES) / max(geom_queries, 1))
+    if dominant in trav:
+        bytes_total += items * per_query
+    dur_s = stage_ms[dominant] / 1e3 / n_launch
+    achieved = bytes_total / n_launch / dur_s / 1e9 if dur_s > 0 else 0.0
+    kernel_ms = sum(stage_ms.values())
+
+    cpu = cpu_baseline(scene_name, flat) if world == 1 and not args.no_cpu else None
+
+    steps_s = total_ms / 1e3
+    line = {
+        "metric": "Mpaths/s", "value": paths * args.steps / steps_s / 1e6, "unit": "Mpaths/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_gpu": spp,
+                   "integrator": INTEGRATOR, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
+                   "paths_per_step": int(paths), "partition": f"sample ranges x{world}, scene replicated",
+                   "l2": "no explicit flush: each step streams >1 GB of wavefront state, far above the 126 MB L2"},
+        "mrays_per_s": (rays_closest + rays_any) * args.steps / steps_s / 1e6,
+        "rays": {"closest_per_path": rays_closest / paths, "any_hit_per_path": rays_any / paths,
+                 "lights_accel_per_path": rays_lights / paths},
+        "e2e": {"value": paths * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes + acc_bytes,
+                "d2h_bytes_per_step": acc_bytes, "steps": e2e_steps,
+                "call": "spcu_upload_scene + spcu_render (host buffers)"},
+        "gpu_launches": int(launches * args.steps),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "share_of_step": stage_ms[dominant] / kernel_ms if kernel_ms else None,
+                     "launches": n_launch, "items_per_launch": items / n_launch,
+                     "bytes_per_item": bytes_total / max(items, 1),
+                     "note": "shading stages are instruction-issue bound, not HBM bound (profiles/)"},
+        "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if stage_launches.get(k)},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =====================================================================================================================
+def ref_binary() -> Path | None:
+    p = ROOT / "oracle" / "_ref" / "SimplePath"
+    return p if p.exists() else None
+
+
+def run_reference_binary(scene_path: Path, spp: int, threads: int, timeout: float) -> float:
+    """Stock reference executable; render seconds from its own Stopwatch line (main.cpp:138-141).  The process hangs at
+    exit (AccumulatedLogger), so it is killed as soon as the line is seen."""
+    proc = subprocess.Popen(["stdbuf", "-o0", str(ref_binary()), "--threads", str(threads), "--samples", str(spp),
+                             "--integrator", INTEGRATOR, scene_path.name],
+                            cwd=scene_path.parent, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    deadline = time.time() + timeout
+    secs, buf = None, ""
+    try:
+        while time.time() < deadline:
+            ch = proc.stdout.read(1)
+            if not ch:
+                break
+            buf += ch
+            m = re.search(r"Elapsed time:\s*([^\n]+)\n", buf)
+            if m:
+                secs = parse_elapsed(m.group(1))
+                break
+    finally:
+        proc.kill()
+        proc.wait()
+    if secs is None:
+        raise RuntimeError(f"reference did not finish within {timeout}s: {buf[-300:]}")
+    return secs
+
+
+def parse_elapsed(text: str) -> float:
+    """Stopwatch::print (base/Stopwatch.h:47-60) writes HH:MM:SS.cc (centiseconds)."""
+    m = re.fullmatch(r"\s*(\d+):(\d+):(\d+)\.(\d+)\s*", text)
+    if not m:
+        raise ValueError(f"cannot parse elapsed time {text!r}")
+    hh, mm, ss, cc = (int(g) for g in m.groups())
+    return hh * 3600.0 + mm * 60.0 + ss + cc / 100.0
+
+
+def reference_sample(scene_name: str, budget_s: float = 15.0):
+    """Bounded sample of the workload for the CPU: same scene and resolution, reduced spp (throughput is spp
+    independent), sized from a 1 spp probe to about `budget_s` seconds."""
+    from simplepath_b200 import scenes
+    path = scenes.ensure(scene_name)
+    w, h, _ = scenes.info(scene_name)
+    threads = os.cpu_count() or 1
+    probe = run_reference_binary(path, 1, threads, 600)
+    spp = int(max(1, min(64, budget_s / max(probe, 1e-3))))
+    return path, w, h, spp, threads
+
+
+def cpu_baseline(scene_name: str, flat) -> dict:
+    """Reference CPU path on this box's host cores, bounded sample.  kind 'reference' = the compiled reference binary;
+    'port' = the oracle's C restatement when that binary is not present."""
+    threads = os.cpu_count() or 1
+    if ref_binary() is not None:
+        path, w, h, spp, threads = reference_sample(scene_name)
+        secs = run_reference_binary(path, spp, threads, 900)
+        return {"value": w * h * spp / secs / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "reference",
+                "sample": f"{scene_name} {w}x{h} at {spp} spp ({w * h * spp} paths, {secs:.2f} s), stock binary "
+                          f"--threads {threads} --integrator {INTEGRATOR}, its own Stopwatch"}
+    from oracle import port
+    from simplepath_b200 import host
+    from simplepath_b200.capi import INTEGRATORS, Partition
+    spp = 1
+    jitter = host.jitter(spp)
+    t0 = time.perf_counter()
+    _, _, st = port.render(flat.pointer(), jitter, Partition(0, 1, 0, spp, spp, INTEGRATORS[INTEGRATOR], 0), threads=threads)
+    secs = time.perf_counter() - t0
+    return {"value": st["paths"] / secs / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
+            "sample": f"{scene_name} at {spp} spp ({st['paths']} paths, {secs:.2f} s), oracle C restatement, OpenMP"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from simplepath_b200 import scenes
+    scene_name, spp_full = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    w, h, _ = scenes.info(scene_name)
+    if ref_binary() is not None:
+        path, w, h, spp, threads = reference_sample(scene_name, budget_s=10.0)
+        kind = "reference"
+
+        def one():
+            return run_reference_binary(path, spp, threads, 900)
+    else:
+        from oracle import port
+        from simplepath_b200 import host
+        from simplepath_b200.capi import INTEGRATORS, Partition
+        flat = host.workload(scene_name)
+        spp, threads, kind = 1, os.cpu_count() or 1, "port"
+        jitter = host.jitter(spp)
+
+        def one():
+            t0 = time.perf_counter()
+            port.render(flat.pointer(), jitter, Partition(0, 1, 0, spp, spp, INTEGRATORS[INTEGRATOR], 0), threads=threads)
+            return time.perf_counter() - t0
+    for _ in range(min(args.warmup, 1)):
+        one()
+    steps = max(1, min(args.steps, 3))
+    secs = [one() for _ in range(steps)]
+    paths = w * h * spp
+    value = paths * steps / sum(secs) / 1e6
+    sample = (f"{scene_name} {w}x{h} at {spp} spp per step ({paths} paths/step; full workload is {spp_full} spp), "
+              f"{'stock reference binary' if kind == 'reference' else 'oracle C restatement'}, {threads} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(secs) / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_step": spp,
+                   "integrator": INTEGRATOR},
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -289,6 +289,18 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 #define SPCU_OPT_COUNT_ 2u
 int spcu_set_option(spcu_ctx* ctx, uint32_t option, uint32_t value);
 
+/* Per-kernel breakdown of the LAST render call (needs SPCU_OPT_STAGE_TIMING = 1 for `ms`): one entry per wavefront
+ * stage, in pipeline order.  items = queue entries the stage processed (paths, rays or vertices), counted on the device. */
+typedef struct spcu_stage_time {
+    char     name[24];
+    uint64_t launches;
+    uint64_t items;
+    float    ms;
+    uint32_t traverses; /* 1 for extend / shadow / mis_trace */
+} spcu_stage_time;
+#define SPCU_MAX_STAGES 16u
+int spcu_stage_times(spcu_ctx* ctx, spcu_stage_time* out, uint32_t capacity, uint32_t* n_out);
+
 /* Bytes of scene data resident on the device after spcu_upload_scene (what one upload copies host->device). */
 uint64_t spcu_scene_bytes(const spcu_ctx* ctx);
 

@@ -98,11 +98,16 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
 
 
+class StageTime(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("items", C.c_uint64), ("ms", C.c_float),
+                ("traverses", C.c_uint32)]
+
+
 EXPORTS = [
     "spcu_create", "spcu_destroy", "spcu_last_error", "spcu_abi_version", "spcu_upload_scene",
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
     "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
-    "spcu_scene_bytes", "spcu_trace_closest_counted",
+    "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times",
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING = 0, 1
 
@@ -154,6 +159,8 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_scene_bytes.restype = C.c_uint64
     lib.spcu_trace_closest_counted.argtypes = [vp, vp, C.c_uint64, vp, vp]
     lib.spcu_trace_closest_counted.restype = C.c_int
+    lib.spcu_stage_times.argtypes = [vp, C.POINTER(StageTime), C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.spcu_stage_times.restype = C.c_int
     if lib.spcu_abi_version() != ABI_VERSION:
         raise SpcuError("libspcu.so ABI version mismatch")
     if path is None:
@@ -220,6 +227,14 @@ class Context:
     def set_option(self, option: int, value: int) -> None:
         self._check(self.lib.spcu_set_option(self.h, option, value), "spcu_set_option")
 
+    def stage_times(self) -> list[dict]:
+        """Per-kernel breakdown of the last render call that asked for stats."""
+        arr = (StageTime * 16)()
+        n = C.c_uint32()
+        self._check(self.lib.spcu_stage_times(self.h, arr, 16, C.byref(n)), "spcu_stage_times")
+        return [{"name": arr[i].name.decode(), "launches": arr[i].launches, "items": arr[i].items, "ms": arr[i].ms,
+                 "traverses": bool(arr[i].traverses)} for i in range(n.value)]
+
     def scene_bytes(self) -> int:
         return int(self.lib.spcu_scene_bytes(self.h))
 
@@ -249,21 +264,29 @@ class Context:
         return Partition(rank, world, sample_begin, spp if sample_end is None else sample_end, spp,
                          INTEGRATORS[integrator], seed)
 
-    def render(self, part: Partition, want_sumsq: bool = True):
-        """Host-buffer render: returns (rgb_sum [H,W,3], lum_sumsq [H,W] | None, stats dict)."""
-        rgb = np.zeros((self.height, self.width, 3), dtype=np.float32)
-        sq = np.zeros((self.height, self.width), dtype=np.float32) if want_sumsq else None
+    def render(self, part: Partition, want_sumsq: bool = True, into=None):
+        """Host-buffer render: returns (rgb_sum [H,W,3], lum_sumsq [H,W] | None, stats dict).  `into` = (rgb, sq) of
+        an earlier call to keep accumulating into."""
+        if into is not None:
+            rgb, sq = into
+            want_sumsq = sq is not None
+        else:
+            rgb = np.zeros((self.height, self.width, 3), dtype=np.float32)
+            sq = np.zeros((self.height, self.width), dtype=np.float32) if want_sumsq else None
         st = Stats()
         self._check(self.lib.spcu_render(self.h, C.byref(part), _ptr(rgb), _ptr(sq) if want_sumsq else None,
                                          C.byref(st)), "spcu_render")
         return rgb, sq, st.as_dict()
 
-    def render_device(self, part: Partition, d_rgb_sum: int, d_lum_sumsq: int | None, stream: int | None = None) -> dict:
+    def render_device(self, part: Partition, d_rgb_sum: int, d_lum_sumsq: int | None, stream: int | None = None,
+                      want_stats: bool = True) -> dict | None:
+        """Accumulate into DEVICE buffers on `stream`.  Without stats the call only enqueues work (no host sync)."""
         st = Stats()
         self._check(self.lib.spcu_render_device(self.h, C.byref(part), C.c_void_p(d_rgb_sum),
-                                                C.c_void_p(d_lum_sumsq) if d_lum_sumsq else None, C.byref(st),
+                                                C.c_void_p(d_lum_sumsq) if d_lum_sumsq else None,
+                                                C.byref(st) if want_stats else None,
                                                 C.c_void_p(stream) if stream else None), "spcu_render_device")
-        return st.as_dict()
+        return st.as_dict() if want_stats else None
 
     def set_wavefront_size(self, n: int) -> None:
         self._check(self.lib.spcu_set_wavefront_size(self.h, n), "spcu_set_wavefront_size")

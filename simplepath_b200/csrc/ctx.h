@@ -87,7 +87,8 @@ struct spcu_ctx
 
     uint32_t                 options[SPCU_OPT_COUNT_] = {};
     std::vector<cudaEvent_t> stage_events; // pairs, when SPCU_OPT_STAGE_TIMING is on
-    std::vector<int>         stage_kinds;
+    std::vector<int>         stage_kinds;  // spcu::Stage of each pair
+    spcu_stage_time          stage_report[spcu::kNumStages] = {};
 };
 
 namespace spcu {

@@ -95,7 +95,9 @@ struct DWave
 
     // NEE BSDF-sampling strategy (Integrator.cpp:518-536)
     float4* mis_d;   // material ray d xyz, t_min   (origin = isect point, t_max = FLT_MAX)
-    float4* mis_col; // material sample colour rgb * (|cos| * weight / pdf)
+    float4* mis_col; // material sample colour rgb, pdf
+    float2* mis_cw;  // |cos(n, wi)|, balance-heuristic weight
+    float4* nee_acc; // light-strategy term of this light, added together with the BSDF-strategy term (:516 + :534)
     int2*   mis_hit; // (light id or -1, occluded flag)
 };
 
@@ -109,5 +111,29 @@ enum Counter : int
     kCntShadeCalls,
     kNumCounters
 };
+
+// wavefront stages, in pipeline order; device item counters live at counters[kNumCounters + stage]
+enum Stage : int
+{
+    kStRaygen = 0,
+    kStExtend,
+    kStShade,
+    kStNeeLight,
+    kStShadow,
+    kStNeeBsdf,
+    kStMisTrace,
+    kStNeeMisAccumulate,
+    kStDirectAccumulate,
+    kStAdvance,
+    kStResolve,
+    kNumStages
+};
+
+__device__ __forceinline__ void count_items(unsigned long long* counters, Stage stage, uint32_t n)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) {
+        atomicAdd(counters + kNumCounters + stage, static_cast<unsigned long long>(n));
+    }
+}
 
 } // namespace spcu

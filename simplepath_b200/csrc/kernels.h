@@ -14,14 +14,14 @@ void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, sp
 
 // Wavefront stages that traverse.  `queue` holds path slots; n_queue is read on the device (no host sync).
 // extend: Scene::intersect_lights then Scene::intersect for every queued path (Integrator.cpp:558-563).
-void launch_extend(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
-                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st);
+void launch_extend(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
 // shadow: Scene::intersect_p of the light-sample visibility ray (Integrator.cpp:503).
-void launch_shadow(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
-                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st);
+void launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
 // mis: Scene::intersect_lights then, on a light hit, Scene::intersect_p of the BSDF-sampled ray (Integrator.cpp:531-532).
-void launch_mis_trace(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
-                      unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st);
+void launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
+                      const uint32_t* d_n_queue, uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
 
 // ---- shade_kernels.cu ------------------------------------------------------------------------------------------
 struct RenderParams
@@ -32,36 +32,49 @@ struct RenderParams
     uint32_t light_index; // index into light_order of the light handled by the NEE stages
 };
 
+// Grid of a persistent-style wavefront kernel: enough CTAs to fill every SM at the kernel's occupancy, never more than
+// the queue can feed.  (The queue length itself lives on the device; max_n is its upper bound.)
+unsigned wavefront_grid(uint32_t max_n, int block, int ctas_per_sm, int sm_count);
+
 void launch_generate_rays(const DScene& s, const uint32_t* d_pix, const uint32_t* d_smp, uint64_t n, spcu_ray* d_rays,
                           cudaStream_t st);
-// raygen: fills slots [0, n) from (pixel list, sample range) and the initial queue (main.cpp:90-98).
-void launch_raygen(const DScene& s, const DWave& w, const uint32_t* d_pix_list, uint32_t pix_begin, uint32_t n_pix,
+
+struct Launch
+{
+    int          sm_count;
+    cudaStream_t stream;
+};
+
+// raygen: fills slots [0, n_pix*n_samples) from the pixel list and the sample range, and the initial queue (main.cpp:90-98).
+void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix,
                    uint32_t sample_begin, uint32_t n_samples, uint32_t* queue, uint32_t* d_n_queue,
-                   unsigned long long* d_counters, cudaStream_t st);
-// shade: hit/miss handling + primary BSDF sample S0 (Integrator.cpp:558-572,627-632).  Surviving paths go to q_out.
-void launch_shade(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in, const uint32_t* d_n_in,
-                  uint32_t max_n, uint32_t* q_out, uint32_t* d_n_out, unsigned long long* d_counters, cudaStream_t st);
+                   unsigned long long* d_counters);
+// shade: hit/miss handling + primary BSDF sample S0 (Integrator.cpp:558-572,627-632).  Surviving paths go to q_live.
+void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
+                  const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters);
 // nee_light: Light::sample for light p.light_index; paths with a usable sample go to q_shadow (Integrator.cpp:497-501).
-void launch_nee_light(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in, const uint32_t* d_n_in,
-                      uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow, unsigned long long* d_counters,
-                      cudaStream_t st);
-// nee_bsdf: light-strategy contribution, second BSDF sample, Light::pdf; paths needing the BSDF-strategy ray go to
-// q_mis (Integrator.cpp:508-530).
-void launch_nee_bsdf(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
+void launch_nee_light(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
+                      const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow,
+                      unsigned long long* d_counters);
+// nee_bsdf: light-strategy term, second BSDF sample, Light::pdf; paths needing the BSDF-strategy ray go to q_mis
+// (Integrator.cpp:503-530).
+void launch_nee_bsdf(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
                      const uint32_t* d_n_shadow, uint32_t max_n, uint32_t* q_mis, uint32_t* d_n_mis,
-                     unsigned long long* d_counters, cudaStream_t st);
-// nee_mis_accumulate: BSDF-strategy contribution after the mis trace (Integrator.cpp:531-535).
-void launch_nee_mis_accumulate(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_mis,
-                               const uint32_t* d_n_mis, uint32_t max_n, cudaStream_t st);
+                     unsigned long long* d_counters);
+// nee_mis_accumulate: adds the vertex's direct-light estimate for this light after the mis trace (Integrator.cpp:531-538).
+void launch_nee_mis_accumulate(const Launch& l, const DScene& s, const DWave& w, const uint32_t* q_mis,
+                               const uint32_t* d_n_mis, uint32_t max_n, unsigned long long* d_counters);
 // direct: DirectLightingIntegrator's per-light term after the shadow trace (Integrator.cpp:296-306).
-void launch_direct_accumulate(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
-                              const uint32_t* d_n_shadow, uint32_t max_n, unsigned long long* d_counters, cudaStream_t st);
-// advance: throughput update, Russian roulette, next segment (Integrator.cpp:601-626); survivors go to q_out.
-void launch_advance(const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in, const uint32_t* d_n_in,
-                    uint32_t max_n, uint32_t* q_out, uint32_t* d_n_out, cudaStream_t st);
+void launch_direct_accumulate(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p,
+                              const uint32_t* q_shadow, const uint32_t* d_n_shadow, uint32_t max_n,
+                              unsigned long long* d_counters);
+// advance: throughput update, Russian roulette, next segment (Integrator.cpp:601-626); survivors go to q_next.
+void launch_advance(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_live,
+                    const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
+                    unsigned long long* d_counters);
 // resolve: per pixel, add this batch's samples in sample order to the accumulators (main.cpp:100).
-void launch_resolve(const DWave& w, const uint32_t* d_pix_list, uint32_t pix_begin, uint32_t n_pix, uint32_t n_samples,
-                    float* d_rgb_sum, float* d_lum_sumsq, cudaStream_t st);
+void launch_resolve(const Launch& l, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t n_samples,
+                    float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters);
 // pixel list of one rank: tiles t with t % stride == offset, 8x8 tiles row major (TileScheduler.h:66-82)
 uint32_t    count_partition_pixels(uint32_t width, uint32_t height, uint32_t tile_offset, uint32_t tile_stride);
 // d_tile_prefix_scratch: one uint32 per owned tile.  Synchronises the stream.

@@ -90,7 +90,497 @@ __global__ void k_build_pixel_list(uint32_t width, uint32_t height, uint32_t til
     }
 }
 
+
+// ---- queue helpers ---------------------------------------------------------------------------------------------------
+// All wavefront kernels are persistent-style: a fixed grid (a multiple of the SM count) strides over the queue, whole
+// warps iterate together so that ballots see all 32 lanes.  Compaction = warp ballot + ONE atomicAdd per warp.
+__device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* n_queue, uint32_t slot, bool pred)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0u) {
+        return;
+    }
+    const int lane   = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t  base   = 0;
+    if (lane == leader) {
+        base = atomicAdd(n_queue, static_cast<uint32_t>(__popc(mask)));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) {
+        queue[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+__device__ __forceinline__ void warp_count(unsigned long long* counter, bool pred, unsigned per = 1u)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if ((threadIdx.x & 31) == 0 && m) {
+        atomicAdd(counter, static_cast<unsigned long long>(__popc(m)) * per);
+    }
+}
+
+__device__ __forceinline__ V3 xyz(const float4 v) { return v3(v.x, v.y, v.z); }
+__device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+__device__ __forceinline__ Rng load_rng(const DWave& w, uint32_t slot, uint64_t seed)
+{
+    return Rng{ w.pixel[slot], w.sample[slot], static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), w.rng_ctr[slot] };
+}
+
+#define FOR_EACH_QUEUED(i, active, n)                                                                  \
+    for (uint32_t base_ = blockIdx.x * blockDim.x, i = base_ + threadIdx.x, active = (i < (n)) ? 1u : 0u; \
+         base_ < (n); base_ += gridDim.x * blockDim.x, i = base_ + threadIdx.x, active = (i < (n)) ? 1u : 0u)
+
+// ---- raygen (main.cpp:90-98): slot = s_local * n_pix + p_local, so neighbouring threads trace neighbouring pixels -------
+__global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                        const uint32_t* pix_list, uint32_t n_pix, uint32_t sample_begin,
+                                                        uint32_t n_samples, uint32_t* queue, uint32_t* n_queue,
+                                                        unsigned long long* counters)
+{
+    const uint32_t n = n_pix * n_samples;
+    count_items(counters, kStRaygen, n);
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        if (active) {
+            const uint32_t pix = __ldg(pix_list + i % n_pix);
+            const uint32_t smp = sample_begin + i / n_pix;
+            float4         o, d;
+            camera_ray(s, pix, smp, o, d);
+            w.pixel[i]      = pix;
+            w.sample[i]     = smp;
+            w.rng_ctr[i]    = 0u;
+            w.ray_o[i]      = o;
+            w.ray_d[i]      = d;
+            w.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            w.radiance[i]   = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            queue[i]        = i;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *n_queue = n;
+        atomicAdd(counters + kCntPaths, static_cast<unsigned long long>(n));
+    }
+}
+
+// Intersection record of the accepted hit: Triangle.h:148-160, Sphere.h:99-104, Plane.h:65-70
+__device__ __forceinline__ void make_isect(const DScene& s, const HitRec& h, V3 o, V3 d, V3& point, V3& normal,
+                                           uint32_t& material)
+{
+    const uint32_t meta = __ldg(s.geom_meta + h.id);
+    const float4   a    = __ldg(s.geom_shade + 3 * h.id + 0);
+    const float4   b    = __ldg(s.geom_shade + 3 * h.id + 1);
+    const float4   c    = __ldg(s.geom_shade + 3 * h.id + 2);
+    material            = SPCU_META_MATERIAL(meta);
+    point               = o + d * h.t; // Ray::operator() (math/Ray.h:30-34)
+    const uint32_t kind = SPCU_META_KIND(meta);
+    if (kind == SPCU_PRIM_TRIANGLE) {
+        const float alpha = 1.0f - h.beta - h.gamma;
+        normal = normalize(v3(fmaf(alpha, a.x, fmaf(h.beta, b.x, h.gamma * c.x)), fmaf(alpha, a.y, fmaf(h.beta, b.y, h.gamma * c.y)),
+                              fmaf(alpha, a.z, fmaf(h.beta, b.z, h.gamma * c.z))));
+    } else if (kind == SPCU_PRIM_SPHERE) {
+        const float4 m0 = __ldg(s.geom_prims + 3 * h.id + 0);
+        const float4 m1 = __ldg(s.geom_prims + 3 * h.id + 1);
+        const float4 m2 = __ldg(s.geom_prims + 3 * h.id + 2);
+        const float  m[12] = { m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w };
+        const V3     lo = xf_point(m, o);
+        const V3     ld = xf_vector(m, d);
+        const V3     n  = v3(fmaf(h.t, ld.x, lo.x), fmaf(h.t, ld.y, lo.y), fmaf(h.t, ld.z, lo.z)); // madd(t, d, o) / k_radius
+        normal = normalize(v3(fmaf(n.x, a.x, fmaf(n.y, b.x, n.z * c.x)), fmaf(n.x, a.y, fmaf(n.y, b.y, n.z * c.y)),
+                              fmaf(n.x, a.z, fmaf(n.y, b.z, n.z * c.z))));
+    } else {
+        normal = v3(b.x, b.y, b.z); // object_to_world(Normal3{0,1,0}) = second column of the normal matrix, NOT normalised
+    }
+}
+
+// ---- shade (Integrator.cpp:558-572, 627-632): miss handling, surface interaction, primary BSDF sample S0 ---------------
+__global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                       const __grid_constant__ RenderParams p, const uint32_t* q_in,
+                                                       const uint32_t* n_in, uint32_t* q_live, uint32_t* n_live,
+                                                       unsigned long long* counters)
+{
+    const uint32_t n = *n_in;
+    count_items(counters, kStShade, n);
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        bool     live    = false;
+        bool     sampled = false;
+        uint32_t slot    = 0;
+        if (active) {
+            slot              = q_in[i];
+            const HitRec h    = w.hit[slot];
+            const float4 ro   = w.ray_o[slot];
+            const float4 rd   = w.ray_d[slot];
+            const V3     o = xyz(ro), d = xyz(rd);
+            if (h.id < 0) {
+                const int2 lh = w.light_hit[slot];
+                if (lh.x >= 0) { // emitter reached, at ANY depth (Integrator.cpp:627-629)
+                    const V3     L  = light_hit_L(s, s.lights[lh.x], d);
+                    const float4 tp = w.throughput[slot];
+                    float4       r  = w.radiance[slot];
+                    r.x += tp.x * L.x;
+                    r.y += tp.y * L.y;
+                    r.z += tp.z * L.z;
+                    w.radiance[slot] = r;
+                }
+            } else {
+                V3       point, normal;
+                uint32_t material;
+                make_isect(s, h, o, d, point, normal, material);
+                w.isect_p[slot] = f4(point, __uint_as_float(material));
+                w.isect_n[slot] = f4(normal, 0.0f);
+                if (p.integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING) {
+                    live = true;
+                } else {
+                    Rng           rng = load_rng(w, slot, p.seed);
+                    const MSample sr  = material_sample(s, material, -d, normal, rng);
+                    w.rng_ctr[slot]   = rng.ctr;
+                    sampled           = true;
+                    if (!(sr.pdf == 0.0f || is_black(sr.color))) {
+                        w.s0_dir[slot] = f4(sr.dir, sr.pdf);
+                        w.s0_col[slot] = f4(sr.color, 0.0f);
+                        live           = true;
+                    }
+                }
+            }
+        }
+        queue_push(q_live, n_live, slot, live);
+        warp_count(counters + kCntShadeCalls, sampled);
+    }
+}
+
+// ---- nee_light (Integrator.cpp:497-501 / :288-292): Light::sample for one light -------------------------------------------
+__global__ void __launch_bounds__(kShadeBlock) k_nee_light(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                           const __grid_constant__ RenderParams p, const uint32_t* q_in,
+                                                           const uint32_t* n_in, uint32_t* q_shadow, uint32_t* n_shadow,
+                                                           unsigned long long* counters)
+{
+    const uint32_t    n     = *n_in;
+    count_items(counters, kStNeeLight, n);
+    const spcu_light& light = s.lights[__ldg(s.light_order + p.light_index)];
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        bool     usable = false;
+        uint32_t slot   = 0;
+        if (active) {
+            slot       = q_in[i];
+            Rng   rng  = load_rng(w, slot, p.seed);
+            float u0, u1;
+            rng_next2(rng, u0, u1);
+            w.rng_ctr[slot]  = rng.ctr;
+            const V3      pt = xyz(w.isect_p[slot]);
+            const V3      nn = xyz(w.isect_n[slot]);
+            const LSample ls = light_sample(s, light, pt, nn, u0, u1);
+            if (!(ls.pdf == 0.0f || is_black(ls.L))) {
+                w.sh_d[slot]    = f4(ls.wi, ls.t_max);
+                w.sh_tmin[slot] = ls.t_min;
+                w.light_L[slot] = f4(ls.L, ls.pdf);
+                usable          = true;
+            }
+        }
+        queue_push(q_shadow, n_shadow, slot, usable);
+    }
+}
+
+// ---- nee_bsdf (Integrator.cpp:503-530): light-strategy term, second BSDF sample, Light::pdf ----------------------------------
+__global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                          const __grid_constant__ RenderParams p, const uint32_t* q_shadow,
+                                                          const uint32_t* n_shadow, uint32_t* q_mis, uint32_t* n_mis,
+                                                          unsigned long long* counters)
+{
+    const uint32_t    n     = *n_shadow;
+    count_items(counters, kStNeeBsdf, n);
+    const spcu_light& light = s.lights[__ldg(s.light_order + p.light_index)];
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        bool     to_mis = false;
+        uint32_t slot   = 0;
+        unsigned calls  = 0;
+        if (active) {
+            slot = q_shadow[i];
+            if (!w.occluded[slot]) { // occluded: estimate_direct_mis returns black, no BSDF strategy either (:503-506)
+                const float4   ip       = w.isect_p[slot];
+                const V3       pt       = xyz(ip);
+                const uint32_t material = __float_as_uint(ip.w);
+                const V3       nn       = xyz(w.isect_n[slot]);
+                const V3       wo       = -xyz(w.ray_d[slot]);
+                const float4   shd      = w.sh_d[slot];
+                const V3       wi       = xyz(shd);
+                const float4   lL       = w.light_L[slot];
+                Rng            rng      = load_rng(w, slot, p.seed);
+
+                // Material::eval / pdf (materials/Material.h:475-490) rebuild the ONB on every call; it is the same basis
+                const Onb onb = onb_from_v(nn);
+                const V3  wol = to_onb(onb, wo), wil = to_onb(onb, wi);
+                V3        A   = v3(0, 0, 0);
+                const V3  f   = material_eval_local(s, material, wol, wil, rng);
+                ++calls;
+                if (!is_black(f)) {
+                    const float bsdf_pdf = material_pdf_local(s, material, wol, wil, rng);
+                    ++calls;
+                    if (bsdf_pdf > 0.0f) {
+                        const float weight = balance2(lL.w, bsdf_pdf);
+                        A                  = f * xyz(lL) * (fabsf(dot(wi, nn)) * weight / lL.w);
+                    }
+                }
+                MSample ms = material_sample_local(s, material, wol, rng);
+                ++calls;
+                w.rng_ctr[slot] = rng.ctr;
+                float lpdf      = 0.0f;
+                if (!(ms.pdf == 0.0f || is_black(ms.color))) {
+                    ms.dir = to_world(onb, ms.dir);
+                    lpdf   = light_pdf(s, light, pt, ms.dir);
+                }
+                if (lpdf != 0.0f) {
+                    const float weight = balance2(ms.pdf, lpdf);
+                    w.mis_d[slot]      = f4(ms.dir, ray_offset(nn, ms.dir));
+                    w.mis_col[slot]    = f4(ms.color, ms.pdf);
+                    w.mis_cw[slot]     = make_float2(fabsf(dot(ms.dir, nn)), weight);
+                    w.nee_acc[slot]    = f4(A, 0.0f);
+                    to_mis             = true;
+                } else if (!is_black(A)) {
+                    const float4 tp = w.throughput[slot];
+                    float4       r  = w.radiance[slot];
+                    r.x += tp.x * A.x;
+                    r.y += tp.y * A.y;
+                    r.z += tp.z * A.z;
+                    w.radiance[slot] = r;
+                }
+            }
+        }
+        queue_push(q_mis, n_mis, slot, to_mis);
+        const unsigned total = __reduce_add_sync(0xffffffffu, calls);
+        if ((threadIdx.x & 31) == 0 && total) {
+            atomicAdd(counters + kCntShadeCalls, static_cast<unsigned long long>(total));
+        }
+    }
+}
+
+// ---- nee_mis_accumulate (Integrator.cpp:531-538): L += throughput * (light term + BSDF-strategy term) ------------------------
+__global__ void __launch_bounds__(kShadeBlock) k_nee_mis_accumulate(const __grid_constant__ DScene s,
+                                                                    const __grid_constant__ DWave w, const uint32_t* q_mis,
+                                                                    const uint32_t* n_mis, unsigned long long* counters)
+{
+    const uint32_t n = *n_mis;
+    count_items(counters, kStNeeMisAccumulate, n);
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        if (active) {
+            const uint32_t slot = q_mis[i];
+            const int2     mh   = w.mis_hit[slot];
+            V3             est  = xyz(w.nee_acc[slot]);
+            if (mh.x >= 0 && mh.y == 0) {
+                const float4 md  = w.mis_d[slot];
+                const float4 mc  = w.mis_col[slot];
+                const float2 cw  = w.mis_cw[slot];
+                const V3     Li  = light_hit_L(s, s.lights[mh.x], xyz(md));
+                est              = est + xyz(mc) * Li * cw.x * cw.y / mc.w;
+            }
+            if (!is_black(est)) {
+                const float4 tp = w.throughput[slot];
+                float4       r  = w.radiance[slot];
+                r.x += tp.x * est.x;
+                r.y += tp.y * est.y;
+                r.z += tp.z * est.z;
+                w.radiance[slot] = r;
+            }
+        }
+    }
+}
+
+// ---- direct_accumulate (Integrator.cpp:296-306): DirectLightingIntegrator's per-light term -----------------------------------
+// Order in the reference: eval first, shadow query only when f != black.  Here the shadow query has already run for every
+// usable light sample (its result does not change the estimate, only the ray count), then eval consumes its random numbers.
+__global__ void __launch_bounds__(kShadeBlock) k_direct_accumulate(const __grid_constant__ DScene s,
+                                                                   const __grid_constant__ DWave w,
+                                                                   const __grid_constant__ RenderParams p,
+                                                                   const uint32_t* q_shadow, const uint32_t* n_shadow,
+                                                                   unsigned long long* counters)
+{
+    const uint32_t n = *n_shadow;
+    count_items(counters, kStDirectAccumulate, n);
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        if (active) {
+            const uint32_t slot     = q_shadow[i];
+            const float4   ip       = w.isect_p[slot];
+            const uint32_t material = __float_as_uint(ip.w);
+            const V3       nn       = xyz(w.isect_n[slot]);
+            const V3       wo       = -xyz(w.ray_d[slot]);
+            const V3       wi       = xyz(w.sh_d[slot]);
+            const float4   lL       = w.light_L[slot];
+            Rng            rng      = load_rng(w, slot, p.seed);
+            const Onb      onb      = onb_from_v(nn);
+            const V3       f        = material_eval_local(s, material, to_onb(onb, wo), to_onb(onb, wi), rng);
+            w.rng_ctr[slot]         = rng.ctr;
+            if (!is_black(f) && !w.occluded[slot]) {
+                const V3 c = f * xyz(lL) * fabsf(dot(wi, nn)) / lL.w;
+                float4   r = w.radiance[slot];
+                r.x += c.x;
+                r.y += c.y;
+                r.z += c.z;
+                w.radiance[slot] = r;
+            }
+        }
+        warp_count(counters + kCntShadeCalls, active != 0u);
+    }
+}
+
+// ---- advance (Integrator.cpp:601-626): throughput update, Russian roulette, next segment -----------------------------------
+__global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                         const __grid_constant__ RenderParams p, const uint32_t* q_live,
+                                                         const uint32_t* n_live, uint32_t* q_next, uint32_t* n_next,
+                                                         unsigned long long* counters)
+{
+    const uint32_t n = *n_live;
+    count_items(counters, kStAdvance, n);
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        bool     alive = false;
+        uint32_t slot  = 0;
+        if (active) {
+            slot              = q_live[i];
+            const float4 sd   = w.s0_dir[slot];
+            const V3     wi   = xyz(sd);
+            const V3     col  = xyz(w.s0_col[slot]);
+            const V3     nn   = xyz(w.isect_n[slot]);
+            const float  cosine = fabsf(dot(wi, nn));
+            V3           tp   = xyz(w.throughput[slot]) * (cosine * col / sd.w);
+            alive             = true;
+            if (p.depth >= s.rr_depth) {
+                const float lum = luminance(tp);
+                if (lum < 0.1f) {
+                    const float q   = max_std(0.05f, lum / 0.1f); // probability of continuing
+                    Rng         rng = load_rng(w, slot, p.seed);
+                    const float u   = rng_next1(rng);
+                    w.rng_ctr[slot] = rng.ctr;
+                    if (u < q) {
+                        tp = tp / q;
+                    } else {
+                        alive = false;
+                    }
+                }
+            }
+            if (alive) {
+                const float4 ip     = w.isect_p[slot];
+                w.throughput[slot]  = f4(tp, 0.0f);
+                w.ray_o[slot]       = make_float4(ip.x, ip.y, ip.z, ray_offset_cos(cosine));
+                w.ray_d[slot]       = f4(wi, kFltMax);
+            }
+        }
+        queue_push(q_next, n_next, slot, alive);
+    }
+}
+
+// ---- resolve (main.cpp:100): per pixel, add this batch's samples in sample order ------------------------------------------
+__global__ void __launch_bounds__(kShadeBlock) k_resolve(const __grid_constant__ DWave w, const uint32_t* pix_list,
+                                                         uint32_t n_pix, uint32_t n_samples, float* rgb_sum, float* lum_sumsq,
+                                                         unsigned long long* counters)
+{
+    count_items(counters, kStResolve, n_pix * n_samples);
+    FOR_EACH_QUEUED(i, active, n_pix)
+    {
+        if (active) {
+            const uint32_t pix = __ldg(pix_list + i);
+            float r = rgb_sum[3 * pix + 0], g = rgb_sum[3 * pix + 1], b = rgb_sum[3 * pix + 2];
+            float sq = lum_sumsq ? lum_sumsq[pix] : 0.0f;
+            for (uint32_t k = 0; k < n_samples; ++k) {
+                const float4 L = w.radiance[k * n_pix + i];
+                r += L.x;
+                g += L.y;
+                b += L.z;
+                const float lum = luminance(v3(L.x, L.y, L.z));
+                sq += lum * lum;
+            }
+            rgb_sum[3 * pix + 0] = r;
+            rgb_sum[3 * pix + 1] = g;
+            rgb_sum[3 * pix + 2] = b;
+            if (lum_sumsq) {
+                lum_sumsq[pix] = sq;
+            }
+        }
+    }
+}
+
 } // namespace
+
+unsigned wavefront_grid(uint32_t max_n, int block, int ctas_per_sm, int sm_count)
+{
+    const uint64_t need = (static_cast<uint64_t>(max_n) + block - 1) / block;
+    const uint64_t fill = static_cast<uint64_t>(std::max(1, ctas_per_sm)) * std::max(1, sm_count);
+    return static_cast<unsigned>(std::max<uint64_t>(1, std::min(need, fill)));
+}
+
+template <typename K>
+static int ctas_per_sm(K kernel, int block)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block, 0) != cudaSuccess || n < 1) {
+        n = 1;
+    }
+    return n;
+}
+
+#define WAVEFRONT_LAUNCH(kernel, l, max_n, ...)                                                       \
+    do {                                                                                              \
+        if ((max_n) == 0) return;                                                                     \
+        static const int occ_ = ctas_per_sm(kernel, kShadeBlock);                                     \
+        kernel<<<wavefront_grid((max_n), kShadeBlock, occ_, (l).sm_count), kShadeBlock, 0, (l).stream>>>(__VA_ARGS__); \
+    } while (0)
+
+void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix,
+                   uint32_t sample_begin, uint32_t n_samples, uint32_t* queue, uint32_t* d_n_queue,
+                   unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_raygen, l, n_pix * n_samples, s, w, d_pix_list, n_pix, sample_begin, n_samples, queue, d_n_queue,
+                     d_counters);
+}
+
+void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
+                  const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_shade, l, max_n, s, w, p, q_in, d_n_in, q_live, d_n_live, d_counters);
+}
+
+void launch_nee_light(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
+                      const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow,
+                      unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_nee_light, l, max_n, s, w, p, q_in, d_n_in, q_shadow, d_n_shadow, d_counters);
+}
+
+void launch_nee_bsdf(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
+                     const uint32_t* d_n_shadow, uint32_t max_n, uint32_t* q_mis, uint32_t* d_n_mis,
+                     unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_nee_bsdf, l, max_n, s, w, p, q_shadow, d_n_shadow, q_mis, d_n_mis, d_counters);
+}
+
+void launch_nee_mis_accumulate(const Launch& l, const DScene& s, const DWave& w, const uint32_t* q_mis,
+                               const uint32_t* d_n_mis, uint32_t max_n, unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_nee_mis_accumulate, l, max_n, s, w, q_mis, d_n_mis, d_counters);
+}
+
+void launch_direct_accumulate(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p,
+                              const uint32_t* q_shadow, const uint32_t* d_n_shadow, uint32_t max_n,
+                              unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_direct_accumulate, l, max_n, s, w, p, q_shadow, d_n_shadow, d_counters);
+}
+
+void launch_advance(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_live,
+                    const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
+                    unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_advance, l, max_n, s, w, p, q_live, d_n_live, q_next, d_n_next, d_counters);
+}
+
+void launch_resolve(const Launch& l, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t n_samples,
+                    float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_resolve, l, n_pix, w, d_pix_list, n_pix, n_samples, d_rgb_sum, d_lum_sumsq, d_counters);
+}
 
 void launch_generate_rays(const DScene& s, const uint32_t* d_pix, const uint32_t* d_smp, uint64_t n, spcu_ray* d_rays,
                           cudaStream_t st)

@@ -1,25 +1,372 @@
-// spcu_render / spcu_render_device: the wavefront loop (host orchestration).
+// spcu_render / spcu_render_device: host orchestration of the wavefront loop.
+//
+// One call renders a partition (a set of 8x8 tiles x a sample range) in batches of at most `wavefront_size` paths:
+//
+//   raygen -> for depth in [0, max_depth):  extend -> shade -> { per light: nee_light -> shadow -> nee_bsdf -> mis ->
+//             nee_mis_accumulate } -> advance        -> resolve (per-pixel sums, in sample order)
+//
+// Every stage is a persistent-style kernel reading its queue length from device memory, so a batch is enqueued without
+// any host synchronisation; queues are compacted on the device (warp ballot + one atomic per warp).
 #include "ctx.h"
 
+#include <chrono>
+
 using namespace spcu;
+
+namespace {
+
+enum Queue { kQCur = 0, kQNext, kQLive, kQShadow, kQMis };
+constexpr int kCounterBlock = kNumCounters + kNumStages; // + per-stage item counters
+
+const char* const kStageNames[kNumStages] = { "raygen",   "extend",    "shade",     "nee_light",         "shadow",           "nee_bsdf",
+                                              "mis_trace", "nee_mis_accumulate", "direct_accumulate", "advance", "resolve" };
+inline bool stage_traverses(int st) { return st == kStExtend || st == kStShadow || st == kStMisTrace; }
+
+template <typename T>
+int wave_array(spcu_ctx* c, T*& ptr, size_t n)
+{
+    c->wave_bufs.emplace_back();
+    CK(c, c->wave_bufs.back().reserve(std::max<size_t>(n, 1) * sizeof(T)));
+    ptr = c->wave_bufs.back().as<T>();
+    return SPCU_OK;
+}
+
+int ensure_wave(spcu_ctx* c, uint32_t capacity)
+{
+    if (c->wave.capacity >= capacity) {
+        return SPCU_OK;
+    }
+    for (auto& b : c->wave_bufs) {
+        b.release();
+    }
+    c->wave_bufs.clear();
+    c->wave_bufs.reserve(32);
+    c->wave.capacity = 0;
+    DWave& w         = c->wave;
+    int    rc;
+#define WAVE(field) \
+    if ((rc = wave_array(c, w.field, capacity)) != SPCU_OK) return rc
+    WAVE(pixel);
+    WAVE(sample);
+    WAVE(rng_ctr);
+    WAVE(ray_o);
+    WAVE(ray_d);
+    WAVE(throughput);
+    WAVE(radiance);
+    WAVE(hit);
+    WAVE(light_hit);
+    WAVE(isect_p);
+    WAVE(isect_n);
+    WAVE(s0_dir);
+    WAVE(s0_col);
+    WAVE(sh_d);
+    WAVE(sh_tmin);
+    WAVE(light_L);
+    WAVE(occluded);
+    WAVE(mis_d);
+    WAVE(mis_col);
+    WAVE(mis_cw);
+    WAVE(nee_acc);
+    WAVE(mis_hit);
+#undef WAVE
+    for (auto& q : c->queues) {
+        CK(c, q.reserve(static_cast<size_t>(capacity) * sizeof(uint32_t)));
+    }
+    CK(c, c->queue_counts.reserve(kMaxQueueCounts * sizeof(uint32_t)));
+    CK(c, c->counters.reserve(kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters)));
+    w.capacity = capacity;
+    return SPCU_OK;
+}
+
+int ensure_pixel_list(spcu_ctx* c, const spcu_partition& part)
+{
+    if (c->pix_list_stride == part.tile_stride && c->pix_list_offset == part.tile_offset) {
+        return SPCU_OK;
+    }
+    const uint32_t w = c->ds.width, h = c->ds.height;
+    const uint32_t n_pix   = count_partition_pixels(w, h, part.tile_offset, part.tile_stride);
+    const uint32_t n_tiles = ((w + 7) / 8) * ((h + 7) / 8);
+    const uint32_t owned   = part.tile_offset < n_tiles ? (n_tiles - part.tile_offset + part.tile_stride - 1) / part.tile_stride : 0;
+    // pixel list followed by the per-tile prefix scratch
+    CK(c, c->pix_list.reserve((static_cast<size_t>(n_pix) + owned + 1) * sizeof(uint32_t)));
+    CK(c, build_pixel_list(w, h, part.tile_offset, part.tile_stride, c->pix_list.as<uint32_t>(),
+                           c->pix_list.as<uint32_t>() + n_pix, c->stream));
+    c->pix_list_offset = part.tile_offset;
+    c->pix_list_stride = part.tile_stride;
+    c->pix_list_n      = n_pix;
+    return SPCU_OK;
+}
+
+// Optional per-launch timing: an event pair around every kernel launch, summed per stage kind afterwards.
+struct StageTimer
+{
+    spcu_ctx*    c;
+    bool         on;
+    cudaStream_t st;
+    size_t       used = 0;
+
+    void begin(int kind)
+    {
+        ++launches[kind];
+        if (!on) return;
+        if (used + 2 > c->stage_events.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            c->stage_events.push_back(a);
+            c->stage_events.push_back(b);
+        }
+        c->stage_kinds.resize(c->stage_events.size() / 2);
+        c->stage_kinds[used / 2] = kind;
+        cudaEventRecord(c->stage_events[used], st);
+    }
+    void end()
+    {
+        if (!on) return;
+        cudaEventRecord(c->stage_events[used + 1], st);
+        used += 2;
+    }
+    uint64_t launches[kNumStages] = {};
+
+    void collect(float& trace_ms, float& shade_ms)
+    {
+        trace_ms = shade_ms = 0.0f;
+        for (size_t i = 0; i < used; i += 2) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, c->stage_events[i], c->stage_events[i + 1]);
+            const int st = c->stage_kinds[i / 2];
+            c->stage_report[st].ms += ms;
+            (stage_traverses(st) ? trace_ms : shade_ms) += ms;
+        }
+    }
+};
+
+int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq, spcu_stats* stats,
+                cudaStream_t caller_stream, bool have_caller_stream)
+{
+    if (int rc = need_scene(c); rc != SPCU_OK) return rc;
+    if (!part || !d_rgb_sum) {
+        return fail(c, SPCU_ERR_INVALID, "partition or accumulator is NULL");
+    }
+    const DScene& s = c->ds;
+    if (part->tile_stride == 0 || part->tile_offset >= part->tile_stride) {
+        return fail(c, SPCU_ERR_INVALID, "bad tile partition %u/%u", part->tile_offset, part->tile_stride);
+    }
+    if (part->sample_begin > part->sample_end || part->sample_end > part->spp_total || part->spp_total > s.spp) {
+        return fail(c, SPCU_ERR_INVALID, "bad sample range [%u,%u) of %u (jitter table holds %u)", part->sample_begin,
+                    part->sample_end, part->spp_total, s.spp);
+    }
+    if (part->integrator > SPCU_INTEGRATOR_DIRECT_LIGHTING) {
+        return fail(c, SPCU_ERR_INVALID, "unknown integrator %u", part->integrator);
+    }
+    // The caller's stream (spcu_render_device) orders this call after the caller's earlier work on that stream.
+    const cudaStream_t st = have_caller_stream ? caller_stream : c->stream;
+
+    if (int rc = ensure_pixel_list(c, *part); rc != SPCU_OK) return rc;
+    const uint32_t n_pix     = c->pix_list_n;
+    const uint32_t n_samples = part->sample_end - part->sample_begin;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+    }
+    if (n_pix == 0 || n_samples == 0) {
+        return SPCU_OK;
+    }
+
+    // batch shape: whole pixel list x as many samples as fit, or a slice of the pixel list x one sample
+    const uint64_t target = c->wavefront_size ? c->wavefront_size : (1ull << 22);
+    uint32_t       pix_per_batch, smp_per_batch;
+    if (n_pix <= target) {
+        pix_per_batch = n_pix;
+        smp_per_batch = static_cast<uint32_t>(std::min<uint64_t>(n_samples, std::max<uint64_t>(1, target / n_pix)));
+    } else {
+        pix_per_batch = static_cast<uint32_t>(target);
+        smp_per_batch = 1;
+    }
+    const uint32_t capacity = pix_per_batch * smp_per_batch;
+    if (int rc = ensure_wave(c, capacity); rc != SPCU_OK) return rc;
+
+    const uint32_t n_lights    = s.n_lights;
+    const uint32_t max_depth   = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING ? std::min(1u, s.max_depth) : s.max_depth;
+    const bool     nee         = part->integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE;
+    const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING;
+    const uint32_t counts_need = 1 + max_depth * (2 + 2 * n_lights);
+    if (counts_need > static_cast<uint32_t>(kMaxQueueCounts)) {
+        return fail(c, SPCU_ERR_LIMIT, "max_depth x lights needs %u queue counters (limit %d)", counts_need, kMaxQueueCounts);
+    }
+
+    auto*          d_counters = c->counters.as<unsigned long long>();
+    TraceCounters* d_cnt      = c->options[SPCU_OPT_COUNT_NODES] ? reinterpret_cast<TraceCounters*>(d_counters + kCounterBlock) : nullptr;
+    uint32_t*      d_counts   = c->queue_counts.as<uint32_t>();
+    uint32_t*      q[kNumQueues];
+    for (int i = 0; i < kNumQueues; ++i) {
+        q[i] = c->queues[i].as<uint32_t>();
+    }
+    const uint32_t* d_pix_list = c->pix_list.as<uint32_t>();
+    const Launch    L{ c->sm_count, st };
+    StageTimer      timer{ c, c->options[SPCU_OPT_STAGE_TIMING] != 0, st };
+    uint64_t        launches = 0;
+
+    CK(c, cudaMemsetAsync(d_counters, 0, kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters), st));
+    CK(c, cudaEventRecord(c->ev0, st));
+
+    for (uint32_t pb = 0; pb < n_pix; pb += pix_per_batch) {
+        const uint32_t np = std::min(pix_per_batch, n_pix - pb);
+        for (uint32_t sb = 0; sb < n_samples; sb += smp_per_batch) {
+            const uint32_t ns    = std::min(smp_per_batch, n_samples - sb);
+            const uint32_t max_n = np * ns;
+            CK(c, cudaMemsetAsync(d_counts, 0, counts_need * sizeof(uint32_t), st));
+            uint32_t next_count = 0;
+            auto     new_count  = [&]() { return d_counts + next_count++; };
+
+            uint32_t* n_cur = new_count();
+            timer.begin(kStRaygen);
+            launch_raygen(L, s, c->wave, d_pix_list + pb, np, part->sample_begin + sb, ns, q[kQCur], n_cur, d_counters);
+            timer.end();
+            ++launches;
+
+            uint32_t* q_cur  = q[kQCur];
+            uint32_t* q_next = q[kQNext];
+            for (uint32_t depth = 0; depth < max_depth; ++depth) {
+                RenderParams p{ part->seed, part->integrator, depth, 0 };
+                timer.begin(kStExtend);
+                launch_extend(L, s, c->wave, q_cur, n_cur, max_n, d_counters, d_cnt);
+                timer.end();
+                uint32_t* n_live = new_count();
+                timer.begin(kStShade);
+                launch_shade(L, s, c->wave, p, q_cur, n_cur, max_n, q[kQLive], n_live, d_counters);
+                timer.end();
+                launches += 2;
+                if (nee || direct) {
+                    for (uint32_t li = 0; li < n_lights; ++li) {
+                        p.light_index      = li;
+                        uint32_t* n_shadow = new_count();
+                        timer.begin(kStNeeLight);
+                        launch_nee_light(L, s, c->wave, p, q[kQLive], n_live, max_n, q[kQShadow], n_shadow, d_counters);
+                        timer.end();
+                        timer.begin(kStShadow);
+                        launch_shadow(L, s, c->wave, q[kQShadow], n_shadow, max_n, d_counters, d_cnt);
+                        timer.end();
+                        launches += 2;
+                        if (direct) {
+                            timer.begin(kStDirectAccumulate);
+                            launch_direct_accumulate(L, s, c->wave, p, q[kQShadow], n_shadow, max_n, d_counters);
+                            timer.end();
+                            ++launches;
+                            continue;
+                        }
+                        uint32_t* n_mis = new_count();
+                        timer.begin(kStNeeBsdf);
+                        launch_nee_bsdf(L, s, c->wave, p, q[kQShadow], n_shadow, max_n, q[kQMis], n_mis, d_counters);
+                        timer.end();
+                        timer.begin(kStMisTrace);
+                        launch_mis_trace(L, s, c->wave, q[kQMis], n_mis, max_n, d_counters, d_cnt);
+                        timer.end();
+                        timer.begin(kStNeeMisAccumulate);
+                        launch_nee_mis_accumulate(L, s, c->wave, q[kQMis], n_mis, max_n, d_counters);
+                        timer.end();
+                        launches += 3;
+                    }
+                }
+                if (direct) {
+                    break;
+                }
+                uint32_t* n_next = new_count();
+                timer.begin(kStAdvance);
+                launch_advance(L, s, c->wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
+                timer.end();
+                ++launches;
+                std::swap(q_cur, q_next);
+                n_cur = n_next;
+            }
+            timer.begin(kStResolve);
+            launch_resolve(L, c->wave, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
+            timer.end();
+            ++launches;
+            CK(c, cudaGetLastError());
+        }
+    }
+    CK(c, cudaEventRecord(c->ev1, st));
+
+    if (stats) {
+        CK(c, cudaEventSynchronize(c->ev1));
+        unsigned long long h[kCounterBlock];
+        TraceCounters      tc{};
+        CK(c, cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(&tc, d_counters + kCounterBlock, sizeof tc, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        stats->paths           = h[kCntPaths];
+        stats->rays_closest    = h[kCntRaysClosest];
+        stats->rays_any        = h[kCntRaysAny];
+        stats->rays_lights     = h[kCntRaysLights];
+        stats->shade_calls     = h[kCntShadeCalls];
+        stats->nodes_visited   = tc.nodes;
+        stats->prims_tested    = tc.tris;
+        stats->xf_prims_tested = tc.xf;
+        stats->kernel_launches = launches;
+        CK(c, cudaEventElapsedTime(&stats->device_ms, c->ev0, c->ev1));
+        for (int i = 0; i < kNumStages; ++i) {
+            spcu_stage_time& r = c->stage_report[i];
+            std::memset(&r, 0, sizeof r);
+            std::snprintf(r.name, sizeof r.name, "%s", kStageNames[i]);
+            r.launches  = timer.launches[i];
+            r.items     = h[kNumCounters + i];
+            r.traverses = stage_traverses(i) ? 1u : 0u;
+        }
+        timer.collect(stats->trace_ms, stats->shade_ms);
+    }
+    return SPCU_OK;
+}
+
+} // namespace
 
 extern "C" {
 
 int spcu_render_device(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq, spcu_stats* stats,
                        void* stream)
 {
-    if (int rc = need_scene(c); rc != SPCU_OK) return rc;
-    return fail(c, SPCU_ERR_INVALID, "render stage not linked into this build");
+    // stream == NULL means the legacy default stream, as in the CUDA runtime
+    return render_impl(c, part, d_rgb_sum, d_lum_sumsq, stats, static_cast<cudaStream_t>(stream), true);
 }
 
 int spcu_render(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, float* lum_sumsq, spcu_stats* stats)
 {
     if (int rc = need_scene(c); rc != SPCU_OK) return rc;
-    return fail(c, SPCU_ERR_INVALID, "render stage not linked into this build");
+    if (!rgb_sum) {
+        return fail(c, SPCU_ERR_INVALID, "rgb_sum is NULL");
+    }
+    const size_t n_pixels = static_cast<size_t>(c->ds.width) * c->ds.height;
+    CK(c, c->host_rgb.reserve(n_pixels * 3 * sizeof(float)));
+    CK(c, cudaMemcpyAsync(c->host_rgb.p, rgb_sum, n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    float* d_sq = nullptr;
+    if (lum_sumsq) {
+        CK(c, c->host_sq.reserve(n_pixels * sizeof(float)));
+        CK(c, cudaMemcpyAsync(c->host_sq.p, lum_sumsq, n_pixels * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        d_sq = c->host_sq.as<float>();
+    }
+    if (int rc = render_impl(c, part, c->host_rgb.as<float>(), d_sq, stats, nullptr, false); rc != SPCU_OK) return rc;
+    CK(c, cudaMemcpyAsync(rgb_sum, c->host_rgb.p, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (lum_sumsq) {
+        CK(c, cudaMemcpyAsync(lum_sumsq, c->host_sq.p, n_pixels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SPCU_OK;
+}
+
+int spcu_stage_times(spcu_ctx* c, spcu_stage_time* out, uint32_t capacity, uint32_t* n_out)
+{
+    if (!c || !out || !n_out) {
+        return fail(c, SPCU_ERR_INVALID, "NULL argument");
+    }
+    const uint32_t n = std::min<uint32_t>(capacity, kNumStages);
+    std::memcpy(out, c->stage_report, n * sizeof(spcu_stage_time));
+    *n_out = n;
+    return SPCU_OK;
 }
 
 int spcu_trace_closest_fast(spcu_ctx* c, const spcu_ray* rays, uint64_t n, spcu_hit* hits)
 {
+    // The renderer's extend stage IS the exact reference-order traversal in this build.
     return spcu_trace_closest(c, rays, n, hits);
 }
-}
+
+} // extern "C"

@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
                                                         unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack[kStackShared * kTraceBlock];
-    const uint32_t     i      = blockIdx.x * kTraceBlock + threadIdx.x;
-    const bool         active = i < *n_queue;
+    const uint32_t     n = *n_queue;
+    count_items(counters, kStExtend, n);
     TraceCounters      local{ 0, 0, 0 };
+    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
+    const uint32_t i      = base + threadIdx.x;
+    const bool     active = i < n;
     if (active) {
         const uint32_t slot = queue[i];
         const float4   o    = w.ray_o[slot];
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
     }
     warp_count(counters + kCntRaysClosest, active);
     warp_count(counters + kCntRaysLights, active);
+    }
     if (kCount) {
         flush_counters(local, cnt);
     }
@@ -129,9 +133,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
                                                         unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack[kStackShared * kTraceBlock];
-    const uint32_t     i      = blockIdx.x * kTraceBlock + threadIdx.x;
-    const bool         active = i < *n_queue;
+    const uint32_t     n = *n_queue;
+    count_items(counters, kStShadow, n);
     TraceCounters      local{ 0, 0, 0 };
+    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
+    const uint32_t i      = base + threadIdx.x;
+    const bool     active = i < n;
     if (active) {
         const uint32_t slot = queue[i];
         const float4   p    = w.isect_p[slot];
@@ -140,6 +147,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
         w.occluded[slot] = scene_any_hit<kCount>(s, r, d.w, stack + threadIdx.x, &local) ? 1 : 0;
     }
     warp_count(counters + kCntRaysAny, active);
+    }
     if (kCount) {
         flush_counters(local, cnt);
     }
@@ -153,10 +161,13 @@ __global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant
                                                            unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack[kStackShared * kTraceBlock];
-    const uint32_t     i      = blockIdx.x * kTraceBlock + threadIdx.x;
-    const bool         active = i < *n_queue;
+    const uint32_t     n = *n_queue;
+    count_items(counters, kStMisTrace, n);
     TraceCounters      local{ 0, 0, 0 };
-    bool               traced_any = false;
+    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
+    const uint32_t i          = base + threadIdx.x;
+    const bool     active     = i < n;
+    bool           traced_any = false;
     if (active) {
         const uint32_t slot = queue[i];
         const float4   p    = w.isect_p[slot];
@@ -175,6 +186,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant
     }
     warp_count(counters + kCntRaysLights, active);
     warp_count(counters + kCntRaysAny, traced_any);
+    }
     if (kCount) {
         flush_counters(local, cnt);
     }
@@ -210,37 +222,46 @@ void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, sp
     k_trace_lights<<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits);
 }
 
-void launch_extend(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
-                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st)
+template <typename K>
+static int trace_ctas_per_sm(K kernel)
 {
-    if (max_n == 0) return;
-    if (d_cnt) {
-        k_extend<true><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, d_cnt);
-    } else {
-        k_extend<false><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, nullptr);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTraceBlock, 0) != cudaSuccess || n < 1) {
+        n = 1;
     }
+    return n;
 }
 
-void launch_shadow(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
-                   unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st)
+#define TRACE_STAGE_LAUNCH(kernel)                                                                                     \
+    do {                                                                                                               \
+        if (max_n == 0) return;                                                                                        \
+        if (d_cnt) {                                                                                                   \
+            static const int occ_ = trace_ctas_per_sm(kernel<true>);                                                   \
+            kernel<true><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(          \
+                s, w, queue, d_n_queue, d_counters, d_cnt);                                                            \
+        } else {                                                                                                       \
+            static const int occ_ = trace_ctas_per_sm(kernel<false>);                                                  \
+            kernel<false><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(         \
+                s, w, queue, d_n_queue, d_counters, nullptr);                                                          \
+        }                                                                                                              \
+    } while (0)
+
+void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    if (max_n == 0) return;
-    if (d_cnt) {
-        k_shadow<true><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, d_cnt);
-    } else {
-        k_shadow<false><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, nullptr);
-    }
+    TRACE_STAGE_LAUNCH(k_extend);
 }
 
-void launch_mis_trace(const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue, uint32_t max_n,
-                      unsigned long long* d_counters, TraceCounters* d_cnt, cudaStream_t st)
+void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    if (max_n == 0) return;
-    if (d_cnt) {
-        k_mis_trace<true><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, d_cnt);
-    } else {
-        k_mis_trace<false><<<grid_for(max_n), kTraceBlock, 0, st>>>(s, w, queue, d_n_queue, d_counters, nullptr);
-    }
+    TRACE_STAGE_LAUNCH(k_shadow);
+}
+
+void launch_mis_trace(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                      uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
+{
+    TRACE_STAGE_LAUNCH(k_mis_trace);
 }
 
 } // namespace spcu

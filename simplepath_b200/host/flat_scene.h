@@ -40,6 +40,12 @@ FlatScene flatten_scene(const sp::Scene& scene);
 // spp x 2 pixel jitter exactly as main.cpp:67-71,96 draws it (RSequenceSampler::get_next_2D).
 std::vector<float> jitter_table(unsigned spp);
 
+// The reference's AccumulatedLogger singleton joins its worker thread from a static destructor and never returns
+// (base/AccumulatedLogger.h:34-37 starts the thread before the condition variable it waits on is constructed), so a
+// process that parsed a scene hangs at exit.  This registers (once) an exit handler that flushes stdio and leaves
+// through _exit with the real status; called after the logger exists, it runs before the logger's destructor.
+void arm_exit_guard();
+
 // Binary (de)serialisation so tests on a box without the reference can reuse a flattened scene.
 void      save_flat_scene(const FlatScene& fs, const std::string& path);
 FlatScene load_flat_scene(const std::string& path);

@@ -29,7 +29,7 @@ import raybatches  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 NAMES = ["g_spheres", "g_spheres_ibl", "g_example", "g_bunny", "g_elf"]
-RENDERS = {"g_spheres": 256, "g_spheres_ibl": 256, "g_example": 256, "g_bunny": 128}
+RENDERS = {"g_spheres": 1024, "g_spheres_ibl": 1024, "g_example": 1024, "g_bunny": 1024, "g_elf": 1024}
 N_EACH = 4096
 
 

@@ -47,6 +47,7 @@ INTEGRATOR = "iterative_rrnee"
 STAGE_BYTES = {
     "raygen": 84, "extend": 60, "shade": 196, "nee_light": 92, "shadow": 41, "nee_bsdf": 177, "mis_trace": 44,
     "nee_mis_accumulate": 116, "direct_accumulate": 113, "advance": 152, "resolve": 28,
+    "paths": 20,  # persistent path kernel: 4 B pixel id in, 16 B radiance sample out; everything else stays on chip
 }
 NODE_BYTES, TRI_BYTES, XF_BYTES = 64, 48, 96
 
@@ -122,6 +123,7 @@ def run_cuda(args) -> None:
     spp_total = spp * world
     jitter = host.jitter(spp_total)
     ctx = capi.Context(local_rank)
+    ctx.set_option(capi.OPT_PIPELINE, capi.PIPELINE_PATHS if args.pipeline == "paths" else capi.PIPELINE_WAVEFRONT)
     ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
     part = ctx.partition(spp=spp_total, integrator=INTEGRATOR, sample_begin=rank * spp, sample_end=(rank + 1) * spp,
                          seed=args.seed)
@@ -155,26 +157,33 @@ def run_cuda(args) -> None:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ctx.set_option(capi.OPT_STAGE_TIMING, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms: dict[str, float] = {}
-    stage_launches: dict[str, int] = {}
-    stage_items: dict[str, int] = {}
-    last = None
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        last = step(True)   # stats readback = one small D2H per step; it is part of the step
-        for s in ctx.stage_times():
-            stage_ms[s["name"]] = stage_ms.get(s["name"], 0.0) + s["ms"]
-            stage_launches[s["name"]] = stage_launches.get(s["name"], 0) + s["launches"]
-            stage_items[s["name"]] = stage_items.get(s["name"], 0) + s["items"]
+        step(False)          # nothing but kernel launches (and the NCCL reduce) between the two events
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
+
+    # ---- per-kernel CUDA-event durations, same workload, directly after the timed steps (one event pair per launch
+    # would perturb the headline number in the wavefront pipeline, so they are taken on their own steps) -----------
+    ctx.set_option(capi.OPT_STAGE_TIMING, 1)
+    stage_ms: dict[str, float] = {}
+    stage_launches: dict[str, int] = {}
+    stage_items: dict[str, int] = {}
+    last = None
+    stage_steps = max(1, min(args.steps, 3))
+    for _ in range(stage_steps):
+        last = step(True)
+        for s in ctx.stage_times():
+            stage_ms[s["name"]] = stage_ms.get(s["name"], 0.0) + s["ms"]
+            stage_launches[s["name"]] = stage_launches.get(s["name"], 0) + s["launches"]
+            stage_items[s["name"]] = stage_items.get(s["name"], 0) + s["items"]
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     ctx.set_option(capi.OPT_STAGE_TIMING, 0)
 
@@ -219,11 +228,13 @@ def run_cuda(args) -> None:
     n_launch = max(stage_launches[dominant], 1)
     items = stage_items[dominant]
     bytes_total = items * STAGE_BYTES[dominant]
-    trav = {"extend", "shadow", "mis_trace"}
+    trav = {"extend", "shadow", "mis_trace", "paths"}
     geom_queries = counted["rays_closest"] + counted["rays_any"]
     per_query = ((counted["nodes_visited"] * NODE_BYTES + counted["prims_tested"] * TRI_BYTES +
                   counted["xf_prims_tested"] * XF_BYTES) / max(geom_queries, 1))
-    if dominant in trav:
+    if dominant == "paths":  # one item = one path = (closest + any-hit) geometry queries
+        bytes_total += geom_queries * per_query * (items / max(counted["paths"], 1))
+    elif dominant in trav:
         bytes_total += items * per_query
     dur_s = stage_ms[dominant] / 1e3 / n_launch
     achieved = bytes_total / n_launch / dur_s / 1e9 if dur_s > 0 else 0.0
@@ -237,7 +248,7 @@ def run_cuda(args) -> None:
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_gpu": spp,
-                   "integrator": INTEGRATOR, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
+                   "integrator": INTEGRATOR, "pipeline": args.pipeline, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
                    "paths_per_step": int(paths), "partition": f"sample ranges x{world}, scene replicated",
                    "l2": "no explicit flush: each step streams >1 GB of wavefront state, far above the 126 MB L2"},
         "mrays_per_s": (rays_closest + rays_any) * args.steps / steps_s / 1e6,
@@ -246,7 +257,7 @@ def run_cuda(args) -> None:
         "e2e": {"value": paths * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes + acc_bytes,
                 "d2h_bytes_per_step": acc_bytes, "steps": e2e_steps,
                 "call": "spcu_upload_scene + spcu_render (host buffers)"},
-        "gpu_launches": int(launches * args.steps),
+        "gpu_launches": int(launches / world * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -254,7 +265,7 @@ def run_cuda(args) -> None:
                      "launches": n_launch, "items_per_launch": items / n_launch,
                      "bytes_per_item": bytes_total / max(items, 1),
                      "note": "shading stages are instruction-issue bound, not HBM bound (profiles/)"},
-        "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if stage_launches.get(k)},
+        "stages_ms_per_step": {k: v / stage_steps for k, v in stage_ms.items() if stage_launches.get(k)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -394,6 +405,8 @@ def main() -> None:
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipeline", default="wavefront", choices=["paths", "wavefront"],
+                    help="kernel organisation (SPCU_OPT_PIPELINE); same estimator and random numbers either way")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

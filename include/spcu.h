@@ -286,7 +286,15 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
  *   SPCU_OPT_STAGE_TIMING: spcu_stats.{trace_ms,shade_ms} are measured with one CUDA-event pair per launch. */
 #define SPCU_OPT_COUNT_NODES 0u
 #define SPCU_OPT_STAGE_TIMING 1u
-#define SPCU_OPT_COUNT_ 2u
+/*   SPCU_OPT_PIPELINE    : which kernel organisation renders (same stages, same random numbers, same estimator):
+ *                          SPCU_PIPELINE_WAVEFRONT (default) = one kernel per stage with compacted queues in HBM
+ *                          between them; SPCU_PIPELINE_PATHS = one persistent kernel per batch, paths live in
+ *                          registers and are regenerated in place.  The default is the one that measures faster on
+ *                          the BASELINE.json workloads (profiles/). */
+#define SPCU_OPT_PIPELINE 2u
+#define SPCU_OPT_COUNT_ 3u
+#define SPCU_PIPELINE_WAVEFRONT 0u
+#define SPCU_PIPELINE_PATHS 1u
 int spcu_set_option(spcu_ctx* ctx, uint32_t option, uint32_t value);
 
 /* Per-kernel breakdown of the LAST render call (needs SPCU_OPT_STAGE_TIMING = 1 for `ms`): one entry per wavefront

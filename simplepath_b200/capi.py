@@ -109,7 +109,8 @@ EXPORTS = [
     "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times",
 ]
-OPT_COUNT_NODES, OPT_STAGE_TIMING = 0, 1
+OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE = 0, 1, 2
+PIPELINE_WAVEFRONT, PIPELINE_PATHS = 0, 1
 
 
 class SpcuError(RuntimeError):

@@ -84,6 +84,7 @@ struct spcu_ctx
     spcu::DevBuf              pix_list;
     uint32_t                  pix_list_offset = ~0u, pix_list_stride = 0, pix_list_n = 0;
     spcu::DevBuf              host_rgb, host_sq; // device accumulators of the host-buffer entry point
+    spcu::DevBuf              path_radiance;     // float4 per slot of a batch (SPCU_PIPELINE_PATHS)
 
     uint32_t                 options[SPCU_OPT_COUNT_] = {};
     std::vector<cudaEvent_t> stage_events; // pairs, when SPCU_OPT_STAGE_TIMING is on

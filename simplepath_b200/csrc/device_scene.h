@@ -126,6 +126,7 @@ enum Stage : int
     kStDirectAccumulate,
     kStAdvance,
     kStResolve,
+    kStPaths, // the persistent path kernel (all of the above but resolve, fused)
     kNumStages
 };
 

@@ -75,6 +75,12 @@ void launch_advance(const Launch& l, const DScene& s, const DWave& w, const Rend
 // resolve: per pixel, add this batch's samples in sample order to the accumulators (main.cpp:100).
 void launch_resolve(const Launch& l, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t n_samples,
                     float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters);
+// ---- path_kernels.cu ------------------------------------------------------------------------------------------------
+// The persistent path kernel: every slot of the batch from camera to termination in one launch; d_radiance[slot] = L.
+void launch_paths(const Launch& l, const DScene& s, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t sample_begin,
+                  uint32_t n_samples, uint64_t seed, uint32_t integrator, float4* d_radiance, unsigned long long* d_counters,
+                  TraceCounters* d_cnt);
+
 // pixel list of one rank: tiles t with t % stride == offset, 8x8 tiles row major (TileScheduler.h:66-82)
 uint32_t    count_partition_pixels(uint32_t width, uint32_t height, uint32_t tile_offset, uint32_t tile_stride);
 // d_tile_prefix_scratch: one uint32 per owned tile.  Synchronises the stream.

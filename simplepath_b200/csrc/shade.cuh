@@ -792,6 +792,59 @@ __device__ __forceinline__ V3 light_hit_L(const DScene& s, const spcu_light& l, 
     return ibl_lookup(s, l, spherical_phi(w) * kInv2Pi, spherical_theta(w) * kInvPi);
 }
 
+__device__ __forceinline__ V3 xyz(const float4 v) { return v3(v.x, v.y, v.z); }
+__device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+// PerspectiveCamera::generate_ray_impl (Cameras/Camera.h:119-129): direction = normalize(px*col0 + py*col1 + col2),
+// products and sums rounded separately as in the canonical reference build; normalize() there is the SSE rsqrt
+// estimate + one Newton step (math/Math.h:205-227), which no GPU instruction reproduces — here it is the correctly
+// rounded reciprocal square root, so directions agree to a few ulp, not bitwise.
+__device__ __forceinline__ void camera_ray(const DScene& s, uint32_t pix, uint32_t smp, float4& o, float4& d)
+{
+    const uint32_t x  = pix % s.width;
+    const uint32_t y  = pix / s.width;
+    const float    px = __fadd_rn(static_cast<float>(static_cast<int>(x)), __ldg(s.jitter + 2 * smp + 0)); // main.cpp:97
+    const float    py = __fadd_rn(static_cast<float>(static_cast<int>(y)), __ldg(s.jitter + 2 * smp + 1));
+    const float*   m  = s.camera;
+    const float    dx = __fadd_rn(__fadd_rn(__fmul_rn(px, m[0]), __fmul_rn(py, m[3])), m[6]);
+    const float    dy = __fadd_rn(__fadd_rn(__fmul_rn(px, m[1]), __fmul_rn(py, m[4])), m[7]);
+    const float    dz = __fadd_rn(__fadd_rn(__fmul_rn(px, m[2]), __fmul_rn(py, m[5])), m[8]);
+    const float    len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fadd_rn(__fmul_rn(dz, dz), 0.0f));
+    const float    inv  = __frsqrt_rn(len2);
+    o = make_float4(m[9], m[10], m[11], 0.001f);                                             // RayLimits default t_min
+    d = make_float4(__fmul_rn(dx, inv), __fmul_rn(dy, inv), __fmul_rn(dz, inv), FLT_MAX);     // ... and t_max
+}
+
+// Intersection record of the accepted hit: Triangle.h:148-160, Sphere.h:99-104, Plane.h:65-70
+__device__ __forceinline__ void make_isect(const DScene& s, const HitRec& h, V3 o, V3 d, V3& point, V3& normal,
+                                           uint32_t& material)
+{
+    const uint32_t meta = __ldg(s.geom_meta + h.id);
+    const float4   a    = __ldg(s.geom_shade + 3 * h.id + 0);
+    const float4   b    = __ldg(s.geom_shade + 3 * h.id + 1);
+    const float4   c    = __ldg(s.geom_shade + 3 * h.id + 2);
+    material            = SPCU_META_MATERIAL(meta);
+    point               = o + d * h.t; // Ray::operator() (math/Ray.h:30-34)
+    const uint32_t kind = SPCU_META_KIND(meta);
+    if (kind == SPCU_PRIM_TRIANGLE) {
+        const float alpha = 1.0f - h.beta - h.gamma;
+        normal = normalize(v3(fmaf(alpha, a.x, fmaf(h.beta, b.x, h.gamma * c.x)), fmaf(alpha, a.y, fmaf(h.beta, b.y, h.gamma * c.y)),
+                              fmaf(alpha, a.z, fmaf(h.beta, b.z, h.gamma * c.z))));
+    } else if (kind == SPCU_PRIM_SPHERE) {
+        const float4 m0 = __ldg(s.geom_prims + 3 * h.id + 0);
+        const float4 m1 = __ldg(s.geom_prims + 3 * h.id + 1);
+        const float4 m2 = __ldg(s.geom_prims + 3 * h.id + 2);
+        const float  m[12] = { m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w };
+        const V3     lo = xf_point(m, o);
+        const V3     ld = xf_vector(m, d);
+        const V3     n  = v3(fmaf(h.t, ld.x, lo.x), fmaf(h.t, ld.y, lo.y), fmaf(h.t, ld.z, lo.z)); // madd(t, d, o) / k_radius
+        normal = normalize(v3(fmaf(n.x, a.x, fmaf(n.y, b.x, n.z * c.x)), fmaf(n.x, a.y, fmaf(n.y, b.y, n.z * c.y)),
+                              fmaf(n.x, a.z, fmaf(n.y, b.z, n.z * c.z))));
+    } else {
+        normal = v3(b.x, b.y, b.z); // object_to_world(Normal3{0,1,0}) = second column of the normal matrix, NOT normalised
+    }
+}
+
 // balance_heuristic(1, f_pdf, 1, g_pdf) (math/Math.h:91-94)
 __device__ __forceinline__ float balance2(float f_pdf, float g_pdf)
 {

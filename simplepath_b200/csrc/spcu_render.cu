@@ -19,7 +19,7 @@ enum Queue { kQCur = 0, kQNext, kQLive, kQShadow, kQMis };
 constexpr int kCounterBlock = kNumCounters + kNumStages; // + per-stage item counters
 
 const char* const kStageNames[kNumStages] = { "raygen",   "extend",    "shade",     "nee_light",         "shadow",           "nee_bsdf",
-                                              "mis_trace", "nee_mis_accumulate", "direct_accumulate", "advance", "resolve" };
+                                              "mis_trace", "nee_mis_accumulate", "direct_accumulate", "advance", "resolve", "paths" };
 inline bool stage_traverses(int st) { return st == kStExtend || st == kStShadow || st == kStMisTrace; }
 
 template <typename T>
@@ -141,6 +141,90 @@ struct StageTimer
     }
 };
 
+// Device counters -> spcu_stats (+ the per-stage report).  Synchronises `st`.
+int read_back_stats(spcu_ctx* c, cudaStream_t st, spcu_stats* stats, uint64_t launches, StageTimer& timer)
+{
+    auto* d_counters = c->counters.as<unsigned long long>();
+    CK(c, cudaEventSynchronize(c->ev1));
+    unsigned long long h[kCounterBlock];
+    TraceCounters      tc{};
+    CK(c, cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(&tc, d_counters + kCounterBlock, sizeof tc, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    stats->paths           = h[kCntPaths];
+    stats->rays_closest    = h[kCntRaysClosest];
+    stats->rays_any        = h[kCntRaysAny];
+    stats->rays_lights     = h[kCntRaysLights];
+    stats->shade_calls     = h[kCntShadeCalls];
+    stats->nodes_visited   = tc.nodes;
+    stats->prims_tested    = tc.tris;
+    stats->xf_prims_tested = tc.xf;
+    stats->kernel_launches = launches;
+    CK(c, cudaEventElapsedTime(&stats->device_ms, c->ev0, c->ev1));
+    for (int i = 0; i < kNumStages; ++i) {
+        spcu_stage_time& r = c->stage_report[i];
+        std::memset(&r, 0, sizeof r);
+        std::snprintf(r.name, sizeof r.name, "%s", kStageNames[i]);
+        r.launches  = timer.launches[i];
+        r.items     = h[kNumCounters + i];
+        r.traverses = stage_traverses(i) ? 1u : 0u;
+    }
+    timer.collect(stats->trace_ms, stats->shade_ms);
+    return SPCU_OK;
+}
+
+// SPCU_PIPELINE_PATHS: one persistent kernel per batch (path_kernels.cu) + resolve.
+int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq, spcu_stats* stats,
+                 cudaStream_t st, uint32_t n_pix, uint32_t n_samples)
+{
+    const DScene& s = c->ds;
+    // batch = whole pixel list x as many samples as fit in the radiance buffer (16 B per path)
+    const uint64_t target = c->wavefront_size ? c->wavefront_size : (1ull << 27);
+    uint32_t       pix_per_batch, smp_per_batch;
+    if (n_pix <= target) {
+        pix_per_batch = n_pix;
+        smp_per_batch = static_cast<uint32_t>(std::min<uint64_t>(n_samples, std::max<uint64_t>(1, target / n_pix)));
+    } else {
+        pix_per_batch = static_cast<uint32_t>(target);
+        smp_per_batch = 1;
+    }
+    const size_t capacity = static_cast<size_t>(pix_per_batch) * smp_per_batch;
+    CK(c, c->path_radiance.reserve(capacity * sizeof(float4)));
+    CK(c, c->counters.reserve(kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters)));
+    auto*          d_counters = c->counters.as<unsigned long long>();
+    TraceCounters* d_cnt = c->options[SPCU_OPT_COUNT_NODES] ? reinterpret_cast<TraceCounters*>(d_counters + kCounterBlock) : nullptr;
+    const uint32_t* d_pix_list = c->pix_list.as<uint32_t>();
+    const Launch    L{ c->sm_count, st };
+    StageTimer      timer{ c, c->options[SPCU_OPT_STAGE_TIMING] != 0, st };
+    uint64_t        launches = 0;
+    DWave           view{};
+    view.radiance = c->path_radiance.as<float4>();
+
+    CK(c, cudaMemsetAsync(d_counters, 0, kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters), st));
+    CK(c, cudaEventRecord(c->ev0, st));
+    for (uint32_t pb = 0; pb < n_pix; pb += pix_per_batch) {
+        const uint32_t np = std::min(pix_per_batch, n_pix - pb);
+        for (uint32_t sb = 0; sb < n_samples; sb += smp_per_batch) {
+            const uint32_t ns = std::min(smp_per_batch, n_samples - sb);
+            timer.begin(kStPaths);
+            launch_paths(L, s, d_pix_list + pb, np, part->sample_begin + sb, ns, part->seed, part->integrator, view.radiance,
+                         d_counters, d_cnt);
+            timer.end();
+            timer.begin(kStResolve);
+            launch_resolve(L, view, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
+            timer.end();
+            launches += 2;
+            CK(c, cudaGetLastError());
+        }
+    }
+    CK(c, cudaEventRecord(c->ev1, st));
+    if (stats) {
+        if (int rc = read_back_stats(c, st, stats, launches, timer); rc != SPCU_OK) return rc;
+        c->stage_report[kStPaths].items = stats->paths;
+    }
+    return SPCU_OK;
+}
+
 int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq, spcu_stats* stats,
                 cudaStream_t caller_stream, bool have_caller_stream)
 {
@@ -170,6 +254,10 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     }
     if (n_pix == 0 || n_samples == 0) {
         return SPCU_OK;
+    }
+
+    if (c->options[SPCU_OPT_PIPELINE] == SPCU_PIPELINE_PATHS) {
+        return render_paths(c, part, d_rgb_sum, d_lum_sumsq, stats, st, n_pix, n_samples);
     }
 
     // batch shape: whole pixel list x as many samples as fit, or a slice of the pixel list x one sample
@@ -288,31 +376,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     CK(c, cudaEventRecord(c->ev1, st));
 
     if (stats) {
-        CK(c, cudaEventSynchronize(c->ev1));
-        unsigned long long h[kCounterBlock];
-        TraceCounters      tc{};
-        CK(c, cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
-        CK(c, cudaMemcpyAsync(&tc, d_counters + kCounterBlock, sizeof tc, cudaMemcpyDeviceToHost, st));
-        CK(c, cudaStreamSynchronize(st));
-        stats->paths           = h[kCntPaths];
-        stats->rays_closest    = h[kCntRaysClosest];
-        stats->rays_any        = h[kCntRaysAny];
-        stats->rays_lights     = h[kCntRaysLights];
-        stats->shade_calls     = h[kCntShadeCalls];
-        stats->nodes_visited   = tc.nodes;
-        stats->prims_tested    = tc.tris;
-        stats->xf_prims_tested = tc.xf;
-        stats->kernel_launches = launches;
-        CK(c, cudaEventElapsedTime(&stats->device_ms, c->ev0, c->ev1));
-        for (int i = 0; i < kNumStages; ++i) {
-            spcu_stage_time& r = c->stage_report[i];
-            std::memset(&r, 0, sizeof r);
-            std::snprintf(r.name, sizeof r.name, "%s", kStageNames[i]);
-            r.launches  = timer.launches[i];
-            r.items     = h[kNumCounters + i];
-            r.traverses = stage_traverses(i) ? 1u : 0u;
-        }
-        timer.collect(stats->trace_ms, stats->shade_ms);
+        if (int rc = read_back_stats(c, st, stats, launches, timer); rc != SPCU_OK) return rc;
     }
     return SPCU_OK;
 }

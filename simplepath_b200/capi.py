@@ -11,7 +11,8 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "csrc" / "libspcu.so"
+import os
+LIB_PATH = Path(os.environ.get("SPCU_LIB", PKG / "csrc" / "libspcu.so"))  # SPCU_LIB: experiments with another build
 
 ABI_VERSION = 1
 INTEGRATORS = {"iterative_rrnee": 0, "brute_force_iterative_rr": 1, "direct_lighting": 2}

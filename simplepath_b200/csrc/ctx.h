@@ -50,7 +50,7 @@ struct DevBuf
     }
 };
 
-constexpr int      kNumQueues      = 5;        // cur, next, live, shadow, mis
+constexpr int      kNumQueues      = 6;        // cur, next, live, shadow, lit, mis
 constexpr int      kMaxQueueCounts = 4096;     // device queue-length words zeroed once per batch
 constexpr uint64_t kBatchRays      = 1u << 22; // rays per chunk of the batch query entry points
 

@@ -130,6 +130,25 @@ enum Stage : int
     kNumStages
 };
 
+// Queue compaction: warp ballot + ONE atomicAdd per warp; all 32 lanes of the warp must call it together.
+__device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* n_queue, uint32_t slot, bool pred)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0u) {
+        return;
+    }
+    const int lane   = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t  base   = 0;
+    if (lane == leader) {
+        base = atomicAdd(n_queue, static_cast<uint32_t>(__popc(mask)));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) {
+        queue[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+    }
+}
+
 __device__ __forceinline__ void count_items(unsigned long long* counters, Stage stage, uint32_t n)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) {

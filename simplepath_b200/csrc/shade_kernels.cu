@@ -74,24 +74,6 @@ __global__ void k_build_pixel_list(uint32_t width, uint32_t height, uint32_t til
 // ---- queue helpers ---------------------------------------------------------------------------------------------------
 // All wavefront kernels are persistent-style: a fixed grid (a multiple of the SM count) strides over the queue, whole
 // warps iterate together so that ballots see all 32 lanes.  Compaction = warp ballot + ONE atomicAdd per warp.
-__device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* n_queue, uint32_t slot, bool pred)
-{
-    const unsigned mask = __ballot_sync(0xffffffffu, pred);
-    if (mask == 0u) {
-        return;
-    }
-    const int lane   = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    uint32_t  base   = 0;
-    if (lane == leader) {
-        base = atomicAdd(n_queue, static_cast<uint32_t>(__popc(mask)));
-    }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) {
-        queue[base + __popc(mask & ((1u << lane) - 1u))] = slot;
-    }
-}
-
 __device__ __forceinline__ void warp_count(unsigned long long* counter, bool pred, unsigned per = 1u)
 {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
@@ -245,8 +227,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
         uint32_t slot   = 0;
         unsigned calls  = 0;
         if (active) {
-            slot = q_shadow[i];
-            if (!w.occluded[slot]) { // occluded: estimate_direct_mis returns black, no BSDF strategy either (:503-506)
+            slot = q_shadow[i]; // the shadow stage queued unoccluded samples only (Integrator.cpp:503-506)
+            {
                 const float4   ip       = w.isect_p[slot];
                 const V3       pt       = xyz(ip);
                 const uint32_t material = __float_as_uint(ip.w);

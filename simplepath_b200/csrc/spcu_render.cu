@@ -15,7 +15,7 @@ using namespace spcu;
 
 namespace {
 
-enum Queue { kQCur = 0, kQNext, kQLive, kQShadow, kQMis };
+enum Queue { kQCur = 0, kQNext, kQLive, kQShadow, kQLit, kQMis };
 constexpr int kCounterBlock = kNumCounters + kNumStages; // + per-stage item counters
 
 const char* const kStageNames[kNumStages] = { "raygen",   "extend",    "shade",     "nee_light",         "shadow",           "nee_bsdf",
@@ -261,7 +261,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     }
 
     // batch shape: whole pixel list x as many samples as fit, or a slice of the pixel list x one sample
-    const uint64_t target = c->wavefront_size ? c->wavefront_size : (1ull << 22);
+    const uint64_t target = c->wavefront_size ? c->wavefront_size : (1ull << 24);
     uint32_t       pix_per_batch, smp_per_batch;
     if (n_pix <= target) {
         pix_per_batch = n_pix;
@@ -277,7 +277,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     const uint32_t max_depth   = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING ? std::min(1u, s.max_depth) : s.max_depth;
     const bool     nee         = part->integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE;
     const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING;
-    const uint32_t counts_need = 1 + max_depth * (2 + 2 * n_lights);
+    const uint32_t counts_need = 1 + max_depth * (2 + 3 * n_lights);
     if (counts_need > static_cast<uint32_t>(kMaxQueueCounts)) {
         return fail(c, SPCU_ERR_LIMIT, "max_depth x lights needs %u queue counters (limit %d)", counts_need, kMaxQueueCounts);
     }
@@ -331,8 +331,10 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                         timer.begin(kStNeeLight);
                         launch_nee_light(L, s, c->wave, p, q[kQLive], n_live, max_n, q[kQShadow], n_shadow, d_counters);
                         timer.end();
+                        uint32_t* n_lit = direct ? nullptr : new_count();
                         timer.begin(kStShadow);
-                        launch_shadow(L, s, c->wave, q[kQShadow], n_shadow, max_n, d_counters, d_cnt);
+                        launch_shadow(L, s, c->wave, q[kQShadow], n_shadow, max_n, direct ? nullptr : q[kQLit], n_lit, d_counters,
+                                      d_cnt);
                         timer.end();
                         launches += 2;
                         if (direct) {
@@ -344,7 +346,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                         }
                         uint32_t* n_mis = new_count();
                         timer.begin(kStNeeBsdf);
-                        launch_nee_bsdf(L, s, c->wave, p, q[kQShadow], n_shadow, max_n, q[kQMis], n_mis, d_counters);
+                        launch_nee_bsdf(L, s, c->wave, p, q[kQLit], n_lit, max_n, q[kQMis], n_mis, d_counters);
                         timer.end();
                         timer.begin(kStMisTrace);
                         launch_mis_trace(L, s, c->wave, q[kQMis], n_mis, max_n, d_counters, d_cnt);

@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
 // shadow: Integrator.cpp:503 — Scene::intersect_p of the light sample's visibility ray.
 template <bool kCount>
 __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
-                                                        const uint32_t* queue, const uint32_t* n_queue,
-                                                        unsigned long long* counters, TraceCounters* cnt)
+                                                        const uint32_t* queue, const uint32_t* n_queue, uint32_t* q_lit,
+                                                        uint32_t* n_lit, unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack[kStackShared * kTraceBlock];
     const uint32_t     n = *n_queue;
@@ -139,12 +139,19 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
     for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
     const uint32_t i      = base + threadIdx.x;
     const bool     active = i < n;
+    uint32_t       slot   = 0;
+    bool           lit    = false;
     if (active) {
-        const uint32_t slot = queue[i];
-        const float4   p    = w.isect_p[slot];
-        const float4   d    = w.sh_d[slot];
-        const Ray      r{ p.x, p.y, p.z, d.x, d.y, d.z, w.sh_tmin[slot] };
-        w.occluded[slot] = scene_any_hit<kCount>(s, r, d.w, stack + threadIdx.x, &local) ? 1 : 0;
+        slot             = queue[i];
+        const float4 p   = w.isect_p[slot];
+        const float4 d   = w.sh_d[slot];
+        const Ray    r{ p.x, p.y, p.z, d.x, d.y, d.z, w.sh_tmin[slot] };
+        const bool   occ = scene_any_hit<kCount>(s, r, d.w, stack + threadIdx.x, &local);
+        w.occluded[slot] = occ ? 1 : 0;
+        lit              = !occ;
+    }
+    if (q_lit) { // survivors only go on to the BSDF stages: occluded samples contribute nothing (Integrator.cpp:503-506)
+        queue_push(q_lit, n_lit, slot, lit);
     }
     warp_count(counters + kCntRaysAny, active);
     }
@@ -253,9 +260,18 @@ void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint3
 }
 
 void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
+                   uint32_t max_n, uint32_t* q_lit, uint32_t* d_n_lit, unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    TRACE_STAGE_LAUNCH(k_shadow);
+    if (max_n == 0) return;
+    if (d_cnt) {
+        static const int occ_ = trace_ctas_per_sm(k_shadow<true>);
+        k_shadow<true><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, queue, d_n_queue, q_lit, d_n_lit, d_counters, d_cnt);
+    } else {
+        static const int occ_ = trace_ctas_per_sm(k_shadow<false>);
+        k_shadow<false><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, queue, d_n_queue, q_lit, d_n_lit, d_counters, nullptr);
+    }
 }
 
 void launch_mis_trace(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,

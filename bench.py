@@ -104,7 +104,7 @@ class ClockSampler:
 def run_cuda(args) -> None:
     import torch
     import torch.distributed as dist
-    from simplepath_b200 import capi, host
+    from simplepath_b200 import capi, distributed, host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -125,8 +125,7 @@ def run_cuda(args) -> None:
     ctx = capi.Context(local_rank)
     ctx.set_option(capi.OPT_PIPELINE, capi.PIPELINE_PATHS if args.pipeline == "paths" else capi.PIPELINE_WAVEFRONT)
     ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
-    part = ctx.partition(spp=spp_total, integrator=INTEGRATOR, sample_begin=rank * spp, sample_end=(rank + 1) * spp,
-                         seed=args.seed)
+    part = distributed.sample_partition(rank, world, spp, INTEGRATOR, args.seed)
 
     rgb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
     sq = torch.zeros((h, w), dtype=torch.float32, device="cuda")
@@ -135,8 +134,7 @@ def run_cuda(args) -> None:
     def step(want_stats: bool):
         rgb.zero_(); sq.zero_()
         st = ctx.render_device(part, rgb.data_ptr(), sq.data_ptr(), stream.cuda_stream, want_stats=want_stats)
-        if world > 1:
-            dist.reduce(rgb, dst=0); dist.reduce(sq, dst=0)
+        distributed.reduce_to_root(rgb, sq)   # NCCL over NVLink, inside the timed region
         return st
 
     def barrier():
@@ -268,7 +266,7 @@ def run_cuda(args) -> None:
         "stages_ms_per_step": {k: v / stage_steps for k, v in stage_ms.items() if stage_launches.get(k)},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -383,7 +381,7 @@ def run_reference(args) -> None:
     value = paths * steps / sum(secs) / 1e6
     sample = (f"{scene_name} {w}x{h} at {spp} spp per step ({paths} paths/step; full workload is {spp_full} spp), "
               f"{'stock reference binary' if kind == 'reference' else 'oracle C restatement'}, {threads} threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(secs) / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -392,10 +390,29 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, torchrun notices)
+    goes to stderr instead; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main() -> None:
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

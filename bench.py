@@ -124,6 +124,7 @@ def run_cuda(args) -> None:
     jitter = host.jitter(spp_total)
     ctx = capi.Context(local_rank)
     ctx.set_option(capi.OPT_PIPELINE, capi.PIPELINE_PATHS if args.pipeline == "paths" else capi.PIPELINE_WAVEFRONT)
+    ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_ORDERED if args.traversal == "ordered" else capi.TRAVERSAL_EXACT)
     ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
     part = distributed.sample_partition(rank, world, spp, INTEGRATOR, args.seed)
 
@@ -246,7 +247,7 @@ def run_cuda(args) -> None:
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_gpu": spp,
-                   "integrator": INTEGRATOR, "pipeline": args.pipeline, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
+                   "integrator": INTEGRATOR, "pipeline": args.pipeline, "traversal": args.traversal, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
                    "paths_per_step": int(paths), "partition": f"sample ranges x{world}, scene replicated",
                    "l2": "no explicit flush: each step streams >1 GB of wavefront state, far above the 126 MB L2"},
         "mrays_per_s": (rays_closest + rays_any) * args.steps / steps_s / 1e6,
@@ -422,6 +423,8 @@ def main() -> None:
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traversal", default="exact", choices=["exact", "ordered"],
+                    help="closest-hit walk of the extend stage (SPCU_OPT_TRAVERSAL)")
     ap.add_argument("--pipeline", default="wavefront", choices=["paths", "wavefront"],
                     help="kernel organisation (SPCU_OPT_PIPELINE); same estimator and random numbers either way")
     args = ap.parse_args()

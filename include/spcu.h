@@ -260,8 +260,11 @@ int spcu_trace_closest(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit
 int spcu_trace_any(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, uint8_t* out);
 /* Scene::intersect_lights (base/Scene.h:69-72): closest light (ID order of lights[]) and distance. */
 int spcu_trace_lights(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits);
-/* Same three queries through the ordered ("fast") traversal used by the renderer's extend stage. */
-int spcu_trace_closest_fast(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits);
+/* Scene::intersect through the ORDERED walk (nearer child first; the renderer's extend stage uses it when
+ * SPCU_OPT_TRAVERSAL = SPCU_TRAVERSAL_ORDERED).  Same boxes, primitive tests and arithmetic as spcu_trace_closest; the
+ * answers differ only on epsilon ties (counted by tests/test_gpu_trace.py and stated in DESIGN.md).  counters (may be
+ * NULL) = { internal nodes visited, triangle tests, sphere/plane tests }. */
+int spcu_trace_closest_fast(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits, uint64_t counters[3]);
 
 /* Camera::generate_ray for (pixel, sample) pairs (Cameras/Camera.h:119-129 + main.cpp:96-98):
  * rays[i] for pixel index pix[i] (= y*width+x) and sample index smp[i]. host pointers. */
@@ -292,7 +295,12 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
  *                          registers and are regenerated in place.  The default is the one that measures faster on
  *                          the BASELINE.json workloads (profiles/). */
 #define SPCU_OPT_PIPELINE 2u
-#define SPCU_OPT_COUNT_ 3u
+/*   SPCU_OPT_TRAVERSAL   : closest-hit walk of the extend stage: SPCU_TRAVERSAL_EXACT (default) = the reference's own
+ *                          order, bit-exact IDs; SPCU_TRAVERSAL_ORDERED = nearer child first (see spcu_trace_closest_fast). */
+#define SPCU_OPT_TRAVERSAL 3u
+#define SPCU_OPT_COUNT_ 4u
+#define SPCU_TRAVERSAL_EXACT 0u
+#define SPCU_TRAVERSAL_ORDERED 1u
 #define SPCU_PIPELINE_WAVEFRONT 0u
 #define SPCU_PIPELINE_PATHS 1u
 int spcu_set_option(spcu_ctx* ctx, uint32_t option, uint32_t value);

@@ -110,7 +110,8 @@ EXPORTS = [
     "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times",
 ]
-OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE = 0, 1, 2
+OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL = 0, 1, 2, 3
+TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
 PIPELINE_WAVEFRONT, PIPELINE_PATHS = 0, 1
 
 
@@ -142,9 +143,11 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_abi_version.restype = C.c_int
     lib.spcu_upload_scene.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(C.c_float), C.c_uint32]
     lib.spcu_upload_scene.restype = C.c_int
-    for fn in (lib.spcu_trace_closest, lib.spcu_trace_lights, lib.spcu_trace_closest_fast):
+    for fn in (lib.spcu_trace_closest, lib.spcu_trace_lights):
         fn.argtypes = [vp, vp, C.c_uint64, vp]
         fn.restype = C.c_int
+    lib.spcu_trace_closest_fast.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    lib.spcu_trace_closest_fast.restype = C.c_int
     lib.spcu_trace_any.argtypes = [vp, vp, C.c_uint64, vp]
     lib.spcu_trace_any.restype = C.c_int
     lib.spcu_generate_rays.argtypes = [vp, vp, vp, C.c_uint64, vp]
@@ -241,7 +244,13 @@ class Context:
         return int(self.lib.spcu_scene_bytes(self.h))
 
     def trace_closest_fast(self, rays):
-        return self._trace(self.lib.spcu_trace_closest_fast, rays, "spcu_trace_closest_fast")
+        """Ordered walk: (hits, [internal nodes visited, triangle tests, sphere/plane tests])"""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        cnt = np.zeros(3, dtype=np.uint64)
+        self._check(self.lib.spcu_trace_closest_fast(self.h, _ptr(rays), rays.shape[0], _ptr(hits), _ptr(cnt)),
+                    "spcu_trace_closest_fast")
+        return hits, cnt
 
     def trace_lights(self, rays):
         return self._trace(self.lib.spcu_trace_lights, rays, "spcu_trace_lights")

@@ -53,6 +53,7 @@ struct DevBuf
 constexpr int      kNumQueues      = 6;        // cur, next, live, shadow, lit, mis
 constexpr int      kMaxQueueCounts = 4096;     // device queue-length words zeroed once per batch
 constexpr uint64_t kBatchRays      = 1u << 22; // rays per chunk of the batch query entry points
+constexpr uint32_t kMaxMaterialSegments = 15;  // materials beyond share the last segment
 
 } // namespace spcu
 
@@ -85,6 +86,8 @@ struct spcu_ctx
     uint32_t                  pix_list_offset = ~0u, pix_list_stride = 0, pix_list_n = 0;
     spcu::DevBuf              host_rgb, host_sq; // device accumulators of the host-buffer entry point
     spcu::DevBuf              path_radiance;     // float4 per slot of a batch (SPCU_PIPELINE_PATHS)
+    spcu::DevBuf              sorted_queue;      // material-sorted hand-over between extend and shade
+    uint32_t                  n_materials = 0;
 
     uint32_t                 options[SPCU_OPT_COUNT_] = {};
     std::vector<cudaEvent_t> stage_events; // pairs, when SPCU_OPT_STAGE_TIMING is on

@@ -101,6 +101,17 @@ struct DWave
     int2*   mis_hit; // (light id or -1, occluded flag)
 };
 
+// Output of the extend stage: path vertices grouped by material, so that warps of the shading stages run one material's
+// code (SURVEY.md §7 "sort/compact by material before shading").  Segment m < n_segments-1 holds hits on material m (the
+// last material segment also takes any higher index), segment n_segments-1 holds misses.
+struct SortedQueue
+{
+    uint32_t* slots;  // [n_segments][capacity]
+    uint32_t* counts; // [n_segments], zeroed per depth
+    uint32_t  n_segments;
+    uint32_t  capacity;
+};
+
 // indices into the device counter block (unsigned long long[kNumCounters])
 enum Counter : int
 {

@@ -9,13 +9,17 @@ namespace spcu {
 // ---- trace_kernels.cu (compiled with --fmad=false; exact, reference-order traversal) ---------------------------
 void launch_trace_closest(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, TraceCounters* d_cnt,
                           cudaStream_t st);
+// the ordered ("fast") walk: nearer child first, ties towards the higher reference-order ID (trace.cuh)
+void launch_trace_closest_ordered(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, TraceCounters* d_cnt,
+                                  cudaStream_t st);
 void launch_trace_any(const DScene& s, const spcu_ray* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t st);
 void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, cudaStream_t st);
 
 // Wavefront stages that traverse.  `queue` holds path slots; n_queue is read on the device (no host sync).
 // extend: Scene::intersect_lights then Scene::intersect for every queued path (Integrator.cpp:558-563).
 void launch_extend(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
+                   uint32_t max_n, const SortedQueue& sorted, bool ordered, unsigned long long* d_counters,
+                   TraceCounters* d_cnt);
 // shadow: Scene::intersect_p of the light-sample visibility ray (Integrator.cpp:503).
 // Unoccluded entries are compacted into q_lit (may be NULL: then only the per-slot flag is written).
 void launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
@@ -51,8 +55,8 @@ void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint3
                    uint32_t sample_begin, uint32_t n_samples, uint32_t* queue, uint32_t* d_n_queue,
                    unsigned long long* d_counters);
 // shade: hit/miss handling + primary BSDF sample S0 (Integrator.cpp:558-572,627-632).  Surviving paths go to q_live.
-void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
-                  const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters);
+void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const SortedQueue& sorted,
+                  uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters);
 // nee_light: Light::sample for light p.light_index; paths with a usable sample go to q_shadow (Integrator.cpp:497-501).
 void launch_nee_light(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
                       const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow,

@@ -125,11 +125,14 @@ __global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ 
 
 // ---- shade (Integrator.cpp:558-572, 627-632): miss handling, surface interaction, primary BSDF sample S0 ---------------
 __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
-                                                       const __grid_constant__ RenderParams p, const uint32_t* q_in,
-                                                       const uint32_t* n_in, uint32_t* q_live, uint32_t* n_live,
-                                                       unsigned long long* counters)
+                                                       const __grid_constant__ RenderParams p,
+                                                       const __grid_constant__ SortedQueue sorted, uint32_t* q_live,
+                                                       uint32_t* n_live, unsigned long long* counters)
 {
-    const uint32_t n = *n_in;
+  // one material segment after the other: every warp shades a single material (or only misses)
+  for (uint32_t seg = 0; seg < sorted.n_segments; ++seg) {
+    const uint32_t  n    = sorted.counts[seg];
+    const uint32_t* q_in = sorted.slots + static_cast<size_t>(seg) * sorted.capacity;
     count_items(counters, kStShade, n);
     FOR_EACH_QUEUED(i, active, n)
     {
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
         queue_push(q_live, n_live, slot, live);
         warp_count(counters + kCntShadeCalls, sampled);
     }
+  }
 }
 
 // ---- nee_light (Integrator.cpp:497-501 / :288-292): Light::sample for one light -------------------------------------------
@@ -466,10 +470,10 @@ void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint3
                      d_counters);
 }
 
-void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
-                  const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters)
+void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const SortedQueue& sorted,
+                  uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_shade, l, max_n, s, w, p, q_in, d_n_in, q_live, d_n_live, d_counters);
+    WAVEFRONT_LAUNCH(k_shade, l, max_n, s, w, p, sorted, q_live, d_n_live, d_counters);
 }
 
 void launch_nee_light(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,

@@ -154,7 +154,7 @@ void spcu_destroy(spcu_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : { &c->geom_nodes, &c->geom_prims, &c->geom_shade, &c->geom_meta, &c->light_nodes, &c->lights,
                        &c->light_order, &c->materials, &c->bxdfs, &c->pool, &c->jitter, &c->q_rays, &c->q_out, &c->q_aux,
-                       &c->q_cnt, &c->queue_counts, &c->counters, &c->pix_list, &c->host_rgb, &c->host_sq, &c->path_radiance }) {
+                       &c->q_cnt, &c->queue_counts, &c->counters, &c->pix_list, &c->host_rgb, &c->host_sq, &c->path_radiance, &c->sorted_queue }) {
         b->release();
     }
     for (auto& b : c->wave_bufs) {
@@ -281,6 +281,7 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     d.pool         = c->pool.as<const float>();
     d.jitter       = c->jitter.as<const float>();
     d.spp          = spp;
+    c->n_materials = s->n_materials;
     c->have_scene      = true;
     c->pix_list_stride = 0; // invalidate the cached pixel list
     return SPCU_OK;
@@ -292,7 +293,7 @@ uint64_t spcu_scene_bytes(const spcu_ctx* c)
 }
 
 // ---- batch queries -----------------------------------------------------------------------------------------------------
-enum class Query { closest, lights, any };
+enum class Query { closest, closest_ordered, lights, any };
 
 static int run_query(spcu_ctx* c, Query q, const spcu_ray* rays, uint64_t n, void* out, uint64_t* counters3)
 {
@@ -316,6 +317,9 @@ static int run_query(spcu_ctx* c, Query q, const spcu_ray* rays, uint64_t n, voi
         switch (q) {
         case Query::closest:
             launch_trace_closest(c->ds, c->q_rays.as<spcu_ray>(), m, c->q_out.as<spcu_hit>(), d_cnt, c->stream);
+            break;
+        case Query::closest_ordered:
+            launch_trace_closest_ordered(c->ds, c->q_rays.as<spcu_ray>(), m, c->q_out.as<spcu_hit>(), d_cnt, c->stream);
             break;
         case Query::lights:
             launch_trace_lights(c->ds, c->q_rays.as<spcu_ray>(), m, c->q_out.as<spcu_hit>(), c->stream);
@@ -347,6 +351,11 @@ int spcu_trace_closest(spcu_ctx* c, const spcu_ray* rays, uint64_t n, spcu_hit* 
 int spcu_trace_closest_counted(spcu_ctx* c, const spcu_ray* rays, uint64_t n, spcu_hit* hits, uint64_t counters[3])
 {
     return run_query(c, Query::closest, rays, n, hits, counters);
+}
+
+int spcu_trace_closest_fast(spcu_ctx* c, const spcu_ray* rays, uint64_t n, spcu_hit* hits, uint64_t counters[3])
+{
+    return run_query(c, Query::closest_ordered, rays, n, hits, counters);
 }
 
 int spcu_trace_lights(spcu_ctx* c, const spcu_ray* rays, uint64_t n, spcu_hit* hits)

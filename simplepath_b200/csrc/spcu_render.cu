@@ -277,7 +277,9 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     const uint32_t max_depth   = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING ? std::min(1u, s.max_depth) : s.max_depth;
     const bool     nee         = part->integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE;
     const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING;
-    const uint32_t counts_need = 1 + max_depth * (2 + 3 * n_lights);
+    const uint32_t n_segments  = std::min<uint32_t>(c->n_materials, kMaxMaterialSegments) + 1u; // + the miss segment
+    const uint32_t counts_need = 1 + max_depth * (2 + 3 * n_lights + n_segments);
+    CK(c, c->sorted_queue.reserve(static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)));
     if (counts_need > static_cast<uint32_t>(kMaxQueueCounts)) {
         return fail(c, SPCU_ERR_LIMIT, "max_depth x lights needs %u queue counters (limit %d)", counts_need, kMaxQueueCounts);
     }
@@ -316,12 +318,15 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
             uint32_t* q_next = q[kQNext];
             for (uint32_t depth = 0; depth < max_depth; ++depth) {
                 RenderParams p{ part->seed, part->integrator, depth, 0 };
+                SortedQueue sorted{ c->sorted_queue.as<uint32_t>(), d_counts + next_count, n_segments, capacity };
+                next_count += n_segments;
                 timer.begin(kStExtend);
-                launch_extend(L, s, c->wave, q_cur, n_cur, max_n, d_counters, d_cnt);
+                launch_extend(L, s, c->wave, q_cur, n_cur, max_n, sorted, c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED,
+                              d_counters, d_cnt);
                 timer.end();
                 uint32_t* n_live = new_count();
                 timer.begin(kStShade);
-                launch_shade(L, s, c->wave, p, q_cur, n_cur, max_n, q[kQLive], n_live, d_counters);
+                launch_shade(L, s, c->wave, p, sorted, max_n, q[kQLive], n_live, d_counters);
                 timer.end();
                 launches += 2;
                 if (nee || direct) {
@@ -427,12 +432,6 @@ int spcu_stage_times(spcu_ctx* c, spcu_stage_time* out, uint32_t capacity, uint3
     std::memcpy(out, c->stage_report, n * sizeof(spcu_stage_time));
     *n_out = n;
     return SPCU_OK;
-}
-
-int spcu_trace_closest_fast(spcu_ctx* c, const spcu_ray* rays, uint64_t n, spcu_hit* hits)
-{
-    // The renderer's extend stage IS the exact reference-order traversal in this build.
-    return spcu_trace_closest(c, rays, n, hits);
 }
 
 } // extern "C"

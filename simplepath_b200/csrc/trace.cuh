@@ -66,6 +66,17 @@ __device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix,
            slab_axis(loz, hiz, r.oz, inv.z, t0, t1);
 }
 
+// Same test, also returning the entry distance t0 (used by the ordered traversal to visit the nearer child first).
+__device__ __forceinline__ bool slab_t0(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
+                                        const RayInv& inv, float t_max, float& t0_out)
+{
+    float      t0 = r.t_min, t1 = t_max;
+    const bool ok = slab_axis(lox, hix, r.ox, inv.x, t0, t1) && slab_axis(loy, hiy, r.oy, inv.y, t0, t1) &&
+                    slab_axis(loz, hiz, r.oz, inv.z, t0, t1);
+    t0_out = t0;
+    return ok;
+}
+
 // Triangle::intersect_impl (shapes/Triangle.h:97-146)
 __device__ __forceinline__ bool tri_hit(const float4 p0, const float4 p1, const float4 p2, const Ray& r, float t_max,
                                         float& t_out, float& beta_out, float& gamma_out)
@@ -296,8 +307,19 @@ __device__ __forceinline__ void load_right(const float4* nodes, int32_t idx, Nod
     c1 = { v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, __float_as_int(v3.y), __float_as_uint(v3.w) };
 }
 
+constexpr int32_t kDone = 0x7fffffff; // traversal cursor: no work left
+
 // Closest hit over ListAccelerator[unbounded..., BVH] (shapes/ListAccelerator.h:36-62 + BVHAccelerator.h:45-77,110-113).
 // `t_max` enters as the query's limit and leaves as the accepted distance; returns the accepted primitive or -1.
+//
+// Order and arithmetic are the reference's: children left then right, the right child's box tested against the t_max the
+// left subtree left behind, leaf primitives in list order, a hit replaces the result (equal t: the later one wins).
+// The loop is shaped for SIMD efficiency ("while-while"): all lanes first walk internal nodes — one iteration = both child
+// boxes of one node, branch-free apart from the final select — until each holds a leaf, then all lanes test leaf
+// primitives.  The cursor is either a fresh internal node (>= 0), a popped node whose RIGHT child is pending
+// (`retest`), a leaf (< 0), or kDone.  The right child is pre-filtered with the current t_max before it is pushed: the
+// slab test is monotone in t_max (also through its NaN rule), so a box that fails now fails later too, and nothing that
+// the reference would enter is skipped; it is re-tested when popped, exactly where the reference tests it.
 template <bool kCount, typename Prims>
 __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& prims, const Ray& r, float& t_max,
                                                float& beta, float& gamma, int32_t* stack_smem, TraceCounters* cnt)
@@ -320,11 +342,37 @@ __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& p
     Stack        stack;
     stack.sh = stack_smem;
 
-    int32_t  link  = acc.root; // the root's own bounds are never tested (BVHAccelerator.h:138-142)
-    uint32_t count = acc.root_count;
-    for (;;) {
-        if (link < 0) {
-            // NodeLeaf -> ListAccelerator::intersect_impl over the leaf's primitives
+    int32_t  link   = acc.root; // the root's own bounds are never tested (BVHAccelerator.h:138-142)
+    uint32_t count  = acc.root_count;
+    bool     retest = false;
+    while (link != kDone) {
+        // ---- internal nodes --------------------------------------------------------------------------------------
+        while (link >= 0 && link != kDone) {
+            NodeHalf c0, c1;
+            load_node(acc.nodes, link, c0, c1);
+            if (kCount && !retest) ++cnt->nodes;
+            const bool h0 = !retest && slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
+            const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
+            if (h0) {
+                if (h1) {
+                    stack.push(link); // right child pending: re-tested against the t_max of that moment
+                }
+                link   = c0.child;
+                count  = c0.count;
+                retest = false;
+            } else if (h1) {
+                link   = c1.child;
+                count  = c1.count;
+                retest = false;
+            } else if (stack.n > 0) {
+                link   = stack.pop();
+                retest = true;
+            } else {
+                link = kDone;
+            }
+        }
+        // ---- leaf: NodeLeaf -> ListAccelerator::intersect_impl over the leaf's primitives ------------------------
+        if (link != kDone) {
             const uint32_t first = static_cast<uint32_t>(~link);
             const uint32_t n     = count & SPCU_LEAF_COUNT_MASK;
             const bool     mixed = (count & SPCU_LEAF_MIXED_FLAG) != 0u;
@@ -336,45 +384,136 @@ __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& p
                     gamma  = g;
                 }
             }
+            if (stack.n > 0) {
+                link   = stack.pop();
+                retest = true;
+            } else {
+                link = kDone;
+            }
+        }
+    }
+    return hit_id;
+}
+
+// Ordered ("fast") closest hit: same boxes, same primitive tests, same arithmetic, but at every internal node the child
+// whose box the ray enters first is visited first and the other is deferred with its entry distance; a deferred child
+// is dropped when popped if the hit found meanwhile is closer than that entry.  The closest hit is the same as the
+// reference-order walk finds, with two provisos that the parity tests count and state:
+//  * equal-t candidates: the reference keeps the LAST one it visits, and IDs are assigned in its visiting order, so
+//    ties are resolved here towards the higher ID — the same answer whenever the reference visits all tied candidates;
+//  * the slab test is not conservative with respect to the primitive tests (different roundings), and it is evaluated
+//    against whatever t_max the walk has reached; another visiting order can therefore cull, or fail to cull, a box
+//    whose primitive grazes the current hit distance.  These are the "epsilon-tie mismatches".
+// Stack entry = (node << 1 | child, entry distance): 8 bytes, first kStackSharedOrdered levels in shared memory.
+constexpr int kStackSharedOrdered = 12; // 12 levels x 128 threads x 8 B = 12 KB, the same footprint as the exact walk
+
+struct OrderedStack
+{
+    int2* sh; // &smem[threadIdx.x]
+    int2  loc[SPCU_MAX_BVH_DEPTH + 2 - kStackSharedOrdered];
+    int   n = 0;
+
+    __device__ __forceinline__ void push(int32_t key, float t0)
+    {
+        const int2 v = make_int2(key, __float_as_int(t0));
+        if (n < kStackSharedOrdered) {
+            sh[n * kTraceBlock] = v;
         } else {
-            // NodeInternal: left child now, right child after the left subtree
+            loc[n - kStackSharedOrdered] = v;
+        }
+        ++n;
+    }
+    __device__ __forceinline__ int2 pop()
+    {
+        --n;
+        return (n < kStackSharedOrdered) ? sh[n * kTraceBlock] : loc[n - kStackSharedOrdered];
+    }
+};
+
+template <bool kCount>
+__device__ __forceinline__ int32_t closest_hit_ordered(const DAccel& acc, const GeomPrims& prims, const Ray& r, float& t_max,
+                                                       float& beta, float& gamma, int32_t* stack_smem, TraceCounters* cnt)
+{
+    int32_t hit_id = -1;
+    float   t, b, g;
+    beta = gamma = 0.0f;
+    for (uint32_t i = 0; i < acc.n_unbounded; ++i) { // the unbounded list is scanned first, in order, as in the reference
+        if (prims.template test<kCount>(i, true, r, t_max, t, b, g, cnt)) {
+            t_max  = t;
+            hit_id = static_cast<int32_t>(i);
+            beta   = b;
+            gamma  = g;
+        }
+    }
+    const RayInv inv = make_inv(r);
+    OrderedStack stack;
+    stack.sh = reinterpret_cast<int2*>(stack_smem - threadIdx.x) + threadIdx.x; // same 12 KB block, 8-byte entries
+
+    int32_t  link  = acc.root;
+    uint32_t count = acc.root_count;
+    while (link != kDone) {
+        while (link >= 0 && link != kDone) {
             NodeHalf c0, c1;
             load_node(acc.nodes, link, c0, c1);
             if (kCount) ++cnt->nodes;
-            if (slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max)) {
-                stack.push(link);
+            float      e0, e1;
+            const bool h0 = slab_t0(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max, e0);
+            const bool h1 = slab_t0(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max, e1);
+            if (h0 && h1) {
+                const bool left_first = !(e1 < e0); // equal entries: the reference's order, left first
+                stack.push((link << 1) | (left_first ? 1 : 0), left_first ? e1 : e0);
+                link  = left_first ? c0.child : c1.child;
+                count = left_first ? c0.count : c1.count;
+            } else if (h0) {
                 link  = c0.child;
                 count = c0.count;
-                continue;
-            }
-            if (slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max)) {
+            } else if (h1) {
                 link  = c1.child;
                 count = c1.count;
-                continue;
+            } else {
+                link = kDone;
+                while (stack.n > 0) {
+                    const int2 e = stack.pop();
+                    if (!(__int_as_float(e.y) > t_max)) { // still reachable: entry not beyond the current hit
+                        const float4 v3 = __ldg(acc.nodes + 4 * (e.x >> 1) + 3);
+                        link            = (e.x & 1) ? __float_as_int(v3.y) : __float_as_int(v3.x);
+                        count           = (e.x & 1) ? __float_as_uint(v3.w) : __float_as_uint(v3.z);
+                        break;
+                    }
+                }
             }
         }
-        // return to the innermost node whose right child is pending
-        bool descended = false;
-        while (stack.n > 0) {
-            const int32_t idx = stack.pop();
-            NodeHalf      c1;
-            load_right(acc.nodes, idx, c1);
-            if (slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max)) {
-                link      = c1.child;
-                count     = c1.count;
-                descended = true;
-                break;
+        if (link != kDone) {
+            const uint32_t first = static_cast<uint32_t>(~link);
+            const uint32_t n     = count & SPCU_LEAF_COUNT_MASK;
+            const bool     mixed = (count & SPCU_LEAF_MIXED_FLAG) != 0u;
+            for (uint32_t i = 0; i < n; ++i) {
+                const int32_t id = static_cast<int32_t>(first + i);
+                if (prims.template test<kCount>(first + i, mixed, r, t_max, t, b, g, cnt) && (t < t_max || id > hit_id)) {
+                    t_max  = t;
+                    hit_id = id;
+                    beta   = b;
+                    gamma  = g;
+                }
             }
-        }
-        if (!descended) {
-            break;
+            link = kDone;
+            while (stack.n > 0) {
+                const int2 e = stack.pop();
+                if (!(__int_as_float(e.y) > t_max)) {
+                    const float4 v3 = __ldg(acc.nodes + 4 * (e.x >> 1) + 3);
+                    link            = (e.x & 1) ? __float_as_int(v3.y) : __float_as_int(v3.x);
+                    count           = (e.x & 1) ? __float_as_uint(v3.w) : __float_as_uint(v3.z);
+                    break;
+                }
+            }
         }
     }
     return hit_id;
 }
 
 // Any hit over one accelerator (ListAccelerator::intersect_p_impl :64-67, NodeInternal::intersect_p :79-90):
-// limits never change, first accepted primitive ends the query.
+// limits never change, so a right child that passes its box test when its parent is visited needs no re-test: the
+// stack holds nodes whose right child is simply entered when popped.  First accepted primitive ends the query.
 template <bool kCount, typename AnyTest>
 __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, const Ray& r, float t_max,
                                         int32_t* stack_smem, TraceCounters* cnt)
@@ -390,8 +529,31 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
 
     int32_t  link  = acc.root;
     uint32_t count = acc.root_count;
-    for (;;) {
-        if (link < 0) {
+    while (link != kDone) {
+        while (link >= 0 && link != kDone) {
+            NodeHalf c0, c1;
+            load_node(acc.nodes, link, c0, c1);
+            if (kCount) ++cnt->nodes;
+            const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
+            const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
+            if (h0) {
+                if (h1) {
+                    stack.push(link);
+                }
+                link  = c0.child;
+                count = c0.count;
+            } else if (h1) {
+                link  = c1.child;
+                count = c1.count;
+            } else if (stack.n > 0) {
+                const float4 v3 = __ldg(acc.nodes + 4 * stack.pop() + 3);
+                link            = __float_as_int(v3.y);
+                count           = __float_as_uint(v3.w);
+            } else {
+                link = kDone;
+            }
+        }
+        if (link != kDone) {
             const uint32_t first = static_cast<uint32_t>(~link);
             const uint32_t n     = count & SPCU_LEAF_COUNT_MASK;
             const bool     mixed = (count & SPCU_LEAF_MIXED_FLAG) != 0u;
@@ -400,35 +562,16 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
                     return true;
                 }
             }
-        } else {
-            NodeHalf c0, c1;
-            load_node(acc.nodes, link, c0, c1);
-            if (kCount) ++cnt->nodes;
-            const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
-            const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
-            // limits are constant here, so both boxes can be tested at once; order of descent stays left, right
-            if (h0) {
-                if (h1) {
-                    stack.push(link);
-                }
-                link  = c0.child;
-                count = c0.count;
-                continue;
-            }
-            if (h1) {
-                link  = c1.child;
-                count = c1.count;
-                continue;
+            if (stack.n > 0) {
+                const float4 v3 = __ldg(acc.nodes + 4 * stack.pop() + 3);
+                link            = __float_as_int(v3.y);
+                count           = __float_as_uint(v3.w);
+            } else {
+                link = kDone;
             }
         }
-        if (stack.n == 0) {
-            return false;
-        }
-        const int32_t idx = stack.pop();
-        const float4  v3  = __ldg(acc.nodes + 4 * idx + 3);
-        link              = __float_as_int(v3.y);
-        count             = __float_as_uint(v3.w);
     }
+    return false;
 }
 
 // Scene::intersect_p (base/Scene.h:79-82): geometry accelerator, then lights accelerator.

@@ -63,6 +63,25 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
     }
 }
 
+template <bool kCount>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_closest_ordered(const __grid_constant__ DScene s, const spcu_ray* rays,
+                                                                       uint64_t n, spcu_hit* hits, TraceCounters* cnt)
+{
+    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    const uint64_t     i = static_cast<uint64_t>(blockIdx.x) * kTraceBlock + threadIdx.x;
+    TraceCounters      local{ 0, 0, 0 };
+    if (i < n) {
+        float           t_max, beta, gamma;
+        const Ray       r = load_ray(rays, i, t_max);
+        const GeomPrims gp{ s.geom_prims, s.geom_meta };
+        const int32_t   id = closest_hit_ordered<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local);
+        hits[i]            = spcu_hit{ id, t_max };
+    }
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
 __global__ void __launch_bounds__(kTraceBlock) k_trace_any(const __grid_constant__ DScene s, const spcu_ray* rays, uint64_t n,
                                                            uint8_t* out)
 {
@@ -89,11 +108,30 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_lights(const __grid_const
     }
 }
 
+// Material-sorted hand-over: lanes of a warp that share a segment reserve their places with ONE atomic per segment.
+__device__ __forceinline__ void segment_push(const SortedQueue& q, uint32_t seg, uint32_t slot, bool active)
+{
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!active) {
+        return;
+    }
+    const unsigned peers  = __match_any_sync(act, seg);
+    const int      lane   = threadIdx.x & 31;
+    const int      leader = __ffs(peers) - 1;
+    uint32_t       base   = 0;
+    if (lane == leader) {
+        base = atomicAdd(q.counts + seg, static_cast<uint32_t>(__popc(peers)));
+    }
+    base = __shfl_sync(peers, base, leader);
+    q.slots[static_cast<size_t>(seg) * q.capacity + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+}
+
 // ---- wavefront stages ----------------------------------------------------------------------------------------------
 // extend: Integrator.cpp:558-563.  intersect_lights first; a light hit shrinks t_max for the geometry query.
-template <bool kCount>
+template <bool kCount, bool kOrdered>
 __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                         const uint32_t* queue, const uint32_t* n_queue,
+                                                        const __grid_constant__ SortedQueue sorted,
                                                         unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack[kStackShared * kTraceBlock];
@@ -103,21 +141,26 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
     for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
     const uint32_t i      = base + threadIdx.x;
     const bool     active = i < n;
+    uint32_t slot = 0, seg = 0;
     if (active) {
-        const uint32_t slot = queue[i];
-        const float4   o    = w.ray_o[slot];
-        const float4   d    = w.ray_d[slot];
-        const Ray      r{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
-        float          t_max = d.w, beta, gamma;
+        slot             = queue[i];
+        const float4 o   = w.ray_o[slot];
+        const float4 d   = w.ray_d[slot];
+        const Ray    r{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
+        float        t_max = d.w, beta, gamma;
 
         const LightPrims lp{ s.lights };
         const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack + threadIdx.x, nullptr);
         w.light_hit[slot]   = make_int2(li, __float_as_int(t_max));
 
         const GeomPrims gp{ s.geom_prims, s.geom_meta };
-        const int32_t   gi = closest_hit<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local);
+        const int32_t   gi = kOrdered ? closest_hit_ordered<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local)
+                                      : closest_hit<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local);
         w.hit[slot]        = HitRec{ gi, t_max, beta, gamma };
+        // hand the vertex to the shading stage sorted by material: misses in the last segment
+        seg = gi < 0 ? sorted.n_segments - 1u : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + gi)), sorted.n_segments - 2u);
     }
+    segment_push(sorted, seg, slot, active);
     warp_count(counters + kCntRaysClosest, active);
     warp_count(counters + kCntRaysLights, active);
     }
@@ -217,6 +260,17 @@ void launch_trace_closest(const DScene& s, const spcu_ray* d_rays, uint64_t n, s
     }
 }
 
+void launch_trace_closest_ordered(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, TraceCounters* d_cnt,
+                                  cudaStream_t st)
+{
+    if (n == 0) return;
+    if (d_cnt) {
+        k_trace_closest_ordered<true><<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits, d_cnt);
+    } else {
+        k_trace_closest_ordered<false><<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits, nullptr);
+    }
+}
+
 void launch_trace_any(const DScene& s, const spcu_ray* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t st)
 {
     if (n == 0) return;
@@ -253,10 +307,28 @@ static int trace_ctas_per_sm(K kernel)
         }                                                                                                              \
     } while (0)
 
-void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
+template <bool kCount, bool kOrdered>
+static void launch_extend_variant(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
+                                  const uint32_t* d_n_queue, uint32_t max_n, const SortedQueue& sorted,
+                                  unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    TRACE_STAGE_LAUNCH(k_extend);
+    static const int occ_ = trace_ctas_per_sm(k_extend<kCount, kOrdered>);
+    k_extend<kCount, kOrdered><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
+        s, w, queue, d_n_queue, sorted, d_counters, d_cnt);
+}
+
+void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                   uint32_t max_n, const SortedQueue& sorted, bool ordered, unsigned long long* d_counters,
+                   TraceCounters* d_cnt)
+{
+    if (max_n == 0) return;
+    if (d_cnt) {
+        ordered ? launch_extend_variant<true, true>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, d_cnt)
+                : launch_extend_variant<true, false>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, d_cnt);
+    } else {
+        ordered ? launch_extend_variant<false, true>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, nullptr)
+                : launch_extend_variant<false, false>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, nullptr);
+    }
 }
 
 void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,

@@ -113,6 +113,24 @@ def test_pipelines_agree(ctx, scene):
     assert bad.mean() < 0.02
 
 
+def test_ordered_traversal_renders_the_same_image(ctx, scene):
+    """SPCU_TRAVERSAL_ORDERED changes which boxes are visited, not what is hit (up to epsilon ties)."""
+    name, flat, vec = scene
+    if CURRENT["pipeline"] != capi.PIPELINE_WAVEFRONT:
+        pytest.skip("the ordered walk is an option of the wavefront's extend stage")
+    jitter = vec["jitter"]
+    upload(ctx, flat, jitter)
+    exact, _, st_e = ctx.render(ctx.partition(seed=123))
+    ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_ORDERED)
+    try:
+        fast, _, st_f = ctx.render(ctx.partition(seed=123))
+    finally:
+        ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_EXACT)
+    differing = (exact != fast).any(axis=-1).mean()
+    assert differing < 0.002, f"{name}: {differing:.3%} of pixels differ between the exact and the ordered walk"
+    assert abs(st_e["rays_closest"] - st_f["rays_closest"]) <= 0.001 * st_e["rays_closest"] + 4
+
+
 def test_partitions_are_exact(ctx, scene):
     """Tile partitions touch disjoint pixels and sample ranges accumulate in sample order, so any split of the work
     — by tiles, by samples, or into small wavefronts — gives the bit-identical image."""

@@ -278,7 +278,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     const bool     nee         = part->integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE;
     const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING;
     const uint32_t n_segments  = std::min<uint32_t>(c->n_materials, kMaxMaterialSegments) + 1u; // + the miss segment
-    const uint32_t counts_need = 1 + max_depth * (2 + 3 * n_lights + n_segments);
+    const uint32_t counts_need = 1 + max_depth * (3 + 4 * n_lights + n_segments);
     CK(c, c->sorted_queue.reserve(static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)));
     if (counts_need > static_cast<uint32_t>(kMaxQueueCounts)) {
         return fail(c, SPCU_ERR_LIMIT, "max_depth x lights needs %u queue counters (limit %d)", counts_need, kMaxQueueCounts);
@@ -321,7 +321,8 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 SortedQueue sorted{ c->sorted_queue.as<uint32_t>(), d_counts + next_count, n_segments, capacity };
                 next_count += n_segments;
                 timer.begin(kStExtend);
-                launch_extend(L, s, c->wave, q_cur, n_cur, max_n, sorted, c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED,
+                launch_extend(L, s, c->wave, q_cur, n_cur, max_n, new_count(), sorted,
+                              c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED,
                               d_counters, d_cnt);
                 timer.end();
                 uint32_t* n_live = new_count();
@@ -338,7 +339,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                         timer.end();
                         uint32_t* n_lit = direct ? nullptr : new_count();
                         timer.begin(kStShadow);
-                        launch_shadow(L, s, c->wave, q[kQShadow], n_shadow, max_n, direct ? nullptr : q[kQLit], n_lit, d_counters,
+                        launch_shadow(L, s, c->wave, q[kQShadow], n_shadow, max_n, new_count(), direct ? nullptr : q[kQLit], n_lit, d_counters,
                                       d_cnt);
                         timer.end();
                         launches += 2;

@@ -307,10 +307,14 @@ __device__ __forceinline__ void load_right(const float4* nodes, int32_t idx, Nod
     c1 = { v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, __float_as_int(v3.y), __float_as_uint(v3.w) };
 }
 
-constexpr int32_t kDone = 0x7fffffff; // traversal cursor: no work left
+constexpr int32_t kDone      = 0x7fffffff; // traversal cursor: no work left
+constexpr int     kAllLeaves = 0x7fffffff; // "run to completion"
 
-// Closest hit over ListAccelerator[unbounded..., BVH] (shapes/ListAccelerator.h:36-62 + BVHAccelerator.h:45-77,110-113).
-// `t_max` enters as the query's limit and leaves as the accepted distance; returns the accepted primitive or -1.
+// ---------------------------------------------------------------------------------------------------------------------
+// Closest hit over ListAccelerator[unbounded..., BVH] (shapes/ListAccelerator.h:36-62 + BVHAccelerator.h:45-77,110-113),
+// as a RESUMABLE walk: closest_begin scans the unbounded list and sets the cursor, closest_run advances the BVH part by
+// at most `max_leaves` leaf visits and can be called again.  The persistent traversal kernels use that to hand new rays
+// to lanes whose walk has ended while the other lanes of the warp keep going.
 //
 // Order and arithmetic are the reference's: children left then right, the right child's box tested against the t_max the
 // left subtree left behind, leaf primitives in list order, a hit replaces the result (equal t: the later one wins).
@@ -320,81 +324,120 @@ constexpr int32_t kDone = 0x7fffffff; // traversal cursor: no work left
 // (`retest`), a leaf (< 0), or kDone.  The right child is pre-filtered with the current t_max before it is pushed: the
 // slab test is monotone in t_max (also through its NaN rule), so a box that fails now fails later too, and nothing that
 // the reference would enter is skipped; it is re-tested when popped, exactly where the reference tests it.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ClosestWalk
+{
+    int32_t  link;
+    uint32_t count;
+    bool     retest;
+    int32_t  hit_id; // accepted primitive or -1
+    float    t_max;  // in: the query's limit; out: the accepted distance
+    float    beta, gamma;
+};
+
+template <bool kCount, typename Prims>
+__device__ __forceinline__ void closest_begin(const DAccel& acc, const Prims& prims, const Ray& r, ClosestWalk& w,
+                                              TraceCounters* cnt)
+{
+    float t, b, g;
+    w.hit_id = -1;
+    w.beta = w.gamma = 0.0f;
+    // top-level list: unbounded primitives first, in list order; a hit shrinks t_max and replaces the result
+    for (uint32_t i = 0; i < acc.n_unbounded; ++i) {
+        if (prims.template test<kCount>(i, true, r, w.t_max, t, b, g, cnt)) {
+            w.t_max  = t;
+            w.hit_id = static_cast<int32_t>(i);
+            w.beta   = b;
+            w.gamma  = g;
+        }
+    }
+    w.link   = acc.root; // the root's own bounds are never tested (BVHAccelerator.h:138-142)
+    w.count  = acc.root_count;
+    w.retest = false;
+}
+
+// `mask` = the lanes that execute this call together (the full warp, or __activemask() of a converged subset).  Loop
+// conditions are warp votes over `mask`, so every lane of the group runs the same number of iterations and the
+// compiler's reconvergence points sit INSIDE the loops: lanes holding an internal node really do step in lockstep
+// (without the votes each lane ends up running its own copy of the loop, serialised — ncu showed 2-4 of 32 lanes active).
+template <bool kCount, typename Prims>
+__device__ __forceinline__ void closest_run(const DAccel& acc, const Prims& prims, const Ray& r, const RayInv& inv,
+                                            ClosestWalk& w, Stack& stack, int max_leaves, TraceCounters* cnt, unsigned mask)
+{
+    float t, b, g;
+    while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
+        // ---- internal nodes --------------------------------------------------------------------------------------
+        while (__any_sync(mask, w.link >= 0 && w.link != kDone)) {
+            if (w.link >= 0 && w.link != kDone) {
+                NodeHalf c0, c1;
+                load_node(acc.nodes, w.link, c0, c1);
+                if (kCount && !w.retest) ++cnt->nodes;
+                const bool h0 = !w.retest && slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, w.t_max);
+                const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, w.t_max);
+                if (h0) {
+                    if (h1) {
+                        stack.push(w.link); // right child pending: re-tested against the t_max of that moment
+                    }
+                    w.link   = c0.child;
+                    w.count  = c0.count;
+                    w.retest = false;
+                } else if (h1) {
+                    w.link   = c1.child;
+                    w.count  = c1.count;
+                    w.retest = false;
+                } else if (stack.n > 0) {
+                    w.link   = stack.pop();
+                    w.retest = true;
+                } else {
+                    w.link = kDone;
+                }
+            }
+        }
+        // ---- leaf: NodeLeaf -> ListAccelerator::intersect_impl over the leaf's primitives ------------------------
+        const bool     leaf  = w.link != kDone;
+        const uint32_t first = static_cast<uint32_t>(~w.link);
+        const uint32_t n     = leaf ? (w.count & SPCU_LEAF_COUNT_MASK) : 0u;
+        const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
+        const uint32_t n_max = __reduce_max_sync(mask, n);
+        for (uint32_t i = 0; i < n_max; ++i) {
+            if (i < n && prims.template test<kCount>(first + i, mixed, r, w.t_max, t, b, g, cnt)) {
+                w.t_max  = t;
+                w.hit_id = static_cast<int32_t>(first + i);
+                w.beta   = b;
+                w.gamma  = g;
+            }
+        }
+        if (leaf) {
+            if (stack.n > 0) {
+                w.link   = stack.pop();
+                w.retest = true;
+            } else {
+                w.link = kDone;
+            }
+        }
+        --max_leaves;
+    }
+}
+
+// One-shot form: `t_max` enters as the query's limit and leaves as the accepted distance; returns the primitive or -1.
 template <bool kCount, typename Prims>
 __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& prims, const Ray& r, float& t_max,
                                                float& beta, float& gamma, int32_t* stack_smem, TraceCounters* cnt)
 {
-    int32_t hit_id = -1;
-    float   t, b, g;
-    beta = gamma = 0.0f;
-
-    // top-level list: unbounded primitives first, in list order; a hit shrinks t_max and replaces the result
-    for (uint32_t i = 0; i < acc.n_unbounded; ++i) {
-        if (prims.template test<kCount>(i, true, r, t_max, t, b, g, cnt)) {
-            t_max  = t;
-            hit_id = static_cast<int32_t>(i);
-            beta   = b;
-            gamma  = g;
-        }
-    }
-
+    ClosestWalk w;
+    w.t_max = t_max;
+    closest_begin<kCount>(acc, prims, r, w, cnt);
     const RayInv inv = make_inv(r);
     Stack        stack;
     stack.sh = stack_smem;
-
-    int32_t  link   = acc.root; // the root's own bounds are never tested (BVHAccelerator.h:138-142)
-    uint32_t count  = acc.root_count;
-    bool     retest = false;
-    while (link != kDone) {
-        // ---- internal nodes --------------------------------------------------------------------------------------
-        while (link >= 0 && link != kDone) {
-            NodeHalf c0, c1;
-            load_node(acc.nodes, link, c0, c1);
-            if (kCount && !retest) ++cnt->nodes;
-            const bool h0 = !retest && slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
-            const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
-            if (h0) {
-                if (h1) {
-                    stack.push(link); // right child pending: re-tested against the t_max of that moment
-                }
-                link   = c0.child;
-                count  = c0.count;
-                retest = false;
-            } else if (h1) {
-                link   = c1.child;
-                count  = c1.count;
-                retest = false;
-            } else if (stack.n > 0) {
-                link   = stack.pop();
-                retest = true;
-            } else {
-                link = kDone;
-            }
-        }
-        // ---- leaf: NodeLeaf -> ListAccelerator::intersect_impl over the leaf's primitives ------------------------
-        if (link != kDone) {
-            const uint32_t first = static_cast<uint32_t>(~link);
-            const uint32_t n     = count & SPCU_LEAF_COUNT_MASK;
-            const bool     mixed = (count & SPCU_LEAF_MIXED_FLAG) != 0u;
-            for (uint32_t i = 0; i < n; ++i) {
-                if (prims.template test<kCount>(first + i, mixed, r, t_max, t, b, g, cnt)) {
-                    t_max  = t;
-                    hit_id = static_cast<int32_t>(first + i);
-                    beta   = b;
-                    gamma  = g;
-                }
-            }
-            if (stack.n > 0) {
-                link   = stack.pop();
-                retest = true;
-            } else {
-                link = kDone;
-            }
-        }
-    }
-    return hit_id;
+    closest_run<kCount>(acc, prims, r, inv, w, stack, kAllLeaves, cnt, __activemask());
+    t_max = w.t_max;
+    beta  = w.beta;
+    gamma = w.gamma;
+    return w.hit_id;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
 // Ordered ("fast") closest hit: same boxes, same primitive tests, same arithmetic, but at every internal node the child
 // whose box the ray enters first is visited first and the other is deferred with its entry distance; a deferred child
 // is dropped when popped if the hit found meanwhile is closer than that entry.  The closest hit is the same as the
@@ -405,6 +448,7 @@ __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& p
 //    against whatever t_max the walk has reached; another visiting order can therefore cull, or fail to cull, a box
 //    whose primitive grazes the current hit distance.  These are the "epsilon-tie mismatches".
 // Stack entry = (node << 1 | child, entry distance): 8 bytes, first kStackSharedOrdered levels in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
 constexpr int kStackSharedOrdered = 12; // 12 levels x 128 threads x 8 B = 12 KB, the same footprint as the exact walk
 
 struct OrderedStack
@@ -413,6 +457,10 @@ struct OrderedStack
     int2  loc[SPCU_MAX_BVH_DEPTH + 2 - kStackSharedOrdered];
     int   n = 0;
 
+    __device__ __forceinline__ void attach(int32_t* stack_smem)
+    {
+        sh = reinterpret_cast<int2*>(stack_smem - threadIdx.x) + threadIdx.x; // same 12 KB block, 8-byte entries
+    }
     __device__ __forceinline__ void push(int32_t key, float t0)
     {
         const int2 v = make_int2(key, __float_as_int(t0));
@@ -430,90 +478,161 @@ struct OrderedStack
     }
 };
 
+// next deferred child that is still reachable, or kDone
+__device__ __forceinline__ void ordered_pop(const DAccel& acc, OrderedStack& stack, ClosestWalk& w)
+{
+    w.link = kDone;
+    while (stack.n > 0) {
+        const int2 e = stack.pop();
+        if (!(__int_as_float(e.y) > w.t_max)) { // entry not beyond the current hit
+            const float4 v3 = __ldg(acc.nodes + 4 * (e.x >> 1) + 3);
+            w.link          = (e.x & 1) ? __float_as_int(v3.y) : __float_as_int(v3.x);
+            w.count         = (e.x & 1) ? __float_as_uint(v3.w) : __float_as_uint(v3.z);
+            return;
+        }
+    }
+}
+
+template <bool kCount>
+__device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const GeomPrims& prims, const Ray& r, const RayInv& inv,
+                                                    ClosestWalk& w, OrderedStack& stack, int max_leaves, TraceCounters* cnt,
+                                                    unsigned mask)
+{
+    float t, b, g;
+    while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
+        while (__any_sync(mask, w.link >= 0 && w.link != kDone)) {
+            if (w.link >= 0 && w.link != kDone) {
+                NodeHalf c0, c1;
+                load_node(acc.nodes, w.link, c0, c1);
+                if (kCount) ++cnt->nodes;
+                float      e0, e1;
+                const bool h0 = slab_t0(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, w.t_max, e0);
+                const bool h1 = slab_t0(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, w.t_max, e1);
+                if (h0 && h1) {
+                    const bool left_first = !(e1 < e0); // equal entries: the reference's order, left first
+                    stack.push((w.link << 1) | (left_first ? 1 : 0), left_first ? e1 : e0);
+                    w.link  = left_first ? c0.child : c1.child;
+                    w.count = left_first ? c0.count : c1.count;
+                } else if (h0) {
+                    w.link  = c0.child;
+                    w.count = c0.count;
+                } else if (h1) {
+                    w.link  = c1.child;
+                    w.count = c1.count;
+                } else {
+                    ordered_pop(acc, stack, w);
+                }
+            }
+        }
+        const bool     leaf  = w.link != kDone;
+        const uint32_t first = static_cast<uint32_t>(~w.link);
+        const uint32_t n     = leaf ? (w.count & SPCU_LEAF_COUNT_MASK) : 0u;
+        const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
+        const uint32_t n_max = __reduce_max_sync(mask, n);
+        for (uint32_t i = 0; i < n_max; ++i) {
+            const int32_t id = static_cast<int32_t>(first + i);
+            if (i < n && prims.template test<kCount>(first + i, mixed, r, w.t_max, t, b, g, cnt) && (t < w.t_max || id > w.hit_id)) {
+                w.t_max  = t;
+                w.hit_id = id;
+                w.beta   = b;
+                w.gamma  = g;
+            }
+        }
+        if (leaf) {
+            ordered_pop(acc, stack, w);
+        }
+        --max_leaves;
+    }
+}
+
 template <bool kCount>
 __device__ __forceinline__ int32_t closest_hit_ordered(const DAccel& acc, const GeomPrims& prims, const Ray& r, float& t_max,
                                                        float& beta, float& gamma, int32_t* stack_smem, TraceCounters* cnt)
 {
-    int32_t hit_id = -1;
-    float   t, b, g;
-    beta = gamma = 0.0f;
-    for (uint32_t i = 0; i < acc.n_unbounded; ++i) { // the unbounded list is scanned first, in order, as in the reference
-        if (prims.template test<kCount>(i, true, r, t_max, t, b, g, cnt)) {
-            t_max  = t;
-            hit_id = static_cast<int32_t>(i);
-            beta   = b;
-            gamma  = g;
-        }
-    }
+    ClosestWalk w;
+    w.t_max = t_max;
+    closest_begin<kCount>(acc, prims, r, w, cnt); // the unbounded list is scanned first, in order, as in the reference
     const RayInv inv = make_inv(r);
     OrderedStack stack;
-    stack.sh = reinterpret_cast<int2*>(stack_smem - threadIdx.x) + threadIdx.x; // same 12 KB block, 8-byte entries
-
-    int32_t  link  = acc.root;
-    uint32_t count = acc.root_count;
-    while (link != kDone) {
-        while (link >= 0 && link != kDone) {
-            NodeHalf c0, c1;
-            load_node(acc.nodes, link, c0, c1);
-            if (kCount) ++cnt->nodes;
-            float      e0, e1;
-            const bool h0 = slab_t0(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max, e0);
-            const bool h1 = slab_t0(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max, e1);
-            if (h0 && h1) {
-                const bool left_first = !(e1 < e0); // equal entries: the reference's order, left first
-                stack.push((link << 1) | (left_first ? 1 : 0), left_first ? e1 : e0);
-                link  = left_first ? c0.child : c1.child;
-                count = left_first ? c0.count : c1.count;
-            } else if (h0) {
-                link  = c0.child;
-                count = c0.count;
-            } else if (h1) {
-                link  = c1.child;
-                count = c1.count;
-            } else {
-                link = kDone;
-                while (stack.n > 0) {
-                    const int2 e = stack.pop();
-                    if (!(__int_as_float(e.y) > t_max)) { // still reachable: entry not beyond the current hit
-                        const float4 v3 = __ldg(acc.nodes + 4 * (e.x >> 1) + 3);
-                        link            = (e.x & 1) ? __float_as_int(v3.y) : __float_as_int(v3.x);
-                        count           = (e.x & 1) ? __float_as_uint(v3.w) : __float_as_uint(v3.z);
-                        break;
-                    }
-                }
-            }
-        }
-        if (link != kDone) {
-            const uint32_t first = static_cast<uint32_t>(~link);
-            const uint32_t n     = count & SPCU_LEAF_COUNT_MASK;
-            const bool     mixed = (count & SPCU_LEAF_MIXED_FLAG) != 0u;
-            for (uint32_t i = 0; i < n; ++i) {
-                const int32_t id = static_cast<int32_t>(first + i);
-                if (prims.template test<kCount>(first + i, mixed, r, t_max, t, b, g, cnt) && (t < t_max || id > hit_id)) {
-                    t_max  = t;
-                    hit_id = id;
-                    beta   = b;
-                    gamma  = g;
-                }
-            }
-            link = kDone;
-            while (stack.n > 0) {
-                const int2 e = stack.pop();
-                if (!(__int_as_float(e.y) > t_max)) {
-                    const float4 v3 = __ldg(acc.nodes + 4 * (e.x >> 1) + 3);
-                    link            = (e.x & 1) ? __float_as_int(v3.y) : __float_as_int(v3.x);
-                    count           = (e.x & 1) ? __float_as_uint(v3.w) : __float_as_uint(v3.z);
-                    break;
-                }
-            }
-        }
-    }
-    return hit_id;
+    stack.attach(stack_smem);
+    closest_run_ordered<kCount>(acc, prims, r, inv, w, stack, kAllLeaves, cnt, __activemask());
+    t_max = w.t_max;
+    beta  = w.beta;
+    gamma = w.gamma;
+    return w.hit_id;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
 // Any hit over one accelerator (ListAccelerator::intersect_p_impl :64-67, NodeInternal::intersect_p :79-90):
 // limits never change, so a right child that passes its box test when its parent is visited needs no re-test: the
 // stack holds nodes whose right child is simply entered when popped.  First accepted primitive ends the query.
+// Resumable like the closest walk: any_run returns kAnyRunning / kAnyHit / kAnyMiss.
+// ---------------------------------------------------------------------------------------------------------------------
+struct AnyWalk
+{
+    int32_t  link;
+    uint32_t count;
+};
+constexpr int kAnyRunning = 0, kAnyHit = 1, kAnyMiss = 2;
+
+__device__ __forceinline__ void any_pop(const DAccel& acc, Stack& stack, AnyWalk& w)
+{
+    if (stack.n > 0) {
+        const float4 v3 = __ldg(acc.nodes + 4 * stack.pop() + 3);
+        w.link          = __float_as_int(v3.y);
+        w.count         = __float_as_uint(v3.w);
+    } else {
+        w.link = kDone;
+    }
+}
+
+template <bool kCount, typename AnyTest>
+__device__ __forceinline__ int any_run(const DAccel& acc, const AnyTest& test, const Ray& r, const RayInv& inv, float t_max,
+                                       AnyWalk& w, Stack& stack, int max_leaves, TraceCounters* cnt, unsigned mask)
+{
+    bool hit = false;
+    while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
+        while (__any_sync(mask, w.link >= 0 && w.link != kDone)) {
+            if (w.link >= 0 && w.link != kDone) {
+                NodeHalf c0, c1;
+                load_node(acc.nodes, w.link, c0, c1);
+                if (kCount) ++cnt->nodes;
+                const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
+                const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
+                if (h0) {
+                    if (h1) {
+                        stack.push(w.link);
+                    }
+                    w.link  = c0.child;
+                    w.count = c0.count;
+                } else if (h1) {
+                    w.link  = c1.child;
+                    w.count = c1.count;
+                } else {
+                    any_pop(acc, stack, w);
+                }
+            }
+        }
+        const bool     leaf  = w.link != kDone;
+        const uint32_t first = static_cast<uint32_t>(~w.link);
+        const uint32_t n     = leaf ? (w.count & SPCU_LEAF_COUNT_MASK) : 0u;
+        const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
+        const uint32_t n_max = __reduce_max_sync(mask, n);
+        for (uint32_t i = 0; i < n_max; ++i) {
+            if (i < n && !hit && test(first + i, mixed, cnt)) {
+                hit = true; // first accepted primitive ends this lane's query; the others finish theirs
+            }
+        }
+        if (hit) {
+            w.link = kDone;
+        } else if (leaf) {
+            any_pop(acc, stack, w);
+        }
+        --max_leaves;
+    }
+    return hit ? kAnyHit : (w.link == kDone ? kAnyMiss : kAnyRunning);
+}
+
 template <bool kCount, typename AnyTest>
 __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, const Ray& r, float t_max,
                                         int32_t* stack_smem, TraceCounters* cnt)
@@ -526,52 +645,16 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
     const RayInv inv = make_inv(r);
     Stack        stack;
     stack.sh = stack_smem;
+    AnyWalk w{ acc.root, acc.root_count };
+    return any_run<kCount>(acc, test, r, inv, t_max, w, stack, kAllLeaves, cnt, __activemask()) == kAnyHit;
+}
 
-    int32_t  link  = acc.root;
-    uint32_t count = acc.root_count;
-    while (link != kDone) {
-        while (link >= 0 && link != kDone) {
-            NodeHalf c0, c1;
-            load_node(acc.nodes, link, c0, c1);
-            if (kCount) ++cnt->nodes;
-            const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
-            const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
-            if (h0) {
-                if (h1) {
-                    stack.push(link);
-                }
-                link  = c0.child;
-                count = c0.count;
-            } else if (h1) {
-                link  = c1.child;
-                count = c1.count;
-            } else if (stack.n > 0) {
-                const float4 v3 = __ldg(acc.nodes + 4 * stack.pop() + 3);
-                link            = __float_as_int(v3.y);
-                count           = __float_as_uint(v3.w);
-            } else {
-                link = kDone;
-            }
-        }
-        if (link != kDone) {
-            const uint32_t first = static_cast<uint32_t>(~link);
-            const uint32_t n     = count & SPCU_LEAF_COUNT_MASK;
-            const bool     mixed = (count & SPCU_LEAF_MIXED_FLAG) != 0u;
-            for (uint32_t i = 0; i < n; ++i) {
-                if (test(first + i, mixed, cnt)) {
-                    return true;
-                }
-            }
-            if (stack.n > 0) {
-                const float4 v3 = __ldg(acc.nodes + 4 * stack.pop() + 3);
-                link            = __float_as_int(v3.y);
-                count           = __float_as_uint(v3.w);
-            } else {
-                link = kDone;
-            }
-        }
-    }
-    return false;
+// Lights half of Scene::intersect_p: only sphere lights occlude.
+__device__ __forceinline__ bool lights_any_hit(const DScene& s, const Ray& r, float t_max, int32_t* stack_smem)
+{
+    const LightPrims lp{ s.lights };
+    auto light_test = [&](uint32_t id, bool, TraceCounters*) { return lp.test_any(id, r, t_max); };
+    return any_hit<false>(s.lights_accel, light_test, r, t_max, stack_smem, nullptr);
 }
 
 // Scene::intersect_p (base/Scene.h:79-82): geometry accelerator, then lights accelerator.
@@ -587,9 +670,7 @@ __device__ __forceinline__ bool scene_any_hit(const DScene& s, const Ray& r, flo
     if (any_hit<kCount>(s.geom, geom_test, r, t_max, stack_smem, cnt)) {
         return true;
     }
-    const LightPrims lp{ s.lights };
-    auto light_test = [&](uint32_t id, bool, TraceCounters*) { return lp.test_any(id, r, t_max); };
-    return any_hit<false>(s.lights_accel, light_test, r, t_max, stack_smem, nullptr);
+    return lights_any_hit(s, r, t_max, stack_smem);
 }
 
 } // namespace spcu

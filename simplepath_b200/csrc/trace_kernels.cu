@@ -127,42 +127,141 @@ __device__ __forceinline__ void segment_push(const SortedQueue& q, uint32_t seg,
 }
 
 // ---- wavefront stages ----------------------------------------------------------------------------------------------
+// Work distribution of the persistent traversal stages.  Secondary rays have a violently skewed cost (bunny scene, random
+// rays: median 1 node visit, mean 15, p99 121, max 438): a warp that takes 32 rays and waits for its slowest runs at 3-4
+// active lanes (ncu, profiles/r01e_*).  Here lanes are refilled individually: a lane whose walk has ended draws the next
+// queue entry while the other lanes keep walking, so long rays pile up side by side in a warp instead of each stalling 31
+// finished lanes.  Entries are handed out from ONE global cursor in chunks of kChunk per warp (one global atomic per
+// chunk), so the whole grid drains the queue evenly and no CTA is left with a private tail.
+constexpr int      kLeavesPerRound = 2;  // leaf visits a lane may make before the warp looks for idle lanes again
+constexpr uint32_t kChunk          = 64; // queue entries a warp reserves at a time
+
+struct LaneFeed
+{
+    uint32_t* cursor; // global, zero at kernel start
+    uint32_t  n;
+    uint32_t  next = 0, end = 0; // this warp's current chunk (identical in all lanes)
+
+    // all 32 lanes call; lanes with want == true receive an index (0xffffffff: the queue is exhausted)
+    __device__ __forceinline__ uint32_t draw(bool want)
+    {
+        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        if (mask == 0u) {
+            return 0xffffffffu;
+        }
+        const int      lane = threadIdx.x & 31;
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+        const uint32_t k    = __popc(mask);
+        uint32_t       idx  = 0xffffffffu;
+        const uint32_t have = end - next;
+        if (want && rank < have) {
+            idx = next + rank;
+        }
+        if (k <= have) {
+            next += k;
+            return idx;
+        }
+        // chunk used up: reserve the next one (k - have <= 32 <= kChunk entries are still owed)
+        uint32_t base = 0;
+        if (lane == 0) {
+            base = atomicAdd(cursor, kChunk);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (want && rank >= have) {
+            const uint32_t i = base + (rank - have);
+            idx              = i < n ? i : 0xffffffffu;
+        }
+        next = min(n, base + (k - have));
+        end  = min(n, base + kChunk);
+        return idx;
+    }
+};
+
+// per-segment push from divergent code: the lanes that arrive together (converged) aggregate among themselves
+__device__ __forceinline__ void segment_push_converged(const SortedQueue& q, uint32_t seg, uint32_t slot)
+{
+    const unsigned act    = __activemask();
+    const unsigned peers  = __match_any_sync(act, seg);
+    const int      lane   = threadIdx.x & 31;
+    const int      leader = __ffs(peers) - 1;
+    uint32_t       base   = 0;
+    if (lane == leader) {
+        base = atomicAdd(q.counts + seg, static_cast<uint32_t>(__popc(peers)));
+    }
+    base = __shfl_sync(peers, base, leader);
+    q.slots[static_cast<size_t>(seg) * q.capacity + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+}
+
 // extend: Integrator.cpp:558-563.  intersect_lights first; a light hit shrinks t_max for the geometry query.
 template <bool kCount, bool kOrdered>
 __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
-                                                        const uint32_t* queue, const uint32_t* n_queue,
+                                                        const uint32_t* queue, const uint32_t* n_queue, uint32_t* cursor,
                                                         const __grid_constant__ SortedQueue sorted,
                                                         unsigned long long* counters, TraceCounters* cnt)
 {
-    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
     const uint32_t     n = *n_queue;
     count_items(counters, kStExtend, n);
-    TraceCounters      local{ 0, 0, 0 };
-    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
-    const uint32_t i      = base + threadIdx.x;
-    const bool     active = i < n;
-    uint32_t slot = 0, seg = 0;
-    if (active) {
-        slot             = queue[i];
-        const float4 o   = w.ray_o[slot];
-        const float4 d   = w.ray_d[slot];
-        const Ray    r{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
-        float        t_max = d.w, beta, gamma;
+    LaneFeed feed;
+    feed.cursor = cursor;
+    feed.n      = n;
 
-        const LightPrims lp{ s.lights };
-        const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack + threadIdx.x, nullptr);
-        w.light_hit[slot]   = make_int2(li, __float_as_int(t_max));
+    TraceCounters   local{ 0, 0, 0 };
+    const GeomPrims gp{ s.geom_prims, s.geom_meta };
+    Stack           stack;
+    OrderedStack    ostack;
+    stack.sh = stack_smem + threadIdx.x;
+    ostack.attach(stack_smem + threadIdx.x);
+    Ray         r{};
+    RayInv      inv{};
+    ClosestWalk walk{};
+    walk.link       = kDone;
+    uint32_t slot   = 0;
+    unsigned traced = 0;
+    bool     have   = false;
 
-        const GeomPrims gp{ s.geom_prims, s.geom_meta };
-        const int32_t   gi = kOrdered ? closest_hit_ordered<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local)
-                                      : closest_hit<kCount>(s.geom, gp, r, t_max, beta, gamma, stack + threadIdx.x, &local);
-        w.hit[slot]        = HitRec{ gi, t_max, beta, gamma };
-        // hand the vertex to the shading stage sorted by material: misses in the last segment
-        seg = gi < 0 ? sorted.n_segments - 1u : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + gi)), sorted.n_segments - 2u);
+    for (;;) {
+        // ---- lanes without a ray draw the next queue entries ------------------------------------------------------------
+        const uint32_t i = feed.draw(!have);
+        if (!have && i != 0xffffffffu) {
+            slot           = queue[i];
+            const float4 o = w.ray_o[slot];
+            const float4 d = w.ray_d[slot];
+            r              = Ray{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
+            inv            = make_inv(r);
+            float t_max = d.w, beta, gamma;
+            // Scene::intersect_lights (a handful of lights: walked in one go)
+            const LightPrims lp{ s.lights };
+            const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack_smem + threadIdx.x, nullptr);
+            w.light_hit[slot]   = make_int2(li, __float_as_int(t_max));
+            walk.t_max          = t_max;
+            closest_begin<kCount>(s.geom, gp, r, walk, &local);
+            stack.n = ostack.n = 0;
+            have               = true;
+            ++traced;
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0u) {
+            break; // nothing in flight and nothing left to draw
+        }
+        // ---- a bounded piece of every lane's walk (lanes without a ray vote along with a finished cursor) -----------------
+        if (kOrdered) {
+            closest_run_ordered<kCount>(s.geom, gp, r, inv, walk, ostack, kLeavesPerRound, &local, 0xffffffffu);
+        } else {
+            closest_run<kCount>(s.geom, gp, r, inv, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
+        }
+        if (have && walk.link == kDone) {
+            w.hit[slot] = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
+            // hand the vertex to the shading stage sorted by material: misses in the last segment
+            const uint32_t seg = walk.hit_id < 0 ? sorted.n_segments - 1u
+                                                 : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + walk.hit_id)), sorted.n_segments - 2u);
+            segment_push_converged(sorted, seg, slot);
+            have = false;
+        }
     }
-    segment_push(sorted, seg, slot, active);
-    warp_count(counters + kCntRaysClosest, active);
-    warp_count(counters + kCntRaysLights, active);
+    const unsigned total = __reduce_add_sync(0xffffffffu, traced);
+    if ((threadIdx.x & 31) == 0 && total) {
+        atomicAdd(counters + kCntRaysClosest, static_cast<unsigned long long>(total));
+        atomicAdd(counters + kCntRaysLights, static_cast<unsigned long long>(total));
     }
     if (kCount) {
         flush_counters(local, cnt);
@@ -172,31 +271,92 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
 // shadow: Integrator.cpp:503 — Scene::intersect_p of the light sample's visibility ray.
 template <bool kCount>
 __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
-                                                        const uint32_t* queue, const uint32_t* n_queue, uint32_t* q_lit,
-                                                        uint32_t* n_lit, unsigned long long* counters, TraceCounters* cnt)
+                                                        const uint32_t* queue, const uint32_t* n_queue, uint32_t* cursor,
+                                                        uint32_t* q_lit, uint32_t* n_lit, unsigned long long* counters,
+                                                        TraceCounters* cnt)
 {
-    __shared__ int32_t stack[kStackShared * kTraceBlock];
+    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
     const uint32_t     n = *n_queue;
     count_items(counters, kStShadow, n);
-    TraceCounters      local{ 0, 0, 0 };
-    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
-    const uint32_t i      = base + threadIdx.x;
-    const bool     active = i < n;
-    uint32_t       slot   = 0;
-    bool           lit    = false;
-    if (active) {
-        slot             = queue[i];
-        const float4 p   = w.isect_p[slot];
-        const float4 d   = w.sh_d[slot];
-        const Ray    r{ p.x, p.y, p.z, d.x, d.y, d.z, w.sh_tmin[slot] };
-        const bool   occ = scene_any_hit<kCount>(s, r, d.w, stack + threadIdx.x, &local);
-        w.occluded[slot] = occ ? 1 : 0;
-        lit              = !occ;
+    LaneFeed feed;
+    feed.cursor = cursor;
+    feed.n      = n;
+
+    TraceCounters   local{ 0, 0, 0 };
+    const GeomPrims gp{ s.geom_prims, s.geom_meta };
+    Stack           stack;
+    stack.sh = stack_smem + threadIdx.x;
+    Ray      r{};
+    RayInv   inv{};
+    AnyWalk  walk{ kDone, 0 };
+    float    t_max  = 0.0f;
+    uint32_t slot   = 0;
+    unsigned traced = 0;
+    bool     have   = false;
+    int      status = kAnyMiss;
+
+    for (;;) {
+        const uint32_t i = feed.draw(!have);
+        if (!have && i != 0xffffffffu) {
+            slot           = queue[i];
+            const float4 p = w.isect_p[slot];
+            const float4 d = w.sh_d[slot];
+            r              = Ray{ p.x, p.y, p.z, d.x, d.y, d.z, w.sh_tmin[slot] };
+            inv            = make_inv(r);
+            t_max          = d.w;
+            stack.n        = 0;
+            walk           = AnyWalk{ s.geom.root, s.geom.root_count };
+            have           = true;
+            status         = kAnyRunning;
+            ++traced;
+            // ListAccelerator::intersect_p_impl: unbounded primitives first
+            for (uint32_t k = 0; k < s.geom.n_unbounded; ++k) {
+                float t, b, g;
+                if (gp.template test<kCount>(k, true, r, t_max, t, b, g, &local)) {
+                    status    = kAnyHit;
+                    walk.link = kDone;
+                    break;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0u) {
+            break;
+        }
+        {
+            auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
+                float t, b, g;
+                return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
+            };
+            const int st = any_run<kCount>(s.geom, geom_test, r, inv, t_max, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
+            if (have && status == kAnyRunning) {
+                status = st;
+            }
+        }
+        if (have && status != kAnyRunning) {
+            // Scene::intersect_p: geometry, then the lights accelerator (base/Scene.h:79-82)
+            if (status == kAnyMiss && lights_any_hit(s, r, t_max, stack_smem + threadIdx.x)) {
+                status = kAnyHit;
+            }
+            const bool occ   = status == kAnyHit;
+            w.occluded[slot] = occ ? 1 : 0;
+            if (q_lit && !occ) { // survivors only go on to the BSDF stages (Integrator.cpp:503-506)
+                const unsigned act    = __activemask();
+                const int      lane   = threadIdx.x & 31;
+                const int      leader = __ffs(act) - 1;
+                uint32_t       base   = 0;
+                if (lane == leader) {
+                    base = atomicAdd(n_lit, static_cast<uint32_t>(__popc(act)));
+                }
+                base = __shfl_sync(act, base, leader);
+                q_lit[base + __popc(act & ((1u << lane) - 1u))] = slot;
+            }
+            have      = false;
+            walk.link = kDone;
+        }
     }
-    if (q_lit) { // survivors only go on to the BSDF stages: occluded samples contribute nothing (Integrator.cpp:503-506)
-        queue_push(q_lit, n_lit, slot, lit);
-    }
-    warp_count(counters + kCntRaysAny, active);
+    const unsigned total = __reduce_add_sync(0xffffffffu, traced);
+    if ((threadIdx.x & 31) == 0 && total) {
+        atomicAdd(counters + kCntRaysAny, static_cast<unsigned long long>(total));
     }
     if (kCount) {
         flush_counters(local, cnt);
@@ -309,40 +469,41 @@ static int trace_ctas_per_sm(K kernel)
 
 template <bool kCount, bool kOrdered>
 static void launch_extend_variant(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
-                                  const uint32_t* d_n_queue, uint32_t max_n, const SortedQueue& sorted,
+                                  const uint32_t* d_n_queue, uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted,
                                   unsigned long long* d_counters, TraceCounters* d_cnt)
 {
     static const int occ_ = trace_ctas_per_sm(k_extend<kCount, kOrdered>);
     k_extend<kCount, kOrdered><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-        s, w, queue, d_n_queue, sorted, d_counters, d_cnt);
+        s, w, queue, d_n_queue, d_cursor, sorted, d_counters, d_cnt);
 }
 
 void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, const SortedQueue& sorted, bool ordered, unsigned long long* d_counters,
-                   TraceCounters* d_cnt)
+                   uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered,
+                   unsigned long long* d_counters, TraceCounters* d_cnt)
 {
     if (max_n == 0) return;
     if (d_cnt) {
-        ordered ? launch_extend_variant<true, true>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, d_cnt)
-                : launch_extend_variant<true, false>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, d_cnt);
+        ordered ? launch_extend_variant<true, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, d_cnt)
+                : launch_extend_variant<true, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, d_cnt);
     } else {
-        ordered ? launch_extend_variant<false, true>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, nullptr)
-                : launch_extend_variant<false, false>(l, s, w, queue, d_n_queue, max_n, sorted, d_counters, nullptr);
+        ordered ? launch_extend_variant<false, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, nullptr)
+                : launch_extend_variant<false, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, nullptr);
     }
 }
 
 void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t* q_lit, uint32_t* d_n_lit, unsigned long long* d_counters, TraceCounters* d_cnt)
+                   uint32_t max_n, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit, unsigned long long* d_counters,
+                   TraceCounters* d_cnt)
 {
     if (max_n == 0) return;
     if (d_cnt) {
         static const int occ_ = trace_ctas_per_sm(k_shadow<true>);
         k_shadow<true><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, queue, d_n_queue, q_lit, d_n_lit, d_counters, d_cnt);
+            s, w, queue, d_n_queue, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
     } else {
         static const int occ_ = trace_ctas_per_sm(k_shadow<false>);
         k_shadow<false><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, queue, d_n_queue, q_lit, d_n_lit, d_counters, nullptr);
+            s, w, queue, d_n_queue, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
     }
 }
 

@@ -39,6 +39,7 @@ WORKLOADS = {
     "material_spheres_256_16spp": ("c1_material_spheres_const", 16),
     "bunny_1080p_256spp": ("c3_bunny", 256),
     "elf_1080p_256spp": ("c4_elf", 256),
+    "lucy_4k_256spp": ("c5_lucy", 256),
 }
 DEFAULT_WORKLOAD = "example_scene_1080p_64spp"
 INTEGRATOR = "iterative_rrnee"

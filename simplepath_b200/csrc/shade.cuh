@@ -211,7 +211,7 @@ __device__ __forceinline__ V3 beckmann_sample(V3 wi, float ax, float ay, float U
 
 // BeckmannDistribution::sample_wh_impl (Material.cpp:117-157).  In the visible-area branch the two get_next_1D()
 // arguments are ONE draw call (rng.cuh).  The other branch keeps the reference's 2*phi (golden ratio) factor.
-__device__ __forceinline__ V3 beckmann_sample_wh(const spcu_bxdf& bx, V3 wo, Rng& rng)
+static __device__ __noinline__ V3 beckmann_sample_wh(const spcu_bxdf& bx, V3 wo, Rng& rng)
 {
     if (!bx.sample_visible) {
         float tan2, phi;
@@ -400,7 +400,7 @@ __device__ __forceinline__ V3 bxdf_rho(const spcu_bxdf& bx, V3 wo, Rng& rng)
 
 // ---- materials (materials/Material.h:456-806) ----------------------------------------------------------------------------
 // OneSampleMaterial::get_selection_weights :545-572 — a fresh 16-sample albedo estimate per BxDF on EVERY call
-__device__ __forceinline__ void selection_weights(const spcu_bxdf* bx, uint32_t n, V3 wo, Rng& rng, float* w)
+static __device__ __noinline__ void selection_weights(const spcu_bxdf* bx, uint32_t n, V3 wo, Rng& rng, float* w)
 {
     float sum = 0.0f;
 #pragma unroll 1

@@ -46,11 +46,33 @@ INTEGRATOR = "iterative_rrnee"
 
 # ---- byte model: algorithmic bytes per item of each wavefront stage, excluding traversal ---------------
 STAGE_BYTES = {
-    "raygen": 84, "extend": 60, "shade": 196, "nee_light": 92, "shadow": 41, "nee_bsdf": 177, "mis_trace": 44,
-    "nee_mis_accumulate": 116, "direct_accumulate": 113, "advance": 152, "resolve": 28,
+    # 32-byte records of csrc/device_scene.h: what a stage must read and write per queue entry
+    "raygen": 88,               # pixel id in; RayRec, PathRec, RNG counter, queue entry out
+    "extend": 72,               # queue, RayRec in; ExtendRec, sorted-queue entry out (+ traversal bytes)
+    "shade": 240,               # queue, ExtendRec, RayRec, PathRec, shading record + meta in; VertexRec, SampleRec, queue out
+    "nee_light": 108,           # queue, VertexRec, PathRec in; LightRec, counter, queue out
+    "shadow": 56,               # queue, VertexRec.p, LightRec in; queue out (+ traversal bytes)
+    "nee_bsdf": 188,            # queue, VertexRec, LightRec, PathRec, RayRec.d in; MisRec, counter, queue out
+    "mis_trace": 44,            # queue, VertexRec.p, MisRec.d in; light/occluded out (+ traversal bytes)
+    "nee_mis_accumulate": 116,  # queue, MisRec, PathRec in; PathRec.L out
+    "direct_accumulate": 116,
+    "advance": 156,             # queue, SampleRec, VertexRec, PathRec in; PathRec.tp, RayRec, counter, queue out
+    "resolve": 20,              # radiance sample in, per-pixel sums amortised
     "paths": 20,  # persistent path kernel: 4 B pixel id in, 16 B radiance sample out; everything else stays on chip
 }
 NODE_BYTES, TRI_BYTES, XF_BYTES = 64, 48, 96
+
+
+def measured_traffic_per_item(stage: str, workload: str) -> tuple[float | None, str | None]:
+    """DRAM bytes per item of a stage as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum over every
+    launch of one render of this workload, divided by the stage's items: profiles/traffic_probe.py + traffic_join.py)."""
+    for path in sorted((ROOT / "profiles").glob("ncu_traffic_r*.json"), reverse=True):
+        d = json.loads(path.read_text())
+        if d.get("probe", {}).get("workload") == workload and stage in d.get("stages", {}):
+            v = d["stages"][stage].get("dram_bytes_per_item")
+            if v is not None:
+                return float(v), path.name
+    return None, None
 
 
 def peaks() -> tuple[float, str]:
@@ -239,6 +261,7 @@ def run_cuda(args) -> None:
     dur_s = stage_ms[dominant] / 1e3 / n_launch
     achieved = bytes_total / n_launch / dur_s / 1e9 if dur_s > 0 else 0.0
     kernel_ms = sum(stage_ms.values())
+    traffic_item, traffic_src = measured_traffic_per_item(dominant, args.workload)
 
     cpu = cpu_baseline(scene_name, flat) if world == 1 and not args.no_cpu else None
 
@@ -260,7 +283,9 @@ def run_cuda(args) -> None:
         "gpu_launches": int(launches / world * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": traffic_item * items / n_launch if traffic_item is not None else None,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
                      "share_of_step": stage_ms[dominant] / kernel_ms if kernel_ms else None,
                      "launches": n_launch, "items_per_launch": items / n_launch,
                      "bytes_per_item": bytes_total / max(items, 1),

@@ -41,7 +41,7 @@ struct DScene
     uint32_t     spp;
 };
 
-// Closest-hit record of the extend stage: 16 bytes, one vector store.
+// Closest-hit record as the traversal code produces it (id, distance, triangle barycentrics).
 struct alignas(16) HitRec
 {
     int32_t id;    // reference-order primitive ID or -1
@@ -57,48 +57,67 @@ struct TraceCounters
     unsigned long long xf;
 };
 
-// ---- wavefront state (structure of arrays over path slots) -----------------------------------------------
-// One slot = one camera sample in flight.  Every array has `capacity` entries; all float4 arrays are 16-byte
-// vector loads/stores, coalesced when queues are dense.
+// ---- wavefront state ---------------------------------------------------------------------------------------------
+// One slot = one camera sample in flight.  Queues are compacted (and sorted by material), so stages reach their slots
+// in scattered order: a 4-byte or 16-byte field of a structure-of-arrays layout then costs a whole 32-byte DRAM sector
+// (ncu on round 1's SoA layout: 1.5-2.7x the algorithmic bytes, profiles/ncu_traffic_r01_c2.json).  The state is
+// therefore an array of 32-byte-aligned records per kind, each holding what one stage reads or writes TOGETHER, every
+// access a pair of 16-byte vector loads/stores that use their sector completely.
+struct alignas(32) PathRec // identity + accumulators of the path
+{
+    float4 tp; // throughput rgb, pixel index (bits)
+    float4 L;  // radiance rgb,   global sample index (bits)
+};
+struct alignas(32) RayRec // sp::Ray + sp::RayLimits of the current segment
+{
+    float4 o; // o.xyz, t_min
+    float4 d; // d.xyz, t_max
+};
+struct alignas(32) VertexRec // surface interaction kept across the NEE stages of one vertex + the RNG draw counter
+{
+    float4 p; // point xyz, material index (bits)
+    float4 n; // shading normal xyz, RNG draw counter (bits; lives here because every shading stage touches this record)
+};
+struct alignas(32) ExtendRec // result of the extend stage
+{
+    HitRec hit;      // Scene::intersect
+    int32_t light;   // Scene::intersect_lights: light id or -1 ...
+    float   light_t; // ... and its distance
+    float   pad[2];
+};
+struct alignas(32) SampleRec // primary BSDF sample S0 of the vertex (Integrator.cpp:569)
+{
+    float4 dir; // wi xyz, pdf
+    float4 col; // rgb, (unused)
+};
+struct alignas(32) LightRec // light sample of the NEE light strategy (Integrator.cpp:497-516); the ray starts at VertexRec::p
+{
+    float4 wi;  // direction xyz, t_max
+    float4 aux; // t_min, light pdf, (u, v) of an image-based light's sample — its radiance is looked up again from them;
+                // the other lights' radiance is a constant of the light
+};
+struct alignas(64) MisRec // NEE BSDF strategy (Integrator.cpp:518-536)
+{
+    float4  d;        // material ray d xyz, t_min (origin = VertexRec::p, t_max = FLT_MAX)
+    float4  col;      // material sample colour rgb, pdf
+    float4  cwa;      // |cos(n, wi)|, balance-heuristic weight, light-strategy term A.r, A.g
+    float   ab;       // A.b
+    int32_t light;    // mis trace: light reached or -1
+    int32_t occluded; // mis trace: Scene::intersect_p of the same ray
+    float   pad;
+};
+
 struct DWave
 {
-    uint32_t capacity;
-
-    // camera-sample identity of a slot and its random-number draw counter (RNG contract: rng.cuh)
-    uint32_t* pixel;   // global pixel index y*w+x
-    uint32_t* sample;  // global sample index
-    uint32_t* rng_ctr; // number of draw calls made so far on this path
-
-    // current path segment: sp::Ray + sp::RayLimits (32 B as two float4)
-    float4* ray_o; // o.xyz, t_min
-    float4* ray_d; // d.xyz, t_max
-
-    float4* throughput; // rgb, (unused)
-    float4* radiance;   // L rgb, (unused)
-
-    HitRec* hit;       // Scene::intersect result
-    int2*   light_hit; // Scene::intersect_lights result: (light id, float bits of distance)
-
-    // surface interaction kept across the NEE stages of one vertex
-    float4* isect_p; // point xyz, material index (as int bits)
-    float4* isect_n; // shading normal xyz, (unused)
-
-    // primary BSDF sample S0 of the vertex (Integrator.cpp:569): direction, colour, pdf
-    float4* s0_dir; // wi xyz, pdf
-    float4* s0_col; // rgb, (unused)
-
-    // NEE light-sampling strategy (Integrator.cpp:497-516); the shadow ray starts at isect_p
-    float4*  sh_d;    // shadow ray d, t_max
-    float*   sh_tmin; // shadow ray t_min
-    float4*  light_L; // light sample radiance rgb, light pdf
-    uint8_t* occluded;
-
-    // NEE BSDF-sampling strategy (Integrator.cpp:518-536)
-    float4* mis_d;   // material ray d xyz, t_min   (origin = isect point, t_max = FLT_MAX)
-    float4* mis_col; // material sample colour rgb, pdf
-    float2* mis_cw;  // |cos(n, wi)|, balance-heuristic weight
-    float4* nee_acc; // light-strategy term of this light, added together with the BSDF-strategy term (:516 + :534)
-    int2*   mis_hit; // (light id or -1, occluded flag)
+    uint32_t   capacity;
+    PathRec*   path;
+    RayRec*    ray;
+    VertexRec* vertex;
+    ExtendRec* extend;
+    SampleRec* s0;
+    LightRec*  light;
+    MisRec*    mis;
+    uint8_t*   occluded; // direct lighting only: shadow result per slot
 };
 
 // Output of the extend stage: path vertices grouped by material, so that warps of the shading stages run one material's

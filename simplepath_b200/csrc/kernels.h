@@ -80,8 +80,9 @@ void launch_advance(const Launch& l, const DScene& s, const DWave& w, const Rend
                     const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
                     unsigned long long* d_counters);
 // resolve: per pixel, add this batch's samples in sample order to the accumulators (main.cpp:100).
-void launch_resolve(const Launch& l, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t n_samples,
-                    float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters);
+// d_radiance[(k * n_pix + i) * stride] = radiance sample k of pixel-list entry i (float4 units).
+void launch_resolve(const Launch& l, const float4* d_radiance, uint32_t stride, const uint32_t* d_pix_list, uint32_t n_pix,
+                    uint32_t n_samples, float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters);
 // ---- path_kernels.cu ------------------------------------------------------------------------------------------------
 // The persistent path kernel: every slot of the batch from camera to termination in one launch; d_radiance[slot] = L.
 void launch_paths(const Launch& l, const DScene& s, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t sample_begin,

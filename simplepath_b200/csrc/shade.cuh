@@ -701,6 +701,7 @@ struct LSample
     float pdf;
     V3    wi;
     float t_min, t_max;
+    float u, v; // image-based light: the sampled map coordinates (its L is ibl_lookup(u, v)); 0 otherwise
 };
 
 // Light::sample (Lights/Light.h:38-49) over SphereLight (ObjectLight::sample_impl :81-90 + Sphere::sample
@@ -709,6 +710,7 @@ __device__ __forceinline__ LSample light_sample(const DScene& s, const spcu_ligh
 {
     LSample out;
     out.t_max = kFltMax;
+    out.u = out.v = 0.0f;
     if (l.kind == SPCU_LIGHT_SPHERE) {
         const V3 obs = xf_point(l.world_to_object, p);
         V3       local;
@@ -750,6 +752,8 @@ __device__ __forceinline__ LSample light_sample(const DScene& s, const spcu_ligh
             out.wi  = xf_vector(l.light_to_world, v3(st * cp, ct, st * sp));
             out.pdf = (st == 0.0f) ? 0.0f : map_pdf / (2.0f * sqr(kPi) * st);
             out.L   = ibl_lookup(s, l, d0, d1);
+            out.u   = d0;
+            out.v   = d1;
         }
     }
     out.t_min = ray_offset(n, out.wi);

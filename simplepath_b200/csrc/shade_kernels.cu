@@ -83,9 +83,10 @@ __device__ __forceinline__ void warp_count(unsigned long long* counter, bool pre
 }
 
 
-__device__ __forceinline__ Rng load_rng(const DWave& w, uint32_t slot, uint64_t seed)
+// records are moved as pairs of 16-byte vectors
+__device__ __forceinline__ Rng make_rng(const PathRec& pr, uint32_t ctr, uint64_t seed)
 {
-    return Rng{ w.pixel[slot], w.sample[slot], static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), w.rng_ctr[slot] };
+    return Rng{ __float_as_uint(pr.tp.w), __float_as_uint(pr.L.w), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), ctr };
 }
 
 #define FOR_EACH_QUEUED(i, active, n)                                                                  \
@@ -105,16 +106,12 @@ __global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ 
         if (active) {
             const uint32_t pix = __ldg(pix_list + i % n_pix);
             const uint32_t smp = sample_begin + i / n_pix;
-            float4         o, d;
-            camera_ray(s, pix, smp, o, d);
-            w.pixel[i]      = pix;
-            w.sample[i]     = smp;
-            w.rng_ctr[i]    = 0u;
-            w.ray_o[i]      = o;
-            w.ray_d[i]      = d;
-            w.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-            w.radiance[i]   = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            queue[i]        = i;
+            RayRec         ray;
+            camera_ray(s, pix, smp, ray.o, ray.d);
+            w.ray[i]      = ray;
+            w.path[i]     = PathRec{ make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pix)), make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(smp)) };
+            w.vertex[i].n = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u)); // RNG draw counter = 0
+            queue[i]      = i;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -140,41 +137,37 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
         bool     sampled = false;
         uint32_t slot    = 0;
         if (active) {
-            slot              = q_in[i];
-            const HitRec h    = w.hit[slot];
-            const float4 ro   = w.ray_o[slot];
-            const float4 rd   = w.ray_d[slot];
-            const V3     o = xyz(ro), d = xyz(rd);
-            if (h.id < 0) {
-                const int2 lh = w.light_hit[slot];
-                if (lh.x >= 0) { // emitter reached, at ANY depth (Integrator.cpp:627-629)
-                    const V3     L  = light_hit_L(s, s.lights[lh.x], d);
-                    const float4 tp = w.throughput[slot];
-                    float4       r  = w.radiance[slot];
-                    r.x += tp.x * L.x;
-                    r.y += tp.y * L.y;
-                    r.z += tp.z * L.z;
-                    w.radiance[slot] = r;
+            slot               = q_in[i];
+            const ExtendRec ex = w.extend[slot];
+            const RayRec    ry = w.ray[slot];
+            const V3        o = xyz(ry.o), d = xyz(ry.d);
+            if (ex.hit.id < 0) {
+                if (ex.light >= 0) { // emitter reached, at ANY depth (Integrator.cpp:627-629)
+                    const V3 L  = light_hit_L(s, s.lights[ex.light], d);
+                    PathRec  pr = w.path[slot];
+                    pr.L.x += pr.tp.x * L.x;
+                    pr.L.y += pr.tp.y * L.y;
+                    pr.L.z += pr.tp.z * L.z;
+                    w.path[slot].L = pr.L;
                 }
             } else {
                 V3       point, normal;
                 uint32_t material;
-                make_isect(s, h, o, d, point, normal, material);
-                w.isect_p[slot] = f4(point, __uint_as_float(material));
-                w.isect_n[slot] = f4(normal, 0.0f);
+                make_isect(s, ex.hit, o, d, point, normal, material);
+                uint32_t ctr = __float_as_uint(w.vertex[slot].n.w);
                 if (p.integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING) {
                     live = true;
                 } else {
-                    Rng           rng = load_rng(w, slot, p.seed);
+                    Rng           rng = make_rng(w.path[slot], ctr, p.seed);
                     const MSample sr  = material_sample(s, material, -d, normal, rng);
-                    w.rng_ctr[slot]   = rng.ctr;
+                    ctr               = rng.ctr;
                     sampled           = true;
                     if (!(sr.pdf == 0.0f || is_black(sr.color))) {
-                        w.s0_dir[slot] = f4(sr.dir, sr.pdf);
-                        w.s0_col[slot] = f4(sr.color, 0.0f);
-                        live           = true;
+                        w.s0[slot] = SampleRec{ f4(sr.dir, sr.pdf), f4(sr.color, 0.0f) };
+                        live       = true;
                     }
                 }
+                w.vertex[slot] = VertexRec{ f4(point, __uint_as_float(material)), f4(normal, __uint_as_float(ctr)) };
             }
         }
         queue_push(q_live, n_live, slot, live);
@@ -197,23 +190,28 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_light(const __grid_constant
         bool     usable = false;
         uint32_t slot   = 0;
         if (active) {
-            slot       = q_in[i];
-            Rng   rng  = load_rng(w, slot, p.seed);
-            float u0, u1;
+            slot               = q_in[i];
+            const VertexRec vx = w.vertex[slot];
+            Rng             rng = make_rng(w.path[slot], __float_as_uint(vx.n.w), p.seed);
+            float           u0, u1;
             rng_next2(rng, u0, u1);
-            w.rng_ctr[slot]  = rng.ctr;
-            const V3      pt = xyz(w.isect_p[slot]);
-            const V3      nn = xyz(w.isect_n[slot]);
-            const LSample ls = light_sample(s, light, pt, nn, u0, u1);
+            w.vertex[slot].n.w = __uint_as_float(rng.ctr);
+            const LSample ls   = light_sample(s, light, xyz(vx.p), xyz(vx.n), u0, u1);
             if (!(ls.pdf == 0.0f || is_black(ls.L))) {
-                w.sh_d[slot]    = f4(ls.wi, ls.t_max);
-                w.sh_tmin[slot] = ls.t_min;
-                w.light_L[slot] = f4(ls.L, ls.pdf);
-                usable          = true;
+                w.light[slot] = LightRec{ f4(ls.wi, ls.t_max), make_float4(ls.t_min, ls.pdf, ls.u, ls.v) };
+                usable        = true;
             }
         }
         queue_push(q_shadow, n_shadow, slot, usable);
     }
+}
+
+// radiance of a stored light sample: an image-based light is looked up again from the sample's (u, v); every other
+// light's sample carries the light's constant radiance (Lights/Light.h:81-90,155-161,226-249)
+__device__ __forceinline__ V3 light_sample_L(const DScene& s, const spcu_light& light, const LightRec& lr)
+{
+    return light.kind == SPCU_LIGHT_ENV_IBL ? ibl_lookup(s, light, lr.aux.z, lr.aux.w)
+                                            : v3(light.radiance[0], light.radiance[1], light.radiance[2]);
 }
 
 // ---- nee_bsdf (Integrator.cpp:503-530): light-strategy term, second BSDF sample, Light::pdf ----------------------------------
@@ -232,54 +230,58 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
         unsigned calls  = 0;
         if (active) {
             slot = q_shadow[i]; // the shadow stage queued unoccluded samples only (Integrator.cpp:503-506)
-            {
-                const float4   ip       = w.isect_p[slot];
-                const V3       pt       = xyz(ip);
-                const uint32_t material = __float_as_uint(ip.w);
-                const V3       nn       = xyz(w.isect_n[slot]);
-                const V3       wo       = -xyz(w.ray_d[slot]);
-                const float4   shd      = w.sh_d[slot];
-                const V3       wi       = xyz(shd);
-                const float4   lL       = w.light_L[slot];
-                Rng            rng      = load_rng(w, slot, p.seed);
+            const VertexRec vx       = w.vertex[slot];
+            const LightRec  lr       = w.light[slot];
+            const PathRec   pr       = w.path[slot];
+            const V3        pt       = xyz(vx.p);
+            const uint32_t  material = __float_as_uint(vx.p.w);
+            const V3        nn       = xyz(vx.n);
+            const V3        wo       = -xyz(w.ray[slot].d);
+            const V3        wi       = xyz(lr.wi);
+            const float     lpdf_s   = lr.aux.y;
+            const V3        lL       = light_sample_L(s, light, lr);
+            Rng             rng      = make_rng(pr, __float_as_uint(vx.n.w), p.seed);
 
-                // Material::eval / pdf (materials/Material.h:475-490) rebuild the ONB on every call; it is the same basis
-                const Onb onb = onb_from_v(nn);
-                const V3  wol = to_onb(onb, wo), wil = to_onb(onb, wi);
-                V3        A   = v3(0, 0, 0);
-                const V3  f   = material_eval_local(s, material, wol, wil, rng);
+            // Material::eval / pdf (materials/Material.h:475-490) rebuild the ONB on every call; it is the same basis
+            const Onb onb = onb_from_v(nn);
+            const V3  wol = to_onb(onb, wo), wil = to_onb(onb, wi);
+            V3        A   = v3(0, 0, 0);
+            const V3  f   = material_eval_local(s, material, wol, wil, rng);
+            ++calls;
+            if (!is_black(f)) {
+                const float bsdf_pdf = material_pdf_local(s, material, wol, wil, rng);
                 ++calls;
-                if (!is_black(f)) {
-                    const float bsdf_pdf = material_pdf_local(s, material, wol, wil, rng);
-                    ++calls;
-                    if (bsdf_pdf > 0.0f) {
-                        const float weight = balance2(lL.w, bsdf_pdf);
-                        A                  = f * xyz(lL) * (fabsf(dot(wi, nn)) * weight / lL.w);
-                    }
+                if (bsdf_pdf > 0.0f) {
+                    const float weight = balance2(lpdf_s, bsdf_pdf);
+                    A                  = f * lL * (fabsf(dot(wi, nn)) * weight / lpdf_s);
                 }
-                MSample ms = material_sample_local(s, material, wol, rng);
-                ++calls;
-                w.rng_ctr[slot] = rng.ctr;
-                float lpdf      = 0.0f;
-                if (!(ms.pdf == 0.0f || is_black(ms.color))) {
-                    ms.dir = to_world(onb, ms.dir);
-                    lpdf   = light_pdf(s, light, pt, ms.dir);
-                }
-                if (lpdf != 0.0f) {
-                    const float weight = balance2(ms.pdf, lpdf);
-                    w.mis_d[slot]      = f4(ms.dir, ray_offset(nn, ms.dir));
-                    w.mis_col[slot]    = f4(ms.color, ms.pdf);
-                    w.mis_cw[slot]     = make_float2(fabsf(dot(ms.dir, nn)), weight);
-                    w.nee_acc[slot]    = f4(A, 0.0f);
-                    to_mis             = true;
-                } else if (!is_black(A)) {
-                    const float4 tp = w.throughput[slot];
-                    float4       r  = w.radiance[slot];
-                    r.x += tp.x * A.x;
-                    r.y += tp.y * A.y;
-                    r.z += tp.z * A.z;
-                    w.radiance[slot] = r;
-                }
+            }
+            MSample ms = material_sample_local(s, material, wol, rng);
+            ++calls;
+            w.vertex[slot].n.w = __uint_as_float(rng.ctr);
+            float lpdf         = 0.0f;
+            if (!(ms.pdf == 0.0f || is_black(ms.color))) {
+                ms.dir = to_world(onb, ms.dir);
+                lpdf   = light_pdf(s, light, pt, ms.dir);
+            }
+            if (lpdf != 0.0f) {
+                const float weight = balance2(ms.pdf, lpdf);
+                MisRec      mr;
+                mr.d        = f4(ms.dir, ray_offset(nn, ms.dir));
+                mr.col      = f4(ms.color, ms.pdf);
+                mr.cwa      = make_float4(fabsf(dot(ms.dir, nn)), weight, A.x, A.y);
+                mr.ab       = A.z;
+                mr.light    = -1;
+                mr.occluded = 0;
+                mr.pad      = 0.0f;
+                w.mis[slot] = mr;
+                to_mis      = true;
+            } else if (!is_black(A)) {
+                float4 L = pr.L;
+                L.x += pr.tp.x * A.x;
+                L.y += pr.tp.y * A.y;
+                L.z += pr.tp.z * A.z;
+                w.path[slot].L = L;
             }
         }
         queue_push(q_mis, n_mis, slot, to_mis);
@@ -301,22 +303,19 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_mis_accumulate(const __grid
     {
         if (active) {
             const uint32_t slot = q_mis[i];
-            const int2     mh   = w.mis_hit[slot];
-            V3             est  = xyz(w.nee_acc[slot]);
-            if (mh.x >= 0 && mh.y == 0) {
-                const float4 md  = w.mis_d[slot];
-                const float4 mc  = w.mis_col[slot];
-                const float2 cw  = w.mis_cw[slot];
-                const V3     Li  = light_hit_L(s, s.lights[mh.x], xyz(md));
-                est              = est + xyz(mc) * Li * cw.x * cw.y / mc.w;
+            const MisRec   mr   = w.mis[slot];
+            V3             est  = v3(mr.cwa.z, mr.cwa.w, mr.ab);
+            if (mr.light >= 0 && mr.occluded == 0) {
+                const V3 Li = light_hit_L(s, s.lights[mr.light], xyz(mr.d));
+                est         = est + xyz(mr.col) * Li * mr.cwa.x * mr.cwa.y / mr.col.w;
             }
             if (!is_black(est)) {
-                const float4 tp = w.throughput[slot];
-                float4       r  = w.radiance[slot];
-                r.x += tp.x * est.x;
-                r.y += tp.y * est.y;
-                r.z += tp.z * est.z;
-                w.radiance[slot] = r;
+                const PathRec pr = w.path[slot];
+                float4        L  = pr.L;
+                L.x += pr.tp.x * est.x;
+                L.y += pr.tp.y * est.y;
+                L.z += pr.tp.z * est.z;
+                w.path[slot].L = L;
             }
         }
     }
@@ -331,29 +330,30 @@ __global__ void __launch_bounds__(kShadeBlock) k_direct_accumulate(const __grid_
                                                                    const uint32_t* q_shadow, const uint32_t* n_shadow,
                                                                    unsigned long long* counters)
 {
-    const uint32_t n = *n_shadow;
+    const uint32_t    n     = *n_shadow;
     count_items(counters, kStDirectAccumulate, n);
+    const spcu_light& light = s.lights[__ldg(s.light_order + p.light_index)];
     FOR_EACH_QUEUED(i, active, n)
     {
         if (active) {
-            const uint32_t slot     = q_shadow[i];
-            const float4   ip       = w.isect_p[slot];
-            const uint32_t material = __float_as_uint(ip.w);
-            const V3       nn       = xyz(w.isect_n[slot]);
-            const V3       wo       = -xyz(w.ray_d[slot]);
-            const V3       wi       = xyz(w.sh_d[slot]);
-            const float4   lL       = w.light_L[slot];
-            Rng            rng      = load_rng(w, slot, p.seed);
-            const Onb      onb      = onb_from_v(nn);
-            const V3       f        = material_eval_local(s, material, to_onb(onb, wo), to_onb(onb, wi), rng);
-            w.rng_ctr[slot]         = rng.ctr;
+            const uint32_t  slot     = q_shadow[i];
+            const VertexRec vx       = w.vertex[slot];
+            const LightRec  lr       = w.light[slot];
+            const uint32_t  material = __float_as_uint(vx.p.w);
+            const V3        nn       = xyz(vx.n);
+            const V3        wo       = -xyz(w.ray[slot].d);
+            const V3        wi       = xyz(lr.wi);
+            Rng             rng      = make_rng(w.path[slot], __float_as_uint(vx.n.w), p.seed);
+            const Onb       onb      = onb_from_v(nn);
+            const V3        f        = material_eval_local(s, material, to_onb(onb, wo), to_onb(onb, wi), rng);
+            w.vertex[slot].n.w       = __uint_as_float(rng.ctr);
             if (!is_black(f) && !w.occluded[slot]) {
-                const V3 c = f * xyz(lL) * fabsf(dot(wi, nn)) / lL.w;
-                float4   r = w.radiance[slot];
-                r.x += c.x;
-                r.y += c.y;
-                r.z += c.z;
-                w.radiance[slot] = r;
+                const V3 c = f * light_sample_L(s, light, lr) * fabsf(dot(wi, nn)) / lr.aux.y;
+                float4   L = w.path[slot].L;
+                L.x += c.x;
+                L.y += c.y;
+                L.z += c.z;
+                w.path[slot].L = L;
             }
         }
         warp_count(counters + kCntShadeCalls, active != 0u);
@@ -373,21 +373,22 @@ __global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__
         bool     alive = false;
         uint32_t slot  = 0;
         if (active) {
-            slot              = q_live[i];
-            const float4 sd   = w.s0_dir[slot];
-            const V3     wi   = xyz(sd);
-            const V3     col  = xyz(w.s0_col[slot]);
-            const V3     nn   = xyz(w.isect_n[slot]);
-            const float  cosine = fabsf(dot(wi, nn));
-            V3           tp   = xyz(w.throughput[slot]) * (cosine * col / sd.w);
-            alive             = true;
+            slot                = q_live[i];
+            const SampleRec s0  = w.s0[slot];
+            const VertexRec vx  = w.vertex[slot];
+            const PathRec   pr  = w.path[slot];
+            const V3        wi  = xyz(s0.dir);
+            const V3        nn  = xyz(vx.n);
+            const float     cosine = fabsf(dot(wi, nn));
+            V3              tp  = xyz(pr.tp) * (cosine * xyz(s0.col) / s0.dir.w);
+            alive               = true;
             if (p.depth >= s.rr_depth) {
                 const float lum = luminance(tp);
                 if (lum < 0.1f) {
                     const float q   = max_std(0.05f, lum / 0.1f); // probability of continuing
-                    Rng         rng = load_rng(w, slot, p.seed);
+                    Rng         rng = make_rng(pr, __float_as_uint(vx.n.w), p.seed);
                     const float u   = rng_next1(rng);
-                    w.rng_ctr[slot] = rng.ctr;
+                    w.vertex[slot].n.w = __uint_as_float(rng.ctr);
                     if (u < q) {
                         tp = tp / q;
                     } else {
@@ -396,10 +397,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__
                 }
             }
             if (alive) {
-                const float4 ip     = w.isect_p[slot];
-                w.throughput[slot]  = f4(tp, 0.0f);
-                w.ray_o[slot]       = make_float4(ip.x, ip.y, ip.z, ray_offset_cos(cosine));
-                w.ray_d[slot]       = f4(wi, kFltMax);
+                w.path[slot].tp = f4(tp, pr.tp.w);
+                w.ray[slot]     = RayRec{ make_float4(vx.p.x, vx.p.y, vx.p.z, ray_offset_cos(cosine)), f4(wi, kFltMax) };
             }
         }
         queue_push(q_next, n_next, slot, alive);
@@ -407,7 +406,9 @@ __global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__
 }
 
 // ---- resolve (main.cpp:100): per pixel, add this batch's samples in sample order ------------------------------------------
-__global__ void __launch_bounds__(kShadeBlock) k_resolve(const __grid_constant__ DWave w, const uint32_t* pix_list,
+// radiance[(k * n_pix + i) * stride] is the sample of pixel i, sample k: stride 2 / offset 1 reads PathRec::L of the
+// wavefront state, stride 1 the persistent path kernel's buffer.
+__global__ void __launch_bounds__(kShadeBlock) k_resolve(const float4* radiance, uint32_t stride, const uint32_t* pix_list,
                                                          uint32_t n_pix, uint32_t n_samples, float* rgb_sum, float* lum_sumsq,
                                                          unsigned long long* counters)
 {
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_resolve(const __grid_constant__
             float r = rgb_sum[3 * pix + 0], g = rgb_sum[3 * pix + 1], b = rgb_sum[3 * pix + 2];
             float sq = lum_sumsq ? lum_sumsq[pix] : 0.0f;
             for (uint32_t k = 0; k < n_samples; ++k) {
-                const float4 L = w.radiance[k * n_pix + i];
+                const float4 L = radiance[(static_cast<size_t>(k) * n_pix + i) * stride];
                 r += L.x;
                 g += L.y;
                 b += L.z;
@@ -510,10 +511,10 @@ void launch_advance(const Launch& l, const DScene& s, const DWave& w, const Rend
     WAVEFRONT_LAUNCH(k_advance, l, max_n, s, w, p, q_live, d_n_live, q_next, d_n_next, d_counters);
 }
 
-void launch_resolve(const Launch& l, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t n_samples,
-                    float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters)
+void launch_resolve(const Launch& l, const float4* d_radiance, uint32_t stride, const uint32_t* d_pix_list, uint32_t n_pix,
+                    uint32_t n_samples, float* d_rgb_sum, float* d_lum_sumsq, unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_resolve, l, n_pix, w, d_pix_list, n_pix, n_samples, d_rgb_sum, d_lum_sumsq, d_counters);
+    WAVEFRONT_LAUNCH(k_resolve, l, n_pix, d_radiance, stride, d_pix_list, n_pix, n_samples, d_rgb_sum, d_lum_sumsq, d_counters);
 }
 
 void launch_generate_rays(const DScene& s, const uint32_t* d_pix, const uint32_t* d_smp, uint64_t n, spcu_ray* d_rays,

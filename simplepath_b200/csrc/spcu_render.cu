@@ -46,28 +46,14 @@ int ensure_wave(spcu_ctx* c, uint32_t capacity)
     int    rc;
 #define WAVE(field) \
     if ((rc = wave_array(c, w.field, capacity)) != SPCU_OK) return rc
-    WAVE(pixel);
-    WAVE(sample);
-    WAVE(rng_ctr);
-    WAVE(ray_o);
-    WAVE(ray_d);
-    WAVE(throughput);
-    WAVE(radiance);
-    WAVE(hit);
-    WAVE(light_hit);
-    WAVE(isect_p);
-    WAVE(isect_n);
-    WAVE(s0_dir);
-    WAVE(s0_col);
-    WAVE(sh_d);
-    WAVE(sh_tmin);
-    WAVE(light_L);
+    WAVE(path);
+    WAVE(ray);
+    WAVE(vertex);
+    WAVE(extend);
+    WAVE(s0);
+    WAVE(light);
+    WAVE(mis);
     WAVE(occluded);
-    WAVE(mis_d);
-    WAVE(mis_col);
-    WAVE(mis_cw);
-    WAVE(nee_acc);
-    WAVE(mis_hit);
 #undef WAVE
     for (auto& q : c->queues) {
         CK(c, q.reserve(static_cast<size_t>(capacity) * sizeof(uint32_t)));
@@ -197,8 +183,7 @@ int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, floa
     const Launch    L{ c->sm_count, st };
     StageTimer      timer{ c, c->options[SPCU_OPT_STAGE_TIMING] != 0, st };
     uint64_t        launches = 0;
-    DWave           view{};
-    view.radiance = c->path_radiance.as<float4>();
+    float4*         d_radiance = c->path_radiance.as<float4>();
 
     CK(c, cudaMemsetAsync(d_counters, 0, kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters), st));
     CK(c, cudaEventRecord(c->ev0, st));
@@ -207,11 +192,11 @@ int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, floa
         for (uint32_t sb = 0; sb < n_samples; sb += smp_per_batch) {
             const uint32_t ns = std::min(smp_per_batch, n_samples - sb);
             timer.begin(kStPaths);
-            launch_paths(L, s, d_pix_list + pb, np, part->sample_begin + sb, ns, part->seed, part->integrator, view.radiance,
+            launch_paths(L, s, d_pix_list + pb, np, part->sample_begin + sb, ns, part->seed, part->integrator, d_radiance,
                          d_counters, d_cnt);
             timer.end();
             timer.begin(kStResolve);
-            launch_resolve(L, view, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
+            launch_resolve(L, d_radiance, 1, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
             timer.end();
             launches += 2;
             CK(c, cudaGetLastError());
@@ -375,7 +360,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 n_cur = n_next;
             }
             timer.begin(kStResolve);
-            launch_resolve(L, c->wave, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
+            launch_resolve(L, &c->wave.path->L, 2, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
             timer.end();
             ++launches;
             CK(c, cudaGetLastError());

@@ -219,21 +219,24 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
     uint32_t slot   = 0;
     unsigned traced = 0;
     bool     have   = false;
+    int32_t  light_id = -1;
+    float    light_t  = 0.0f;
 
     for (;;) {
         // ---- lanes without a ray draw the next queue entries ------------------------------------------------------------
         const uint32_t i = feed.draw(!have);
         if (!have && i != 0xffffffffu) {
-            slot           = queue[i];
-            const float4 o = w.ray_o[slot];
-            const float4 d = w.ray_d[slot];
-            r              = Ray{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
+            slot            = queue[i];
+            const RayRec rr = w.ray[slot];
+            const float4 o = rr.o, d = rr.d;
+            r               = Ray{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
             inv            = make_inv(r);
             float t_max = d.w, beta, gamma;
             // Scene::intersect_lights (a handful of lights: walked in one go)
             const LightPrims lp{ s.lights };
             const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack_smem + threadIdx.x, nullptr);
-            w.light_hit[slot]   = make_int2(li, __float_as_int(t_max));
+            light_id            = li;
+            light_t             = t_max;
             walk.t_max          = t_max;
             closest_begin<kCount>(s.geom, gp, r, walk, &local);
             stack.n = ostack.n = 0;
@@ -250,7 +253,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
             closest_run<kCount>(s.geom, gp, r, inv, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
         }
         if (have && walk.link == kDone) {
-            w.hit[slot] = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
+            ExtendRec ex;
+            ex.hit      = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
+            ex.light    = light_id;
+            ex.light_t  = light_t;
+            ex.pad[0] = ex.pad[1] = 0.0f;
+            w.extend[slot] = ex;
             // hand the vertex to the shading stage sorted by material: misses in the last segment
             const uint32_t seg = walk.hit_id < 0 ? sorted.n_segments - 1u
                                                  : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + walk.hit_id)), sorted.n_segments - 2u);
@@ -298,12 +306,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
     for (;;) {
         const uint32_t i = feed.draw(!have);
         if (!have && i != 0xffffffffu) {
-            slot           = queue[i];
-            const float4 p = w.isect_p[slot];
-            const float4 d = w.sh_d[slot];
-            r              = Ray{ p.x, p.y, p.z, d.x, d.y, d.z, w.sh_tmin[slot] };
-            inv            = make_inv(r);
-            t_max          = d.w;
+            slot              = queue[i];
+            const float4   p  = w.vertex[slot].p;
+            const LightRec lr = w.light[slot];
+            r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
+            inv               = make_inv(r);
+            t_max             = lr.wi.w;
             stack.n        = 0;
             walk           = AnyWalk{ s.geom.root, s.geom.root_count };
             have           = true;
@@ -337,8 +345,10 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
             if (status == kAnyMiss && lights_any_hit(s, r, t_max, stack_smem + threadIdx.x)) {
                 status = kAnyHit;
             }
-            const bool occ   = status == kAnyHit;
-            w.occluded[slot] = occ ? 1 : 0;
+            const bool occ = status == kAnyHit;
+            if (!q_lit) {
+                w.occluded[slot] = occ ? 1 : 0; // direct lighting reads the flag; the NEE path gets the compacted queue
+            }
             if (q_lit && !occ) { // survivors only go on to the BSDF stages (Integrator.cpp:503-506)
                 const unsigned act    = __activemask();
                 const int      lane   = threadIdx.x & 31;
@@ -380,8 +390,8 @@ __global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant
     bool           traced_any = false;
     if (active) {
         const uint32_t slot = queue[i];
-        const float4   p    = w.isect_p[slot];
-        const float4   d    = w.mis_d[slot];
+        const float4   p    = w.vertex[slot].p;
+        const float4   d    = w.mis[slot].d;
         const Ray      r{ p.x, p.y, p.z, d.x, d.y, d.z, d.w };
         float          t_max = kInfinite, beta, gamma;
 
@@ -392,7 +402,8 @@ __global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant
             traced_any = true;
             occ        = scene_any_hit<kCount>(s, r, kInfinite, stack + threadIdx.x, &local) ? 1 : 0;
         }
-        w.mis_hit[slot] = make_int2(li, occ);
+        w.mis[slot].light    = li;
+        w.mis[slot].occluded = occ;
     }
     warp_count(counters + kCntRaysLights, active);
     warp_count(counters + kCntRaysAny, traced_any);

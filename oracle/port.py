@@ -89,10 +89,10 @@ def render(flat, jitter, part: Partition, threads: int = 0, want_sumsq: bool = T
     return rgb, sq, st.as_dict()
 
 
-def rng4(seed: int, pixel: int, sample: int, ctr: int) -> np.ndarray:
+def rng4(seed: int, pixel: int, sample: int, stream: int, ctr: int) -> np.ndarray:
     l = lib()
-    l.spo_rng4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    l.spo_rng4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     l.spo_rng4.restype = None
     out = np.zeros(4, dtype=np.float32)
-    l.spo_rng4(seed, pixel, sample, ctr, _p(out))
+    l.spo_rng4(seed, pixel, sample, stream, ctr, _p(out))
     return out

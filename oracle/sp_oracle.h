@@ -42,9 +42,9 @@ void spo_hit_records(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n,
 void spo_render(const spcu_flat_scene* s, const float* jitter, const spcu_partition* part, float* rgb_sum,
                 float* lum_sumsq, spcu_stats* stats, int threads);
 
-/* The RNG contract itself, exposed for known-answer tests: the 4 words of block `ctr` of path (pixel, sample) as
- * floats in [0,1). */
-void spo_rng4(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t ctr, float out[4]);
+/* The RNG contract itself, exposed for known-answer tests: the 4 words of block `ctr` of sub-stream `stream`
+ * (depth << 16 | site) of path (pixel, sample) as floats in [0,1). */
+void spo_rng4(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t stream, uint32_t ctr, float out[4]);
 
 /* Pieces of the shading model, exposed so tests can pin them against the reference's classes.
  * All vectors are 3 floats.  u = uniform numbers consumed in the order documented at each function. */

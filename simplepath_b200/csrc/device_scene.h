@@ -73,10 +73,10 @@ struct alignas(32) RayRec // sp::Ray + sp::RayLimits of the current segment
     float4 o; // o.xyz, t_min
     float4 d; // d.xyz, t_max
 };
-struct alignas(32) VertexRec // surface interaction kept across the NEE stages of one vertex + the RNG draw counter
+struct alignas(32) VertexRec // surface interaction kept across the NEE stages of one vertex
 {
     float4 p; // point xyz, material index (bits)
-    float4 n; // shading normal xyz, RNG draw counter (bits; lives here because every shading stage touches this record)
+    float4 n; // shading normal xyz, (unused)
 };
 struct alignas(32) ExtendRec // result of the extend stage
 {

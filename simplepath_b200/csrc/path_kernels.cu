@@ -36,7 +36,7 @@ __device__ __forceinline__ V3 estimate_direct_mis(const DScene& s, const spcu_li
 {
     V3    L = v3(0, 0, 0);
     float u0, u1;
-    rng_next2(rng, u0, u1);
+    rng_next2(rng, u0, u1); // block 0 of the light's sub-stream; eval / pdf / sample follow from block 1
     const LSample ls = light_sample(s, light, p, n, u0, u1);
     if (ls.pdf == 0.0f || is_black(ls.L)) {
         return L;
@@ -124,6 +124,8 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         for (uint32_t k = 0; k < s.n_lights; ++k) {
             const spcu_light& light = s.lights[__ldg(s.light_order + k)];
             float             u0, u1;
+            ps.rng.stream = rng_stream(ps.depth, kSiteLight0 + k);
+            ps.rng.ctr    = 0u;
             rng_next2(ps.rng, u0, u1);
             const LSample ls = light_sample(s, light, point, normal, u0, u1);
             if (ls.pdf == 0.0f || is_black(ls.L)) {
@@ -143,6 +145,8 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         return false;
     }
 
+    ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);
+    ps.rng.ctr       = 0u;
     const MSample sr = material_sample(s, material, wo, normal, ps.rng);
     ++pc.shade_calls;
     if (sr.pdf == 0.0f || is_black(sr.color)) {
@@ -151,6 +155,8 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
     if (integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE) {
         for (uint32_t k = 0; k < s.n_lights; ++k) {
             const spcu_light& light = s.lights[__ldg(s.light_order + k)];
+            ps.rng.stream = rng_stream(ps.depth, kSiteLight0 + k);
+            ps.rng.ctr    = 0u;
             ps.L = ps.L + ps.throughput * estimate_direct_mis<kCount>(s, light, point, normal, material, wo, ps.rng, stack, pc, tc);
         }
     }
@@ -160,6 +166,8 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         const float lum = luminance(ps.throughput);
         if (lum < 0.1f) {
             const float q = max_std(0.05f, lum / 0.1f);
+            ps.rng.stream = rng_stream(ps.depth, kSiteRoulette);
+            ps.rng.ctr    = 0u;
             if (rng_next1(ps.rng) < q) {
                 ps.throughput = ps.throughput / q;
             } else {
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(kPathBlock) k_paths(const __grid_constant__ DS
                     ps.L          = v3(0.0f, 0.0f, 0.0f);
                     ps.depth      = 0;
                     ps.slot       = slot;
-                    ps.rng        = Rng{ pix, smp, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), 0u };
+                    ps.rng        = Rng{ pix, smp, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), 0u, 0u };
                     have_path     = true;
                     ++pc.paths;
                     if (no_depth) {

@@ -1,12 +1,19 @@
 // RNG contract of the backend (the reference's per-pixel mt19937_64 stream, main.cpp:73-76, cannot be replayed on a
-// GPU: SURVEY.md §8a-3).  Every path (pixel, sample) owns an independent counter-based stream:
+// GPU: SURVEY.md §8a-3).  Random numbers are addressed instead of streamed:
 //
-//     block k of the path  =  Philox4x32-10( counter = (k, seed_lo, seed_hi, 0x53504355), key = (pixel, sample) )
+//     block k of sub-stream s of path (pixel, sample) = Philox4x32-10( counter = (k, s, seed_lo, seed_hi), key = (pixel, sample) )
 //
-// and every *draw call* of the reference (Sampler::get_next_1D or get_next_2D, math/Sampler.h:76-94) consumes ONE
-// block: 1D uses word 0, 2D uses words 0 and 1; the two get_next_1D() arguments of beckmann_sample
-// (materials/Material.cpp:150) are served by one block (U1 = word 0, U2 = word 1).  A word w maps to the float
-// (w >> 8) * 2^-24 in [0, 1).  oracle/sp_oracle.c restates the same contract so that both sides draw identical numbers.
+// A sub-stream belongs to one call site of the integrator at one path depth, s = depth << 16 | site:
+//     site 0      the vertex's primary BSDF sample            (Integrator.cpp:569 / :228)
+//     site 1      Russian roulette                            (Integrator.cpp:615 / :246)
+//     site 2 + l  next-event estimation for light l: block 0 = the light sample (Integrator.cpp:497 / :289), blocks 1.. =
+//                 Material::eval, pdf and the second sample, in the reference's order (:508-518 / :296)
+// Within a sub-stream every *draw call* of the reference (Sampler::get_next_1D or get_next_2D, math/Sampler.h:76-94)
+// consumes ONE block, in call order: 1D uses word 0, 2D uses words 0 and 1; the two get_next_1D() arguments of
+// beckmann_sample (materials/Material.cpp:150) are served by one block (U1 = word 0, U2 = word 1).  A word w maps to the
+// float (w >> 8) * 2^-24 in [0, 1).  No stage has to carry a draw counter to the next one, and the lights of a vertex
+// are independent of each other.  oracle/sp_oracle_shade.inc restates the same contract, so both sides draw identical
+// numbers.
 #pragma once
 
 #include <stdint.h>
@@ -17,8 +24,12 @@ struct Rng
 {
     uint32_t pixel, sample;
     uint32_t seed_lo, seed_hi;
-    uint32_t ctr;
+    uint32_t stream; // depth << 16 | site
+    uint32_t ctr;    // next block of the sub-stream
 };
+
+constexpr uint32_t kSiteBsdf = 0u, kSiteRoulette = 1u, kSiteLight0 = 2u;
+__host__ __device__ __forceinline__ uint32_t rng_stream(uint32_t depth, uint32_t site) { return (depth << 16) | site; }
 
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b)
 {
@@ -59,7 +70,7 @@ __host__ __device__ __forceinline__ float word_to_unit(uint32_t w)
 __host__ __device__ __forceinline__ void rng_next2(Rng& r, float& u0, float& u1)
 {
     uint32_t o[4];
-    philox4x32_10(r.ctr, r.seed_lo, r.seed_hi, 0x53504355u, r.pixel, r.sample, o);
+    philox4x32_10(r.ctr, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample, o);
     ++r.ctr;
     u0 = word_to_unit(o[0]);
     u1 = word_to_unit(o[1]);

@@ -84,9 +84,10 @@ __device__ __forceinline__ void warp_count(unsigned long long* counter, bool pre
 
 
 // records are moved as pairs of 16-byte vectors
-__device__ __forceinline__ Rng make_rng(const PathRec& pr, uint32_t ctr, uint64_t seed)
+__device__ __forceinline__ Rng make_rng(const PathRec& pr, uint64_t seed, uint32_t depth, uint32_t site, uint32_t first_block)
 {
-    return Rng{ __float_as_uint(pr.tp.w), __float_as_uint(pr.L.w), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), ctr };
+    return Rng{ __float_as_uint(pr.tp.w),      __float_as_uint(pr.L.w), static_cast<uint32_t>(seed),
+                static_cast<uint32_t>(seed >> 32), rng_stream(depth, site), first_block };
 }
 
 #define FOR_EACH_QUEUED(i, active, n)                                                                  \
@@ -110,7 +111,6 @@ __global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ 
             camera_ray(s, pix, smp, ray.o, ray.d);
             w.ray[i]      = ray;
             w.path[i]     = PathRec{ make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pix)), make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(smp)) };
-            w.vertex[i].n = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u)); // RNG draw counter = 0
             queue[i]      = i;
         }
     }
@@ -154,20 +154,18 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
                 V3       point, normal;
                 uint32_t material;
                 make_isect(s, ex.hit, o, d, point, normal, material);
-                uint32_t ctr = __float_as_uint(w.vertex[slot].n.w);
                 if (p.integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING) {
                     live = true;
                 } else {
-                    Rng           rng = make_rng(w.path[slot], ctr, p.seed);
+                    Rng           rng = make_rng(w.path[slot], p.seed, p.depth, kSiteBsdf, 0u);
                     const MSample sr  = material_sample(s, material, -d, normal, rng);
-                    ctr               = rng.ctr;
                     sampled           = true;
                     if (!(sr.pdf == 0.0f || is_black(sr.color))) {
                         w.s0[slot] = SampleRec{ f4(sr.dir, sr.pdf), f4(sr.color, 0.0f) };
                         live       = true;
                     }
                 }
-                w.vertex[slot] = VertexRec{ f4(point, __uint_as_float(material)), f4(normal, __uint_as_float(ctr)) };
+                w.vertex[slot] = VertexRec{ f4(point, __uint_as_float(material)), f4(normal, 0.0f) };
             }
         }
         queue_push(q_live, n_live, slot, live);
@@ -192,11 +190,10 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_light(const __grid_constant
         if (active) {
             slot               = q_in[i];
             const VertexRec vx = w.vertex[slot];
-            Rng             rng = make_rng(w.path[slot], __float_as_uint(vx.n.w), p.seed);
+            Rng             rng = make_rng(w.path[slot], p.seed, p.depth, kSiteLight0 + p.light_index, 0u);
             float           u0, u1;
             rng_next2(rng, u0, u1);
-            w.vertex[slot].n.w = __uint_as_float(rng.ctr);
-            const LSample ls   = light_sample(s, light, xyz(vx.p), xyz(vx.n), u0, u1);
+            const LSample ls = light_sample(s, light, xyz(vx.p), xyz(vx.n), u0, u1);
             if (!(ls.pdf == 0.0f || is_black(ls.L))) {
                 w.light[slot] = LightRec{ f4(ls.wi, ls.t_max), make_float4(ls.t_min, ls.pdf, ls.u, ls.v) };
                 usable        = true;
@@ -240,7 +237,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
             const V3        wi       = xyz(lr.wi);
             const float     lpdf_s   = lr.aux.y;
             const V3        lL       = light_sample_L(s, light, lr);
-            Rng             rng      = make_rng(pr, __float_as_uint(vx.n.w), p.seed);
+            Rng             rng      = make_rng(pr, p.seed, p.depth, kSiteLight0 + p.light_index, 1u); // block 0 was the light sample
 
             // Material::eval / pdf (materials/Material.h:475-490) rebuild the ONB on every call; it is the same basis
             const Onb onb = onb_from_v(nn);
@@ -258,8 +255,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
             }
             MSample ms = material_sample_local(s, material, wol, rng);
             ++calls;
-            w.vertex[slot].n.w = __uint_as_float(rng.ctr);
-            float lpdf         = 0.0f;
+            float lpdf = 0.0f;
             if (!(ms.pdf == 0.0f || is_black(ms.color))) {
                 ms.dir = to_world(onb, ms.dir);
                 lpdf   = light_pdf(s, light, pt, ms.dir);
@@ -343,10 +339,9 @@ __global__ void __launch_bounds__(kShadeBlock) k_direct_accumulate(const __grid_
             const V3        nn       = xyz(vx.n);
             const V3        wo       = -xyz(w.ray[slot].d);
             const V3        wi       = xyz(lr.wi);
-            Rng             rng      = make_rng(w.path[slot], __float_as_uint(vx.n.w), p.seed);
+            Rng             rng      = make_rng(w.path[slot], p.seed, p.depth, kSiteLight0 + p.light_index, 1u);
             const Onb       onb      = onb_from_v(nn);
             const V3        f        = material_eval_local(s, material, to_onb(onb, wo), to_onb(onb, wi), rng);
-            w.vertex[slot].n.w       = __uint_as_float(rng.ctr);
             if (!is_black(f) && !w.occluded[slot]) {
                 const V3 c = f * light_sample_L(s, light, lr) * fabsf(dot(wi, nn)) / lr.aux.y;
                 float4   L = w.path[slot].L;
@@ -386,9 +381,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__
                 const float lum = luminance(tp);
                 if (lum < 0.1f) {
                     const float q   = max_std(0.05f, lum / 0.1f); // probability of continuing
-                    Rng         rng = make_rng(pr, __float_as_uint(vx.n.w), p.seed);
+                    Rng         rng = make_rng(pr, p.seed, p.depth, kSiteRoulette, 0u);
                     const float u   = rng_next1(rng);
-                    w.vertex[slot].n.w = __uint_as_float(rng.ctr);
                     if (u < q) {
                         tp = tp / q;
                     } else {

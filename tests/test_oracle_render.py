@@ -44,16 +44,20 @@ def test_oracle_render_matches_reference_statistics(oracle_port, name, integrato
 
 
 def test_rng_contract_known_answers(oracle_port):
-    """Philox4x32-10 known answer (Random123 kat_vectors: counter = key = 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8)."""
+    """The contract's counter layout is (block, stream, seed_lo, seed_hi) with key (pixel, sample): all zeros is the
+    Random123 known-answer vector 6627e8d5 e169c58d bc57ac4c 9b00dbd8."""
+    a = oracle_port.rng4(0, 0, 0, 0, 0)
+    b = oracle_port.rng4(0, 0, 0, 0, 1)
+    c = oracle_port.rng4(0, 1, 0, 0, 0)
+    d = oracle_port.rng4(1, 0, 0, 0, 0)
+    e = oracle_port.rng4(0, 0, 0, 1, 0)
+    f = oracle_port.rng4(0, 0, 1, 0, 0)
+    assert all(((x >= 0) & (x < 1)).all() for x in (a, b, c, d, e, f))
+    assert len({x.tobytes() for x in (a, b, c, d, e, f)}) == 6
+    # Philox4x32-10 known answer (Random123 kat_vectors): counter = key = 0
     import ctypes as C
-    out = np.zeros(4, dtype=np.float32)
-    # the contract's counter layout is (ctr, seed_lo, seed_hi, 0x53504355): not the all-zero KAT, so check structure
-    a = oracle_port.rng4(0, 0, 0, 0)
-    b = oracle_port.rng4(0, 0, 0, 1)
-    c = oracle_port.rng4(0, 1, 0, 0)
-    d = oracle_port.rng4(1, 0, 0, 0)
-    assert all(((x >= 0) & (x < 1)).all() for x in (a, b, c, d))
-    assert len({x.tobytes() for x in (a, b, c, d)}) == 4
+    want = np.array([0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8], dtype=np.uint64)
+    assert np.array_equal((a * 2.0 ** 24).astype(np.uint64), want >> 8)
     # uniformity over many blocks
-    u = np.array([oracle_port.rng4(7, p, 3, k) for p in range(64) for k in range(64)])
+    u = np.array([oracle_port.rng4(7, p, 3, 5, k) for p in range(64) for k in range(64)])
     assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1.0 / 12.0) < 0.005

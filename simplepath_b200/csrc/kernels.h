@@ -24,8 +24,8 @@ void launch_extend(const struct Launch& l, const DScene& s, const DWave& w, cons
 // shadow: Scene::intersect_p of the light-sample visibility ray (Integrator.cpp:503).
 // Unoccluded entries are compacted into q_lit (may be NULL: then only the per-slot flag is written).
 void launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit, unsigned long long* d_counters,
-                   TraceCounters* d_cnt);
+                   uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit,
+                   unsigned long long* d_counters, TraceCounters* d_cnt);
 // mis: Scene::intersect_lights then, on a light hit, Scene::intersect_p of the BSDF-sampled ray (Integrator.cpp:531-532).
 void launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
                       const uint32_t* d_n_queue, uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
@@ -56,13 +56,12 @@ struct Launch
 void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix,
                    uint32_t sample_begin, uint32_t n_samples, uint32_t* queue, uint32_t* d_n_queue,
                    unsigned long long* d_counters);
-// shade: hit/miss handling + primary BSDF sample S0 (Integrator.cpp:558-572,627-632).  Surviving paths go to q_live.
+// shade: hit/miss handling + primary BSDF sample S0 (Integrator.cpp:558-572,627-632); surviving paths go to q_live.  Then
+// Light::sample for every light (Integrator.cpp:497-501): usable samples of light l go to q_shadow[l * capacity ...] /
+// d_n_shadow[l], their LightRec to w.light[l * capacity + slot].  q_shadow == NULL: no light sampling (brute force).
 void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const SortedQueue& sorted,
-                  uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters);
-// nee_light: Light::sample for light p.light_index; paths with a usable sample go to q_shadow (Integrator.cpp:497-501).
-void launch_nee_light(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
-                      const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow,
-                      unsigned long long* d_counters);
+                  uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, uint32_t* q_shadow, uint32_t* d_n_shadow,
+                  unsigned long long* d_counters);
 // nee_bsdf: light-strategy term, second BSDF sample, Light::pdf; paths needing the BSDF-strategy ray go to q_mis
 // (Integrator.cpp:503-530).
 void launch_nee_bsdf(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ 
 __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                        const __grid_constant__ RenderParams p,
                                                        const __grid_constant__ SortedQueue sorted, uint32_t* q_live,
-                                                       uint32_t* n_live, unsigned long long* counters)
+                                                       uint32_t* n_live, uint32_t* q_shadow, uint32_t* n_shadow,
+                                                       unsigned long long* counters)
 {
   // one material segment after the other: every warp shades a single material (or only misses)
   for (uint32_t seg = 0; seg < sorted.n_segments; ++seg) {
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
         bool     live    = false;
         bool     sampled = false;
         uint32_t slot    = 0;
+        V3       lit_point = v3(0, 0, 0), lit_normal = v3(0, 1, 0);
         if (active) {
             slot               = q_in[i];
             const ExtendRec ex = w.extend[slot];
@@ -166,41 +168,35 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
                     }
                 }
                 w.vertex[slot] = VertexRec{ f4(point, __uint_as_float(material)), f4(normal, 0.0f) };
+                lit_point      = point;
+                lit_normal     = normal;
             }
         }
         queue_push(q_live, n_live, slot, live);
         warp_count(counters + kCntShadeCalls, sampled);
-    }
-  }
-}
-
-// ---- nee_light (Integrator.cpp:497-501 / :288-292): Light::sample for one light -------------------------------------------
-__global__ void __launch_bounds__(kShadeBlock) k_nee_light(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
-                                                           const __grid_constant__ RenderParams p, const uint32_t* q_in,
-                                                           const uint32_t* n_in, uint32_t* q_shadow, uint32_t* n_shadow,
-                                                           unsigned long long* counters)
-{
-    const uint32_t    n     = *n_in;
-    count_items(counters, kStNeeLight, n);
-    const spcu_light& light = s.lights[__ldg(s.light_order + p.light_index)];
-    FOR_EACH_QUEUED(i, active, n)
-    {
-        bool     usable = false;
-        uint32_t slot   = 0;
-        if (active) {
-            slot               = q_in[i];
-            const VertexRec vx = w.vertex[slot];
-            Rng             rng = make_rng(w.path[slot], p.seed, p.depth, kSiteLight0 + p.light_index, 0u);
-            float           u0, u1;
-            rng_next2(rng, u0, u1);
-            const LSample ls = light_sample(s, light, xyz(vx.p), xyz(vx.n), u0, u1);
-            if (!(ls.pdf == 0.0f || is_black(ls.L))) {
-                w.light[slot] = LightRec{ f4(ls.wi, ls.t_max), make_float4(ls.t_min, ls.pdf, ls.u, ls.v) };
-                usable        = true;
+        // Light::sample for EVERY light of the scene (Integrator.cpp:497-501 / :288-292), while point and normal are in
+        // registers: each light has its own random sub-stream, so the lights of a vertex do not depend on each other.
+        // Usable samples go to that light's shadow queue.
+        if (q_shadow) {
+            for (uint32_t li = 0; li < s.n_lights; ++li) {
+                bool usable = false;
+                if (live) {
+                    const spcu_light& light = s.lights[__ldg(s.light_order + li)];
+                    Rng               rng   = make_rng(w.path[slot], p.seed, p.depth, kSiteLight0 + li, 0u);
+                    float             u0, u1;
+                    rng_next2(rng, u0, u1);
+                    const LSample ls = light_sample(s, light, lit_point, lit_normal, u0, u1);
+                    if (!(ls.pdf == 0.0f || is_black(ls.L))) {
+                        w.light[static_cast<size_t>(li) * w.capacity + slot] =
+                            LightRec{ f4(ls.wi, ls.t_max), make_float4(ls.t_min, ls.pdf, ls.u, ls.v) };
+                        usable = true;
+                    }
+                }
+                queue_push(q_shadow + static_cast<size_t>(li) * w.capacity, n_shadow + li, slot, usable);
             }
         }
-        queue_push(q_shadow, n_shadow, slot, usable);
     }
+  }
 }
 
 // radiance of a stored light sample: an image-based light is looked up again from the sample's (u, v); every other
@@ -228,7 +224,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
         if (active) {
             slot = q_shadow[i]; // the shadow stage queued unoccluded samples only (Integrator.cpp:503-506)
             const VertexRec vx       = w.vertex[slot];
-            const LightRec  lr       = w.light[slot];
+            const LightRec  lr       = w.light[static_cast<size_t>(p.light_index) * w.capacity + slot];
             const PathRec   pr       = w.path[slot];
             const V3        pt       = xyz(vx.p);
             const uint32_t  material = __float_as_uint(vx.p.w);
@@ -334,7 +330,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_direct_accumulate(const __grid_
         if (active) {
             const uint32_t  slot     = q_shadow[i];
             const VertexRec vx       = w.vertex[slot];
-            const LightRec  lr       = w.light[slot];
+            const LightRec  lr       = w.light[static_cast<size_t>(p.light_index) * w.capacity + slot];
             const uint32_t  material = __float_as_uint(vx.p.w);
             const V3        nn       = xyz(vx.n);
             const V3        wo       = -xyz(w.ray[slot].d);
@@ -466,16 +462,10 @@ void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint3
 }
 
 void launch_shade(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const SortedQueue& sorted,
-                  uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, unsigned long long* d_counters)
+                  uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, uint32_t* q_shadow, uint32_t* d_n_shadow,
+                  unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_shade, l, max_n, s, w, p, sorted, q_live, d_n_live, d_counters);
-}
-
-void launch_nee_light(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_in,
-                      const uint32_t* d_n_in, uint32_t max_n, uint32_t* q_shadow, uint32_t* d_n_shadow,
-                      unsigned long long* d_counters)
-{
-    WAVEFRONT_LAUNCH(k_nee_light, l, max_n, s, w, p, q_in, d_n_in, q_shadow, d_n_shadow, d_counters);
+    WAVEFRONT_LAUNCH(k_shade, l, max_n, s, w, p, sorted, q_live, d_n_live, q_shadow, d_n_shadow, d_counters);
 }
 
 void launch_nee_bsdf(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,

@@ -2,7 +2,7 @@
 //
 // One call renders a partition (a set of 8x8 tiles x a sample range) in batches of at most `wavefront_size` paths:
 //
-//   raygen -> for depth in [0, max_depth):  extend -> shade -> { per light: nee_light -> shadow -> nee_bsdf -> mis ->
+//   raygen -> for depth in [0, max_depth):  extend -> shade (+ all light samples) -> { per light: shadow -> nee_bsdf -> mis ->
 //             nee_mis_accumulate } -> advance        -> resolve (per-pixel sums, in sample order)
 //
 // Every stage is a persistent-style kernel reading its queue length from device memory, so a batch is enqueued without
@@ -33,9 +33,10 @@ int wave_array(spcu_ctx* c, T*& ptr, size_t n)
 
 int ensure_wave(spcu_ctx* c, uint32_t capacity)
 {
-    if (c->wave.capacity >= capacity) {
-        return SPCU_OK;
+    if (c->wave.capacity == capacity && c->wave_lights == c->ds.n_lights) {
+        return SPCU_OK; // (capacity is also the stride of the per-light planes, so it must match exactly)
     }
+    c->wave_lights = c->ds.n_lights;
     for (auto& b : c->wave_bufs) {
         b.release();
     }
@@ -51,12 +52,13 @@ int ensure_wave(spcu_ctx* c, uint32_t capacity)
     WAVE(vertex);
     WAVE(extend);
     WAVE(s0);
-    WAVE(light);
+    if ((rc = wave_array(c, w.light, static_cast<size_t>(capacity) * std::max(1u, c->ds.n_lights))) != SPCU_OK) return rc;
     WAVE(mis);
     WAVE(occluded);
 #undef WAVE
-    for (auto& q : c->queues) {
-        CK(c, q.reserve(static_cast<size_t>(capacity) * sizeof(uint32_t)));
+    for (int i = 0; i < kNumQueues; ++i) { // the shadow queue has one plane per light
+        const size_t planes = (i == kQShadow) ? std::max(1u, c->ds.n_lights) : 1u;
+        CK(c, c->queues[i].reserve(static_cast<size_t>(capacity) * planes * sizeof(uint32_t)));
     }
     CK(c, c->queue_counts.reserve(kMaxQueueCounts * sizeof(uint32_t)));
     CK(c, c->counters.reserve(kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters)));
@@ -310,27 +312,27 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                               c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED,
                               d_counters, d_cnt);
                 timer.end();
-                uint32_t* n_live = new_count();
+                uint32_t* n_live   = new_count();
+                uint32_t* n_shadow = d_counts + next_count; // one shadow queue (and counter) per light
+                next_count += n_lights;
+                uint32_t* q_shadow = (nee || direct) ? q[kQShadow] : nullptr;
                 timer.begin(kStShade);
-                launch_shade(L, s, c->wave, p, sorted, max_n, q[kQLive], n_live, d_counters);
+                launch_shade(L, s, c->wave, p, sorted, max_n, q[kQLive], n_live, q_shadow, n_shadow, d_counters);
                 timer.end();
                 launches += 2;
                 if (nee || direct) {
                     for (uint32_t li = 0; li < n_lights; ++li) {
-                        p.light_index      = li;
-                        uint32_t* n_shadow = new_count();
-                        timer.begin(kStNeeLight);
-                        launch_nee_light(L, s, c->wave, p, q[kQLive], n_live, max_n, q[kQShadow], n_shadow, d_counters);
-                        timer.end();
-                        uint32_t* n_lit = direct ? nullptr : new_count();
+                        p.light_index           = li;
+                        uint32_t* q_shadow_l    = q_shadow + static_cast<size_t>(li) * capacity;
+                        uint32_t* n_lit         = direct ? nullptr : new_count();
                         timer.begin(kStShadow);
-                        launch_shadow(L, s, c->wave, q[kQShadow], n_shadow, max_n, new_count(), direct ? nullptr : q[kQLit], n_lit, d_counters,
-                                      d_cnt);
+                        launch_shadow(L, s, c->wave, q_shadow_l, n_shadow + li, max_n, li, new_count(), direct ? nullptr : q[kQLit], n_lit,
+                                      d_counters, d_cnt);
                         timer.end();
-                        launches += 2;
+                        launches += 1;
                         if (direct) {
                             timer.begin(kStDirectAccumulate);
-                            launch_direct_accumulate(L, s, c->wave, p, q[kQShadow], n_shadow, max_n, d_counters);
+                            launch_direct_accumulate(L, s, c->wave, p, q_shadow_l, n_shadow + li, max_n, d_counters);
                             timer.end();
                             ++launches;
                             continue;

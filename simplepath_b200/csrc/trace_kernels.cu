@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
 // shadow: Integrator.cpp:503 — Scene::intersect_p of the light sample's visibility ray.
 template <bool kCount>
 __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
-                                                        const uint32_t* queue, const uint32_t* n_queue, uint32_t* cursor,
-                                                        uint32_t* q_lit, uint32_t* n_lit, unsigned long long* counters,
-                                                        TraceCounters* cnt)
+                                                        const uint32_t* queue, const uint32_t* n_queue, uint32_t light_index,
+                                                        uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit,
+                                                        unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
     const uint32_t     n = *n_queue;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
         if (!have && i != 0xffffffffu) {
             slot              = queue[i];
             const float4   p  = w.vertex[slot].p;
-            const LightRec lr = w.light[slot];
+            const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
             r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
             inv               = make_inv(r);
             t_max             = lr.wi.w;
@@ -503,18 +503,18 @@ void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint3
 }
 
 void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit, unsigned long long* d_counters,
-                   TraceCounters* d_cnt)
+                   uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit,
+                   unsigned long long* d_counters, TraceCounters* d_cnt)
 {
     if (max_n == 0) return;
     if (d_cnt) {
         static const int occ_ = trace_ctas_per_sm(k_shadow<true>);
         k_shadow<true><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, queue, d_n_queue, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
+            s, w, queue, d_n_queue, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
     } else {
         static const int occ_ = trace_ctas_per_sm(k_shadow<false>);
         k_shadow<false><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, queue, d_n_queue, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
+            s, w, queue, d_n_queue, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
     }
 }
 

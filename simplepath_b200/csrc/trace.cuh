@@ -77,6 +77,22 @@ __device__ __forceinline__ bool slab_t0(float lox, float loy, float loz, float h
     return ok;
 }
 
+// Early outs of the triangle test that decide `q <= 0` / `q >= 1` for q = fl(num / den) WITHOUT dividing.  They only
+// fire when the IEEE quotient is certain to satisfy the comparison, so the decision is the reference's bit for bit:
+//   * num == 0, or num and den of strictly opposite signs  =>  q is -0, +0 or negative  =>  q <= 0;
+//   * |num| >= |den| with equal signs                      =>  the exact quotient is >= 1, and so is its rounding.
+// Everything else (including NaN operands, for which every comparison below is false, and quotients that round up to
+// 1 or underflow to 0) falls through to the real division.  Most triangle tests of a leaf end here: the walk is
+// issue-bound and an IEEE division costs about ten instructions.
+__device__ __forceinline__ bool quotient_not_positive(float num, float den)
+{
+    return num == 0.0f || (num < 0.0f && den > 0.0f) || (num > 0.0f && den < 0.0f);
+}
+__device__ __forceinline__ bool quotient_outside_unit(float num, float den)
+{
+    return quotient_not_positive(num, den) || fabsf(num) >= fabsf(den);
+}
+
 // Triangle::intersect_impl (shapes/Triangle.h:97-146)
 __device__ __forceinline__ bool tri_hit(const float4 p0, const float4 p1, const float4 p2, const Ray& r, float t_max,
                                         float& t_out, float& beta_out, float& gamma_out)
@@ -94,7 +110,11 @@ __device__ __forceinline__ bool tri_hit(const float4 p0, const float4 p1, const 
     if (denom == 0.0f) {
         return false;
     }
-    const float beta = __fdiv_rn(__fmaf_rn(J, EIHF, __fmaf_rn(K, GFDI, __fmul_rn(L, DHEG))), denom);
+    const float beta_num = __fmaf_rn(J, EIHF, __fmaf_rn(K, GFDI, __fmul_rn(L, DHEG)));
+    if (quotient_outside_unit(beta_num, denom)) { // beta <= 0 || beta >= 1 decided without the division
+        return false;
+    }
+    const float beta = __fdiv_rn(beta_num, denom);
     if (beta <= 0.0f || beta >= 1.0f) {
         return false;
     }
@@ -102,7 +122,11 @@ __device__ __forceinline__ bool tri_hit(const float4 p0, const float4 p1, const 
     const float JCAL = __fmaf_rn(J, C, -__fmul_rn(A, L));
     const float BLKC = __fmaf_rn(B, L, -__fmul_rn(K, C));
 
-    const float gamma = __fdiv_rn(__fmaf_rn(I, AKJB, __fmaf_rn(H, JCAL, __fmul_rn(G, BLKC))), denom);
+    const float gamma_num = __fmaf_rn(I, AKJB, __fmaf_rn(H, JCAL, __fmul_rn(G, BLKC)));
+    if (quotient_not_positive(gamma_num, denom)) { // gamma <= 0 decided without the division
+        return false;
+    }
+    const float gamma = __fdiv_rn(gamma_num, denom);
     if (gamma <= 0.0f || __fadd_rn(beta, gamma) >= 1.0f) {
         return false;
     }
@@ -365,8 +389,10 @@ __device__ __forceinline__ void closest_run(const DAccel& acc, const Prims& prim
                                             ClosestWalk& w, Stack& stack, int max_leaves, TraceCounters* cnt, unsigned mask)
 {
     float t, b, g;
+#pragma unroll 1
     while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
         // ---- internal nodes --------------------------------------------------------------------------------------
+#pragma unroll 1
         while (__any_sync(mask, w.link >= 0 && w.link != kDone)) {
             if (w.link >= 0 && w.link != kDone) {
                 NodeHalf c0, c1;
@@ -399,6 +425,7 @@ __device__ __forceinline__ void closest_run(const DAccel& acc, const Prims& prim
         const uint32_t n     = leaf ? (w.count & SPCU_LEAF_COUNT_MASK) : 0u;
         const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
         const uint32_t n_max = __reduce_max_sync(mask, n);
+#pragma unroll 1
         for (uint32_t i = 0; i < n_max; ++i) {
             if (i < n && prims.template test<kCount>(first + i, mixed, r, w.t_max, t, b, g, cnt)) {
                 w.t_max  = t;
@@ -499,7 +526,9 @@ __device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Geo
                                                     unsigned mask)
 {
     float t, b, g;
+#pragma unroll 1
     while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
+#pragma unroll 1
         while (__any_sync(mask, w.link >= 0 && w.link != kDone)) {
             if (w.link >= 0 && w.link != kDone) {
                 NodeHalf c0, c1;
@@ -529,6 +558,7 @@ __device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Geo
         const uint32_t n     = leaf ? (w.count & SPCU_LEAF_COUNT_MASK) : 0u;
         const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
         const uint32_t n_max = __reduce_max_sync(mask, n);
+#pragma unroll 1
         for (uint32_t i = 0; i < n_max; ++i) {
             const int32_t id = static_cast<int32_t>(first + i);
             if (i < n && prims.template test<kCount>(first + i, mixed, r, w.t_max, t, b, g, cnt) && (t < w.t_max || id > w.hit_id)) {
@@ -591,7 +621,9 @@ __device__ __forceinline__ int any_run(const DAccel& acc, const AnyTest& test, c
                                        AnyWalk& w, Stack& stack, int max_leaves, TraceCounters* cnt, unsigned mask)
 {
     bool hit = false;
+#pragma unroll 1
     while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
+#pragma unroll 1
         while (__any_sync(mask, w.link >= 0 && w.link != kDone)) {
             if (w.link >= 0 && w.link != kDone) {
                 NodeHalf c0, c1;
@@ -618,6 +650,7 @@ __device__ __forceinline__ int any_run(const DAccel& acc, const AnyTest& test, c
         const uint32_t n     = leaf ? (w.count & SPCU_LEAF_COUNT_MASK) : 0u;
         const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
         const uint32_t n_max = __reduce_max_sync(mask, n);
+#pragma unroll 1
         for (uint32_t i = 0; i < n_max; ++i) {
             if (i < n && !hit && test(first + i, mixed, cnt)) {
                 hit = true; // first accepted primitive ends this lane's query; the others finish theirs

@@ -128,6 +128,9 @@ def run_cuda(args) -> None:
     import torch
     import torch.distributed as dist
     from simplepath_b200 import capi, distributed, host
+    if not capi.LIB_PATH.exists() and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        import __graft_entry__   # the library normally travels with the snapshot; build it here if it did not
+        __graft_entry__.build()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

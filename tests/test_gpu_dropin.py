@@ -39,3 +39,20 @@ def test_driver_reports_errors_like_the_reference(tmp_path):
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
     assert proc.returncode != 0
     assert "no device path" in proc.stdout
+
+
+@pytest.mark.skipif(not host.DRIVER.exists() or not host.available(), reason="host plugin not built (needs the reference sources)")
+def test_driver_over_two_devices_is_bit_identical(tmp_path):
+    """SPCU_DEVICES=2: tiles interleaved over two GPUs touch disjoint pixels, so the image equals the one-GPU image."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sp = scenes.ensure("g_bunny", tmp_path)
+    images = []
+    for n in (1, 2):
+        env = dict(os.environ, SPCU_SEED="5", SPCU_DEVICES=str(n))
+        proc = subprocess.run([str(host.DRIVER), "--samples", "4", "--integrator", "cuda", sp.name], cwd=tmp_path, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+        assert proc.returncode == 0, proc.stdout[-2000:]
+        images.append(scenes.read_pfm(tmp_path / "image.pfm"))
+    assert images[0].tobytes() == images[1].tobytes()

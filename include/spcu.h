@@ -58,6 +58,7 @@ extern "C" {
 #define SPCU_INTEGRATOR_ITERATIVE_RRNEE 0u   /* Integrator.cpp:550-635 (north star)  */
 #define SPCU_INTEGRATOR_BRUTE_FORCE_RR 1u    /* Integrator.cpp:211-266               */
 #define SPCU_INTEGRATOR_DIRECT_LIGHTING 2u   /* Integrator.cpp:277-312               */
+#define SPCU_INTEGRATOR_WHITTED 3u           /* Integrator.cpp:314-368 (tail recursion over specular bounces, unrolled) */
 
 /* ---- rays and hits ------------------------------------------------------------------------ */
 /* One query: sp::Ray (math/Ray.h:21-49) + sp::RayLimits (math/Ray.h:13-19). 32 bytes. */

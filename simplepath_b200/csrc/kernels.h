@@ -78,6 +78,10 @@ void launch_direct_accumulate(const Launch& l, const DScene& s, const DWave& w, 
 void launch_advance(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_live,
                     const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
                     unsigned long long* d_counters);
+// whitted_advance: the Whitted integrator's BSDF sample; specular samples continue as the next segment (Integrator.cpp:357-363).
+void launch_whitted_advance(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_live,
+                            const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
+                            unsigned long long* d_counters);
 // resolve: per pixel, add this batch's samples in sample order to the accumulators (main.cpp:100).
 // d_radiance[(k * n_pix + i) * stride] = radiance sample k of pixel-list entry i (float4 units).
 void launch_resolve(const Launch& l, const float4* d_radiance, uint32_t stride, const uint32_t* d_pix_list, uint32_t n_pix,

@@ -95,7 +95,8 @@ struct PathState
 };
 
 // One path vertex of IntegratorIterativeRRNEE::do_integrate (Integrator.cpp:556-632), BruteForceIntegratorIterativeRR
-// (:219-263, nee == false) or DirectLightingIntegrator (:277-312).  Returns false when the path ends at this vertex.
+// (:219-263, nee == false), DirectLightingIntegrator (:277-312) or WhittedIntegrator (:323-368).  Returns false when the
+// path ends at this vertex.
 template <bool kCount>
 __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator, PathState& ps, int32_t* stack,
                                             PathCounters& pc, TraceCounters* tc)
@@ -120,7 +121,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
     make_isect(s, HitRec{ gi, t_max, beta, gamma }, ps.o, ps.d, point, normal, material);
     const V3 wo = -ps.d;
 
-    if (integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING) {
+    if (integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || integrator == SPCU_INTEGRATOR_WHITTED) {
         for (uint32_t k = 0; k < s.n_lights; ++k) {
             const spcu_light& light = s.lights[__ldg(s.light_order + k)];
             float             u0, u1;
@@ -142,7 +143,23 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
                 ps.L = ps.L + f * ls.L * fabsf(dot(ls.wi, normal)) / ls.pdf;
             }
         }
-        return false;
+        if (integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING) {
+            return false;
+        }
+        // WhittedIntegrator (Integrator.cpp:357-363): follow the BSDF sample only when it is specular, default limits,
+        // radiance of the reflected ray added unweighted
+        ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);
+        ps.rng.ctr       = 0u;
+        const MSample ms = material_sample(s, material, wo, normal, ps.rng);
+        ++pc.shade_calls;
+        if (ms.pdf == 0.0f || is_black(ms.color) || !ms.specular) {
+            return false;
+        }
+        ps.o     = point;
+        ps.d     = ms.dir;
+        ps.t_min = kRayEpsilon;
+        ++ps.depth;
+        return ps.depth < s.max_depth;
     }
 
     ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);

@@ -296,9 +296,10 @@ struct MSample
     V3    color;
     V3    dir;
     float pdf;
+    bool  specular; // is_specular(properties) (materials/BSDFProperties.h:48-50); only the Whitted integrator reads it
 };
 
-__device__ __forceinline__ MSample degenerate_sample() { return MSample{ v3(0, 0, 0), v3(0, 0, 0), 0.0f }; }
+__device__ __forceinline__ MSample degenerate_sample() { return MSample{ v3(0, 0, 0), v3(0, 0, 0), 0.0f, false }; }
 __device__ __forceinline__ V3 bxdf_r(const spcu_bxdf& bx) { return v3(bx.r[0], bx.r[1], bx.r[2]); }
 
 // BRDF::eval: LambertianBRDF :334-337, SpecularReflectionBRDF :371-374, MicrofacetReflection :424-440
@@ -352,15 +353,17 @@ __device__ __forceinline__ MSample bxdf_sample(const spcu_bxdf& bx, V3 wo, Rng& 
         const float r = sqrtf(max_std(0.0f, 1.0f - y * y));
         float       sp, cp;
         sincosf(2.0f * kPi * u1, &sp, &cp);
-        s.dir   = v3(r * cp, y, r * sp);
-        s.color = bxdf_r(bx);
-        s.pdf   = kInv2Pi;
+        s.dir      = v3(r * cp, y, r * sp);
+        s.color    = bxdf_r(bx);
+        s.pdf      = kInv2Pi;
+        s.specular = false;
         return s;
     }
     if (bx.kind == SPCU_BXDF_SPECULAR) {
         s.dir   = v3(-wo.x, wo.y, -wo.z);
-        s.color = fresnel_dielectric(cos_theta(s.dir), 1.0f, 1.5f) * bxdf_r(bx) / abs_cos_theta(s.dir);
-        s.pdf   = 1.0f;
+        s.color    = fresnel_dielectric(cos_theta(s.dir), 1.0f, 1.5f) * bxdf_r(bx) / abs_cos_theta(s.dir);
+        s.pdf      = 1.0f;
+        s.specular = true;
         return s;
     }
     if (wo.y == 0.0f) {
@@ -375,9 +378,10 @@ __device__ __forceinline__ MSample bxdf_sample(const spcu_bxdf& bx, V3 wo, Rng& 
     if (!same_hemisphere(wo, wi)) {
         return degenerate_sample();
     }
-    s.pdf   = distribution_pdf(bx, wo, wh) / (4.0f * dp);
-    s.color = bxdf_eval(bx, wo, wi);
-    s.dir   = wi;
+    s.pdf      = distribution_pdf(bx, wo, wh) / (4.0f * dp);
+    s.color    = bxdf_eval(bx, wo, wi);
+    s.dir      = wi;
+    s.specular = false;
     return s;
 }
 
@@ -455,7 +459,7 @@ __device__ __forceinline__ MSample one_sample_sample(const DScene& s, const spcu
     for (uint32_t i = 0; i < n; ++i) {
         inner += pdfs[i];
     }
-    MSample out{ v3(0, 0, 0), r.dir, 0.0f };
+    MSample out{ v3(0, 0, 0), r.dir, 0.0f, r.specular }; // result.properties of the selected BxDF (:666)
     for (uint32_t i = 0; i < n; ++i) {
         if (pdfs[i] > 0.0f) {
             out.color = out.color + balance1(pdfs[i], inner) * values[i];
@@ -524,8 +528,9 @@ __device__ __forceinline__ MSample material_sample_local(const DScene& s, uint32
         const float f = fresnel_dielectric(cos_theta(wo), 1.0f, m.ior);
         if (rng_next1(rng) < f) {
             r.dir   = v3(-wo.x, wo.y, -wo.z);
-            r.color = f * v3(m.specular[0], m.specular[1], m.specular[2]) / abs_cos_theta(r.dir);
-            r.pdf   = f;
+            r.color    = f * v3(m.specular[0], m.specular[1], m.specular[2]) / abs_cos_theta(r.dir);
+            r.pdf      = f;
+            r.specular = true;
             break;
         }
         chain.f[chain.depth]   = f;

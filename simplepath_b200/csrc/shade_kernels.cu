@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
                 V3       point, normal;
                 uint32_t material;
                 make_isect(s, ex.hit, o, d, point, normal, material);
-                if (p.integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING) {
-                    live = true;
+                if (p.integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || p.integrator == SPCU_INTEGRATOR_WHITTED) {
+                    live = true; // these sample the lights first; Whitted draws its BSDF sample afterwards (whitted_advance)
                 } else {
                     Rng           rng = make_rng(w.path[slot], p.seed, p.depth, kSiteBsdf, 0u);
                     const MSample sr  = material_sample(s, material, -d, normal, rng);
@@ -395,6 +395,34 @@ __global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__
     }
 }
 
+// ---- whitted_advance (Integrator.cpp:357-363): follow the BSDF sample only when it is specular; the reflected ray gets
+// default RayLimits and its radiance is added unweighted (the reference's `L += do_integrate(outgoing_ray, ...)`) ------------
+__global__ void __launch_bounds__(kShadeBlock) k_whitted_advance(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                                 const __grid_constant__ RenderParams p, const uint32_t* q_live,
+                                                                 const uint32_t* n_live, uint32_t* q_next, uint32_t* n_next,
+                                                                 unsigned long long* counters)
+{
+    const uint32_t n = *n_live;
+    count_items(counters, kStAdvance, n);
+    FOR_EACH_QUEUED(i, active, n)
+    {
+        bool     alive = false;
+        uint32_t slot  = 0;
+        if (active) {
+            slot               = q_live[i];
+            const VertexRec vx = w.vertex[slot];
+            Rng             rng = make_rng(w.path[slot], p.seed, p.depth, kSiteBsdf, 0u);
+            const MSample   ms  = material_sample(s, __float_as_uint(vx.p.w), -xyz(w.ray[slot].d), xyz(vx.n), rng);
+            if (!(ms.pdf == 0.0f || is_black(ms.color)) && ms.specular) {
+                w.ray[slot] = RayRec{ make_float4(vx.p.x, vx.p.y, vx.p.z, kEps), f4(ms.dir, kFltMax) };
+                alive       = true;
+            }
+        }
+        queue_push(q_next, n_next, slot, alive);
+        warp_count(counters + kCntShadeCalls, active != 0u);
+    }
+}
+
 // ---- resolve (main.cpp:100): per pixel, add this batch's samples in sample order ------------------------------------------
 // radiance[(k * n_pix + i) * stride] is the sample of pixel i, sample k: stride 2 / offset 1 reads PathRec::L of the
 // wavefront state, stride 1 the persistent path kernel's buffer.
@@ -493,6 +521,13 @@ void launch_advance(const Launch& l, const DScene& s, const DWave& w, const Rend
                     unsigned long long* d_counters)
 {
     WAVEFRONT_LAUNCH(k_advance, l, max_n, s, w, p, q_live, d_n_live, q_next, d_n_next, d_counters);
+}
+
+void launch_whitted_advance(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_live,
+                            const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
+                            unsigned long long* d_counters)
+{
+    WAVEFRONT_LAUNCH(k_whitted_advance, l, max_n, s, w, p, q_live, d_n_live, q_next, d_n_next, d_counters);
 }
 
 void launch_resolve(const Launch& l, const float4* d_radiance, uint32_t stride, const uint32_t* d_pix_list, uint32_t n_pix,

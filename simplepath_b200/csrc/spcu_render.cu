@@ -227,7 +227,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
         return fail(c, SPCU_ERR_INVALID, "bad sample range [%u,%u) of %u (jitter table holds %u)", part->sample_begin,
                     part->sample_end, part->spp_total, s.spp);
     }
-    if (part->integrator > SPCU_INTEGRATOR_DIRECT_LIGHTING) {
+    if (part->integrator > SPCU_INTEGRATOR_WHITTED) {
         return fail(c, SPCU_ERR_INVALID, "unknown integrator %u", part->integrator);
     }
     // The caller's stream (spcu_render_device) orders this call after the caller's earlier work on that stream.
@@ -263,7 +263,8 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     const uint32_t n_lights    = s.n_lights;
     const uint32_t max_depth   = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING ? std::min(1u, s.max_depth) : s.max_depth;
     const bool     nee         = part->integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE;
-    const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING;
+    const bool     whitted     = part->integrator == SPCU_INTEGRATOR_WHITTED;
+    const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || whitted; // per-light direct term
     const uint32_t n_segments  = std::min<uint32_t>(c->n_materials, kMaxMaterialSegments) + 1u; // + the miss segment
     const uint32_t counts_need = 1 + max_depth * (3 + 4 * n_lights + n_segments);
     CK(c, c->sorted_queue.reserve(static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)));
@@ -350,12 +351,16 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                         launches += 3;
                     }
                 }
-                if (direct) {
+                if (direct && !whitted) {
                     break;
                 }
                 uint32_t* n_next = new_count();
                 timer.begin(kStAdvance);
-                launch_advance(L, s, c->wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
+                if (whitted) {
+                    launch_whitted_advance(L, s, c->wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
+                } else {
+                    launch_advance(L, s, c->wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
+                }
                 timer.end();
                 ++launches;
                 std::swap(q_cur, q_next);

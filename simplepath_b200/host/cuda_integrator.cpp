@@ -22,6 +22,7 @@ std::uint32_t integrator_code(const std::string& name)
     if (name == "iterative_rrnee") return SPCU_INTEGRATOR_ITERATIVE_RRNEE;
     if (name == "brute_force_iterative_rr") return SPCU_INTEGRATOR_BRUTE_FORCE_RR;
     if (name == "direct_lighting") return SPCU_INTEGRATOR_DIRECT_LIGHTING;
+    if (name == "whitted") return SPCU_INTEGRATOR_WHITTED;
     throw std::runtime_error("CudaIntegrator: no device path for integrator '" + name + "'");
 }
 

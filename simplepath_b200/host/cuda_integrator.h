@@ -32,7 +32,7 @@ public:
         int         device     = 0;                 // first CUDA device
         int         n_devices  = 1;                 // tile-interleaved across devices [device, device + n_devices)
         unsigned    spp        = 16;                // samples per pixel of the lazy whole-frame render (integrate_impl)
-        std::string inner      = "iterative_rrnee"; // iterative_rrnee | brute_force_iterative_rr | direct_lighting
+        std::string inner      = "iterative_rrnee"; // iterative_rrnee | brute_force_iterative_rr | direct_lighting | whitted
         std::uint64_t seed     = 0;
     };
 
@@ -40,7 +40,7 @@ public:
     explicit CudaIntegrator(Options options);
     ~CudaIntegrator() override;
 
-    // "cuda", "cuda_direct_lighting", "cuda_brute_force_iterative_rr": remembers which reference integrator the next
+    // "cuda", "cuda_direct_lighting", "cuda_brute_force_iterative_rr", "cuda_whitted": remembers which reference integrator the next
     // default-constructed CudaIntegrator reproduces.  Returns false for names that are not ours.
     static bool select(std::string_view name);
 

@@ -67,7 +67,7 @@ def main() -> None:
         if name in RENDERS:
             n = RENDERS[name]
             rend = {}
-            for integ in ("iterative_rrnee", "direct_lighting", "brute_force_iterative_rr"):
+            for integ in ("iterative_rrnee", "direct_lighting", "brute_force_iterative_rr", "whitted"):
                 rgb, mean, var, secs = rs.render(integ, n, 8)
                 rend[f"{integ}.rgb"] = rgb
                 rend[f"{integ}.lum_mean"] = mean

@@ -35,7 +35,7 @@ def test_driver_writes_the_same_image(ctx, tmp_path, name, flag, integrator):
 
 @pytest.mark.skipif(not host.DRIVER.exists(), reason="host plugin not built")
 def test_driver_reports_errors_like_the_reference(tmp_path):
-    proc = subprocess.run([str(host.DRIVER), "--integrator", "cuda_whitted", "nothing.sp"], cwd=tmp_path,
+    proc = subprocess.run([str(host.DRIVER), "--integrator", "cuda_mandelbrot", "nothing.sp"], cwd=tmp_path,
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
     assert proc.returncode != 0
     assert "no device path" in proc.stdout

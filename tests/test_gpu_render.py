@@ -16,7 +16,7 @@ from simplepath_b200.flat import FlatSceneData
 
 pytestmark = pytest.mark.gpu
 SCENES = ["g_spheres", "g_spheres_ibl", "g_example", "g_bunny", "g_elf"]
-INTEGRATORS = ["iterative_rrnee", "brute_force_iterative_rr", "direct_lighting"]
+INTEGRATORS = ["iterative_rrnee", "brute_force_iterative_rr", "direct_lighting", "whitted"]
 
 
 def lum(c):
@@ -66,7 +66,7 @@ def test_per_pixel_vs_oracle(ctx, oracle_port, scene, integrator):
         assert abs(st[key] - want_st[key]) <= 0.01 * want_st[key] + 8, (key, st[key], want_st[key])
     assert abs(st["shade_calls"] - want_st["shade_calls"]) <= 0.01 * want_st["shade_calls"] + 8
     # (direct lighting: the reference skips the shadow query when f == 0; the wavefront pipeline traces it anyway)
-    assert abs(st["rays_any"] - want_st["rays_any"]) <= (0.25 if integrator == "direct_lighting" else 0.01) * want_st["rays_any"] + 8
+    assert abs(st["rays_any"] - want_st["rays_any"]) <= (0.25 if integrator in ("direct_lighting", "whitted") else 0.01) * want_st["rays_any"] + 8
 
 
 @pytest.mark.parametrize("integrator", INTEGRATORS)

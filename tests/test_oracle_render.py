@@ -16,7 +16,8 @@ def lum(c):
 
 
 CASES = [("g_spheres", "iterative_rrnee"), ("g_spheres_ibl", "direct_lighting"), ("g_example", "iterative_rrnee"),
-         ("g_example", "brute_force_iterative_rr"), ("g_bunny", "iterative_rrnee"), ("g_elf", "direct_lighting")]
+         ("g_example", "brute_force_iterative_rr"), ("g_bunny", "iterative_rrnee"), ("g_elf", "direct_lighting"), ("g_spheres", "whitted"),
+         ("g_bunny", "whitted")]
 
 
 @pytest.mark.parametrize("name,integrator", CASES)

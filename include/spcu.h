@@ -299,7 +299,10 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 /*   SPCU_OPT_TRAVERSAL   : closest-hit walk of the extend stage: SPCU_TRAVERSAL_EXACT (default) = the reference's own
  *                          order, bit-exact IDs; SPCU_TRAVERSAL_ORDERED = nearer child first (see spcu_trace_closest_fast). */
 #define SPCU_OPT_TRAVERSAL 3u
-#define SPCU_OPT_COUNT_ 4u
+/*   SPCU_OPT_GENERIC_KERNELS : 1 = always run the kernels compiled for every scene feature (default 0: spcu_upload_scene picks
+ *                          the smallest compiled feature set that covers the scene).  Takes effect at the next upload. */
+#define SPCU_OPT_GENERIC_KERNELS 4u
+#define SPCU_OPT_COUNT_ 5u
 #define SPCU_TRAVERSAL_EXACT 0u
 #define SPCU_TRAVERSAL_ORDERED 1u
 #define SPCU_PIPELINE_WAVEFRONT 0u

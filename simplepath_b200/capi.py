@@ -110,7 +110,7 @@ EXPORTS = [
     "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times",
 ]
-OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL = 0, 1, 2, 3
+OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
 PIPELINE_WAVEFRONT, PIPELINE_PATHS = 0, 1
 

@@ -88,6 +88,7 @@ struct spcu_ctx
     spcu::DevBuf              path_radiance;     // float4 per slot of a batch (SPCU_PIPELINE_PATHS)
     spcu::DevBuf              sorted_queue;      // material-sorted hand-over between extend and shade
     uint32_t                  n_materials = 0;
+    int                       features    = 0; // feature set of the uploaded scene (features.h)
     uint32_t                  wave_lights = 0; // light planes the wavefront buffers were sized for
 
     uint32_t                 options[SPCU_OPT_COUNT_] = {};

@@ -3,6 +3,7 @@
 #pragma once
 
 #include "device_scene.h"
+#include "features.h"
 
 namespace spcu {
 
@@ -50,6 +51,7 @@ struct Launch
 {
     int          sm_count;
     cudaStream_t stream;
+    int          features; // FeatFull::id / FeatAnalytic::id (features.h): which instantiation of the kernels the scene needs
 };
 
 // raygen: fills slots [0, n_pix*n_samples) from the pixel list and the sample range, and the initial queue (main.cpp:90-98).

@@ -30,40 +30,40 @@ struct PathCounters
 __device__ __forceinline__ Ray make_ray(V3 o, V3 d, float t_min) { return Ray{ o.x, o.y, o.z, d.x, d.y, d.z, t_min }; }
 
 // estimate_direct_mis (Integrators/Integrator.cpp:486-539) for one light
-template <bool kCount>
+template <bool kCount, typename F>
 __device__ __forceinline__ V3 estimate_direct_mis(const DScene& s, const spcu_light& light, V3 p, V3 n, uint32_t material,
                                                   V3 wo, Rng& rng, int32_t* stack, PathCounters& pc, TraceCounters* tc)
 {
     V3    L = v3(0, 0, 0);
     float u0, u1;
     rng_next2(rng, u0, u1); // block 0 of the light's sub-stream; eval / pdf / sample follow from block 1
-    const LSample ls = light_sample(s, light, p, n, u0, u1);
+    const LSample ls = light_sample<F>(s, light, p, n, u0, u1);
     if (ls.pdf == 0.0f || is_black(ls.L)) {
         return L;
     }
     ++pc.rays_any;
-    if (scene_any_hit<kCount>(s, make_ray(p, ls.wi, ls.t_min), ls.t_max, stack, tc)) {
+    if (scene_any_hit<kCount, F>(s, make_ray(p, ls.wi, ls.t_min), ls.t_max, stack, tc)) {
         return L;
     }
     const Onb onb = onb_from_v(n);
     const V3  wol = to_onb(onb, wo), wil = to_onb(onb, ls.wi);
-    const V3  f   = material_eval_local(s, material, wol, wil, rng);
+    const V3  f   = material_eval_local<F>(s, material, wol, wil, rng);
     ++pc.shade_calls;
     if (!is_black(f)) {
-        const float bsdf_pdf = material_pdf_local(s, material, wol, wil, rng);
+        const float bsdf_pdf = material_pdf_local<F>(s, material, wol, wil, rng);
         ++pc.shade_calls;
         if (bsdf_pdf > 0.0f) {
             const float weight = balance2(ls.pdf, bsdf_pdf);
             L                  = f * ls.L * (fabsf(dot(ls.wi, n)) * weight / ls.pdf);
         }
     }
-    MSample ms = material_sample_local(s, material, wol, rng);
+    MSample ms = material_sample_local<F>(s, material, wol, rng);
     ++pc.shade_calls;
     if (ms.pdf == 0.0f || is_black(ms.color)) {
         return L;
     }
     ms.dir           = to_world(onb, ms.dir);
-    const float lpdf = light_pdf(s, light, p, ms.dir);
+    const float lpdf = light_pdf<F>(s, light, p, ms.dir);
     if (lpdf == 0.0f) {
         return L;
     }
@@ -71,13 +71,13 @@ __device__ __forceinline__ V3 estimate_direct_mis(const DScene& s, const spcu_li
     const Ray   mr     = make_ray(p, ms.dir, ray_offset(n, ms.dir));
     float       t_max  = kInfinite, beta, gamma;
     ++pc.rays_lights;
-    const LightPrims lp{ s.lights };
+    const LightPrimsT<F> lp{ s.lights };
     const int32_t    li = closest_hit<false>(s.lights_accel, lp, mr, t_max, beta, gamma, stack, nullptr);
     if (li >= 0) {
         ++pc.rays_any;
         // limits are NOT shrunk to the light's distance: a sphere light occludes itself, as in the reference (:531-532)
-        if (!scene_any_hit<kCount>(s, mr, kInfinite, stack, tc)) {
-            const V3 Li = light_hit_L(s, s.lights[li], ms.dir);
+        if (!scene_any_hit<kCount, F>(s, mr, kInfinite, stack, tc)) {
+            const V3 Li = light_hit_L<F>(s, s.lights[li], ms.dir);
             L           = L + ms.color * Li * fabsf(dot(ms.dir, n)) * weight / ms.pdf;
         }
     }
@@ -97,7 +97,7 @@ struct PathState
 // One path vertex of IntegratorIterativeRRNEE::do_integrate (Integrator.cpp:556-632), BruteForceIntegratorIterativeRR
 // (:219-263, nee == false), DirectLightingIntegrator (:277-312) or WhittedIntegrator (:323-368).  Returns false when the
 // path ends at this vertex.
-template <bool kCount>
+template <bool kCount, typename F>
 __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator, PathState& ps, int32_t* stack,
                                             PathCounters& pc, TraceCounters* tc)
 {
@@ -105,20 +105,20 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
     float     t_max = kInfinite, beta, gamma;
 
     ++pc.rays_lights;
-    const LightPrims lp{ s.lights };
+    const LightPrimsT<F> lp{ s.lights };
     const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack, nullptr);
     ++pc.rays_closest;
-    const GeomPrims gp{ s.geom_prims, s.geom_meta };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     const int32_t   gi = closest_hit<kCount>(s.geom, gp, r, t_max, beta, gamma, stack, tc);
     if (gi < 0) {
         if (li >= 0) {
-            ps.L = ps.L + ps.throughput * light_hit_L(s, s.lights[li], ps.d);
+            ps.L = ps.L + ps.throughput * light_hit_L<F>(s, s.lights[li], ps.d);
         }
         return false;
     }
     V3       point, normal;
     uint32_t material;
-    make_isect(s, HitRec{ gi, t_max, beta, gamma }, ps.o, ps.d, point, normal, material);
+    make_isect<F>(s, HitRec{ gi, t_max, beta, gamma }, ps.o, ps.d, point, normal, material);
     const V3 wo = -ps.d;
 
     if (integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || integrator == SPCU_INTEGRATOR_WHITTED) {
@@ -128,18 +128,18 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
             ps.rng.stream = rng_stream(ps.depth, kSiteLight0 + k);
             ps.rng.ctr    = 0u;
             rng_next2(ps.rng, u0, u1);
-            const LSample ls = light_sample(s, light, point, normal, u0, u1);
+            const LSample ls = light_sample<F>(s, light, point, normal, u0, u1);
             if (ls.pdf == 0.0f || is_black(ls.L)) {
                 continue;
             }
             const Onb onb = onb_from_v(normal);
-            const V3  f   = material_eval_local(s, material, to_onb(onb, wo), to_onb(onb, ls.wi), ps.rng);
+            const V3  f   = material_eval_local<F>(s, material, to_onb(onb, wo), to_onb(onb, ls.wi), ps.rng);
             ++pc.shade_calls;
             if (is_black(f)) {
                 continue;
             }
             ++pc.rays_any;
-            if (!scene_any_hit<kCount>(s, make_ray(point, ls.wi, ls.t_min), ls.t_max, stack, tc)) {
+            if (!scene_any_hit<kCount, F>(s, make_ray(point, ls.wi, ls.t_min), ls.t_max, stack, tc)) {
                 ps.L = ps.L + f * ls.L * fabsf(dot(ls.wi, normal)) / ls.pdf;
             }
         }
@@ -150,7 +150,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         // radiance of the reflected ray added unweighted
         ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);
         ps.rng.ctr       = 0u;
-        const MSample ms = material_sample(s, material, wo, normal, ps.rng);
+        const MSample ms = material_sample<F>(s, material, wo, normal, ps.rng);
         ++pc.shade_calls;
         if (ms.pdf == 0.0f || is_black(ms.color) || !ms.specular) {
             return false;
@@ -164,7 +164,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
 
     ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);
     ps.rng.ctr       = 0u;
-    const MSample sr = material_sample(s, material, wo, normal, ps.rng);
+    const MSample sr = material_sample<F>(s, material, wo, normal, ps.rng);
     ++pc.shade_calls;
     if (sr.pdf == 0.0f || is_black(sr.color)) {
         return false;
@@ -174,7 +174,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
             const spcu_light& light = s.lights[__ldg(s.light_order + k)];
             ps.rng.stream = rng_stream(ps.depth, kSiteLight0 + k);
             ps.rng.ctr    = 0u;
-            ps.L = ps.L + ps.throughput * estimate_direct_mis<kCount>(s, light, point, normal, material, wo, ps.rng, stack, pc, tc);
+            ps.L = ps.L + ps.throughput * estimate_direct_mis<kCount, F>(s, light, point, normal, material, wo, ps.rng, stack, pc, tc);
         }
     }
     const float cosine = fabsf(dot(sr.dir, normal));
@@ -199,7 +199,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
     return ps.depth < s.max_depth;
 }
 
-template <bool kCount>
+template <bool kCount, typename F>
 __global__ void __launch_bounds__(kPathBlock) k_paths(const __grid_constant__ DScene s, const uint32_t* __restrict__ pix_list,
                                                       uint32_t n_pix, uint32_t sample_begin, uint32_t n_samples, uint64_t seed,
                                                       uint32_t integrator, float4* __restrict__ radiance,
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kPathBlock) k_paths(const __grid_constant__ DS
         }
         // ---- one vertex for every lane that carries a path --------------------------------------------------------
         if (have_path) {
-            if (!path_vertex<kCount>(s, integrator, ps, stack, pc, kCount ? &tc : nullptr)) {
+            if (!path_vertex<kCount, F>(s, integrator, ps, stack, pc, kCount ? &tc : nullptr)) {
                 radiance[ps.slot] = make_float4(ps.L.x, ps.L.y, ps.L.z, 0.0f);
                 have_path         = false;
             }
@@ -315,6 +315,23 @@ int ctas_per_sm(K kernel)
 
 } // namespace
 
+template <typename F>
+static void launch_paths_variant(const Launch& l, const DScene& s, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t sample_begin,
+                                 uint32_t n_samples, uint64_t seed, uint32_t integrator, float4* d_radiance,
+                                 unsigned long long* d_counters, TraceCounters* d_cnt)
+{
+    const uint32_t n = n_pix * n_samples;
+    if (d_cnt) {
+        static const int occ = ctas_per_sm(k_paths<true, F>);
+        k_paths<true, F><<<wavefront_grid(n, kPathBlock, occ, l.sm_count), kPathBlock, 0, l.stream>>>(
+            s, d_pix_list, n_pix, sample_begin, n_samples, seed, integrator, d_radiance, d_counters, d_cnt);
+    } else {
+        static const int occ = ctas_per_sm(k_paths<false, F>);
+        k_paths<false, F><<<wavefront_grid(n, kPathBlock, occ, l.sm_count), kPathBlock, 0, l.stream>>>(
+            s, d_pix_list, n_pix, sample_begin, n_samples, seed, integrator, d_radiance, d_counters, nullptr);
+    }
+}
+
 void launch_paths(const Launch& l, const DScene& s, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t sample_begin,
                   uint32_t n_samples, uint64_t seed, uint32_t integrator, float4* d_radiance, unsigned long long* d_counters,
                   TraceCounters* d_cnt)
@@ -323,14 +340,12 @@ void launch_paths(const Launch& l, const DScene& s, const uint32_t* d_pix_list, 
     if (n == 0) {
         return;
     }
-    if (d_cnt) {
-        static const int occ = ctas_per_sm(k_paths<true>);
-        k_paths<true><<<wavefront_grid(n, kPathBlock, occ, l.sm_count), kPathBlock, 0, l.stream>>>(
-            s, d_pix_list, n_pix, sample_begin, n_samples, seed, integrator, d_radiance, d_counters, d_cnt);
+    if (l.features == FeatAnalytic::id) {
+        launch_paths_variant<FeatAnalytic>(l, s, d_pix_list, n_pix, sample_begin, n_samples, seed, integrator, d_radiance, d_counters,
+                                           d_cnt);
     } else {
-        static const int occ = ctas_per_sm(k_paths<false>);
-        k_paths<false><<<wavefront_grid(n, kPathBlock, occ, l.sm_count), kPathBlock, 0, l.stream>>>(
-            s, d_pix_list, n_pix, sample_begin, n_samples, seed, integrator, d_radiance, d_counters, nullptr);
+        launch_paths_variant<FeatFull>(l, s, d_pix_list, n_pix, sample_begin, n_samples, seed, integrator, d_radiance, d_counters,
+                                       d_cnt);
     }
 }
 

@@ -7,6 +7,7 @@
 #pragma once
 
 #include "device_scene.h"
+#include "features.h"
 #include "rng.cuh"
 
 #include <cfloat>
@@ -303,12 +304,13 @@ __device__ __forceinline__ MSample degenerate_sample() { return MSample{ v3(0, 0
 __device__ __forceinline__ V3 bxdf_r(const spcu_bxdf& bx) { return v3(bx.r[0], bx.r[1], bx.r[2]); }
 
 // BRDF::eval: LambertianBRDF :334-337, SpecularReflectionBRDF :371-374, MicrofacetReflection :424-440
+template <typename F>
 __device__ __forceinline__ V3 bxdf_eval(const spcu_bxdf& bx, V3 wo, V3 wi)
 {
-    if (bx.kind == SPCU_BXDF_LAMBERT) {
+    if (!(F::microfacet || F::specular_bxdf) || bx.kind == SPCU_BXDF_LAMBERT) {
         return bxdf_r(bx);
     }
-    if (bx.kind == SPCU_BXDF_SPECULAR) {
+    if (!F::microfacet || bx.kind == SPCU_BXDF_SPECULAR) {
         return v3(0, 0, 0);
     }
     const float co = abs_cos_theta(wo), ci = abs_cos_theta(wi);
@@ -327,12 +329,13 @@ __device__ __forceinline__ V3 bxdf_eval(const spcu_bxdf& bx, V3 wo, V3 wi)
 }
 
 // BRDF::pdf: Lambert :339-342 (uniform hemisphere), specular :376-381, microfacet :442-449
+template <typename F>
 __device__ __forceinline__ float bxdf_pdf(const spcu_bxdf& bx, V3 wo, V3 wi)
 {
-    if (bx.kind == SPCU_BXDF_LAMBERT) {
+    if (!(F::microfacet || F::specular_bxdf) || bx.kind == SPCU_BXDF_LAMBERT) {
         return kInv2Pi;
     }
-    if (bx.kind == SPCU_BXDF_SPECULAR) {
+    if (!F::microfacet || bx.kind == SPCU_BXDF_SPECULAR) {
         return 0.0f;
     }
     if (!same_hemisphere(wo, wi)) {
@@ -343,10 +346,11 @@ __device__ __forceinline__ float bxdf_pdf(const spcu_bxdf& bx, V3 wo, V3 wi)
 }
 
 // BRDF::sample: Lambert :322-332 (uniform hemisphere, not cosine weighted), specular :362-369, microfacet :398-422
+template <typename F>
 __device__ __forceinline__ MSample bxdf_sample(const spcu_bxdf& bx, V3 wo, Rng& rng)
 {
     MSample s;
-    if (bx.kind == SPCU_BXDF_LAMBERT) {
+    if (!(F::microfacet || F::specular_bxdf) || bx.kind == SPCU_BXDF_LAMBERT) {
         float u0, u1;
         rng_next2(rng, u0, u1);
         const float y = u0;
@@ -359,7 +363,7 @@ __device__ __forceinline__ MSample bxdf_sample(const spcu_bxdf& bx, V3 wo, Rng& 
         s.specular = false;
         return s;
     }
-    if (bx.kind == SPCU_BXDF_SPECULAR) {
+    if (!F::microfacet || bx.kind == SPCU_BXDF_SPECULAR) {
         s.dir   = v3(-wo.x, wo.y, -wo.z);
         s.color    = fresnel_dielectric(cos_theta(s.dir), 1.0f, 1.5f) * bxdf_r(bx) / abs_cos_theta(s.dir);
         s.pdf      = 1.0f;
@@ -379,22 +383,23 @@ __device__ __forceinline__ MSample bxdf_sample(const spcu_bxdf& bx, V3 wo, Rng& 
         return degenerate_sample();
     }
     s.pdf      = distribution_pdf(bx, wo, wh) / (4.0f * dp);
-    s.color    = bxdf_eval(bx, wo, wi);
+    s.color    = bxdf_eval<F>(bx, wo, wi);
     s.dir      = wi;
     s.specular = false;
     return s;
 }
 
 // BRDF::rho: LambertianBRDF overrides it (:344-347, no random numbers); the others run BRDF::rho_impl (:299-310)
+template <typename F>
 __device__ __forceinline__ V3 bxdf_rho(const spcu_bxdf& bx, V3 wo, Rng& rng)
 {
-    if (bx.kind == SPCU_BXDF_LAMBERT) {
+    if (!(F::microfacet || F::specular_bxdf) || bx.kind == SPCU_BXDF_LAMBERT) {
         return bxdf_r(bx) * kPi;
     }
     V3 r = v3(0, 0, 0);
 #pragma unroll 1
     for (unsigned i = 0; i < kRhoEvals; ++i) {
-        const MSample s = bxdf_sample(bx, wo, rng);
+        const MSample s = bxdf_sample<F>(bx, wo, rng);
         if (s.pdf > 0.0f) {
             r = r + s.color * abs_cos_theta(s.dir) / s.pdf;
         }
@@ -404,12 +409,13 @@ __device__ __forceinline__ V3 bxdf_rho(const spcu_bxdf& bx, V3 wo, Rng& rng)
 
 // ---- materials (materials/Material.h:456-806) ----------------------------------------------------------------------------
 // OneSampleMaterial::get_selection_weights :545-572 — a fresh 16-sample albedo estimate per BxDF on EVERY call
+template <typename F>
 static __device__ __noinline__ void selection_weights(const spcu_bxdf* bx, uint32_t n, V3 wo, Rng& rng, float* w)
 {
     float sum = 0.0f;
 #pragma unroll 1
     for (uint32_t i = 0; i < n; ++i) {
-        w[i] = luminance(bxdf_rho(bx[i], wo, rng));
+        w[i] = luminance(bxdf_rho<F>(bx[i], wo, rng));
         sum += w[i];
     }
     for (uint32_t i = 0; i < n; ++i) {
@@ -420,15 +426,16 @@ static __device__ __noinline__ void selection_weights(const spcu_bxdf* bx, uint3
 __device__ __forceinline__ float balance1(float p, float inner) { return inner == 0.0f ? 0.0f : p / inner; } // math/Math.h:82-89
 
 // OneSampleMaterial::sample_impl :577-667
+template <typename F>
 __device__ __forceinline__ MSample one_sample_sample(const DScene& s, const spcu_material& m, V3 wo, Rng& rng)
 {
     const spcu_bxdf* bx = s.bxdfs + m.first_bxdf;
     const uint32_t   n  = m.n_bxdfs;
     if (n == 1) {
-        return bxdf_sample(bx[0], wo, rng);
+        return bxdf_sample<F>(bx[0], wo, rng);
     }
     float w[SPCU_MAX_BXDFS];
-    selection_weights(bx, n, wo, rng, w);
+    selection_weights<F>(bx, n, wo, rng, w);
 
     const float u        = rng_next1(rng);
     float       running  = 0.0f;
@@ -440,7 +447,7 @@ __device__ __forceinline__ MSample one_sample_sample(const DScene& s, const spcu
         }
         running += w[i];
     }
-    const MSample r = bxdf_sample(bx[selected], wo, rng);
+    const MSample r = bxdf_sample<F>(bx[selected], wo, rng);
     if (r.pdf == 0.0f || is_black(r.color)) {
         return degenerate_sample();
     }
@@ -452,8 +459,8 @@ __device__ __forceinline__ MSample one_sample_sample(const DScene& s, const spcu
             values[i] = r.color;
             pdfs[i]   = r.pdf * w[i];
         } else {
-            values[i] = bxdf_eval(bx[i], wo, r.dir);
-            pdfs[i]   = bxdf_pdf(bx[i], wo, r.dir) * w[i];
+            values[i] = bxdf_eval<F>(bx[i], wo, r.dir);
+            pdfs[i]   = bxdf_pdf<F>(bx[i], wo, r.dir) * w[i];
         }
     }
     for (uint32_t i = 0; i < n; ++i) {
@@ -470,27 +477,29 @@ __device__ __forceinline__ MSample one_sample_sample(const DScene& s, const spcu
 }
 
 // OneSampleMaterial::pdf_impl :669-683
+template <typename F>
 __device__ __forceinline__ float one_sample_pdf(const DScene& s, const spcu_material& m, V3 wo, V3 wi, Rng& rng)
 {
     const spcu_bxdf* bx = s.bxdfs + m.first_bxdf;
     float            w[SPCU_MAX_BXDFS];
-    selection_weights(bx, m.n_bxdfs, wo, rng, w);
+    selection_weights<F>(bx, m.n_bxdfs, wo, rng, w);
     float pdf = 0.0f;
     for (uint32_t i = 0; i < m.n_bxdfs; ++i) {
-        pdf += w[i] * bxdf_pdf(bx[i], wo, wi);
+        pdf += w[i] * bxdf_pdf<F>(bx[i], wo, wi);
     }
     return pdf;
 }
 
 // OneSampleMaterial::eval_impl :685-715
+template <typename F>
 __device__ __forceinline__ V3 one_sample_eval(const DScene& s, const spcu_material& m, V3 wo, V3 wi, Rng& rng)
 {
     const spcu_bxdf* bx = s.bxdfs + m.first_bxdf;
     float            w[SPCU_MAX_BXDFS], pdfs[SPCU_MAX_BXDFS];
-    selection_weights(bx, m.n_bxdfs, wo, rng, w);
+    selection_weights<F>(bx, m.n_bxdfs, wo, rng, w);
     float inner = 0.0f;
     for (uint32_t i = 0; i < m.n_bxdfs; ++i) {
-        pdfs[i] = bxdf_pdf(bx[i], wo, wi) * w[i];
+        pdfs[i] = bxdf_pdf<F>(bx[i], wo, wi) * w[i];
     }
     for (uint32_t i = 0; i < m.n_bxdfs; ++i) {
         inner += pdfs[i];
@@ -498,7 +507,7 @@ __device__ __forceinline__ V3 one_sample_eval(const DScene& s, const spcu_materi
     V3 result = v3(0, 0, 0);
     for (uint32_t i = 0; i < m.n_bxdfs; ++i) {
         if (pdfs[i] > 0.0f) {
-            result = result + balance1(pdfs[i], inner) * bxdf_eval(bx[i], wo, wi);
+            result = result + balance1(pdfs[i], inner) * bxdf_eval<F>(bx[i], wo, wi);
         }
     }
     return result;
@@ -514,6 +523,7 @@ struct CoatChain
 };
 
 // ClearcoatMaterial::sample_impl :734-765 over OneSampleMaterial::sample_impl
+template <typename F>
 __device__ __forceinline__ MSample material_sample_local(const DScene& s, uint32_t mat, V3 wo, Rng& rng)
 {
     CoatChain chain;
@@ -522,7 +532,7 @@ __device__ __forceinline__ MSample material_sample_local(const DScene& s, uint32
     for (;;) {
         const spcu_material& m = s.materials[mat];
         if (m.kind == SPCU_MAT_ONE_SAMPLE) {
-            r = one_sample_sample(s, m, wo, rng);
+            r = one_sample_sample<F>(s, m, wo, rng);
             break;
         }
         const float f = fresnel_dielectric(cos_theta(wo), 1.0f, m.ior);
@@ -562,22 +572,24 @@ __device__ __forceinline__ uint32_t walk_coats(const DScene& s, uint32_t mat, V3
     return mat;
 }
 
+template <typename F>
 __device__ __forceinline__ float material_pdf_local(const DScene& s, uint32_t mat, V3 wo, V3 wi, Rng& rng)
 {
     CoatChain      chain;
     const uint32_t base = walk_coats(s, mat, wo, chain);
-    float          pdf  = one_sample_pdf(s, s.materials[base], wo, wi, rng);
+    float          pdf  = one_sample_pdf<F>(s, s.materials[base], wo, wi, rng);
     for (int i = chain.depth - 1; i >= 0; --i) {
         pdf = (1.0f - chain.f[i]) * pdf;
     }
     return pdf;
 }
 
+template <typename F>
 __device__ __forceinline__ V3 material_eval_local(const DScene& s, uint32_t mat, V3 wo, V3 wi, Rng& rng)
 {
     CoatChain      chain;
     const uint32_t base = walk_coats(s, mat, wo, chain);
-    V3             f    = one_sample_eval(s, s.materials[base], wo, wi, rng);
+    V3             f    = one_sample_eval<F>(s, s.materials[base], wo, wi, rng);
     for (int i = chain.depth - 1; i >= 0; --i) {
         f = (1.0f - chain.f[i]) * f;
     }
@@ -585,10 +597,11 @@ __device__ __forceinline__ V3 material_eval_local(const DScene& s, uint32_t mat,
 }
 
 // Material::sample (materials/Material.h:461-473): result direction returned in world space
+template <typename F>
 __device__ __forceinline__ MSample material_sample(const DScene& s, uint32_t mat, V3 wo, V3 n, Rng& rng)
 {
     const Onb onb = onb_from_v(n);
-    MSample   r   = material_sample_local(s, mat, to_onb(onb, wo), rng);
+    MSample   r   = material_sample_local<F>(s, mat, to_onb(onb, wo), rng);
     if (r.pdf == 0.0f || is_black(r.color)) {
         return r;
     }
@@ -711,6 +724,7 @@ struct LSample
 
 // Light::sample (Lights/Light.h:38-49) over SphereLight (ObjectLight::sample_impl :81-90 + Sphere::sample
 // shapes/Sphere.h:20-51), EnvironmentLight (:155-161), ImageBasedEnvironmentLight (:226-249)
+template <typename F>
 __device__ __forceinline__ LSample light_sample(const DScene& s, const spcu_light& l, V3 p, V3 n, float u0, float u1)
 {
     LSample out;
@@ -733,7 +747,7 @@ __device__ __forceinline__ LSample light_sample(const DScene& s, const spcu_ligh
         out.pdf            = sphere_pdf(l, p);
         out.t_max          = sqrtf(dot(to_sample, to_sample)) - ray_offset(sp_normal, -out.wi);
         out.L              = v3(l.radiance[0], l.radiance[1], l.radiance[2]);
-    } else if (l.kind == SPCU_LIGHT_ENV_CONST) {
+    } else if (!F::ibl || l.kind == SPCU_LIGHT_ENV_CONST) {
         out.wi  = sample_uniform_sphere(u0, u1);
         out.pdf = 1.0f / (4.0f * kPi);
         out.L   = v3(l.radiance[0], l.radiance[1], l.radiance[2]);
@@ -767,12 +781,13 @@ __device__ __forceinline__ LSample light_sample(const DScene& s, const spcu_ligh
 
 // Light::pdf: SphereLight -> Sphere::pdf; EnvironmentLight :163-166; ImageBasedEnvironmentLight :251-266 (theta * pi
 // as written there) over Distribution2D::pdf (math/Distribution2D.h:31-38)
+template <typename F>
 __device__ __forceinline__ float light_pdf(const DScene& s, const spcu_light& l, V3 p, V3 wi)
 {
     if (l.kind == SPCU_LIGHT_SPHERE) {
         return sphere_pdf(l, p);
     }
-    if (l.kind == SPCU_LIGHT_ENV_CONST) {
+    if (!F::ibl || l.kind == SPCU_LIGHT_ENV_CONST) {
         return 1.0f / (4.0f * kPi);
     }
     const V3    w     = xf_vector(l.world_to_light, wi);
@@ -792,9 +807,10 @@ __device__ __forceinline__ float light_pdf(const DScene& s, const spcu_light& l,
 
 // LightIntersection::L (Light::intersect_lights_impl: SphereLight :354-361, EnvironmentLight :135-141,
 // ImageBasedEnvironmentLight :196-209)
+template <typename F>
 __device__ __forceinline__ V3 light_hit_L(const DScene& s, const spcu_light& l, V3 dir)
 {
-    if (l.kind != SPCU_LIGHT_ENV_IBL) {
+    if (!F::ibl || l.kind != SPCU_LIGHT_ENV_IBL) {
         return v3(l.radiance[0], l.radiance[1], l.radiance[2]);
     }
     const V3 w = normalize(xf_vector(l.world_to_light, dir));
@@ -825,6 +841,7 @@ __device__ __forceinline__ void camera_ray(const DScene& s, uint32_t pix, uint32
 }
 
 // Intersection record of the accepted hit: Triangle.h:148-160, Sphere.h:99-104, Plane.h:65-70
+template <typename F>
 __device__ __forceinline__ void make_isect(const DScene& s, const HitRec& h, V3 o, V3 d, V3& point, V3& normal,
                                            uint32_t& material)
 {
@@ -835,7 +852,7 @@ __device__ __forceinline__ void make_isect(const DScene& s, const HitRec& h, V3 
     material            = SPCU_META_MATERIAL(meta);
     point               = o + d * h.t; // Ray::operator() (math/Ray.h:30-34)
     const uint32_t kind = SPCU_META_KIND(meta);
-    if (kind == SPCU_PRIM_TRIANGLE) {
+    if (F::triangles && kind == SPCU_PRIM_TRIANGLE) {
         const float alpha = 1.0f - h.beta - h.gamma;
         normal = normalize(v3(fmaf(alpha, a.x, fmaf(h.beta, b.x, h.gamma * c.x)), fmaf(alpha, a.y, fmaf(h.beta, b.y, h.gamma * c.y)),
                               fmaf(alpha, a.z, fmaf(h.beta, b.z, h.gamma * c.z))));

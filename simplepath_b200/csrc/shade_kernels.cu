@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ 
 }
 
 // ---- shade (Integrator.cpp:558-572, 627-632): miss handling, surface interaction, primary BSDF sample S0 ---------------
+template <typename F>
 __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                        const __grid_constant__ RenderParams p,
                                                        const __grid_constant__ SortedQueue sorted, uint32_t* q_live,
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
             const V3        o = xyz(ry.o), d = xyz(ry.d);
             if (ex.hit.id < 0) {
                 if (ex.light >= 0) { // emitter reached, at ANY depth (Integrator.cpp:627-629)
-                    const V3 L  = light_hit_L(s, s.lights[ex.light], d);
+                    const V3 L  = light_hit_L<F>(s, s.lights[ex.light], d);
                     PathRec  pr = w.path[slot];
                     pr.L.x += pr.tp.x * L.x;
                     pr.L.y += pr.tp.y * L.y;
@@ -155,12 +156,12 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
             } else {
                 V3       point, normal;
                 uint32_t material;
-                make_isect(s, ex.hit, o, d, point, normal, material);
+                make_isect<F>(s, ex.hit, o, d, point, normal, material);
                 if (p.integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || p.integrator == SPCU_INTEGRATOR_WHITTED) {
                     live = true; // these sample the lights first; Whitted draws its BSDF sample afterwards (whitted_advance)
                 } else {
                     Rng           rng = make_rng(w.path[slot], p.seed, p.depth, kSiteBsdf, 0u);
-                    const MSample sr  = material_sample(s, material, -d, normal, rng);
+                    const MSample sr  = material_sample<F>(s, material, -d, normal, rng);
                     sampled           = true;
                     if (!(sr.pdf == 0.0f || is_black(sr.color))) {
                         w.s0[slot] = SampleRec{ f4(sr.dir, sr.pdf), f4(sr.color, 0.0f) };
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
                     Rng               rng   = make_rng(w.path[slot], p.seed, p.depth, kSiteLight0 + li, 0u);
                     float             u0, u1;
                     rng_next2(rng, u0, u1);
-                    const LSample ls = light_sample(s, light, lit_point, lit_normal, u0, u1);
+                    const LSample ls = light_sample<F>(s, light, lit_point, lit_normal, u0, u1);
                     if (!(ls.pdf == 0.0f || is_black(ls.L))) {
                         w.light[static_cast<size_t>(li) * w.capacity + slot] =
                             LightRec{ f4(ls.wi, ls.t_max), make_float4(ls.t_min, ls.pdf, ls.u, ls.v) };
@@ -201,13 +202,15 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ D
 
 // radiance of a stored light sample: an image-based light is looked up again from the sample's (u, v); every other
 // light's sample carries the light's constant radiance (Lights/Light.h:81-90,155-161,226-249)
+template <typename F>
 __device__ __forceinline__ V3 light_sample_L(const DScene& s, const spcu_light& light, const LightRec& lr)
 {
-    return light.kind == SPCU_LIGHT_ENV_IBL ? ibl_lookup(s, light, lr.aux.z, lr.aux.w)
+    return F::ibl && light.kind == SPCU_LIGHT_ENV_IBL ? ibl_lookup(s, light, lr.aux.z, lr.aux.w)
                                             : v3(light.radiance[0], light.radiance[1], light.radiance[2]);
 }
 
 // ---- nee_bsdf (Integrator.cpp:503-530): light-strategy term, second BSDF sample, Light::pdf ----------------------------------
+template <typename F>
 __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                           const __grid_constant__ RenderParams p, const uint32_t* q_shadow,
                                                           const uint32_t* n_shadow, uint32_t* q_mis, uint32_t* n_mis,
@@ -232,29 +235,29 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
             const V3        wo       = -xyz(w.ray[slot].d);
             const V3        wi       = xyz(lr.wi);
             const float     lpdf_s   = lr.aux.y;
-            const V3        lL       = light_sample_L(s, light, lr);
+            const V3        lL       = light_sample_L<F>(s, light, lr);
             Rng             rng      = make_rng(pr, p.seed, p.depth, kSiteLight0 + p.light_index, 1u); // block 0 was the light sample
 
             // Material::eval / pdf (materials/Material.h:475-490) rebuild the ONB on every call; it is the same basis
             const Onb onb = onb_from_v(nn);
             const V3  wol = to_onb(onb, wo), wil = to_onb(onb, wi);
             V3        A   = v3(0, 0, 0);
-            const V3  f   = material_eval_local(s, material, wol, wil, rng);
+            const V3  f   = material_eval_local<F>(s, material, wol, wil, rng);
             ++calls;
             if (!is_black(f)) {
-                const float bsdf_pdf = material_pdf_local(s, material, wol, wil, rng);
+                const float bsdf_pdf = material_pdf_local<F>(s, material, wol, wil, rng);
                 ++calls;
                 if (bsdf_pdf > 0.0f) {
                     const float weight = balance2(lpdf_s, bsdf_pdf);
                     A                  = f * lL * (fabsf(dot(wi, nn)) * weight / lpdf_s);
                 }
             }
-            MSample ms = material_sample_local(s, material, wol, rng);
+            MSample ms = material_sample_local<F>(s, material, wol, rng);
             ++calls;
             float lpdf = 0.0f;
             if (!(ms.pdf == 0.0f || is_black(ms.color))) {
                 ms.dir = to_world(onb, ms.dir);
-                lpdf   = light_pdf(s, light, pt, ms.dir);
+                lpdf   = light_pdf<F>(s, light, pt, ms.dir);
             }
             if (lpdf != 0.0f) {
                 const float weight = balance2(ms.pdf, lpdf);
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
 }
 
 // ---- nee_mis_accumulate (Integrator.cpp:531-538): L += throughput * (light term + BSDF-strategy term) ------------------------
+template <typename F>
 __global__ void __launch_bounds__(kShadeBlock) k_nee_mis_accumulate(const __grid_constant__ DScene s,
                                                                     const __grid_constant__ DWave w, const uint32_t* q_mis,
                                                                     const uint32_t* n_mis, unsigned long long* counters)
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_mis_accumulate(const __grid
             const MisRec   mr   = w.mis[slot];
             V3             est  = v3(mr.cwa.z, mr.cwa.w, mr.ab);
             if (mr.light >= 0 && mr.occluded == 0) {
-                const V3 Li = light_hit_L(s, s.lights[mr.light], xyz(mr.d));
+                const V3 Li = light_hit_L<F>(s, s.lights[mr.light], xyz(mr.d));
                 est         = est + xyz(mr.col) * Li * mr.cwa.x * mr.cwa.y / mr.col.w;
             }
             if (!is_black(est)) {
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_mis_accumulate(const __grid
 // ---- direct_accumulate (Integrator.cpp:296-306): DirectLightingIntegrator's per-light term -----------------------------------
 // Order in the reference: eval first, shadow query only when f != black.  Here the shadow query has already run for every
 // usable light sample (its result does not change the estimate, only the ray count), then eval consumes its random numbers.
+template <typename F>
 __global__ void __launch_bounds__(kShadeBlock) k_direct_accumulate(const __grid_constant__ DScene s,
                                                                    const __grid_constant__ DWave w,
                                                                    const __grid_constant__ RenderParams p,
@@ -337,9 +342,9 @@ __global__ void __launch_bounds__(kShadeBlock) k_direct_accumulate(const __grid_
             const V3        wi       = xyz(lr.wi);
             Rng             rng      = make_rng(w.path[slot], p.seed, p.depth, kSiteLight0 + p.light_index, 1u);
             const Onb       onb      = onb_from_v(nn);
-            const V3        f        = material_eval_local(s, material, to_onb(onb, wo), to_onb(onb, wi), rng);
+            const V3        f        = material_eval_local<F>(s, material, to_onb(onb, wo), to_onb(onb, wi), rng);
             if (!is_black(f) && !w.occluded[slot]) {
-                const V3 c = f * light_sample_L(s, light, lr) * fabsf(dot(wi, nn)) / lr.aux.y;
+                const V3 c = f * light_sample_L<F>(s, light, lr) * fabsf(dot(wi, nn)) / lr.aux.y;
                 float4   L = w.path[slot].L;
                 L.x += c.x;
                 L.y += c.y;
@@ -397,6 +402,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_advance(const __grid_constant__
 
 // ---- whitted_advance (Integrator.cpp:357-363): follow the BSDF sample only when it is specular; the reflected ray gets
 // default RayLimits and its radiance is added unweighted (the reference's `L += do_integrate(outgoing_ray, ...)`) ------------
+template <typename F>
 __global__ void __launch_bounds__(kShadeBlock) k_whitted_advance(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                                  const __grid_constant__ RenderParams p, const uint32_t* q_live,
                                                                  const uint32_t* n_live, uint32_t* q_next, uint32_t* n_next,
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_whitted_advance(const __grid_co
             slot               = q_live[i];
             const VertexRec vx = w.vertex[slot];
             Rng             rng = make_rng(w.path[slot], p.seed, p.depth, kSiteBsdf, 0u);
-            const MSample   ms  = material_sample(s, __float_as_uint(vx.p.w), -xyz(w.ray[slot].d), xyz(vx.n), rng);
+            const MSample   ms  = material_sample<F>(s, __float_as_uint(vx.p.w), -xyz(w.ray[slot].d), xyz(vx.n), rng);
             if (!(ms.pdf == 0.0f || is_black(ms.color)) && ms.specular) {
                 w.ray[slot] = RayRec{ make_float4(vx.p.x, vx.p.y, vx.p.z, kEps), f4(ms.dir, kFltMax) };
                 alive       = true;
@@ -481,6 +487,16 @@ static int ctas_per_sm(K kernel, int block)
         kernel<<<wavefront_grid((max_n), kShadeBlock, occ_, (l).sm_count), kShadeBlock, 0, (l).stream>>>(__VA_ARGS__); \
     } while (0)
 
+// shading kernels are instantiated per scene feature set (features.h); the launcher picks the one the scene needs
+#define FEATURE_LAUNCH(kernel, l, max_n, ...)                                \
+    do {                                                                     \
+        if ((l).features == FeatAnalytic::id) {                              \
+            WAVEFRONT_LAUNCH(kernel<FeatAnalytic>, l, max_n, __VA_ARGS__);   \
+        } else {                                                             \
+            WAVEFRONT_LAUNCH(kernel<FeatFull>, l, max_n, __VA_ARGS__);       \
+        }                                                                    \
+    } while (0)
+
 void launch_raygen(const Launch& l, const DScene& s, const DWave& w, const uint32_t* d_pix_list, uint32_t n_pix,
                    uint32_t sample_begin, uint32_t n_samples, uint32_t* queue, uint32_t* d_n_queue,
                    unsigned long long* d_counters)
@@ -493,27 +509,27 @@ void launch_shade(const Launch& l, const DScene& s, const DWave& w, const Render
                   uint32_t max_n, uint32_t* q_live, uint32_t* d_n_live, uint32_t* q_shadow, uint32_t* d_n_shadow,
                   unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_shade, l, max_n, s, w, p, sorted, q_live, d_n_live, q_shadow, d_n_shadow, d_counters);
+    FEATURE_LAUNCH(k_shade, l, max_n, s, w, p, sorted, q_live, d_n_live, q_shadow, d_n_shadow, d_counters);
 }
 
 void launch_nee_bsdf(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_shadow,
                      const uint32_t* d_n_shadow, uint32_t max_n, uint32_t* q_mis, uint32_t* d_n_mis,
                      unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_nee_bsdf, l, max_n, s, w, p, q_shadow, d_n_shadow, q_mis, d_n_mis, d_counters);
+    FEATURE_LAUNCH(k_nee_bsdf, l, max_n, s, w, p, q_shadow, d_n_shadow, q_mis, d_n_mis, d_counters);
 }
 
 void launch_nee_mis_accumulate(const Launch& l, const DScene& s, const DWave& w, const uint32_t* q_mis,
                                const uint32_t* d_n_mis, uint32_t max_n, unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_nee_mis_accumulate, l, max_n, s, w, q_mis, d_n_mis, d_counters);
+    FEATURE_LAUNCH(k_nee_mis_accumulate, l, max_n, s, w, q_mis, d_n_mis, d_counters);
 }
 
 void launch_direct_accumulate(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p,
                               const uint32_t* q_shadow, const uint32_t* d_n_shadow, uint32_t max_n,
                               unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_direct_accumulate, l, max_n, s, w, p, q_shadow, d_n_shadow, d_counters);
+    FEATURE_LAUNCH(k_direct_accumulate, l, max_n, s, w, p, q_shadow, d_n_shadow, d_counters);
 }
 
 void launch_advance(const Launch& l, const DScene& s, const DWave& w, const RenderParams& p, const uint32_t* q_live,
@@ -527,7 +543,7 @@ void launch_whitted_advance(const Launch& l, const DScene& s, const DWave& w, co
                             const uint32_t* d_n_live, uint32_t max_n, uint32_t* q_next, uint32_t* d_n_next,
                             unsigned long long* d_counters)
 {
-    WAVEFRONT_LAUNCH(k_whitted_advance, l, max_n, s, w, p, q_live, d_n_live, q_next, d_n_next, d_counters);
+    FEATURE_LAUNCH(k_whitted_advance, l, max_n, s, w, p, q_live, d_n_live, q_next, d_n_next, d_counters);
 }
 
 void launch_resolve(const Launch& l, const float4* d_radiance, uint32_t stride, const uint32_t* d_pix_list, uint32_t n_pix,

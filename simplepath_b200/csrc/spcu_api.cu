@@ -85,6 +85,22 @@ int validate_accel(spcu_ctx* c, const spcu_accel& a, const char* what)
     return SPCU_OK;
 }
 
+// Smallest compiled feature set (features.h) that covers the scene.
+int scene_features(const spcu_flat_scene& s)
+{
+    bool analytic = s.geom.n_nodes == 0 && s.lights_accel.n_nodes == 0;
+    for (uint32_t i = 0; analytic && i < s.geom.n_prims; ++i) {
+        analytic = SPCU_META_KIND(s.geom_meta[i]) != SPCU_PRIM_TRIANGLE;
+    }
+    for (uint32_t i = 0; analytic && i < s.n_bxdfs; ++i) {
+        analytic = s.bxdfs[i].kind == SPCU_BXDF_LAMBERT;
+    }
+    for (uint32_t i = 0; analytic && i < s.n_lights; ++i) {
+        analytic = s.lights[i].kind != SPCU_LIGHT_ENV_IBL;
+    }
+    return analytic ? FeatAnalytic::id : FeatFull::id;
+}
+
 DAccel device_accel(const spcu_accel& a, const DevBuf& nodes)
 {
     DAccel d;
@@ -282,6 +298,7 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     d.jitter       = c->jitter.as<const float>();
     d.spp          = spp;
     c->n_materials = s->n_materials;
+    c->features    = c->options[SPCU_OPT_GENERIC_KERNELS] ? FeatFull::id : scene_features(*s);
     c->have_scene      = true;
     c->pix_list_stride = 0; // invalidate the cached pixel list
     return SPCU_OK;

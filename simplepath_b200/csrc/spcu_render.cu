@@ -182,7 +182,7 @@ int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, floa
     auto*          d_counters = c->counters.as<unsigned long long>();
     TraceCounters* d_cnt = c->options[SPCU_OPT_COUNT_NODES] ? reinterpret_cast<TraceCounters*>(d_counters + kCounterBlock) : nullptr;
     const uint32_t* d_pix_list = c->pix_list.as<uint32_t>();
-    const Launch    L{ c->sm_count, st };
+    const Launch    L{ c->sm_count, st, c->features };
     StageTimer      timer{ c, c->options[SPCU_OPT_STAGE_TIMING] != 0, st };
     uint64_t        launches = 0;
     float4*         d_radiance = c->path_radiance.as<float4>();
@@ -280,7 +280,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
         q[i] = c->queues[i].as<uint32_t>();
     }
     const uint32_t* d_pix_list = c->pix_list.as<uint32_t>();
-    const Launch    L{ c->sm_count, st };
+    const Launch    L{ c->sm_count, st, c->features };
     StageTimer      timer{ c, c->options[SPCU_OPT_STAGE_TIMING] != 0, st };
     uint64_t        launches = 0;
 

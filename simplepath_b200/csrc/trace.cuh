@@ -9,6 +9,7 @@
 #pragma once
 
 #include "device_scene.h"
+#include "features.h"
 
 #include <cfloat>
 
@@ -204,10 +205,12 @@ __device__ __forceinline__ bool plane_hit(const float4 m0, const float4 m1, cons
 // ---------------------------------------------------------------------------------------------------------------
 // Primitive policies: what a "primitive" of an accelerator is and how it is tested.
 // ---------------------------------------------------------------------------------------------------------------
-struct GeomPrims
+template <typename F>
+struct GeomPrimsT
 {
     const float4*   prims;
     const uint32_t* meta;
+    static constexpr bool kBvh = F::bvh; // the accelerator has internal nodes (false: its root is a leaf)
 
     // GeometricPrimitive::intersect_impl -> Shape::intersect (shapes/Primitive.h:37-44)
     template <bool kCount>
@@ -217,9 +220,9 @@ struct GeomPrims
         const float4   a    = __ldg(prims + 3 * id + 0);
         const float4   b    = __ldg(prims + 3 * id + 1);
         const float4   c    = __ldg(prims + 3 * id + 2);
-        const uint32_t kind = mixed ? SPCU_META_KIND(__ldg(meta + id)) : SPCU_PRIM_TRIANGLE;
+        const uint32_t kind = (mixed || !F::triangles) ? SPCU_META_KIND(__ldg(meta + id)) : SPCU_PRIM_TRIANGLE;
         beta = gamma = 0.0f;
-        if (kind == SPCU_PRIM_TRIANGLE) {
+        if (F::triangles && kind == SPCU_PRIM_TRIANGLE) {
             if (kCount) ++cnt->tris;
             return tri_hit(a, b, c, r, t_max, t, beta, gamma);
         }
@@ -231,9 +234,13 @@ struct GeomPrims
     }
 };
 
-struct LightPrims
+using GeomPrims = GeomPrimsT<FeatFull>;
+
+template <typename F>
+struct LightPrimsT
 {
     const spcu_light* lights;
+    static constexpr bool kBvh = F::bvh; // feature sets without internal nodes have none in the lights accelerator either
 
     __device__ __forceinline__ void load_xf(const spcu_light* l, float4& m0, float4& m1, float4& m2) const
     {
@@ -276,6 +283,7 @@ struct LightPrims
         return sphere_hit(m0, m1, m2, r, t_max, t);
     }
 };
+using LightPrims = LightPrimsT<FeatFull>;
 
 // ---------------------------------------------------------------------------------------------------------------
 // Traversal stack: the first kStackShared levels live in shared memory, laid out [level][thread] so that a warp's
@@ -389,6 +397,21 @@ __device__ __forceinline__ void closest_run(const DAccel& acc, const Prims& prim
                                             ClosestWalk& w, Stack& stack, int max_leaves, TraceCounters* cnt, unsigned mask)
 {
     float t, b, g;
+    if (!Prims::kBvh) { // feature set without internal nodes: the root is a leaf, scanned in list order
+        if (w.link != kDone) {
+            const uint32_t first = static_cast<uint32_t>(~w.link), n = w.count & SPCU_LEAF_COUNT_MASK;
+            for (uint32_t i = 0; i < n; ++i) {
+                if (prims.template test<kCount>(first + i, true, r, w.t_max, t, b, g, cnt)) {
+                    w.t_max  = t;
+                    w.hit_id = static_cast<int32_t>(first + i);
+                    w.beta   = b;
+                    w.gamma  = g;
+                }
+            }
+            w.link = kDone;
+        }
+        return;
+    }
 #pragma unroll 1
     while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
         // ---- internal nodes --------------------------------------------------------------------------------------
@@ -520,12 +543,27 @@ __device__ __forceinline__ void ordered_pop(const DAccel& acc, OrderedStack& sta
     }
 }
 
-template <bool kCount>
-__device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const GeomPrims& prims, const Ray& r, const RayInv& inv,
+template <bool kCount, typename Prims>
+__device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Prims& prims, const Ray& r, const RayInv& inv,
                                                     ClosestWalk& w, OrderedStack& stack, int max_leaves, TraceCounters* cnt,
                                                     unsigned mask)
 {
     float t, b, g;
+    if (!Prims::kBvh) { // no internal nodes: nothing to order, the root leaf in list order (ties: later primitive wins)
+        if (w.link != kDone) {
+            const uint32_t first = static_cast<uint32_t>(~w.link), n = w.count & SPCU_LEAF_COUNT_MASK;
+            for (uint32_t i = 0; i < n; ++i) {
+                if (prims.template test<kCount>(first + i, true, r, w.t_max, t, b, g, cnt)) {
+                    w.t_max  = t;
+                    w.hit_id = static_cast<int32_t>(first + i);
+                    w.beta   = b;
+                    w.gamma  = g;
+                }
+            }
+            w.link = kDone;
+        }
+        return;
+    }
 #pragma unroll 1
     while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
 #pragma unroll 1
@@ -575,8 +613,8 @@ __device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Geo
     }
 }
 
-template <bool kCount>
-__device__ __forceinline__ int32_t closest_hit_ordered(const DAccel& acc, const GeomPrims& prims, const Ray& r, float& t_max,
+template <bool kCount, typename Prims>
+__device__ __forceinline__ int32_t closest_hit_ordered(const DAccel& acc, const Prims& prims, const Ray& r, float& t_max,
                                                        float& beta, float& gamma, int32_t* stack_smem, TraceCounters* cnt)
 {
     ClosestWalk w;
@@ -616,11 +654,21 @@ __device__ __forceinline__ void any_pop(const DAccel& acc, Stack& stack, AnyWalk
     }
 }
 
-template <bool kCount, typename AnyTest>
+template <bool kCount, bool kBvh, typename AnyTest>
 __device__ __forceinline__ int any_run(const DAccel& acc, const AnyTest& test, const Ray& r, const RayInv& inv, float t_max,
                                        AnyWalk& w, Stack& stack, int max_leaves, TraceCounters* cnt, unsigned mask)
 {
     bool hit = false;
+    if (!kBvh) { // the root is a leaf
+        if (w.link != kDone) {
+            const uint32_t first = static_cast<uint32_t>(~w.link), n = w.count & SPCU_LEAF_COUNT_MASK;
+            for (uint32_t i = 0; i < n && !hit; ++i) {
+                hit = test(first + i, true, cnt);
+            }
+            w.link = kDone;
+        }
+        return hit ? kAnyHit : kAnyMiss;
+    }
 #pragma unroll 1
     while (__any_sync(mask, w.link != kDone) && max_leaves > 0) {
 #pragma unroll 1
@@ -666,7 +714,7 @@ __device__ __forceinline__ int any_run(const DAccel& acc, const AnyTest& test, c
     return hit ? kAnyHit : (w.link == kDone ? kAnyMiss : kAnyRunning);
 }
 
-template <bool kCount, typename AnyTest>
+template <bool kCount, bool kBvh, typename AnyTest>
 __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, const Ray& r, float t_max,
                                         int32_t* stack_smem, TraceCounters* cnt)
 {
@@ -679,31 +727,32 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
     Stack        stack;
     stack.sh = stack_smem;
     AnyWalk w{ acc.root, acc.root_count };
-    return any_run<kCount>(acc, test, r, inv, t_max, w, stack, kAllLeaves, cnt, __activemask()) == kAnyHit;
+    return any_run<kCount, kBvh>(acc, test, r, inv, t_max, w, stack, kAllLeaves, cnt, __activemask()) == kAnyHit;
 }
 
 // Lights half of Scene::intersect_p: only sphere lights occlude.
+template <typename F = FeatFull>
 __device__ __forceinline__ bool lights_any_hit(const DScene& s, const Ray& r, float t_max, int32_t* stack_smem)
 {
-    const LightPrims lp{ s.lights };
+    const LightPrimsT<F> lp{ s.lights };
     auto light_test = [&](uint32_t id, bool, TraceCounters*) { return lp.test_any(id, r, t_max); };
-    return any_hit<false>(s.lights_accel, light_test, r, t_max, stack_smem, nullptr);
+    return any_hit<false, F::bvh>(s.lights_accel, light_test, r, t_max, stack_smem, nullptr);
 }
 
 // Scene::intersect_p (base/Scene.h:79-82): geometry accelerator, then lights accelerator.
-template <bool kCount>
+template <bool kCount, typename F = FeatFull>
 __device__ __forceinline__ bool scene_any_hit(const DScene& s, const Ray& r, float t_max, int32_t* stack_smem,
                                               TraceCounters* cnt)
 {
-    const GeomPrims gp{ s.geom_prims, s.geom_meta };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
         float t, b, g;
         return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
     };
-    if (any_hit<kCount>(s.geom, geom_test, r, t_max, stack_smem, cnt)) {
+    if (any_hit<kCount, F::bvh>(s.geom, geom_test, r, t_max, stack_smem, cnt)) {
         return true;
     }
-    return lights_any_hit(s, r, t_max, stack_smem);
+    return lights_any_hit<F>(s, r, t_max, stack_smem);
 }
 
 } // namespace spcu

@@ -193,7 +193,7 @@ __device__ __forceinline__ void segment_push_converged(const SortedQueue& q, uin
 }
 
 // extend: Integrator.cpp:558-563.  intersect_lights first; a light hit shrinks t_max for the geometry query.
-template <bool kCount, bool kOrdered>
+template <bool kCount, bool kOrdered, typename F>
 __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                         const uint32_t* queue, const uint32_t* n_queue, uint32_t* cursor,
                                                         const __grid_constant__ SortedQueue sorted,
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
     feed.n      = n;
 
     TraceCounters   local{ 0, 0, 0 };
-    const GeomPrims gp{ s.geom_prims, s.geom_meta };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     Stack           stack;
     OrderedStack    ostack;
     stack.sh = stack_smem + threadIdx.x;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
             inv            = make_inv(r);
             float t_max = d.w, beta, gamma;
             // Scene::intersect_lights (a handful of lights: walked in one go)
-            const LightPrims lp{ s.lights };
+            const LightPrimsT<F> lp{ s.lights };
             const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack_smem + threadIdx.x, nullptr);
             light_id            = li;
             light_t             = t_max;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
 }
 
 // shadow: Integrator.cpp:503 — Scene::intersect_p of the light sample's visibility ray.
-template <bool kCount>
+template <bool kCount, typename F>
 __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                         const uint32_t* queue, const uint32_t* n_queue, uint32_t light_index,
                                                         uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit,
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
     feed.n      = n;
 
     TraceCounters   local{ 0, 0, 0 };
-    const GeomPrims gp{ s.geom_prims, s.geom_meta };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     Stack           stack;
     stack.sh = stack_smem + threadIdx.x;
     Ray      r{};
@@ -335,14 +335,14 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
                 float t, b, g;
                 return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
             };
-            const int st = any_run<kCount>(s.geom, geom_test, r, inv, t_max, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
+            const int st = any_run<kCount, F::bvh>(s.geom, geom_test, r, inv, t_max, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
             if (have && status == kAnyRunning) {
                 status = st;
             }
         }
         if (have && status != kAnyRunning) {
             // Scene::intersect_p: geometry, then the lights accelerator (base/Scene.h:79-82)
-            if (status == kAnyMiss && lights_any_hit(s, r, t_max, stack_smem + threadIdx.x)) {
+            if (status == kAnyMiss && lights_any_hit<F>(s, r, t_max, stack_smem + threadIdx.x)) {
                 status = kAnyHit;
             }
             const bool occ = status == kAnyHit;
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
 
 // mis: Integrator.cpp:527-532 — intersect_lights of the BSDF-sampled ray and, when it reaches a light, intersect_p
 // with the SAME limits (t_max stays FLT_MAX: a sphere light therefore occludes itself, as in the reference).
-template <bool kCount>
+template <bool kCount, typename F>
 __global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                            const uint32_t* queue, const uint32_t* n_queue,
                                                            unsigned long long* counters, TraceCounters* cnt)
@@ -395,12 +395,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_mis_trace(const __grid_constant
         const Ray      r{ p.x, p.y, p.z, d.x, d.y, d.z, d.w };
         float          t_max = kInfinite, beta, gamma;
 
-        const LightPrims lp{ s.lights };
+        const LightPrimsT<F> lp{ s.lights };
         const int32_t    li  = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack + threadIdx.x, nullptr);
         int              occ = 0;
         if (li >= 0) {
             traced_any = true;
-            occ        = scene_any_hit<kCount>(s, r, kInfinite, stack + threadIdx.x, &local) ? 1 : 0;
+            occ        = scene_any_hit<kCount, F>(s, r, kInfinite, stack + threadIdx.x, &local) ? 1 : 0;
         }
         w.mis[slot].light    = li;
         w.mis[slot].occluded = occ;
@@ -464,28 +464,29 @@ static int trace_ctas_per_sm(K kernel)
     return n;
 }
 
-#define TRACE_STAGE_LAUNCH(kernel)                                                                                     \
-    do {                                                                                                               \
-        if (max_n == 0) return;                                                                                        \
-        if (d_cnt) {                                                                                                   \
-            static const int occ_ = trace_ctas_per_sm(kernel<true>);                                                   \
-            kernel<true><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(          \
-                s, w, queue, d_n_queue, d_counters, d_cnt);                                                            \
-        } else {                                                                                                       \
-            static const int occ_ = trace_ctas_per_sm(kernel<false>);                                                  \
-            kernel<false><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(         \
-                s, w, queue, d_n_queue, d_counters, nullptr);                                                          \
-        }                                                                                                              \
-    } while (0)
-
-template <bool kCount, bool kOrdered>
+// One instantiation per (counting, [ordered,] scene feature set); the launcher picks by the scene's feature set.
+template <bool kCount, bool kOrdered, typename F>
 static void launch_extend_variant(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
                                   const uint32_t* d_n_queue, uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted,
                                   unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    static const int occ_ = trace_ctas_per_sm(k_extend<kCount, kOrdered>);
-    k_extend<kCount, kOrdered><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
+    static const int occ_ = trace_ctas_per_sm(k_extend<kCount, kOrdered, F>);
+    k_extend<kCount, kOrdered, F><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
         s, w, queue, d_n_queue, d_cursor, sorted, d_counters, d_cnt);
+}
+
+template <typename F>
+static void launch_extend_features(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
+                                   const uint32_t* d_n_queue, uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted,
+                                   bool ordered, unsigned long long* d_counters, TraceCounters* d_cnt)
+{
+    if (d_cnt) {
+        ordered ? launch_extend_variant<true, true, F>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, d_cnt)
+                : launch_extend_variant<true, false, F>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, d_cnt);
+    } else {
+        ordered ? launch_extend_variant<false, true, F>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, nullptr)
+                : launch_extend_variant<false, false, F>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, nullptr);
+    }
 }
 
 void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
@@ -493,13 +494,21 @@ void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint3
                    unsigned long long* d_counters, TraceCounters* d_cnt)
 {
     if (max_n == 0) return;
-    if (d_cnt) {
-        ordered ? launch_extend_variant<true, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, d_cnt)
-                : launch_extend_variant<true, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, d_cnt);
+    if (l.features == FeatAnalytic::id) {
+        launch_extend_features<FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
     } else {
-        ordered ? launch_extend_variant<false, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, nullptr)
-                : launch_extend_variant<false, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, d_counters, nullptr);
+        launch_extend_features<FeatFull>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
     }
+}
+
+template <bool kCount, typename F>
+static void launch_shadow_variant(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
+                                  const uint32_t* d_n_queue, uint32_t max_n, uint32_t light_index, uint32_t* d_cursor,
+                                  uint32_t* q_lit, uint32_t* d_n_lit, unsigned long long* d_counters, TraceCounters* d_cnt)
+{
+    static const int occ_ = trace_ctas_per_sm(k_shadow<kCount, F>);
+    k_shadow<kCount, F><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
+        s, w, queue, d_n_queue, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
 }
 
 void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
@@ -507,21 +516,37 @@ void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint3
                    unsigned long long* d_counters, TraceCounters* d_cnt)
 {
     if (max_n == 0) return;
+    const bool analytic = l.features == FeatAnalytic::id;
     if (d_cnt) {
-        static const int occ_ = trace_ctas_per_sm(k_shadow<true>);
-        k_shadow<true><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, queue, d_n_queue, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
+        analytic ? launch_shadow_variant<true, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt)
+                 : launch_shadow_variant<true, FeatFull>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
     } else {
-        static const int occ_ = trace_ctas_per_sm(k_shadow<false>);
-        k_shadow<false><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, queue, d_n_queue, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
+        analytic ? launch_shadow_variant<false, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr)
+                 : launch_shadow_variant<false, FeatFull>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
     }
+}
+
+template <bool kCount, typename F>
+static void launch_mis_variant(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                               uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
+{
+    static const int occ_ = trace_ctas_per_sm(k_mis_trace<kCount, F>);
+    k_mis_trace<kCount, F><<<wavefront_grid(max_n, kTraceBlock, occ_, l.sm_count), kTraceBlock, 0, l.stream>>>(
+        s, w, queue, d_n_queue, d_counters, d_cnt);
 }
 
 void launch_mis_trace(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
                       uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    TRACE_STAGE_LAUNCH(k_mis_trace);
+    if (max_n == 0) return;
+    const bool analytic = l.features == FeatAnalytic::id;
+    if (d_cnt) {
+        analytic ? launch_mis_variant<true, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_counters, d_cnt)
+                 : launch_mis_variant<true, FeatFull>(l, s, w, queue, d_n_queue, max_n, d_counters, d_cnt);
+    } else {
+        analytic ? launch_mis_variant<false, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_counters, nullptr)
+                 : launch_mis_variant<false, FeatFull>(l, s, w, queue, d_n_queue, max_n, d_counters, nullptr);
+    }
 }
 
 } // namespace spcu

@@ -160,6 +160,30 @@ def test_partitions_are_exact(ctx, scene):
     assert small.tobytes() == whole.tobytes() and small_sq.tobytes() == whole_sq.tobytes()
 
 
+@pytest.mark.parametrize("integrator", INTEGRATORS)
+def test_feature_specialised_kernels_render_the_same_image(ctx, scene, integrator):
+    """spcu_upload_scene picks kernels compiled for the scene's feature set (csrc/features.h: no BVH / triangles /
+    microfacet / image-based light code for analytic scenes).  A feature that is absent only removes never-taken branches,
+    so the image must agree with the kernels compiled for everything; compilers may schedule the surviving arithmetic
+    differently (FMA contraction in the shading TUs), hence rounding-level tolerance and equal ray counts within 0.1 %."""
+    name, flat, vec = scene
+    jitter = vec["jitter"]
+    upload(ctx, flat, jitter)
+    part = ctx.partition(integrator=integrator, seed=4242)
+    special, _, st_s = ctx.render(part)
+    ctx.set_option(capi.OPT_GENERIC_KERNELS, 1)
+    try:
+        upload(ctx, flat, jitter)  # the feature set is chosen at upload
+        generic, _, st_g = ctx.render(part)
+    finally:
+        ctx.set_option(capi.OPT_GENERIC_KERNELS, 0)
+        upload(ctx, flat, jitter)
+    bad = (np.abs(special - generic) > 2e-3 * (1.0 + np.abs(generic))).any(axis=-1)
+    assert bad.mean() < 0.01, f"{name}/{integrator}: {bad.mean():.2%} of pixels differ between feature sets"
+    for key in ("rays_closest", "rays_any", "rays_lights", "shade_calls"):
+        assert abs(st_s[key] - st_g[key]) <= 0.001 * st_g[key] + 4, (key, st_s[key], st_g[key])
+
+
 def test_seed_changes_the_image_and_repeats_exactly(ctx, scene):
     name, flat, vec = scene
     jitter = vec["jitter"]

@@ -149,7 +149,8 @@ def run_cuda(args) -> None:
     spp_total = spp * world
     jitter = host.jitter(spp_total)
     ctx = capi.Context(local_rank)
-    ctx.set_option(capi.OPT_PIPELINE, capi.PIPELINE_PATHS if args.pipeline == "paths" else capi.PIPELINE_WAVEFRONT)
+    ctx.set_option(capi.OPT_PIPELINE, {"auto": capi.PIPELINE_AUTO, "smwave": capi.PIPELINE_SMWAVE, "paths": capi.PIPELINE_PATHS,
+                                       "wavefront": capi.PIPELINE_WAVEFRONT}[args.pipeline])
     ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_ORDERED if args.traversal == "ordered" else capi.TRAVERSAL_EXACT)
     ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
     part = distributed.sample_partition(rank, world, spp, INTEGRATOR, args.seed)
@@ -454,7 +455,7 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traversal", default="exact", choices=["exact", "ordered"],
                     help="closest-hit walk of the extend stage (SPCU_OPT_TRAVERSAL)")
-    ap.add_argument("--pipeline", default="wavefront", choices=["paths", "wavefront"],
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "smwave", "paths", "wavefront"],
                     help="kernel organisation (SPCU_OPT_PIPELINE); same estimator and random numbers either way")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":

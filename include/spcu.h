@@ -291,10 +291,13 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 #define SPCU_OPT_COUNT_NODES 0u
 #define SPCU_OPT_STAGE_TIMING 1u
 /*   SPCU_OPT_PIPELINE    : which kernel organisation renders (same stages, same random numbers, same estimator):
- *                          SPCU_PIPELINE_WAVEFRONT (default) = one kernel per stage with compacted queues in HBM
- *                          between them; SPCU_PIPELINE_PATHS = one persistent kernel per batch, paths live in
- *                          registers and are regenerated in place.  The default is the one that measures faster on
- *                          the BASELINE.json workloads (profiles/). */
+ *                          SPCU_PIPELINE_WAVEFRONT = one kernel per stage with compacted queues in HBM between them;
+ *                          SPCU_PIPELINE_PATHS = one persistent kernel per batch, a thread carries a path in registers
+ *                          and regenerates it in place; SPCU_PIPELINE_SMWAVE = the SM-local wavefront: one persistent
+ *                          CTA per SM keeps path state and per-stage work queues in shared memory, warps run one stage
+ *                          for up to 32 queued paths at a time; SPCU_PIPELINE_AUTO (default) = whichever measures
+ *                          faster for the uploaded scene's feature set (profiles/): SMWAVE for analytic
+ *                          scenes, WAVEFRONT for scenes with a BVH. */
 #define SPCU_OPT_PIPELINE 2u
 /*   SPCU_OPT_TRAVERSAL   : closest-hit walk of the extend stage: SPCU_TRAVERSAL_EXACT (default) = the reference's own
  *                          order, bit-exact IDs; SPCU_TRAVERSAL_ORDERED = nearer child first (see spcu_trace_closest_fast). */
@@ -307,6 +310,8 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 #define SPCU_TRAVERSAL_ORDERED 1u
 #define SPCU_PIPELINE_WAVEFRONT 0u
 #define SPCU_PIPELINE_PATHS 1u
+#define SPCU_PIPELINE_SMWAVE 2u
+#define SPCU_PIPELINE_AUTO 3u
 int spcu_set_option(spcu_ctx* ctx, uint32_t option, uint32_t value);
 
 /* Per-kernel breakdown of the LAST render call (needs SPCU_OPT_STAGE_TIMING = 1 for `ms`): one entry per wavefront

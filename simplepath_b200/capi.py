@@ -112,7 +112,7 @@ EXPORTS = [
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
-PIPELINE_WAVEFRONT, PIPELINE_PATHS = 0, 1
+PIPELINE_WAVEFRONT, PIPELINE_PATHS, PIPELINE_SMWAVE, PIPELINE_AUTO = 0, 1, 2, 3
 
 
 class SpcuError(RuntimeError):

@@ -15,16 +15,23 @@ struct FeatFull // anything the flattener can emit
     static constexpr bool microfacet    = true; // MicrofacetReflection / Beckmann (and with it the 16-sample albedo estimate)
     static constexpr bool specular_bxdf = true; // SpecularReflectionBRDF inside a OneSampleMaterial
     static constexpr bool ibl           = true; // ImageBasedEnvironmentLight
+    static constexpr bool multi_bxdf    = true; // a OneSampleMaterial may hold several BxDFs (selection weights, one-sample MIS)
+    static constexpr bool nested_coats  = true; // a ClearcoatMaterial's base may be another ClearcoatMaterial
     static constexpr int  id            = 0;
 };
 
-struct FeatAnalytic // spheres and planes only, Lambert BxDFs (with or without clearcoats), sphere and constant environment lights
+// spheres and planes only; every OneSampleMaterial is ONE Lambert BxDF whose albedo has a normal (finite, non-zero)
+// luminance — its selection weight x / x is then exactly 1 and the one-sample combination is the BxDF itself
+// (materials/Material.h:545-572, 669-715) —, with or without ONE clearcoat over it; sphere and constant environment lights
+struct FeatAnalytic
 {
     static constexpr bool bvh           = false;
     static constexpr bool triangles     = false;
     static constexpr bool microfacet    = false;
     static constexpr bool specular_bxdf = false;
     static constexpr bool ibl           = false;
+    static constexpr bool multi_bxdf    = false;
+    static constexpr bool nested_coats  = false;
     static constexpr int  id            = 1;
 };
 

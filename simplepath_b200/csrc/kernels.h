@@ -94,6 +94,14 @@ void launch_paths(const Launch& l, const DScene& s, const uint32_t* d_pix_list, 
                   uint32_t n_samples, uint64_t seed, uint32_t integrator, float4* d_radiance, unsigned long long* d_counters,
                   TraceCounters* d_cnt);
 
+// ---- smwave_kernels.cu -----------------------------------------------------------------------------------------------
+// The SM-local wavefront: one persistent CTA per SM keeps its paths' state and the per-stage work queues in shared
+// memory; same contract as launch_paths.  smwave_supports: path depth and light count fit the packed per-path flags.
+bool        smwave_supports(const DScene& s);
+cudaError_t launch_smwave(const Launch& l, const DScene& s, const uint32_t* d_pix_list, uint32_t n_pix, uint32_t sample_begin,
+                          uint32_t n_samples, uint64_t seed, uint32_t integrator, float4* d_radiance,
+                          unsigned long long* d_counters, TraceCounters* d_cnt);
+
 // pixel list of one rank: tiles t with t % stride == offset, 8x8 tiles row major (TileScheduler.h:66-82)
 uint32_t    count_partition_pixels(uint32_t width, uint32_t height, uint32_t tile_offset, uint32_t tile_stride);
 // d_tile_prefix_scratch: one uint32 per owned tile.  Synchronises the stream.

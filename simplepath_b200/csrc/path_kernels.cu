@@ -47,10 +47,11 @@ __device__ __forceinline__ V3 estimate_direct_mis(const DScene& s, const spcu_li
     }
     const Onb onb = onb_from_v(n);
     const V3  wol = to_onb(onb, wo), wil = to_onb(onb, ls.wi);
-    const V3  f   = material_eval_local<F>(s, material, wol, wil, rng);
+    const Coats<F> coats = walk_coats<F>(s, material, wol);
+    const V3  f   = material_eval_coats<F>(s, coats, wol, wil, rng);
     ++pc.shade_calls;
     if (!is_black(f)) {
-        const float bsdf_pdf = material_pdf_local<F>(s, material, wol, wil, rng);
+        const float bsdf_pdf = material_pdf_coats<F>(s, coats, wol, wil, rng);
         ++pc.shade_calls;
         if (bsdf_pdf > 0.0f) {
             const float weight = balance2(ls.pdf, bsdf_pdf);

@@ -66,14 +66,32 @@ __host__ __device__ __forceinline__ float word_to_unit(uint32_t w)
     return static_cast<float>(w >> 8) * 5.9604644775390625e-8f; // 2^-24
 }
 
+#ifdef __CUDACC__
+// Words 0 and 1 of a block as ONE out-of-line copy per kernel: the ten rounds are ~70 instructions and a kernel draws
+// at some twenty-five call sites; inlined they were 11 % of the path kernels' SASS, whose limiter is instruction fetch.
+static __device__ __noinline__ uint2 philox_block01(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    uint32_t o[4];
+    philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+    return make_uint2(o[0], o[1]);
+}
+#endif
+
 // One draw call: returns words 0 and 1 as floats in [0,1) and advances the path's counter.
 __host__ __device__ __forceinline__ void rng_next2(Rng& r, float& u0, float& u1)
 {
+#ifdef __CUDA_ARCH__
+    const uint2 w = philox_block01(r.ctr, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample);
+    ++r.ctr;
+    u0 = word_to_unit(w.x);
+    u1 = word_to_unit(w.y);
+#else
     uint32_t o[4];
     philox4x32_10(r.ctr, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample, o);
     ++r.ctr;
     u0 = word_to_unit(o[0]);
     u1 = word_to_unit(o[1]);
+#endif
 }
 
 __host__ __device__ __forceinline__ float rng_next1(Rng& r)

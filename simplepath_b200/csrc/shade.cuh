@@ -431,7 +431,7 @@ __device__ __forceinline__ MSample one_sample_sample(const DScene& s, const spcu
 {
     const spcu_bxdf* bx = s.bxdfs + m.first_bxdf;
     const uint32_t   n  = m.n_bxdfs;
-    if (n == 1) {
+    if (!F::multi_bxdf || n == 1) {
         return bxdf_sample<F>(bx[0], wo, rng);
     }
     float w[SPCU_MAX_BXDFS];
@@ -481,7 +481,10 @@ template <typename F>
 __device__ __forceinline__ float one_sample_pdf(const DScene& s, const spcu_material& m, V3 wo, V3 wi, Rng& rng)
 {
     const spcu_bxdf* bx = s.bxdfs + m.first_bxdf;
-    float            w[SPCU_MAX_BXDFS];
+    if (!F::multi_bxdf) { // one BxDF, weight x / x == 1 (features.h)
+        return bxdf_pdf<F>(bx[0], wo, wi);
+    }
+    float w[SPCU_MAX_BXDFS];
     selection_weights<F>(bx, m.n_bxdfs, wo, rng, w);
     float pdf = 0.0f;
     for (uint32_t i = 0; i < m.n_bxdfs; ++i) {
@@ -495,7 +498,10 @@ template <typename F>
 __device__ __forceinline__ V3 one_sample_eval(const DScene& s, const spcu_material& m, V3 wo, V3 wi, Rng& rng)
 {
     const spcu_bxdf* bx = s.bxdfs + m.first_bxdf;
-    float            w[SPCU_MAX_BXDFS], pdfs[SPCU_MAX_BXDFS];
+    if (!F::multi_bxdf) { // one BxDF: pdf * 1 > 0 for every BxDF this feature set admits, balance p / p == 1
+        return bxdf_eval<F>(bx[0], wo, wi);
+    }
+    float w[SPCU_MAX_BXDFS], pdfs[SPCU_MAX_BXDFS];
     selection_weights<F>(bx, m.n_bxdfs, wo, rng, w);
     float inner = 0.0f;
     for (uint32_t i = 0; i < m.n_bxdfs; ++i) {
@@ -514,86 +520,122 @@ __device__ __forceinline__ V3 one_sample_eval(const DScene& s, const spcu_materi
 }
 
 // ClearcoatMaterial (:723-806) wraps a base material; the reference recurses through m_base, here the chain of coats
-// is walked iteratively (the flattener bounds its length by SPCU_MAX_COAT_DEPTH) and unwound in the same order.
-struct CoatChain
+// is walked iteratively (the flattener bounds its length by SPCU_MAX_COAT_DEPTH; feature sets without nested coats walk
+// at most one, with no arrays and no loops) and unwound in the same order.  The walk does not depend on the incident
+// direction, so eval and pdf of the same (material, wo) share one (material_*_coats).
+template <typename F>
+struct Coats
 {
-    float    f[SPCU_MAX_COAT_DEPTH];
-    uint32_t mat[SPCU_MAX_COAT_DEPTH];
+    static constexpr int kMax = F::nested_coats ? static_cast<int>(SPCU_MAX_COAT_DEPTH) : 1;
+    float    f[kMax];   // Fresnel term of coat i, outermost first
+    uint32_t mat[kMax]; // the coat's material (its specular colour scales the base's sample)
     int      depth;
+    uint32_t base;      // the OneSampleMaterial under the coats
 };
 
-// ClearcoatMaterial::sample_impl :734-765 over OneSampleMaterial::sample_impl
+template <typename F>
+__device__ __forceinline__ Coats<F> walk_coats(const DScene& s, uint32_t mat, V3 wo)
+{
+    Coats<F> c;
+    c.depth = 0;
+#pragma unroll
+    for (int i = 0; i < Coats<F>::kMax; ++i) {
+        if (s.materials[mat].kind != SPCU_MAT_CLEARCOAT) {
+            break;
+        }
+        c.f[i]   = fresnel_dielectric(cos_theta(wo), 1.0f, s.materials[mat].ior);
+        c.mat[i] = mat;
+        c.depth  = i + 1;
+        mat      = s.materials[mat].base;
+    }
+    c.base = mat;
+    return c;
+}
+
+// ClearcoatMaterial::sample_impl :734-765 over OneSampleMaterial::sample_impl.  Coats are entered until one reflects
+// specularly (probability f, one draw per coat) or the base is reached; the base is sampled at ONE place, after the walk,
+// so lanes under different numbers of coats run it together.
 template <typename F>
 __device__ __forceinline__ MSample material_sample_local(const DScene& s, uint32_t mat, V3 wo, Rng& rng)
 {
-    CoatChain chain;
-    chain.depth = 0;
-    MSample r;
-    for (;;) {
-        const spcu_material& m = s.materials[mat];
-        if (m.kind == SPCU_MAT_ONE_SAMPLE) {
-            r = one_sample_sample<F>(s, m, wo, rng);
+    float    cf[Coats<F>::kMax];
+    uint32_t cm[Coats<F>::kMax];
+    int      depth    = 0;
+    bool     specular = false;
+    float    f        = 0.0f;
+#pragma unroll
+    for (int i = 0; i < Coats<F>::kMax; ++i) {
+        if (specular || s.materials[mat].kind != SPCU_MAT_CLEARCOAT) {
             break;
         }
-        const float f = fresnel_dielectric(cos_theta(wo), 1.0f, m.ior);
+        f = fresnel_dielectric(cos_theta(wo), 1.0f, s.materials[mat].ior);
         if (rng_next1(rng) < f) {
-            r.dir   = v3(-wo.x, wo.y, -wo.z);
-            r.color    = f * v3(m.specular[0], m.specular[1], m.specular[2]) / abs_cos_theta(r.dir);
-            r.pdf      = f;
-            r.specular = true;
-            break;
+            specular = true;
+        } else {
+            cf[i] = f;
+            cm[i] = mat;
+            depth = i + 1;
+            mat   = s.materials[mat].base;
         }
-        chain.f[chain.depth]   = f;
-        chain.mat[chain.depth] = mat;
-        ++chain.depth;
-        mat = m.base;
     }
-    for (int i = chain.depth - 1; i >= 0; --i) {
-        if (r.pdf == 0.0f) {
-            break; // `return base_result` at every enclosing level
+    MSample r;
+    if (specular) {
+        const spcu_material& m = s.materials[mat];
+        r.dir      = v3(-wo.x, wo.y, -wo.z);
+        r.color    = f * v3(m.specular[0], m.specular[1], m.specular[2]) / abs_cos_theta(r.dir);
+        r.pdf      = f;
+        r.specular = true;
+    } else {
+        r = one_sample_sample<F>(s, s.materials[mat], wo, rng);
+    }
+#pragma unroll
+    for (int i = Coats<F>::kMax - 1; i >= 0; --i) {
+        if (i < depth && r.pdf != 0.0f) { // pdf == 0: `return base_result` at every enclosing level
+            const spcu_material& m = s.materials[cm[i]];
+            r.pdf                  = (1.0f - cf[i]) * r.pdf;
+            r.color = (v3(1.0f, 1.0f, 1.0f) - cf[i] * v3(m.specular[0], m.specular[1], m.specular[2])) * r.color;
         }
-        const spcu_material& m = s.materials[chain.mat[i]];
-        const float          f = chain.f[i];
-        r.pdf                  = (1.0f - f) * r.pdf;
-        r.color = (v3(1.0f, 1.0f, 1.0f) - f * v3(m.specular[0], m.specular[1], m.specular[2])) * r.color;
     }
     return r;
 }
 
 // product of (1 - f) over the coats, applied innermost first as the recursion unwinds (:767-801)
-__device__ __forceinline__ uint32_t walk_coats(const DScene& s, uint32_t mat, V3 wo, CoatChain& chain)
-{
-    chain.depth = 0;
-    while (s.materials[mat].kind == SPCU_MAT_CLEARCOAT) {
-        chain.f[chain.depth] = fresnel_dielectric(cos_theta(wo), 1.0f, s.materials[mat].ior);
-        ++chain.depth;
-        mat = s.materials[mat].base;
-    }
-    return mat;
-}
-
 template <typename F>
-__device__ __forceinline__ float material_pdf_local(const DScene& s, uint32_t mat, V3 wo, V3 wi, Rng& rng)
+__device__ __forceinline__ float material_pdf_coats(const DScene& s, const Coats<F>& c, V3 wo, V3 wi, Rng& rng)
 {
-    CoatChain      chain;
-    const uint32_t base = walk_coats(s, mat, wo, chain);
-    float          pdf  = one_sample_pdf<F>(s, s.materials[base], wo, wi, rng);
-    for (int i = chain.depth - 1; i >= 0; --i) {
-        pdf = (1.0f - chain.f[i]) * pdf;
+    float pdf = one_sample_pdf<F>(s, s.materials[c.base], wo, wi, rng);
+#pragma unroll
+    for (int i = Coats<F>::kMax - 1; i >= 0; --i) {
+        if (i < c.depth) {
+            pdf = (1.0f - c.f[i]) * pdf;
+        }
     }
     return pdf;
 }
 
 template <typename F>
-__device__ __forceinline__ V3 material_eval_local(const DScene& s, uint32_t mat, V3 wo, V3 wi, Rng& rng)
+__device__ __forceinline__ V3 material_eval_coats(const DScene& s, const Coats<F>& c, V3 wo, V3 wi, Rng& rng)
 {
-    CoatChain      chain;
-    const uint32_t base = walk_coats(s, mat, wo, chain);
-    V3             f    = one_sample_eval<F>(s, s.materials[base], wo, wi, rng);
-    for (int i = chain.depth - 1; i >= 0; --i) {
-        f = (1.0f - chain.f[i]) * f;
+    V3 f = one_sample_eval<F>(s, s.materials[c.base], wo, wi, rng);
+#pragma unroll
+    for (int i = Coats<F>::kMax - 1; i >= 0; --i) {
+        if (i < c.depth) {
+            f = (1.0f - c.f[i]) * f;
+        }
     }
     return f;
+}
+
+template <typename F>
+__device__ __forceinline__ float material_pdf_local(const DScene& s, uint32_t mat, V3 wo, V3 wi, Rng& rng)
+{
+    return material_pdf_coats<F>(s, walk_coats<F>(s, mat, wo), wo, wi, rng);
+}
+
+template <typename F>
+__device__ __forceinline__ V3 material_eval_local(const DScene& s, uint32_t mat, V3 wo, V3 wi, Rng& rng)
+{
+    return material_eval_coats<F>(s, walk_coats<F>(s, mat, wo), wo, wi, rng);
 }
 
 // Material::sample (materials/Material.h:461-473): result direction returned in world space

@@ -242,10 +242,11 @@ __global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant_
             const Onb onb = onb_from_v(nn);
             const V3  wol = to_onb(onb, wo), wil = to_onb(onb, wi);
             V3        A   = v3(0, 0, 0);
-            const V3  f   = material_eval_local<F>(s, material, wol, wil, rng);
+            const Coats<F> coats = walk_coats<F>(s, material, wol);
+            const V3  f   = material_eval_coats<F>(s, coats, wol, wil, rng);
             ++calls;
             if (!is_black(f)) {
-                const float bsdf_pdf = material_pdf_local<F>(s, material, wol, wil, rng);
+                const float bsdf_pdf = material_pdf_coats<F>(s, coats, wol, wil, rng);
                 ++calls;
                 if (bsdf_pdf > 0.0f) {
                     const float weight = balance2(lpdf_s, bsdf_pdf);

@@ -3,6 +3,8 @@
 // There is no CPU fallback anywhere in this file: every entry point either runs CUDA kernels or returns an error.
 #include "ctx.h"
 
+#include <cmath>
+
 using namespace spcu;
 
 namespace spcu {
@@ -93,7 +95,16 @@ int scene_features(const spcu_flat_scene& s)
         analytic = SPCU_META_KIND(s.geom_meta[i]) != SPCU_PRIM_TRIANGLE;
     }
     for (uint32_t i = 0; analytic && i < s.n_bxdfs; ++i) {
-        analytic = s.bxdfs[i].kind == SPCU_BXDF_LAMBERT;
+        // the selection weight of a lone Lambert BxDF is lum(rho) / lum(rho), rho = r * pi: exactly 1 iff that is normal
+        const float* r   = s.bxdfs[i].r;
+        const float  pi  = 3.14159265358979323846f;
+        const float  lum = 0.2126f * (r[0] * pi) + 0.7152f * (r[1] * pi) + 0.0722f * (r[2] * pi);
+        analytic = s.bxdfs[i].kind == SPCU_BXDF_LAMBERT && std::isnormal(lum) && std::isnormal(lum / 16.0f);
+    }
+    for (uint32_t i = 0; analytic && i < s.n_materials; ++i) {
+        const spcu_material& m = s.materials[i];
+        analytic = m.kind == SPCU_MAT_ONE_SAMPLE ? m.n_bxdfs == 1
+                                                 : (m.base < s.n_materials && s.materials[m.base].kind == SPCU_MAT_ONE_SAMPLE);
     }
     for (uint32_t i = 0; analytic && i < s.n_lights; ++i) {
         analytic = s.lights[i].kind != SPCU_LIGHT_ENV_IBL;
@@ -149,6 +160,7 @@ int spcu_create(int device, spcu_ctx** out)
                     prop.minor);
     }
     auto* c     = new spcu_ctx;
+    c->options[SPCU_OPT_PIPELINE] = SPCU_PIPELINE_AUTO;
     c->device   = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -163,7 +163,7 @@ int read_back_stats(spcu_ctx* c, cudaStream_t st, spcu_stats* stats, uint64_t la
 
 // SPCU_PIPELINE_PATHS: one persistent kernel per batch (path_kernels.cu) + resolve.
 int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq, spcu_stats* stats,
-                 cudaStream_t st, uint32_t n_pix, uint32_t n_samples)
+                 cudaStream_t st, uint32_t n_pix, uint32_t n_samples, bool sm_local)
 {
     const DScene& s = c->ds;
     // batch = whole pixel list x as many samples as fit in the radiance buffer (16 B per path)
@@ -194,8 +194,13 @@ int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, floa
         for (uint32_t sb = 0; sb < n_samples; sb += smp_per_batch) {
             const uint32_t ns = std::min(smp_per_batch, n_samples - sb);
             timer.begin(kStPaths);
-            launch_paths(L, s, d_pix_list + pb, np, part->sample_begin + sb, ns, part->seed, part->integrator, d_radiance,
-                         d_counters, d_cnt);
+            if (sm_local) {
+                CK(c, launch_smwave(L, s, d_pix_list + pb, np, part->sample_begin + sb, ns, part->seed, part->integrator,
+                                    d_radiance, d_counters, d_cnt));
+            } else {
+                launch_paths(L, s, d_pix_list + pb, np, part->sample_begin + sb, ns, part->seed, part->integrator, d_radiance,
+                             d_counters, d_cnt);
+            }
             timer.end();
             timer.begin(kStResolve);
             launch_resolve(L, d_radiance, 1, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
@@ -243,8 +248,17 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
         return SPCU_OK;
     }
 
-    if (c->options[SPCU_OPT_PIPELINE] == SPCU_PIPELINE_PATHS) {
-        return render_paths(c, part, d_rgb_sum, d_lum_sumsq, stats, st, n_pix, n_samples);
+    // SPCU_PIPELINE_AUTO: the organisation that measures faster for the scene's feature set
+    uint32_t pipeline = c->options[SPCU_OPT_PIPELINE];
+    if (pipeline == SPCU_PIPELINE_AUTO) {
+        pipeline = (c->features == FeatAnalytic::id && smwave_supports(s)) ? SPCU_PIPELINE_SMWAVE : SPCU_PIPELINE_WAVEFRONT;
+    }
+    if (pipeline == SPCU_PIPELINE_SMWAVE && !smwave_supports(s)) {
+        return fail(c, SPCU_ERR_INVALID, "SPCU_PIPELINE_SMWAVE: max_depth %u / %u lights exceed its packed path flags",
+                    s.max_depth, s.n_lights);
+    }
+    if (pipeline == SPCU_PIPELINE_PATHS || pipeline == SPCU_PIPELINE_SMWAVE) {
+        return render_paths(c, part, d_rgb_sum, d_lum_sumsq, stats, st, n_pix, n_samples, pipeline == SPCU_PIPELINE_SMWAVE);
     }
 
     // batch shape: whole pixel list x as many samples as fit, or a slice of the pixel list x one sample

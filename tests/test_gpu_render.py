@@ -23,7 +23,7 @@ def lum(c):
     return 0.2126 * c[..., 0] + 0.7152 * c[..., 1] + 0.0722 * c[..., 2]
 
 
-PIPELINES = {"paths": capi.PIPELINE_PATHS, "wavefront": capi.PIPELINE_WAVEFRONT}
+PIPELINES = {"smwave": capi.PIPELINE_SMWAVE, "paths": capi.PIPELINE_PATHS, "wavefront": capi.PIPELINE_WAVEFRONT}
 CURRENT = {"pipeline": capi.PIPELINE_WAVEFRONT}
 
 

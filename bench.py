@@ -220,14 +220,14 @@ def run_cuda(args) -> None:
     paths, rays_closest, rays_any, rays_lights, launches = (float(x) for x in counts.tolist())
 
     # ---- end to end through the host-buffer C-ABI (what sp::CudaIntegrator::render_frame does) -------------------
-    h_rgb = np.zeros((h, w, 3), dtype=np.float32)
-    h_sq = np.zeros((h, w), dtype=np.float32)
+    # page-locked result buffers (the device->host read of the step's result runs at PCIe speed)
+    h_rgb = torch.empty((h, w, 3), dtype=torch.float32, pin_memory=True).numpy()
+    h_sq = torch.empty((h, w), dtype=torch.float32, pin_memory=True).numpy()
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_step():
-        h_rgb.fill(0.0); h_sq.fill(0.0)
-        ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)
-        ctx.render(part, into=(h_rgb, h_sq))
+        ctx.upload_scene(flat.pointer(), jitter, keepalive=flat)   # host -> device: the step's inputs (scene + jitter table)
+        ctx.render_frame(part, out=(h_rgb, h_sq))                  # device -> host: the step's result (overwritten, not accumulated)
 
     e2e_step()
     barrier()
@@ -275,15 +275,15 @@ def run_cuda(args) -> None:
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp_per_gpu": spp,
-                   "integrator": INTEGRATOR, "pipeline": args.pipeline, "traversal": args.traversal, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
+                   "integrator": INTEGRATOR, "pipeline": ctx.resolved_pipeline(), "pipeline_option": args.pipeline, "traversal": args.traversal, "max_depth": flat.head["max_depth"], "rr_depth": flat.head["rr_depth"],
                    "paths_per_step": int(paths), "partition": f"sample ranges x{world}, scene replicated",
                    "l2": "no explicit flush: each step streams >1 GB of wavefront state, far above the 126 MB L2"},
         "mrays_per_s": (rays_closest + rays_any) * args.steps / steps_s / 1e6,
         "rays": {"closest_per_path": rays_closest / paths, "any_hit_per_path": rays_any / paths,
                  "lights_accel_per_path": rays_lights / paths},
-        "e2e": {"value": paths * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes + acc_bytes,
+        "e2e": {"value": paths * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes,
                 "d2h_bytes_per_step": acc_bytes, "steps": e2e_steps,
-                "call": "spcu_upload_scene + spcu_render (host buffers)"},
+                "call": "spcu_upload_scene + spcu_render_frame (host buffers, page-locked result)"},
         "gpu_launches": int(launches / world * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -276,6 +276,11 @@ int spcu_generate_rays(spcu_ctx* ctx, const uint32_t* pix, const uint32_t* smp, 
  * luminance(L)^2 (may be NULL).  Host buffers, full image size, accumulated into (caller zeroes). */
 int spcu_render(spcu_ctx* ctx, const spcu_partition* part, float* rgb_sum, float* lum_sumsq,
                 spcu_stats* stats);
+/* Same work, but the outputs are OVERWRITTEN with this partition's sums (pixels outside the partition become 0): nothing
+ * is uploaded, the caller need not zero anything.  What CudaIntegrator::render_frame calls for a whole frame; with
+ * page-locked output buffers the device→host copy runs at PCIe speed. */
+int spcu_render_frame(spcu_ctx* ctx, const spcu_partition* part, float* rgb_sum, float* lum_sumsq,
+                      spcu_stats* stats);
 /* Same, accumulating into DEVICE buffers (so the caller can reduce them across GPUs with NCCL before
  * the single device→host copy).  stream = cudaStream_t as void*, NULL for the default stream. */
 int spcu_render_device(spcu_ctx* ctx, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq,
@@ -313,6 +318,9 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 #define SPCU_PIPELINE_SMWAVE 2u
 #define SPCU_PIPELINE_AUTO 3u
 int spcu_set_option(spcu_ctx* ctx, uint32_t option, uint32_t value);
+/* The kernel organisation (SPCU_PIPELINE_*) the next render of the uploaded scene will run: SPCU_OPT_PIPELINE with
+ * SPCU_PIPELINE_AUTO resolved.  -1 without a scene. */
+int spcu_resolved_pipeline(const spcu_ctx* ctx);
 
 /* Per-kernel breakdown of the LAST render call (needs SPCU_OPT_STAGE_TIMING = 1 for `ms`): one entry per wavefront
  * stage, in pipeline order.  items = queue entries the stage processed (paths, rays or vertices), counted on the device. */

@@ -107,8 +107,8 @@ class StageTime(C.Structure):
 EXPORTS = [
     "spcu_create", "spcu_destroy", "spcu_last_error", "spcu_abi_version", "spcu_upload_scene",
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
-    "spcu_generate_rays", "spcu_render", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
-    "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times",
+    "spcu_generate_rays", "spcu_render", "spcu_render_frame", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
+    "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times", "spcu_resolved_pipeline",
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
@@ -154,6 +154,8 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_generate_rays.restype = C.c_int
     lib.spcu_render.argtypes = [vp, C.POINTER(Partition), vp, vp, C.POINTER(Stats)]
     lib.spcu_render.restype = C.c_int
+    lib.spcu_render_frame.argtypes = [vp, C.POINTER(Partition), vp, vp, C.POINTER(Stats)]
+    lib.spcu_render_frame.restype = C.c_int
     lib.spcu_render_device.argtypes = [vp, C.POINTER(Partition), vp, vp, C.POINTER(Stats), vp]
     lib.spcu_render_device.restype = C.c_int
     lib.spcu_set_wavefront_size.argtypes = [vp, C.c_uint64]
@@ -289,6 +291,20 @@ class Context:
                                          C.byref(st)), "spcu_render")
         return rgb, sq, st.as_dict()
 
+    def render_frame(self, part: Partition, out=None, want_sumsq: bool = True):
+        """Host-buffer render that OVERWRITES its outputs (no accumulator upload, nothing to zero): returns
+        (rgb_sum, lum_sumsq | None, stats).  `out` = (rgb, sq) preallocated, e.g. page-locked, arrays to write into."""
+        if out is not None:
+            rgb, sq = out
+            want_sumsq = sq is not None
+        else:
+            rgb = np.empty((self.height, self.width, 3), dtype=np.float32)
+            sq = np.empty((self.height, self.width), dtype=np.float32) if want_sumsq else None
+        st = Stats()
+        self._check(self.lib.spcu_render_frame(self.h, C.byref(part), _ptr(rgb), _ptr(sq) if want_sumsq else None,
+                                               C.byref(st)), "spcu_render_frame")
+        return rgb, sq, st.as_dict()
+
     def render_device(self, part: Partition, d_rgb_sum: int, d_lum_sumsq: int | None, stream: int | None = None,
                       want_stats: bool = True) -> dict | None:
         """Accumulate into DEVICE buffers on `stream`.  Without stats the call only enqueues work (no host sync)."""
@@ -298,6 +314,13 @@ class Context:
                                                 C.byref(st) if want_stats else None,
                                                 C.c_void_p(stream) if stream else None), "spcu_render_device")
         return st.as_dict() if want_stats else None
+
+    def resolved_pipeline(self) -> str:
+        """The kernel organisation the next render runs (PIPELINE_AUTO resolved for the uploaded scene)."""
+        self.lib.spcu_resolved_pipeline.argtypes = [C.c_void_p]
+        self.lib.spcu_resolved_pipeline.restype = C.c_int
+        code = self.lib.spcu_resolved_pipeline(self.h)
+        return {PIPELINE_WAVEFRONT: "wavefront", PIPELINE_PATHS: "paths", PIPELINE_SMWAVE: "smwave"}.get(code, "none")
 
     def set_wavefront_size(self, n: int) -> None:
         self._check(self.lib.spcu_set_wavefront_size(self.h, n), "spcu_set_wavefront_size")

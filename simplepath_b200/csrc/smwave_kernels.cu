@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kSmBlock, 1)
             // can still fill half a warp, and moves the CTA on when it cannot.  The SM's L1.5 instruction cache is 32 KB and
             // the stages together are ~75 KB of SASS; with every warp on its own stage the issue slots starved on
             // instruction fetch (ncu: stall_no_instruction 2.4-6.3 cycles per issued instruction).
-            const int score = nk + ((k == preferred && nk >= 16) ? 32 : 0);
+            const int score = nk + ((k == preferred && nk >= use_affinity) ? 32 : 0);
             if (score >= best) {
                 best   = score;
                 best_n = nk;
@@ -594,8 +594,10 @@ cudaError_t launch_block(const Launch& l, const DScene& s, const uint32_t* d_pix
         return init;
     }
     static const int affinity = [] {
-        const char* e = getenv("SPCU_SMWAVE_AFFINITY"); // 0 = every warp picks the fullest queue (measured: 2.2 vs 3.3 Gpaths/s)
-        return e ? atoi(e) : 1;
+        // lane classes the CTA's current stage must still fill for a warp to stay with it; 0 = every warp picks the
+        // fullest queue (measured on example_scene: 2.2 against 3.3 Gpaths/s)
+        const char* e = getenv("SPCU_SMWAVE_AFFINITY");
+        return e ? atoi(e) : 16;
     }();
     const uint32_t n    = n_pix * n_samples;
     const unsigned grid = static_cast<unsigned>(std::max<uint32_t>(1u, std::min<uint32_t>(l.sm_count, (n + 255u) / 256u)));

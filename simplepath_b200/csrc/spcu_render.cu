@@ -217,6 +217,16 @@ int render_paths(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, floa
     return SPCU_OK;
 }
 
+// SPCU_PIPELINE_AUTO: the organisation that measures faster for the scene's feature set
+uint32_t resolve_pipeline(const spcu_ctx* c)
+{
+    const uint32_t pipeline = c->options[SPCU_OPT_PIPELINE];
+    if (pipeline != SPCU_PIPELINE_AUTO) {
+        return pipeline;
+    }
+    return (c->features == FeatAnalytic::id && smwave_supports(c->ds)) ? SPCU_PIPELINE_SMWAVE : SPCU_PIPELINE_WAVEFRONT;
+}
+
 int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq, spcu_stats* stats,
                 cudaStream_t caller_stream, bool have_caller_stream)
 {
@@ -248,11 +258,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
         return SPCU_OK;
     }
 
-    // SPCU_PIPELINE_AUTO: the organisation that measures faster for the scene's feature set
-    uint32_t pipeline = c->options[SPCU_OPT_PIPELINE];
-    if (pipeline == SPCU_PIPELINE_AUTO) {
-        pipeline = (c->features == FeatAnalytic::id && smwave_supports(s)) ? SPCU_PIPELINE_SMWAVE : SPCU_PIPELINE_WAVEFRONT;
-    }
+    const uint32_t pipeline = resolve_pipeline(c);
     if (pipeline == SPCU_PIPELINE_SMWAVE && !smwave_supports(s)) {
         return fail(c, SPCU_ERR_INVALID, "SPCU_PIPELINE_SMWAVE: max_depth %u / %u lights exceed its packed path flags",
                     s.max_depth, s.n_lights);
@@ -419,6 +425,35 @@ int spcu_render(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, float* 
     if (lum_sumsq) {
         CK(c, c->host_sq.reserve(n_pixels * sizeof(float)));
         CK(c, cudaMemcpyAsync(c->host_sq.p, lum_sumsq, n_pixels * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        d_sq = c->host_sq.as<float>();
+    }
+    if (int rc = render_impl(c, part, c->host_rgb.as<float>(), d_sq, stats, nullptr, false); rc != SPCU_OK) return rc;
+    CK(c, cudaMemcpyAsync(rgb_sum, c->host_rgb.p, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (lum_sumsq) {
+        CK(c, cudaMemcpyAsync(lum_sumsq, c->host_sq.p, n_pixels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SPCU_OK;
+}
+
+int spcu_resolved_pipeline(const spcu_ctx* c)
+{
+    return (c && c->have_scene) ? static_cast<int>(resolve_pipeline(c)) : -1;
+}
+
+int spcu_render_frame(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, float* lum_sumsq, spcu_stats* stats)
+{
+    if (int rc = need_scene(c); rc != SPCU_OK) return rc;
+    if (!rgb_sum) {
+        return fail(c, SPCU_ERR_INVALID, "rgb_sum is NULL");
+    }
+    const size_t n_pixels = static_cast<size_t>(c->ds.width) * c->ds.height;
+    CK(c, c->host_rgb.reserve(n_pixels * 3 * sizeof(float)));
+    CK(c, cudaMemsetAsync(c->host_rgb.p, 0, n_pixels * 3 * sizeof(float), c->stream));
+    float* d_sq = nullptr;
+    if (lum_sumsq) {
+        CK(c, c->host_sq.reserve(n_pixels * sizeof(float)));
+        CK(c, cudaMemsetAsync(c->host_sq.p, 0, n_pixels * sizeof(float), c->stream));
         d_sq = c->host_sq.as<float>();
     }
     if (int rc = render_impl(c, part, c->host_rgb.as<float>(), d_sq, stats, nullptr, false); rc != SPCU_OK) return rc;

@@ -133,7 +133,7 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
         m_upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     const std::size_t n = static_cast<std::size_t>(scene.image_width) * scene.image_height * 3u;
-    rgb_sum.assign(n, 0.0f);
+    rgb_sum.resize(n); // spcu_render_frame overwrites: nothing to zero, nothing to upload
 
     const auto           n_dev = static_cast<std::uint32_t>(m_devices.size());
     const std::uint32_t  code  = integrator_code(m_options.inner);
@@ -146,10 +146,10 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
         try {
             std::vector<float>& out = (k == 0) ? rgb_sum : partial[k];
             if (k != 0) {
-                out.assign(n, 0.0f);
+                out.resize(n);
             }
             const spcu_partition part{ k, n_dev, 0u, spp, spp, code, m_options.seed };
-            m_devices[k]->check(spcu_render(m_devices[k]->ctx, &part, out.data(), nullptr, &stats[k]), "spcu_render");
+            m_devices[k]->check(spcu_render_frame(m_devices[k]->ctx, &part, out.data(), nullptr, &stats[k]), "spcu_render_frame");
         } catch (const std::exception& e) {
             errors[k] = e.what();
         }

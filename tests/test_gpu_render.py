@@ -184,6 +184,19 @@ def test_feature_specialised_kernels_render_the_same_image(ctx, scene, integrato
         assert abs(st_s[key] - st_g[key]) <= 0.001 * st_g[key] + 4, (key, st_s[key], st_g[key])
 
 
+def test_render_frame_overwrites_and_equals_render(ctx, scene):
+    """spcu_render_frame = spcu_render into zeroed buffers, without the upload: bitwise the same sums, whatever the
+    output buffers held before; pixels outside a tile partition come back as 0."""
+    name, flat, vec = scene
+    upload(ctx, flat, vec["jitter"])
+    part = ctx.partition(seed=31, rank=1, world=2)
+    want, want_sq, st_w = ctx.render(part)
+    junk = (np.full_like(want, np.nan), np.full_like(want_sq, 7.0))
+    got, got_sq, st_g = ctx.render_frame(part, out=junk)
+    assert got.tobytes() == want.tobytes() and got_sq.tobytes() == want_sq.tobytes()
+    assert st_g["paths"] == st_w["paths"]
+
+
 def test_seed_changes_the_image_and_repeats_exactly(ctx, scene):
     name, flat, vec = scene
     jitter = vec["jitter"]

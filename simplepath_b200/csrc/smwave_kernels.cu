@@ -494,34 +494,41 @@ __global__ void __launch_bounds__(kSmBlock, 1)
                      kCount ? &tc : nullptr };
 
     for (;;) {
-        // the queue with the most lane classes that have an item waiting (ties: the later stage, to drain vertices)
+        // The CTA drifts through the stages together: a warp stays with the stage the CTA ran last while that queue can
+        // still fill `use_affinity` lanes, and moves the CTA on when it cannot — to the queue with the most lane classes
+        // that have an item waiting (ties: the later stage, to drain vertices).  The SM's L1.5 instruction cache is 32 KB
+        // and the stages together are ~75 KB of SASS; with every warp on its own stage the issue slots starved on
+        // instruction fetch (ncu: stall_no_instruction 2.4-6.3 cycles per issued instruction, 2.2 against 3.3 Gpaths/s).
         const volatile uint32_t* vh = &q.head[0][0];
         const volatile uint32_t* vt = &q.tail[0][0];
-        const int preferred = use_affinity ? *reinterpret_cast<volatile int*>(&q.preferred) : -1;
-        int       best = 0, stage = 0, best_n = 0;
+        int stage = -1;
+        if (use_affinity) {
+            const int preferred = *reinterpret_cast<volatile int*>(&q.preferred);
+            const int np = __popc(__ballot_sync(0xffffffffu, vh[preferred * 32 + lane] != vt[preferred * 32 + lane]));
+            if (np >= use_affinity) {
+                stage = preferred;
+            }
+        }
+        if (stage < 0) {
+            int best = 0;
 #pragma unroll
-        for (int k = 0; k < kQueues; ++k) {
-            const int nk = __popc(__ballot_sync(0xffffffffu, vh[k * 32 + lane] != vt[k * 32 + lane]));
-            // The CTA drifts through the stages together: a warp stays with the stage the CTA ran last while that queue
-            // can still fill half a warp, and moves the CTA on when it cannot.  The SM's L1.5 instruction cache is 32 KB and
-            // the stages together are ~75 KB of SASS; with every warp on its own stage the issue slots starved on
-            // instruction fetch (ncu: stall_no_instruction 2.4-6.3 cycles per issued instruction).
-            const int score = nk + ((k == preferred && nk >= use_affinity) ? 32 : 0);
-            if (score >= best) {
-                best   = score;
-                best_n = nk;
-                stage  = k;
+            for (int k = 0; k < kQueues; ++k) {
+                const int nk = __popc(__ballot_sync(0xffffffffu, vh[k * 32 + lane] != vt[k * 32 + lane]));
+                if (nk >= best) {
+                    best  = nk;
+                    stage = k;
+                }
             }
-        }
-        if (best_n == 0) {
-            if (*reinterpret_cast<volatile uint32_t*>(&q.live) == 0u) {
-                break;
+            if (best == 0) {
+                if (*reinterpret_cast<volatile uint32_t*>(&q.live) == 0u) {
+                    break;
+                }
+                __nanosleep(64);
+                continue;
             }
-            __nanosleep(64);
-            continue;
-        }
-        if (use_affinity && stage != preferred && lane == 0) {
-            *reinterpret_cast<volatile int*>(&q.preferred) = stage;
+            if (use_affinity && lane == 0) {
+                *reinterpret_cast<volatile int*>(&q.preferred) = stage;
+            }
         }
         const int   idx = q_pop(q, stage, lane);
         const State x{ st, P, static_cast<uint32_t>(max(idx, 0)) * 32u + static_cast<uint32_t>(lane) };

@@ -36,10 +36,18 @@ def load_disasm(path, needle):
 def main():
     sass_csv, dis, needle, fname = sys.argv[1:5]
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+    # the csv holds one section per profiled launch: a "Kernel Name" row, the column header, then one row per instruction;
+    # SPCU_SECTION (default 0) picks the launch
+    import os
     rows = list(csv.reader(open(sass_csv)))
-    hdr = rows[1]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = int(os.environ.get("SPCU_SECTION", "0"))
+    lo = starts[sec]
+    hi = starts[sec + 1] if sec + 1 < len(starts) else len(rows)
+    print("#", rows[lo][1][:120])
+    hdr = rows[lo + 1]
     ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) == len(hdr)]
+    data = [r for r in rows[lo + 2:hi] if len(r) == len(hdr)]
     chains = load_disasm(dis, needle)
     assert len(chains) == len(data), (len(chains), len(data))
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])

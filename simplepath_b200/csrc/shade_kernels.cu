@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(kShadeBlock) k_raygen(const __grid_constant__ 
 }
 
 // ---- shade (Integrator.cpp:558-572, 627-632): miss handling, surface interaction, primary BSDF sample S0 ---------------
+#ifndef SPCU_SHADE_MIN_BLOCKS
+#define SPCU_SHADE_MIN_BLOCKS 8 // 64 registers instead of 80 (bunny: shade 23.3 -> 22.0 ms)
+#endif
 template <typename F>
-__global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+__global__ void __launch_bounds__(kShadeBlock, SPCU_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                        const __grid_constant__ RenderParams p,
                                                        const __grid_constant__ SortedQueue sorted, uint32_t* q_live,
                                                        uint32_t* n_live, uint32_t* q_shadow, uint32_t* n_shadow,
@@ -210,8 +213,11 @@ __device__ __forceinline__ V3 light_sample_L(const DScene& s, const spcu_light& 
 }
 
 // ---- nee_bsdf (Integrator.cpp:503-530): light-strategy term, second BSDF sample, Light::pdf ----------------------------------
+#ifndef SPCU_NEE_MIN_BLOCKS
+#define SPCU_NEE_MIN_BLOCKS 8 // 64 registers instead of 122: 32 warps per SM instead of 16 (bunny: nee_bsdf 37.2 -> 32.7 ms)
+#endif
 template <typename F>
-__global__ void __launch_bounds__(kShadeBlock) k_nee_bsdf(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+__global__ void __launch_bounds__(kShadeBlock, SPCU_NEE_MIN_BLOCKS) k_nee_bsdf(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                           const __grid_constant__ RenderParams p, const uint32_t* q_shadow,
                                                           const uint32_t* n_shadow, uint32_t* q_mis, uint32_t* n_mis,
                                                           unsigned long long* counters)

@@ -469,6 +469,68 @@ __device__ __forceinline__ void closest_run(const DAccel& acc, const Prims& prim
     }
 }
 
+// ---- the same walk as single steps, for kernels that vote per step which phase the warp runs --------------------------
+// (k_extend / k_shadow: while-while leaves lanes that already hold a leaf waiting through the whole node loop — ncu on the
+// bunny scene: the slab tests ran at 5.7 of 32 lanes.)  Per lane the sequence of node and leaf steps is unchanged.
+__device__ __forceinline__ bool at_node(const ClosestWalk& w) { return w.link >= 0 && w.link != kDone; }
+__device__ __forceinline__ bool at_leaf(const ClosestWalk& w) { return w.link < 0; }
+
+// precondition: at_node(w)
+template <bool kCount>
+__device__ __forceinline__ void closest_node_step(const DAccel& acc, const Ray& r, const RayInv& inv, ClosestWalk& w,
+                                                  Stack& stack, TraceCounters* cnt)
+{
+    NodeHalf c0, c1;
+    load_node(acc.nodes, w.link, c0, c1);
+    if (kCount && !w.retest) ++cnt->nodes;
+    const bool h0 = !w.retest && slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, w.t_max);
+    const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, w.t_max);
+    if (h0) {
+        if (h1) {
+            stack.push(w.link); // right child pending: re-tested against the t_max of that moment
+        }
+        w.link   = c0.child;
+        w.count  = c0.count;
+        w.retest = false;
+    } else if (h1) {
+        w.link   = c1.child;
+        w.count  = c1.count;
+        w.retest = false;
+    } else if (stack.n > 0) {
+        w.link   = stack.pop();
+        w.retest = true;
+    } else {
+        w.link = kDone;
+    }
+}
+
+// precondition: at_leaf(w) for every lane of `mask`, the lanes that call together
+template <bool kCount, typename Prims>
+__device__ __forceinline__ void closest_leaf_step(const Prims& prims, const Ray& r, ClosestWalk& w, Stack& stack,
+                                                  TraceCounters* cnt, unsigned mask)
+{
+    float          t, b, g;
+    const uint32_t first = static_cast<uint32_t>(~w.link);
+    const uint32_t n     = w.count & SPCU_LEAF_COUNT_MASK;
+    const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
+    const uint32_t n_max = __reduce_max_sync(mask, n);
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_max; ++i) {
+        if (i < n && prims.template test<kCount>(first + i, mixed, r, w.t_max, t, b, g, cnt)) {
+            w.t_max  = t;
+            w.hit_id = static_cast<int32_t>(first + i);
+            w.beta   = b;
+            w.gamma  = g;
+        }
+    }
+    if (stack.n > 0) {
+        w.link   = stack.pop();
+        w.retest = true;
+    } else {
+        w.link = kDone;
+    }
+}
+
 // One-shot form: `t_max` enters as the query's limit and leaves as the accepted distance; returns the primitive or -1.
 template <bool kCount, typename Prims>
 __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& prims, const Ray& r, float& t_max,
@@ -728,6 +790,57 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
     stack.sh = stack_smem;
     AnyWalk w{ acc.root, acc.root_count };
     return any_run<kCount, kBvh>(acc, test, r, inv, t_max, w, stack, kAllLeaves, cnt, __activemask()) == kAnyHit;
+}
+
+// single steps of the any-hit walk (see closest_node_step)
+__device__ __forceinline__ bool at_node(const AnyWalk& w) { return w.link >= 0 && w.link != kDone; }
+__device__ __forceinline__ bool at_leaf(const AnyWalk& w) { return w.link < 0; }
+
+template <bool kCount>
+__device__ __forceinline__ void any_node_step(const DAccel& acc, const Ray& r, const RayInv& inv, float t_max, AnyWalk& w,
+                                              Stack& stack, TraceCounters* cnt)
+{
+    NodeHalf c0, c1;
+    load_node(acc.nodes, w.link, c0, c1);
+    if (kCount) ++cnt->nodes;
+    const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
+    const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
+    if (h0) {
+        if (h1) {
+            stack.push(w.link);
+        }
+        w.link  = c0.child;
+        w.count = c0.count;
+    } else if (h1) {
+        w.link  = c1.child;
+        w.count = c1.count;
+    } else {
+        any_pop(acc, stack, w);
+    }
+}
+
+// returns true when a primitive of the leaf is hit (the query is over); otherwise the walk moves on
+template <typename AnyTest>
+__device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& test, AnyWalk& w, Stack& stack,
+                                              TraceCounters* cnt, unsigned mask)
+{
+    const uint32_t first = static_cast<uint32_t>(~w.link);
+    const uint32_t n     = w.count & SPCU_LEAF_COUNT_MASK;
+    const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
+    const uint32_t n_max = __reduce_max_sync(mask, n);
+    bool           hit   = false;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_max; ++i) {
+        if (i < n && !hit && test(first + i, mixed, cnt)) {
+            hit = true;
+        }
+    }
+    if (hit) {
+        w.link = kDone;
+    } else {
+        any_pop(acc, stack, w);
+    }
+    return hit;
 }
 
 // Lights half of Scene::intersect_p: only sphere lights occlude.

@@ -135,6 +135,10 @@ __device__ __forceinline__ void segment_push(const SortedQueue& q, uint32_t seg,
 // chunk), so the whole grid drains the queue evenly and no CTA is left with a private tail.
 constexpr int      kLeavesPerRound = 2;  // leaf visits a lane may make before the warp looks for idle lanes again
 constexpr uint32_t kChunk          = 64; // queue entries a warp reserves at a time
+#ifndef SPCU_REFILL_MIN
+#define SPCU_REFILL_MIN 8
+#endif
+constexpr int      kRefillMin      = SPCU_REFILL_MIN; // idle lanes that make a refill worth its set-up code
 
 struct LaneFeed
 {
@@ -222,35 +226,53 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
     int32_t  light_id = -1;
     float    light_t  = 0.0f;
 
+    bool drained = false; // the queue has nothing left to hand out (warp uniform)
     for (;;) {
-        // ---- lanes without a ray draw the next queue entries ------------------------------------------------------------
-        const uint32_t i = feed.draw(!have);
-        if (!have && i != 0xffffffffu) {
-            slot            = queue[i];
-            const RayRec rr = w.ray[slot];
-            const float4 o = rr.o, d = rr.d;
-            r               = Ray{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
-            inv            = make_inv(r);
-            float t_max = d.w, beta, gamma;
-            // Scene::intersect_lights (a handful of lights: walked in one go)
-            const LightPrimsT<F> lp{ s.lights };
-            const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack_smem + threadIdx.x, nullptr);
-            light_id            = li;
-            light_t             = t_max;
-            walk.t_max          = t_max;
-            closest_begin<kCount>(s.geom, gp, r, walk, &local);
-            stack.n = ostack.n = 0;
-            have               = true;
-            ++traced;
-        }
-        if (__ballot_sync(0xffffffffu, have) == 0u) {
+        // ---- phase vote: what do the lanes of this warp hold? ----------------------------------------------------------
+        const int n_node = __popc(__ballot_sync(0xffffffffu, have && at_node(walk)));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && at_leaf(walk)));
+        const int n_idle = 32 - __popc(__ballot_sync(0xffffffffu, have));
+        // ---- refill: lanes without a ray draw the next queue entries, once enough of them wait (the set-up — ray record,
+        // lights accelerator, unbounded primitives — is itself a hundred instructions: better run it for many lanes) ------
+        if (!drained && (n_idle >= kRefillMin || n_node + n_leaf == 0)) {
+            const uint32_t i = feed.draw(!have);
+            drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
+            if (!have && i != 0xffffffffu) {
+                slot            = queue[i];
+                const RayRec rr = w.ray[slot];
+                const float4 o = rr.o, d = rr.d;
+                r               = Ray{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
+                inv            = make_inv(r);
+                float t_max = d.w, beta, gamma;
+                // Scene::intersect_lights (a handful of lights: walked in one go)
+                const LightPrimsT<F> lp{ s.lights };
+                const int32_t    li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack_smem + threadIdx.x, nullptr);
+                light_id            = li;
+                light_t             = t_max;
+                walk.t_max          = t_max;
+                closest_begin<kCount>(s.geom, gp, r, walk, &local);
+                stack.n = ostack.n = 0;
+                have               = true;
+                ++traced;
+            }
+        } else if (n_node + n_leaf == 0) {
             break; // nothing in flight and nothing left to draw
-        }
-        // ---- a bounded piece of every lane's walk (lanes without a ray vote along with a finished cursor) -----------------
-        if (kOrdered) {
+        } else if (kOrdered) {
+            // ---- a bounded piece of every lane's walk (lanes without a ray vote along with a finished cursor) -----------
             closest_run_ordered<kCount>(s.geom, gp, r, inv, walk, ostack, kLeavesPerRound, &local, 0xffffffffu);
-        } else {
+        } else if (!F::bvh) {
             closest_run<kCount>(s.geom, gp, r, inv, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
+        } else if (n_node >= n_leaf) {
+            // ---- ONE step of the phase most lanes are in: an internal node (both child boxes) ... ---------------------------
+            if (have && at_node(walk)) {
+                closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
+            }
+        } else {
+            // ---- ... or a leaf (its primitives in list order) --------------------------------------------------------------
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
+            if (have && at_leaf(walk)) {
+                closest_leaf_step<kCount>(gp, r, walk, stack, &local, leaf_mask);
+            }
         }
         if (have && walk.link == kDone) {
             ExtendRec ex;
@@ -303,42 +325,61 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
     bool     have   = false;
     int      status = kAnyMiss;
 
+    bool drained = false;
+    auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
+        float t, b, g;
+        return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
+    };
     for (;;) {
-        const uint32_t i = feed.draw(!have);
-        if (!have && i != 0xffffffffu) {
-            slot              = queue[i];
-            const float4   p  = w.vertex[slot].p;
-            const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
-            r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
-            inv               = make_inv(r);
-            t_max             = lr.wi.w;
-            stack.n        = 0;
-            walk           = AnyWalk{ s.geom.root, s.geom.root_count };
-            have           = true;
-            status         = kAnyRunning;
-            ++traced;
-            // ListAccelerator::intersect_p_impl: unbounded primitives first
-            for (uint32_t k = 0; k < s.geom.n_unbounded; ++k) {
-                float t, b, g;
-                if (gp.template test<kCount>(k, true, r, t_max, t, b, g, &local)) {
-                    status    = kAnyHit;
-                    walk.link = kDone;
-                    break;
+        const int n_node = __popc(__ballot_sync(0xffffffffu, have && at_node(walk)));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && at_leaf(walk)));
+        const int n_idle = 32 - __popc(__ballot_sync(0xffffffffu, have));
+        if (!drained && (n_idle >= kRefillMin || n_node + n_leaf == 0)) {
+            const uint32_t i = feed.draw(!have);
+            drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
+            if (!have && i != 0xffffffffu) {
+                slot              = queue[i];
+                const float4   p  = w.vertex[slot].p;
+                const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
+                r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
+                inv               = make_inv(r);
+                t_max             = lr.wi.w;
+                stack.n        = 0;
+                walk           = AnyWalk{ s.geom.root, s.geom.root_count };
+                have           = true;
+                status         = kAnyRunning;
+                ++traced;
+                // ListAccelerator::intersect_p_impl: unbounded primitives first
+                for (uint32_t k = 0; k < s.geom.n_unbounded; ++k) {
+                    float t, b, g;
+                    if (gp.template test<kCount>(k, true, r, t_max, t, b, g, &local)) {
+                        status    = kAnyHit;
+                        walk.link = kDone;
+                        break;
+                    }
                 }
             }
-        }
-        if (__ballot_sync(0xffffffffu, have) == 0u) {
+        } else if (n_node + n_leaf == 0) {
             break;
-        }
-        {
-            auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
-                float t, b, g;
-                return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
-            };
-            const int st = any_run<kCount, F::bvh>(s.geom, geom_test, r, inv, t_max, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
+        } else if (!F::bvh) {
+            const int st = any_run<kCount, false>(s.geom, geom_test, r, inv, t_max, walk, stack, kLeavesPerRound, &local, 0xffffffffu);
             if (have && status == kAnyRunning) {
                 status = st;
             }
+        } else if (n_node >= n_leaf) {
+            if (have && at_node(walk)) {
+                any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+            }
+        } else {
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
+            if (have && at_leaf(walk)) {
+                if (any_leaf_step(s.geom, geom_test, walk, stack, &local, leaf_mask)) {
+                    status = kAnyHit;
+                }
+            }
+        }
+        if (have && status == kAnyRunning && walk.link == kDone) {
+            status = kAnyMiss;
         }
         if (have && status != kAnyRunning) {
             // Scene::intersect_p: geometry, then the lights accelerator (base/Scene.h:79-82)

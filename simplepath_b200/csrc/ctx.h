@@ -50,7 +50,7 @@ struct DevBuf
     }
 };
 
-constexpr int      kNumQueues      = 6;        // cur, next, live, shadow, lit, mis
+constexpr int      kNumQueues      = 7;        // cur, next, live, shadow, lit, mis, walk
 constexpr int      kMaxQueueCounts = 4096;     // device queue-length words zeroed once per batch
 constexpr uint64_t kBatchRays      = 1u << 22; // rays per chunk of the batch query entry points
 constexpr uint32_t kMaxMaterialSegments = 15;  // materials beyond share the last segment

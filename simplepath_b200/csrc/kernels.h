@@ -19,14 +19,16 @@ void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, sp
 // Wavefront stages that traverse.  `queue` holds path slots; n_queue is read on the device (no host sync).
 // d_cursor (extend, shadow): a zeroed uint32 in device memory, the stage's global work cursor.
 // extend: Scene::intersect_lights then Scene::intersect for every queued path (Integrator.cpp:558-563).
-void launch_extend(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered,
-                   unsigned long long* d_counters, TraceCounters* d_cnt);
+// q_walk / d_n_walk: a queue (and its zeroed length) for the two-kernel form — `begin` finishes the rays that end at the root
+// of the BVH and parks the others there for the persistent `walk` kernel; NULL: one kernel.  Returns the kernels launched.
+int launch_extend(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                  uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered, uint32_t* q_walk,
+                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt);
 // shadow: Scene::intersect_p of the light-sample visibility ray (Integrator.cpp:503).
 // Unoccluded entries are compacted into q_lit (may be NULL: then only the per-slot flag is written).
-void launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit,
-                   unsigned long long* d_counters, TraceCounters* d_cnt);
+int launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                  uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit, uint32_t* q_walk,
+                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt);
 // mis: Scene::intersect_lights then, on a light hit, Scene::intersect_p of the BSDF-sampled ray (Integrator.cpp:531-532).
 void launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
                       const uint32_t* d_n_queue, uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);

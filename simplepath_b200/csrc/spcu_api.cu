@@ -62,6 +62,9 @@ int validate_accel(spcu_ctx* c, const spcu_accel& a, const char* what)
     if (a.n_unbounded > a.n_prims) {
         return fail(c, SPCU_ERR_INVALID, "%s: n_unbounded > n_prims", what);
     }
+    if (a.n_nodes >= (1u << 30) || a.n_prims >= (1u << 30)) { // traversal cursors keep a flag in bit 30 (trace_kernels.cu)
+        return fail(c, SPCU_ERR_LIMIT, "%s: more than 2^30 nodes or primitives", what);
+    }
     if (a.max_depth > SPCU_MAX_BVH_DEPTH) {
         return fail(c, SPCU_ERR_LIMIT, "%s: BVH depth %u exceeds SPCU_MAX_BVH_DEPTH", what, a.max_depth);
     }

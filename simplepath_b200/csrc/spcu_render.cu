@@ -15,7 +15,7 @@ using namespace spcu;
 
 namespace {
 
-enum Queue { kQCur = 0, kQNext, kQLive, kQShadow, kQLit, kQMis };
+enum Queue { kQCur = 0, kQNext, kQLive, kQShadow, kQLit, kQMis, kQWalk };
 constexpr int kCounterBlock = kNumCounters + kNumStages; // + per-stage item counters
 
 const char* const kStageNames[kNumStages] = { "raygen",   "extend",    "shade",     "nee_light",         "shadow",           "nee_bsdf",
@@ -286,7 +286,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     const bool     whitted     = part->integrator == SPCU_INTEGRATOR_WHITTED;
     const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || whitted; // per-light direct term
     const uint32_t n_segments  = std::min<uint32_t>(c->n_materials, kMaxMaterialSegments) + 1u; // + the miss segment
-    const uint32_t counts_need = 1 + max_depth * (3 + 4 * n_lights + n_segments);
+    const uint32_t counts_need = 1 + max_depth * (4 + 5 * n_lights + n_segments);
     CK(c, c->sorted_queue.reserve(static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)));
     if (counts_need > static_cast<uint32_t>(kMaxQueueCounts)) {
         return fail(c, SPCU_ERR_LIMIT, "max_depth x lights needs %u queue counters (limit %d)", counts_need, kMaxQueueCounts);
@@ -329,9 +329,10 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 SortedQueue sorted{ c->sorted_queue.as<uint32_t>(), d_counts + next_count, n_segments, capacity };
                 next_count += n_segments;
                 timer.begin(kStExtend);
-                launch_extend(L, s, c->wave, q_cur, n_cur, max_n, new_count(), sorted,
-                              c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED,
-                              d_counters, d_cnt);
+                uint32_t* cursor = new_count();
+                launches += launch_extend(L, s, c->wave, q_cur, n_cur, max_n, cursor, sorted,
+                                          c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED, q[kQWalk], new_count(),
+                                          d_counters, d_cnt);
                 timer.end();
                 uint32_t* n_live   = new_count();
                 uint32_t* n_shadow = d_counts + next_count; // one shadow queue (and counter) per light
@@ -340,17 +341,17 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 timer.begin(kStShade);
                 launch_shade(L, s, c->wave, p, sorted, max_n, q[kQLive], n_live, q_shadow, n_shadow, d_counters);
                 timer.end();
-                launches += 2;
+                launches += 1;
                 if (nee || direct) {
                     for (uint32_t li = 0; li < n_lights; ++li) {
                         p.light_index           = li;
                         uint32_t* q_shadow_l    = q_shadow + static_cast<size_t>(li) * capacity;
                         uint32_t* n_lit         = direct ? nullptr : new_count();
                         timer.begin(kStShadow);
-                        launch_shadow(L, s, c->wave, q_shadow_l, n_shadow + li, max_n, li, new_count(), direct ? nullptr : q[kQLit], n_lit,
-                                      d_counters, d_cnt);
+                        uint32_t* cursor_l = new_count();
+                        launches += launch_shadow(L, s, c->wave, q_shadow_l, n_shadow + li, max_n, li, cursor_l,
+                                                  direct ? nullptr : q[kQLit], n_lit, q[kQWalk], new_count(), d_counters, d_cnt);
                         timer.end();
-                        launches += 1;
                         if (direct) {
                             timer.begin(kStDirectAccumulate);
                             launch_direct_accumulate(L, s, c->wave, p, q_shadow_l, n_shadow + li, max_n, d_counters);

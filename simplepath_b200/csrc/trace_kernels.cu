@@ -139,6 +139,10 @@ constexpr uint32_t kChunk          = 64; // queue entries a warp reserves at a t
 #define SPCU_REFILL_MIN 8
 #endif
 constexpr int      kRefillMin      = SPCU_REFILL_MIN; // idle lanes that make a refill worth its set-up code
+#ifndef SPCU_WALK_REFILL_MIN
+#define SPCU_WALK_REFILL_MIN 4
+#endif
+constexpr int      kWalkRefillMin  = SPCU_WALK_REFILL_MIN; // ... when the set-up is three loads (the begin / walk kernels)
 
 struct LaneFeed
 {
@@ -292,6 +296,312 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
     if ((threadIdx.x & 31) == 0 && total) {
         atomicAdd(counters + kCntRaysClosest, static_cast<unsigned long long>(total));
         atomicAdd(counters + kCntRaysLights, static_cast<unsigned long long>(total));
+    }
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-kernel form of the traversal stages for scenes with a BVH (exact walk): `begin` + `walk`.
+//
+// Half of the rays of a path-traced frame never get past the root of the BVH (bunny scene: median 1 node visit), and
+// every ray needs the same hundred instructions of set-up before its walk (ray record, lights accelerator, unbounded
+// primitives).  In the persistent walk kernel those were run for whichever few lanes happened to be idle.  `begin` runs
+// them for ALL rays at full warps — set-up, then the root node's two child boxes — finishes the rays that end there and
+// parks the others (cursor, leaf count, "root's right child pending") in the two spare words of their ExtendRec; `walk`
+// is the persistent phase-voted kernel, whose refill is now three loads.
+//
+// Parked cursor: link with bit 30 flipped when the root is on the stack (node and primitive indices stay below 2^30,
+// checked at upload).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int32_t kPendingBit = 0x40000000;
+__device__ __forceinline__ int32_t park_link(int32_t link, bool root_pending) { return root_pending ? (link ^ kPendingBit) : link; }
+__device__ __forceinline__ int32_t unpark_link(int32_t parked, bool& root_pending)
+{
+    root_pending = parked >= 0 ? (parked & kPendingBit) != 0 : (parked & kPendingBit) == 0;
+    return root_pending ? (parked ^ kPendingBit) : parked;
+}
+
+template <bool kCount, typename F>
+__global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                              const uint32_t* queue, const uint32_t* n_queue,
+                                                              uint32_t* q_walk, uint32_t* n_walk,
+                                                              const __grid_constant__ SortedQueue sorted,
+                                                              unsigned long long* counters, TraceCounters* cnt)
+{
+    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    const uint32_t     n = *n_queue;
+    count_items(counters, kStExtend, n);
+    TraceCounters       local{ 0, 0, 0 };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
+    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
+        const uint32_t i      = base + threadIdx.x;
+        const bool     active = i < n;
+        bool           done = false, parked = false;
+        uint32_t       slot = 0, seg = 0;
+        if (active) {
+            slot            = queue[i];
+            const RayRec rr = w.ray[slot];
+            const float4 o = rr.o, d = rr.d;
+            const Ray    r{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
+            float        t_max = d.w, beta, gamma;
+            // Scene::intersect_lights (a handful of lights: walked in one go); a light hit shrinks t_max for the geometry
+            const LightPrimsT<F> lp{ s.lights };
+            const int32_t        li = closest_hit<false>(s.lights_accel, lp, r, t_max, beta, gamma, stack_smem + threadIdx.x, nullptr);
+            ExtendRec            ex;
+            ex.light   = li;
+            ex.light_t = t_max;
+            ClosestWalk walk;
+            walk.t_max = t_max;
+            closest_begin<kCount>(s.geom, gp, r, walk, &local); // unbounded primitives; cursor at the root
+            Stack stack;
+            stack.sh = stack_smem + threadIdx.x;
+            const RayInv inv = make_inv(r);
+            if (at_node(walk)) {
+                closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local); // the root's two child boxes
+            } else if (at_leaf(walk)) {
+                closest_run<kCount>(s.geom, gp, r, inv, walk, stack, kAllLeaves, &local, __activemask()); // the root is a leaf
+            }
+            ex.hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
+            done   = walk.link == kDone;
+            parked = !done;
+            ex.pad[0] = __int_as_float(park_link(walk.link, stack.n > 0));
+            ex.pad[1] = __uint_as_float(walk.count);
+            w.extend[slot] = ex;
+            // finished vertices go to the shading stage sorted by material: misses in the last segment
+            seg = walk.hit_id < 0 ? sorted.n_segments - 1u
+                                  : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + walk.hit_id)), sorted.n_segments - 2u);
+        }
+        segment_push(sorted, seg, slot, done);
+        queue_push(q_walk, n_walk, slot, parked);
+        warp_count(counters + kCntRaysClosest, active);
+        warp_count(counters + kCntRaysLights, active);
+    }
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+template <bool kCount, typename F>
+__global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                             const uint32_t* q_walk, const uint32_t* n_walk, uint32_t* cursor,
+                                                             const __grid_constant__ SortedQueue sorted, TraceCounters* cnt)
+{
+    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    LaneFeed           feed;
+    feed.cursor = cursor;
+    feed.n      = *n_walk;
+
+    TraceCounters       local{ 0, 0, 0 };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
+    Stack               stack;
+    stack.sh = stack_smem + threadIdx.x;
+    Ray         r{};
+    RayInv      inv{};
+    ClosestWalk walk{};
+    walk.link     = kDone;
+    uint32_t slot = 0;
+    bool     have = false, drained = false;
+
+    for (;;) {
+        const int n_node = __popc(__ballot_sync(0xffffffffu, have && at_node(walk)));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && at_leaf(walk)));
+        if (!drained && (32 - n_node - n_leaf >= kWalkRefillMin || n_node + n_leaf == 0)) {
+            const uint32_t i = feed.draw(!have);
+            drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
+            if (!have && i != 0xffffffffu) {
+                slot               = q_walk[i];
+                const RayRec    rr = w.ray[slot];
+                const ExtendRec ex = w.extend[slot];
+                r                  = Ray{ rr.o.x, rr.o.y, rr.o.z, rr.d.x, rr.d.y, rr.d.z, rr.o.w };
+                inv                = make_inv(r);
+                bool root_pending;
+                walk.link   = unpark_link(__float_as_int(ex.pad[0]), root_pending);
+                walk.count  = __float_as_uint(ex.pad[1]);
+                walk.retest = false;
+                walk.hit_id = ex.hit.id;
+                walk.t_max  = ex.hit.t;
+                walk.beta   = ex.hit.beta;
+                walk.gamma  = ex.hit.gamma;
+                stack.n     = 0;
+                if (root_pending) {
+                    stack.push(s.geom.root);
+                }
+                have = true;
+            }
+        } else if (n_node + n_leaf == 0) {
+            break;
+        } else if (n_node >= n_leaf) {
+            if (have && at_node(walk)) {
+                closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
+            }
+        } else {
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
+            if (have && at_leaf(walk)) {
+                closest_leaf_step<kCount>(gp, r, walk, stack, &local, leaf_mask);
+            }
+        }
+        if (have && walk.link == kDone) {
+            w.extend[slot].hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
+            const uint32_t seg = walk.hit_id < 0 ? sorted.n_segments - 1u
+                                                 : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + walk.hit_id)), sorted.n_segments - 2u);
+            segment_push_converged(sorted, seg, slot);
+            have = false;
+        }
+    }
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+// shadow_begin: the visibility ray's set-up, the unbounded primitives, the lights accelerator (Scene::intersect_p is an
+// OR over both accelerators: base/Scene.h:79-82, so their order is free) and the root's two child boxes.
+template <bool kCount, typename F>
+__global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                              const uint32_t* queue, const uint32_t* n_queue, uint32_t light_index,
+                                                              uint32_t* q_walk, uint32_t* n_walk, uint32_t* q_lit, uint32_t* n_lit,
+                                                              unsigned long long* counters, TraceCounters* cnt)
+{
+    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    const uint32_t     n = *n_queue;
+    count_items(counters, kStShadow, n);
+    TraceCounters       local{ 0, 0, 0 };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
+    for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
+        const uint32_t i      = base + threadIdx.x;
+        const bool     active = i < n;
+        bool           lit = false, parked = false;
+        uint32_t       slot = 0;
+        if (active) {
+            slot              = queue[i];
+            const float4   p  = w.vertex[slot].p;
+            const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
+            const Ray      r{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
+            const float    t_max = lr.wi.w;
+            bool           hit   = false;
+            // ListAccelerator::intersect_p_impl: unbounded primitives first
+            for (uint32_t k = 0; k < s.geom.n_unbounded && !hit; ++k) {
+                float t, b, g;
+                hit = gp.template test<kCount>(k, true, r, t_max, t, b, g, &local);
+            }
+            if (!hit) {
+                hit = lights_any_hit<F>(s, r, t_max, stack_smem + threadIdx.x);
+            }
+            AnyWalk walk{ kDone, 0 };
+            Stack   stack;
+            stack.sh = stack_smem + threadIdx.x;
+            if (!hit) {
+                walk = AnyWalk{ s.geom.root, s.geom.root_count };
+                const RayInv inv = make_inv(r);
+                if (at_node(walk)) {
+                    any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+                } else if (at_leaf(walk)) {
+                    auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
+                        float t, b, g;
+                        return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
+                    };
+                    hit = any_run<kCount, true>(s.geom, geom_test, r, inv, t_max, walk, stack, kAllLeaves, &local, __activemask()) == kAnyHit;
+                    walk.link = kDone;
+                }
+            }
+            parked = !hit && walk.link != kDone;
+            lit    = !hit && !parked;
+            if (parked) {
+                w.extend[slot].pad[0] = __int_as_float(park_link(walk.link, stack.n > 0));
+                w.extend[slot].pad[1] = __uint_as_float(walk.count);
+            } else if (!q_lit) {
+                w.occluded[slot] = hit ? 1 : 0; // direct lighting reads the flag; the NEE path gets the compacted queue
+            }
+        }
+        if (q_lit) { // survivors only go on to the BSDF stages (Integrator.cpp:503-506)
+            queue_push(q_lit, n_lit, slot, lit);
+        }
+        queue_push(q_walk, n_walk, slot, parked);
+        warp_count(counters + kCntRaysAny, active);
+    }
+    if (kCount) {
+        flush_counters(local, cnt);
+    }
+}
+
+template <bool kCount, typename F>
+__global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+                                                             const uint32_t* q_walk, const uint32_t* n_walk, uint32_t light_index,
+                                                             uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit, TraceCounters* cnt)
+{
+    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    LaneFeed           feed;
+    feed.cursor = cursor;
+    feed.n      = *n_walk;
+
+    TraceCounters       local{ 0, 0, 0 };
+    const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
+    Stack               stack;
+    stack.sh = stack_smem + threadIdx.x;
+    Ray      r{};
+    RayInv   inv{};
+    AnyWalk  walk{ kDone, 0 };
+    float    t_max = 0.0f;
+    uint32_t slot  = 0;
+    bool     have = false, drained = false, hit = false;
+    auto     geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
+        float t, b, g;
+        return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
+    };
+
+    for (;;) {
+        const int n_node = __popc(__ballot_sync(0xffffffffu, have && at_node(walk)));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && at_leaf(walk)));
+        if (!drained && (32 - n_node - n_leaf >= kWalkRefillMin || n_node + n_leaf == 0)) {
+            const uint32_t i = feed.draw(!have);
+            drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
+            if (!have && i != 0xffffffffu) {
+                slot              = q_walk[i];
+                const float4   p  = w.vertex[slot].p;
+                const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
+                const ExtendRec ex = w.extend[slot];
+                r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
+                inv               = make_inv(r);
+                t_max             = lr.wi.w;
+                bool root_pending;
+                walk.link  = unpark_link(__float_as_int(ex.pad[0]), root_pending);
+                walk.count = __float_as_uint(ex.pad[1]);
+                stack.n    = 0;
+                if (root_pending) {
+                    stack.push(s.geom.root);
+                }
+                have = true;
+                hit  = false;
+            }
+        } else if (n_node + n_leaf == 0) {
+            break;
+        } else if (n_node >= n_leaf) {
+            if (have && at_node(walk)) {
+                any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+            }
+        } else {
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
+            if (have && at_leaf(walk)) {
+                hit = any_leaf_step(s.geom, geom_test, walk, stack, &local, leaf_mask);
+            }
+        }
+        if (have && walk.link == kDone) {
+            if (!q_lit) {
+                w.occluded[slot] = hit ? 1 : 0;
+            } else if (!hit) {
+                const unsigned act    = __activemask();
+                const int      lane   = threadIdx.x & 31;
+                const int      leader = __ffs(act) - 1;
+                uint32_t       base   = 0;
+                if (lane == leader) {
+                    base = atomicAdd(n_lit, static_cast<uint32_t>(__popc(act)));
+                }
+                base = __shfl_sync(act, base, leader);
+                q_lit[base + __popc(act & ((1u << lane) - 1u))] = slot;
+            }
+            have = false;
+        }
     }
     if (kCount) {
         flush_counters(local, cnt);
@@ -530,16 +840,39 @@ static void launch_extend_features(const Launch& l, const DScene& s, const DWave
     }
 }
 
-void launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered,
-                   unsigned long long* d_counters, TraceCounters* d_cnt)
+// begin + walk (scenes with a BVH, exact walk)
+template <bool kCount>
+static void launch_extend_split(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                                uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, uint32_t* q_walk, uint32_t* d_n_walk,
+                                unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    if (max_n == 0) return;
+    static const int occ_b = trace_ctas_per_sm(k_extend_begin<kCount, FeatFull>);
+    static const int occ_w = trace_ctas_per_sm(k_extend_walk<kCount, FeatFull>);
+    k_extend_begin<kCount, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
+        s, w, queue, d_n_queue, q_walk, d_n_walk, sorted, d_counters, d_cnt);
+    k_extend_walk<kCount, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
+        s, w, q_walk, d_n_walk, d_cursor, sorted, d_cnt);
+}
+
+int launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                  uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered, uint32_t* q_walk,
+                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt)
+{
+    if (max_n == 0) return 0;
     if (l.features == FeatAnalytic::id) {
         launch_extend_features<FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
-    } else {
-        launch_extend_features<FeatFull>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
+        return 1;
     }
+    if (ordered || !q_walk) {
+        launch_extend_features<FeatFull>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
+        return 1;
+    }
+    if (d_cnt) {
+        launch_extend_split<true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt);
+    } else {
+        launch_extend_split<false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr);
+    }
+    return 2;
 }
 
 template <bool kCount, typename F>
@@ -552,12 +885,23 @@ static void launch_shadow_variant(const Launch& l, const DScene& s, const DWave&
         s, w, queue, d_n_queue, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
 }
 
-void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                   uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit,
-                   unsigned long long* d_counters, TraceCounters* d_cnt)
+int launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                  uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit, uint32_t* q_walk,
+                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    if (max_n == 0) return;
+    if (max_n == 0) return 0;
     const bool analytic = l.features == FeatAnalytic::id;
+    if (!analytic && !d_cnt && q_walk) {
+        // begin + walk.  (Not with node counting: `begin` asks the lights accelerator before the BVH, which skips node
+        // visits the reference order would count.)
+        static const int occ_b = trace_ctas_per_sm(k_shadow_begin<false, FeatFull>);
+        static const int occ_w = trace_ctas_per_sm(k_shadow_walk<false, FeatFull>);
+        k_shadow_begin<false, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, queue, d_n_queue, light_index, q_walk, d_n_walk, q_lit, d_n_lit, d_counters, nullptr);
+        k_shadow_walk<false, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, q_walk, d_n_walk, light_index, d_cursor, q_lit, d_n_lit, nullptr);
+        return 2;
+    }
     if (d_cnt) {
         analytic ? launch_shadow_variant<true, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt)
                  : launch_shadow_variant<true, FeatFull>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, d_cnt);
@@ -565,6 +909,7 @@ void launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint3
         analytic ? launch_shadow_variant<false, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr)
                  : launch_shadow_variant<false, FeatFull>(l, s, w, queue, d_n_queue, max_n, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
     }
+    return 1;
 }
 
 template <bool kCount, typename F>

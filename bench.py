@@ -63,11 +63,13 @@ STAGE_BYTES = {
 NODE_BYTES, TRI_BYTES, XF_BYTES = 64, 48, 96
 
 
-def measured_traffic_per_item(stage: str, workload: str) -> tuple[float | None, str | None]:
+def measured_traffic_per_item(stage: str, workload: str, pipeline: str | None = None) -> tuple[float | None, str | None]:
     """DRAM bytes per item of a stage as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum over every
     launch of one render of this workload, divided by the stage's items: profiles/traffic_probe.py + traffic_join.py)."""
     for path in sorted((ROOT / "profiles").glob("ncu_traffic_r*.json"), reverse=True):
         d = json.loads(path.read_text())
+        if pipeline is not None and d.get("probe", {}).get("pipeline") != pipeline:
+            continue
         if d.get("probe", {}).get("workload") == workload and stage in d.get("stages", {}):
             v = d["stages"][stage].get("dram_bytes_per_item")
             if v is not None:
@@ -265,7 +267,7 @@ def run_cuda(args) -> None:
     dur_s = stage_ms[dominant] / 1e3 / n_launch
     achieved = bytes_total / n_launch / dur_s / 1e9 if dur_s > 0 else 0.0
     kernel_ms = sum(stage_ms.values())
-    traffic_item, traffic_src = measured_traffic_per_item(dominant, args.workload)
+    traffic_item, traffic_src = measured_traffic_per_item(dominant, args.workload, ctx.resolved_pipeline())
 
     cpu = cpu_baseline(scene_name, flat) if world == 1 and not args.no_cpu else None
 

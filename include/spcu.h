@@ -341,6 +341,37 @@ uint64_t spcu_scene_bytes(const spcu_ctx* ctx);
  * triangle tests, sphere/plane tests } — the N_node / N_tri / N_xf of the byte model in DESIGN.md. */
 int spcu_trace_closest_counted(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits, uint64_t counters[3]);
 
+/* ---- acceleration-structure construction on the device ------------------------------------- */
+/* World bounds of one bounded primitive, Hitable::get_world_bounds (shapes/Hitable.h:32-35): lower xyz, upper xyz. */
+typedef struct spcu_bounds {
+    float lo[3];
+    float hi[3];
+} spcu_bounds;
+
+/* BVHAccelerator(first, last) (shapes/BVHAccelerator.h:123-129) = construct (:175-209): a node over [first, last) holds
+ * the merged bounds of its primitives (math/BBox.h:60-64, folded in range order); <= k_max_leaf_elements (4, :211)
+ * primitives make a leaf; otherwise the range is std::partition'ed (libstdc++'s bidirectional Hoare scheme, whose
+ * resulting ORDER is part of the contract because primitive IDs are positions) by
+ * center(prim bounds)[d] < center(node bounds)[d] with d = max_dim(size(node bounds)) (math/Vector3.h:653-670), and a
+ * partition with an empty side makes a leaf of any size.
+ *   bounds[n]        primitive bounds in the order the reference holds them BEFORE construction (host)
+ *   non_triangle[n]  may be NULL; 1 marks a sphere (sets SPCU_LEAF_MIXED_FLAG on its leaf)
+ *   first_id         ID of leaf position 0 (= spcu_accel.n_unbounded of the accelerator being built)
+ *   order[n]         out: order[k] = index into bounds[] of the primitive at leaf position k (ID first_id + k)
+ *   nodes[capacity]  out: internal nodes in the flattener's numbering (depth-first pre-order, left subtree first);
+ *                    at most max(n, 1) - 1 are produced
+ *   accel            out: n_prims, n_unbounded, n_nodes, root, root_count, max_depth (nodes = the caller's pointer)
+ *   device_ms        out, may be NULL: CUDA-event time of the construction kernels (copies excluded)
+ * Produces, bit for bit, the arrays the flattener emits for the tree the reference builds from the same sequence
+ * (oracle/ref_harness.cpp spref_build_bvh; tests/test_gpu_build.py).  Finite, non-NaN bounds with lo <= hi are required;
+ * SPCU_ERR_LIMIT when the tree is deeper than SPCU_MAX_BVH_DEPTH or needs more than `capacity` nodes. */
+int spcu_build_bvh(spcu_ctx* ctx, const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id,
+                   uint32_t* order, spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* device_ms);
+
+/* Triangle::get_world_bounds_impl (shapes/Triangle.h:228-237): BBox::extend over the three world-space vertices of
+ * tris[i] (layout of spcu_prim_geom), in vertex order.  Host pointers. */
+int spcu_triangle_bounds(spcu_ctx* ctx, const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ from pathlib import Path
 
 import numpy as np
 
-from simplepath_b200.capi import FlatScene, HIT_DTYPE, RAY_DTYPE, Light, Partition, Stats
+from simplepath_b200.capi import Accel, FlatScene, HIT_DTYPE, RAY_DTYPE, Light, Partition, Stats, run_build
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libsp_oracle.so"
@@ -95,4 +95,28 @@ def rng4(seed: int, pixel: int, sample: int, stream: int, ctr: int) -> np.ndarra
     l.spo_rng4.restype = None
     out = np.zeros(4, dtype=np.float32)
     l.spo_rng4(seed, pixel, sample, stream, ctr, _p(out))
+    return out
+
+
+def build_bvh(bounds, non_triangle=None, first_id: int = 0, capacity: int | None = None) -> dict:
+    """spo_build_bvh: {nodes, order, head, root_bounds}."""
+    l = lib()
+    l.spo_build_bvh.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                C.POINTER(Accel), C.c_void_p]
+    l.spo_build_bvh.restype = C.c_int
+    bounds = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 6)
+
+    def call(*a):
+        if l.spo_build_bvh(*a) != 0:
+            raise RuntimeError("spo_build_bvh: node capacity exceeded")
+    return run_build(call, bounds, non_triangle, first_id, capacity, with_ms=False)
+
+
+def triangle_bounds(tris) -> np.ndarray:
+    l = lib()
+    l.spo_triangle_bounds.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    l.spo_triangle_bounds.restype = None
+    tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 12)
+    out = np.empty((tris.shape[0], 6), dtype=np.float32)
+    l.spo_triangle_bounds(_p(tris), tris.shape[0], _p(out))
     return out

@@ -7,7 +7,7 @@ from pathlib import Path
 
 import numpy as np
 
-from simplepath_b200.capi import FlatScene, HIT_DTYPE, RAY_DTYPE
+from simplepath_b200.capi import Accel, FlatScene, HIT_DTYPE, RAY_DTYPE, run_build
 
 HERE = Path(__file__).resolve().parent
 STRICT = HERE / "_ref" / "libsp_ref.so"        # -ffp-contract=off: the canonical parity build
@@ -114,6 +114,15 @@ class RefScene:
         self.lib.spref_hit_records(self.h, _p(rays), rays.shape[0], _p(out))
         return out
 
+    def geom_bounds(self, n_prims: int) -> np.ndarray:
+        """Hitable::get_world_bounds of every geometry primitive in ID order [n_prims, 6] (zeros for planes)."""
+        self.lib.spref_geom_bounds.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.spref_geom_bounds.restype = C.c_uint32
+        out = np.zeros((n_prims, 6), dtype=np.float32)
+        n = self.lib.spref_geom_bounds(self.h, _p(out))
+        assert n == n_prims, (n, n_prims)
+        return out
+
     def render(self, integrator: str, spp: int, threads: int):
         rgb = np.zeros((self.height, self.width, 3), dtype=np.float32)
         mean = np.zeros((self.height, self.width), dtype=np.float32)
@@ -122,3 +131,18 @@ class RefScene:
         if secs < 0:
             raise ValueError(f"unknown integrator {integrator}")
         return rgb, mean, var, secs
+
+
+def build_bvh(bounds, non_triangle=None, first_id: int = 0, capacity: int | None = None, lib_path: Path = STRICT) -> dict:
+    """The reference's own BVHAccelerator(first, last) over boxes (spref_build_bvh): {nodes, order, head, root_bounds}."""
+    lib = C.CDLL(str(lib_path))
+    lib.spref_build_bvh.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                    C.POINTER(Accel), C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.spref_build_bvh.restype = C.c_int
+    bounds = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 6)
+    err = C.create_string_buffer(512)
+
+    def call(*a):
+        if lib.spref_build_bvh(*a) != 0:
+            raise RuntimeError(f"spref_build_bvh: {err.value.decode()}")
+    return run_build(call, bounds, non_triangle, first_id, capacity, with_ms=False, extra=(err, 512))

@@ -303,6 +303,64 @@ static int guarded(char* err, size_t errlen, F&& f)
     }
 }
 
+
+// ---- BVH construction by the reference's own BVHAccelerator (shapes/BVHAccelerator.h:123-209) ---------------------------
+// A bounded Hitable that is nothing but its world bounds: lets the reference build a tree over arbitrary boxes.
+struct BoxHitable final : Hitable
+{
+    sp::BBox3 box;
+    uint32_t  index;
+    bool      non_triangle;
+
+    std::optional<sp::LightIntersection> intersect_lights_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return {}; }
+    std::optional<sp::Intersection>      intersect_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return {}; }
+    bool                                 intersect_p_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return false; }
+    sp::BBox3                            get_world_bounds_impl() const noexcept override { return box; }
+    bool                                 is_bounded_impl() const noexcept override { return true; }
+};
+
+struct BuildWalker
+{
+    spcu_bvh_node* nodes;
+    uint32_t       capacity;
+    uint32_t       n_nodes   = 0;
+    uint32_t       n_prims   = 0;
+    uint32_t       max_depth = 0;
+    uint32_t       first_id;
+    uint32_t*      order;
+
+    int32_t walk(const BVHAccelerator::NodeBase* node, uint32_t& count_word, uint32_t depth)
+    {
+        if (const auto* leaf = dynamic_cast<const BVHAccelerator::NodeLeaf*>(node)) {
+            const uint32_t first = n_prims;
+            bool           mixed = false;
+            for (const auto& p : leaf->m_primitives.m_primitives) {
+                const auto* b    = static_cast<const BoxHitable*>(p.get());
+                order[n_prims++] = b->index;
+                mixed |= b->non_triangle;
+            }
+            count_word = (n_prims - first) | (mixed ? SPCU_LEAF_MIXED_FLAG : 0u);
+            return ~static_cast<int32_t>(first_id + first);
+        }
+        const auto* inner = static_cast<const BVHAccelerator::NodeInternal*>(node);
+        max_depth         = std::max(max_depth, depth + 1);
+        const uint32_t idx = n_nodes++;
+        if (idx >= capacity) {
+            throw std::runtime_error("spref_build_bvh: node capacity exceeded");
+        }
+        spcu_bvh_node n{};
+        for (int k = 0; k < 2; ++k) {
+            const auto& b = inner->m_children[k]->m_bounds;
+            const float v[6] = { b.get_lower().x, b.get_lower().y, b.get_lower().z, b.get_upper().x, b.get_upper().y, b.get_upper().z };
+            std::memcpy(n.box + 6 * k, v, sizeof v);
+            n.child[k] = walk(inner->m_children[k].get(), n.count[k], depth + 1);
+        }
+        nodes[idx] = n;
+        count_word = 0;
+        return static_cast<int32_t>(idx);
+    }
+};
+
 extern "C" {
 
 // Parse a .sp file with the reference's FileParser (base/FileParser.cpp:928-932).  Relative asset paths in
@@ -511,6 +569,60 @@ double spref_render(spref_scene* s, const char* integrator_name, unsigned spp, u
     }
     const auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// BVHAccelerator(first, last) (shapes/BVHAccelerator.h:123-129,175-209) over n boxes given in INITIAL order
+// (bounds = n x {lo.xyz, hi.xyz}), flattened exactly like the product's flattener numbers a tree: internal nodes in
+// depth-first pre-order, leaf link = ~(first_id + leaf position), order[k] = initial index of the primitive at leaf
+// position k.  root_bounds (6 floats, may be NULL) = BVHAccelerator::get_world_bounds().  Returns 0, -1 on error.
+int spref_build_bvh(const float* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id, uint32_t* order,
+                    spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* root_bounds, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&] {
+        std::vector<std::shared_ptr<const Hitable>> prims;
+        prims.reserve(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            auto         b = std::make_shared<BoxHitable>();
+            const float* f = bounds + 6 * i;
+            // set the members directly: BBox(a, b) would re-sort the corners (math/BBox.h:26-30)
+            b->box.m_min    = sp::Point3{ f[0], f[1], f[2] };
+            b->box.m_max    = sp::Point3{ f[3], f[4], f[5] };
+            b->index        = i;
+            b->non_triangle = non_triangle && non_triangle[i];
+            prims.push_back(std::move(b));
+        }
+        const BVHAccelerator bvh(prims.begin(), prims.end());
+        BuildWalker          w{ nodes, capacity, 0, 0, 0, first_id, order };
+        spcu_accel           a{};
+        a.n_unbounded = first_id;
+        a.root        = w.walk(bvh.m_root.get(), a.root_count, 0);
+        a.n_prims     = first_id + w.n_prims;
+        a.n_nodes     = w.n_nodes;
+        a.max_depth   = w.max_depth;
+        a.nodes       = nodes;
+        *accel        = a;
+        if (root_bounds) {
+            const auto b = bvh.get_world_bounds();
+            const float v[6] = { b.get_lower().x, b.get_lower().y, b.get_lower().z, b.get_upper().x, b.get_upper().y, b.get_upper().z };
+            std::memcpy(root_bounds, v, sizeof v);
+        }
+    });
+}
+
+// Hitable::get_world_bounds() (shapes/Hitable.h:32-35) of every geometry primitive, in ID order: out = n_prims x
+// {lo.xyz, hi.xyz}; unbounded primitives (planes) get zeros.  Returns the number of primitives.
+uint32_t spref_geom_bounds(spref_scene* s, float* out)
+{
+    for (const auto& [prim, id] : s->geom_ids.id) {
+        float* o = out + 6 * static_cast<size_t>(id);
+        std::memset(o, 0, 6 * sizeof(float));
+        if (prim->is_bounded()) {
+            const auto b = prim->get_world_bounds();
+            const float v[6] = { b.get_lower().x, b.get_lower().y, b.get_lower().z, b.get_upper().x, b.get_upper().y, b.get_upper().z };
+            std::memcpy(o, v, sizeof v);
+        }
+    }
+    return static_cast<uint32_t>(s->geom_ids.id.size());
 }
 
 int spref_width(spref_scene* s) { return s->scene->image_width; }

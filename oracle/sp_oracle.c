@@ -504,4 +504,134 @@ void spo_hit_records(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n,
     }
 }
 
+/* ===================================================================================================
+ * BVH construction (shapes/BVHAccelerator.h:175-209)
+ * =================================================================================================== */
+
+/* _mm_min_ps(a, b) / _mm_max_ps(a, b) (math/Vector3.h:383-393): the SECOND operand on a tie (matters for +-0). */
+static inline float sse_min(float a, float b) { return a < b ? a : b; }
+static inline float sse_max(float a, float b) { return a > b ? a : b; }
+
+typedef struct {
+    const spcu_bounds* bounds;
+    const uint8_t*     non_triangle;
+    uint32_t*          order;
+    spcu_bvh_node*     nodes;
+    uint32_t           capacity, n_nodes, first_id, max_depth;
+    int                overflow;
+} build_t;
+
+/* bounds = merge(bounds, prim) over [first, last) in range order (BVHAccelerator.h:181-185).  merge returns
+ * BBox{min(lo, lo'), max(hi, hi')} (math/BBox.h:60-64), and that constructor sorts its corners once more (:26-30). */
+static void build_fold(const build_t* b, uint32_t first, uint32_t last, float lo[3], float hi[3])
+{
+    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; } /* BBox() (math/BBox.h:15-19) */
+    for (uint32_t p = first; p < last; ++p) {
+        const spcu_bounds* x = &b->bounds[b->order[p]];
+        for (int a = 0; a < 3; ++a) {
+            const float l = sse_min(lo[a], x->lo[a]);
+            const float h = sse_max(hi[a], x->hi[a]);
+            lo[a]         = sse_min(l, h);
+            hi[a]         = sse_max(l, h);
+        }
+    }
+}
+
+/* max_dim (math/Vector3.h:653-670) */
+static int build_max_dim(const float v[3])
+{
+    const float x = fabsf(v[0]), y = fabsf(v[1]), z = fabsf(v[2]);
+    if (x > y) return x > z ? 0 : 2;
+    return y > z ? 1 : 2;
+}
+
+/* Returns the link of the subtree over [first, last); writes its bounds and its leaf count word. */
+static int32_t build_construct(build_t* b, uint32_t first, uint32_t last, uint32_t depth, float lo[3], float hi[3],
+                               uint32_t* count_word)
+{
+    build_fold(b, first, last, lo, hi);
+    uint32_t split = first;
+    if (last - first > 4u) { /* k_max_leaf_elements (BVHAccelerator.h:211) */
+        const float size[3] = { hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2] };
+        const int   d       = build_max_dim(size);
+        const float at      = (lo[d] + hi[d]) / 2.0f; /* center (math/BBox.h:114-118) */
+        /* std::partition, libstdc++ bidirectional version (bits/stl_algo.h __partition): Hoare scheme */
+        uint32_t f = first, l = last;
+        for (;;) {
+            for (;;) {
+                if (f == l) goto done;
+                const spcu_bounds* x = &b->bounds[b->order[f]];
+                if ((x->lo[d] + x->hi[d]) / 2.0f < at) ++f; else break;
+            }
+            --l;
+            for (;;) {
+                if (f == l) goto done;
+                const spcu_bounds* x = &b->bounds[b->order[l]];
+                if (!((x->lo[d] + x->hi[d]) / 2.0f < at)) --l; else break;
+            }
+            { const uint32_t t = b->order[f]; b->order[f] = b->order[l]; b->order[l] = t; }
+            ++f;
+        }
+    done:
+        split = f;
+    }
+    if (split == first || split == last) { /* NodeLeaf (also for the small ranges, where split stayed == first) */
+        uint32_t mixed = 0;
+        if (b->non_triangle)
+            for (uint32_t p = first; p < last; ++p) mixed |= b->non_triangle[b->order[p]];
+        *count_word = (last - first) | (mixed ? SPCU_LEAF_MIXED_FLAG : 0u);
+        return ~(int32_t)(b->first_id + first);
+    }
+    if (depth + 1 > b->max_depth) b->max_depth = depth + 1;
+    const uint32_t idx = b->n_nodes++;
+    spcu_bvh_node  n;
+    memset(&n, 0, sizeof n);
+    if (idx >= b->capacity) b->overflow = 1;
+    const uint32_t range[3] = { first, split, last };
+    for (int k = 0; k < 2; ++k) {
+        float clo[3], chi[3];
+        n.child[k] = build_construct(b, range[k], range[k + 1], depth + 1, clo, chi, &n.count[k]);
+        memcpy(n.box + 6 * k, clo, sizeof clo);
+        memcpy(n.box + 6 * k + 3, chi, sizeof chi);
+    }
+    if (idx < b->capacity) b->nodes[idx] = n;
+    *count_word = 0;
+    return (int32_t)idx;
+}
+
+int spo_build_bvh(const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id, uint32_t* order,
+                  spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* root_bounds)
+{
+    build_t b = { bounds, non_triangle, order, nodes, capacity, 0, first_id, 0, 0 };
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    float      lo[3], hi[3];
+    spcu_accel a;
+    memset(&a, 0, sizeof a);
+    a.root        = build_construct(&b, 0, n, 0, lo, hi, &a.root_count);
+    a.n_unbounded = first_id;
+    a.n_prims     = first_id + n;
+    a.n_nodes     = b.n_nodes;
+    a.max_depth   = b.max_depth;
+    a.nodes       = nodes;
+    *accel        = a;
+    if (root_bounds) { memcpy(root_bounds, lo, sizeof lo); memcpy(root_bounds + 3, hi, sizeof hi); }
+    return b.overflow ? -1 : 0;
+}
+
+/* Triangle::get_world_bounds_impl (shapes/Triangle.h:228-237): BBox::extend(p) = { min(p, m_min), max(p, m_max) }
+ * (math/BBox.h:42-46) over the three vertices — here the running value is the SECOND operand. */
+void spo_triangle_bounds(const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        spcu_bounds r = { { INFINITY, INFINITY, INFINITY }, { -INFINITY, -INFINITY, -INFINITY } };
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < 3; ++a) {
+                const float p = tris[i].v[4 * k + a];
+                r.lo[a]       = sse_min(p, r.lo[a]);
+                r.hi[a]       = sse_max(p, r.hi[a]);
+            }
+        out[i] = r;
+    }
+}
+
 #include "sp_oracle_shade.inc"

@@ -58,6 +58,15 @@ void  spo_sphere_light_sample(const spcu_light* l, const float p[3], const float
                               float wi[3], float* pdf, float* t_min, float* t_max);
 float spo_sphere_light_pdf(const spcu_light* l, const float p[3]);
 
+/* BVHAccelerator::construct (shapes/BVHAccelerator.h:175-209) restated sequentially; same arguments and outputs as
+ * spcu_build_bvh (include/spcu.h).  root_bounds (6 floats, may be NULL) = bounds of the root node.  Returns 0, or -1
+ * when `capacity` nodes do not suffice.  Pinned bit for bit against the reference's own BVHAccelerator
+ * (oracle/ref_harness.cpp spref_build_bvh; tests/golden/bvh_build.npz). */
+int spo_build_bvh(const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id, uint32_t* order,
+                  spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* root_bounds);
+/* Triangle::get_world_bounds_impl (shapes/Triangle.h:228-237) */
+void spo_triangle_bounds(const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,8 @@ class Hit(C.Structure):
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("t_min", "<f4"), ("d", "<f4", 3), ("t_max", "<f4")])
 HIT_DTYPE = np.dtype([("id", "<i4"), ("t", "<f4")])
 NODE_DTYPE = np.dtype([("box", "<f4", 12), ("child", "<i4", 2), ("count", "<u4", 2)])
+BOUNDS_DTYPE = np.dtype([("lo", "<f4", 3), ("hi", "<f4", 3)])
+PRIM_DTYPE = np.dtype([("v", "<f4", 12)])
 assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 8 and NODE_DTYPE.itemsize == 64
 
 
@@ -109,6 +111,7 @@ EXPORTS = [
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
     "spcu_generate_rays", "spcu_render", "spcu_render_frame", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times", "spcu_resolved_pipeline",
+    "spcu_build_bvh", "spcu_triangle_bounds",
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
@@ -168,6 +171,11 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_trace_closest_counted.restype = C.c_int
     lib.spcu_stage_times.argtypes = [vp, C.POINTER(StageTime), C.c_uint32, C.POINTER(C.c_uint32)]
     lib.spcu_stage_times.restype = C.c_int
+    lib.spcu_build_bvh.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(Accel),
+                                   C.POINTER(C.c_float)]
+    lib.spcu_build_bvh.restype = C.c_int
+    lib.spcu_triangle_bounds.argtypes = [vp, vp, C.c_uint32, vp]
+    lib.spcu_triangle_bounds.restype = C.c_int
     if lib.spcu_abi_version() != ABI_VERSION:
         raise SpcuError("libspcu.so ABI version mismatch")
     if path is None:
@@ -322,5 +330,41 @@ class Context:
         code = self.lib.spcu_resolved_pipeline(self.h)
         return {PIPELINE_WAVEFRONT: "wavefront", PIPELINE_PATHS: "paths", PIPELINE_SMWAVE: "smwave"}.get(code, "none")
 
+    def build_bvh(self, bounds, non_triangle=None, first_id: int = 0, capacity: int | None = None) -> dict:
+        """BVHAccelerator::construct on the device (spcu_build_bvh): {nodes, order, head (accel fields), device_ms}."""
+        bounds = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 6)
+        return run_build(lambda *a: self._check(self.lib.spcu_build_bvh(self.h, *a), "spcu_build_bvh"),
+                         bounds, non_triangle, first_id, capacity, with_ms=True)
+
+    def triangle_bounds(self, tris) -> np.ndarray:
+        """Triangle::get_world_bounds for spcu_prim_geom records [n, 12] -> [n, 6]."""
+        tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 12)
+        out = np.empty((tris.shape[0], 6), dtype=np.float32)
+        self._check(self.lib.spcu_triangle_bounds(self.h, _ptr(tris), tris.shape[0], _ptr(out)), "spcu_triangle_bounds")
+        return out
+
     def set_wavefront_size(self, n: int) -> None:
         self._check(self.lib.spcu_set_wavefront_size(self.h, n), "spcu_set_wavefront_size")
+
+
+def run_build(call, bounds: np.ndarray, non_triangle, first_id: int, capacity: int | None, with_ms: bool, extra=()) -> dict:
+    """Shared argument marshalling of the three BVH builders (CUDA, oracle restatement, reference harness):
+    call(bounds, n, non_triangle, first_id, order, nodes, capacity, accel, [ms | root_bounds], *extra)."""
+    n = bounds.shape[0]
+    nt = None if non_triangle is None else np.ascontiguousarray(non_triangle, dtype=np.uint8)
+    cap = max(n, 1) - 1 if capacity is None else capacity
+    nodes = np.zeros(max(cap, 1), dtype=NODE_DTYPE)
+    order = np.zeros(max(n, 1), dtype=np.uint32)
+    accel = Accel()
+    if with_ms:
+        tail = C.c_float()
+        call(_ptr(bounds), n, _ptr(nt) if nt is not None else None, first_id, _ptr(order), _ptr(nodes), cap,
+             C.byref(accel), C.byref(tail), *extra)
+        tail_out = {"device_ms": float(tail.value)}
+    else:
+        root = np.zeros(6, dtype=np.float32)
+        call(_ptr(bounds), n, _ptr(nt) if nt is not None else None, first_id, _ptr(order), _ptr(nodes), cap,
+             C.byref(accel), _ptr(root), *extra)
+        tail_out = {"root_bounds": root}
+    head = {k: int(getattr(accel, k)) for k in ("n_prims", "n_unbounded", "n_nodes", "root", "root_count", "max_depth")}
+    return {"nodes": nodes[:head["n_nodes"]].copy(), "order": order[:n].copy(), "head": head, **tail_out}

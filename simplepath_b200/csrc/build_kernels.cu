@@ -1,0 +1,692 @@
+// BVHAccelerator::construct (reference shapes/BVHAccelerator.h:175-209) on the device: spcu_build_bvh, spcu_triangle_bounds.
+//
+// The reference builds its tree by single-threaded recursion: fold the primitives' bounds in range order, split the range
+// with std::partition at the centre of the node's bounds along its widest axis, recurse left then right.  Primitive IDs are
+// positions in the final order, and the flattener numbers internal nodes in depth-first pre-order, so both the ORDER the
+// partition leaves behind and the exact bounds (down to the sign of a zero) are part of the contract.  None of it needs the
+// recursion:
+//
+//   * level-synchronous: all nodes of one depth are processed by a handful of passes over the n primitive positions
+//     (every position knows the node it currently belongs to), ~10 launches per level, no recursion, no per-node launch;
+//   * the bounds fold is order-dependent only through ties (_mm_min_ps / _mm_max_ps return their SECOND operand on a tie,
+//     which shows in +0 / -0): "the last position among the equal minima wins".  A 64-bit key (ordered float | position |
+//     sign) under atomicMin / atomicMax reproduces that with no ordered traversal; warps reduce their contiguous runs with
+//     shuffles first, and a run that IS the whole node stores without an atomic;
+//   * libstdc++'s std::partition (Hoare: swap the first misplaced element from the left with the first from the right) is a
+//     closed-form permutation: with k = number of elements satisfying the predicate, the j-th "false" among positions
+//     [first, k) changes places with the j-th "true" from the right among [k, last).  One exclusive prefix sum of the
+//     predicate over all positions gives every element its partner;
+//   * pre-order index of an internal node = (internal nodes whose range starts further left) + (its depth in the chain of
+//     left children starting at the same position) — a prefix sum over range starts, no tree walk.
+//
+// Compiled WITHOUT fast-math and with --fmad=false (Makefile): (lo + hi) / 2 and hi - lo are IEEE operations.
+#include "ctx.h"
+
+using namespace spcu;
+
+namespace {
+
+constexpr uint32_t kInvalid   = 0xFFFFFFFFu;
+constexpr int      kBlock     = 256;
+constexpr uint32_t kScanTile  = 2048; // bytes per block of the prefix sum: 256 threads x 8
+constexpr uint32_t kPending   = 0;    // node states
+constexpr uint32_t kLeaf      = 1;
+constexpr uint32_t kInternal  = 2;
+constexpr uint32_t kSplitting = 3;    // more than 4 primitives: partition decides between internal and leaf
+
+// Reduction targets of one node for one level: 3 lower-bound keys (atomicMin), 3 upper-bound keys (atomicMax) and, per axis,
+// the first position whose primitive is NOT the degenerate interval [+-0, +-0] (see decode_bounds).
+struct NodeKeys
+{
+    unsigned long long k[6];
+    uint32_t           first_nonzero[3];
+    uint32_t           pad;
+};
+static_assert(sizeof(NodeKeys) == 64, "NodeKeys");
+
+struct Build
+{
+    const spcu_bounds* bounds; // [n] initial order
+    uint32_t           n;
+    uint32_t*          perm;   // [n] perm[position] = index into bounds
+    uint32_t*          seg_of; // [n] node (BFS numbering) the position belongs to at the current level; kInvalid once in a leaf
+    // per node, BFS numbering, capacity 2n
+    uint32_t* first;
+    uint32_t* last;
+    uint32_t* parent;   // parent << 1 | which child; kInvalid for the root
+    uint32_t* left_run; // consecutive left-child steps that lead here (0 for the root and for right children)
+    uint32_t* state;
+    uint32_t* child0;   // children are allocated in pairs: child0, child0 + 1
+    float*    box;      // [6] lo.xyz hi.xyz
+    // per node of the current level (index = node - level_begin)
+    NodeKeys* keys;
+    uint32_t* dim;
+    float*    at;
+    uint32_t* mid;      // partition point of a node that became internal
+    // per position
+    uint8_t*  flag;     // partition predicate; reused for the chain counts of the numbering pass
+    uint32_t* prefix;   // [n + 1] exclusive prefix sum of flag
+    uint32_t* left_misplaced;
+    uint32_t* right_misplaced;
+    uint32_t* n_nodes;  // device counter
+};
+
+// ---- ordered keys ---------------------------------------------------------------------------------------------------
+// float -> uint32, monotone, with -0 folded onto +0 so that the two tie (as they do under < and >).
+__device__ __forceinline__ uint32_t ordered(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    if ((u << 1) == 0u) {
+        u = 0u;
+    }
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float unordered(uint32_t k, uint32_t negative_zero)
+{
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float((u == 0u && negative_zero) ? 0x80000000u : u);
+}
+
+// smallest value; among equal values the LARGEST position; carries the sign bit of the winner
+__device__ __forceinline__ unsigned long long min_key(float f, uint32_t pos)
+{
+    return (static_cast<unsigned long long>(ordered(f)) << 32) | ((0x7FFFFFFFu - pos) << 1) | (__float_as_uint(f) >> 31);
+}
+// largest value; among equal values the LARGEST position
+__device__ __forceinline__ unsigned long long max_key(float f, uint32_t pos)
+{
+    return (static_cast<unsigned long long>(ordered(f)) << 32) | (pos << 1) | (__float_as_uint(f) >> 31);
+}
+
+__device__ __forceinline__ spcu_bounds load_bounds(const spcu_bounds* p)
+{
+    // 24-byte records: three 8-byte loads
+    const float2* q = reinterpret_cast<const float2*>(p);
+    const float2  a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    spcu_bounds   r;
+    r.lo[0] = a.x, r.lo[1] = a.y, r.lo[2] = b.x, r.hi[0] = b.y, r.hi[1] = c.x, r.hi[2] = c.y;
+    return r;
+}
+
+// ---- kernels --------------------------------------------------------------------------------------------------------
+__global__ void k_init(Build b)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += stride) {
+        b.perm[i]   = i;
+        b.seg_of[i] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.first[0] = 0, b.last[0] = b.n, b.parent[0] = kInvalid, b.left_run[0] = 0, b.state[0] = kPending;
+        *b.n_nodes = 1;
+    }
+}
+
+__global__ void k_keys_init(NodeKeys* keys, uint32_t count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        NodeKeys k;
+        k.k[0] = k.k[1] = k.k[2] = ~0ull;
+        k.k[3] = k.k[4] = k.k[5] = 0ull;
+        k.first_nonzero[0] = k.first_nonzero[1] = k.first_nonzero[2] = kInvalid;
+        k.pad                                                        = 0;
+        keys[i]                                                      = k;
+    }
+}
+
+// bounds = merge(bounds, prim->get_world_bounds()) over the node's range (BVHAccelerator.h:181-185), as key reductions.
+__global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin)
+{
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos - lane < b.n; pos += stride) {
+        const uint32_t seg = pos < b.n ? b.seg_of[pos] : kInvalid;
+        unsigned long long k[6];
+        uint32_t           fnz[3];
+        if (seg != kInvalid) {
+            const spcu_bounds x = load_bounds(&b.bounds[b.perm[pos]]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                k[a]     = min_key(x.lo[a], pos);
+                k[3 + a] = max_key(x.hi[a], pos);
+                fnz[a]   = (x.lo[a] == 0.0f && x.hi[a] == 0.0f) ? kInvalid : pos;
+            }
+        } else {
+            k[0] = k[1] = k[2] = ~0ull;
+            k[3] = k[4] = k[5] = 0ull;
+            fnz[0] = fnz[1] = fnz[2] = kInvalid;
+        }
+        // positions of one node are contiguous: reduce each run of equal `seg` towards its first lane
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, seg, off);
+            const bool     take  = lane + off < 32u && other == seg;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const unsigned long long lo = __shfl_down_sync(0xFFFFFFFFu, k[a], off);
+                const unsigned long long hi = __shfl_down_sync(0xFFFFFFFFu, k[3 + a], off);
+                const uint32_t           z  = __shfl_down_sync(0xFFFFFFFFu, fnz[a], off);
+                if (take) {
+                    k[a]     = min(k[a], lo);
+                    k[3 + a] = max(k[3 + a], hi);
+                    fnz[a]   = min(fnz[a], z);
+                }
+            }
+        }
+        const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, seg, 1);
+        const bool     head   = lane == 0u || before != seg;
+        const uint32_t heads  = __ballot_sync(0xFFFFFFFFu, head);
+        if (head && seg != kInvalid) {
+            const uint32_t above   = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
+            const uint32_t run_len = (above ? __ffs(above) - 1u : 32u) - lane;
+            NodeKeys*      dst     = &b.keys[seg - level_begin];
+            if (pos == b.first[seg] && pos + run_len == b.last[seg]) {
+                // the run is the whole node: single writer
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    dst->k[a] = k[a];
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    dst->first_nonzero[a] = fnz[a];
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    atomicMin(&dst->k[a], k[a]);
+                    atomicMax(&dst->k[3 + a], k[3 + a]);
+                    if (fnz[a] != kInvalid) {
+                        atomicMin(&dst->first_nonzero[a], fnz[a]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Keys -> the bounds the reference's sequential fold ends with, bit for bit.  merge() returns BBox{min(lo, lo'), max(hi, hi')}
+// (math/BBox.h:60-64) and that constructor sorts its two corners once more (:26-30): lo = min(l, h), hi = max(l, h), second
+// operand on a tie.  The re-sort only shows while the running interval is [+-0, +-0]: then lo takes h's sign.  So: upper =
+// the last maximum; lower = the last minimum x_j.lo, unless its value is zero and every primitive up to and including
+// position j is the interval [+-0, +-0] on this axis, in which case it is x_j.hi.
+__device__ void decode_bounds(const Build& b, const NodeKeys& nk, float lo[3], float hi[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const unsigned long long kl = nk.k[a], kh = nk.k[3 + a];
+        float                    l = unordered(static_cast<uint32_t>(kl >> 32), static_cast<uint32_t>(kl) & 1u);
+        const float              h = unordered(static_cast<uint32_t>(kh >> 32), static_cast<uint32_t>(kh) & 1u);
+        if (l == 0.0f) {
+            const uint32_t j = 0x7FFFFFFFu - (static_cast<uint32_t>(kl) >> 1);
+            if (j < nk.first_nonzero[a]) {
+                l = b.bounds[b.perm[j]].hi[a];
+            }
+        }
+        lo[a] = l;
+        hi[a] = h;
+    }
+}
+
+// max_dim (math/Vector3.h:653-670)
+__device__ __forceinline__ int max_dim(float x, float y, float z)
+{
+    x = fabsf(x), y = fabsf(y), z = fabsf(z);
+    if (x > y) {
+        return x > z ? 0 : 2;
+    }
+    return y > z ? 1 : 2;
+}
+
+// Leaf or split (BVHAccelerator.h:187-195).
+__global__ void k_decide(Build b, uint32_t level_begin, uint32_t level_count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= level_count) {
+        return;
+    }
+    const uint32_t node = level_begin + i;
+    float          lo[3], hi[3];
+    decode_bounds(b, b.keys[i], lo, hi);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        b.box[6 * node + a]     = lo[a];
+        b.box[6 * node + 3 + a] = hi[a];
+    }
+    if (b.last[node] - b.first[node] <= 4u) { // k_max_leaf_elements (:211)
+        b.state[node] = kLeaf;
+        return;
+    }
+    const int d   = max_dim(__fsub_rn(hi[0], lo[0]), __fsub_rn(hi[1], lo[1]), __fsub_rn(hi[2], lo[2]));
+    b.dim[i]      = static_cast<uint32_t>(d);
+    b.at[i]       = __fdiv_rn(__fadd_rn(lo[d], hi[d]), 2.0f); // center (math/BBox.h:114-118)
+    b.state[node] = kSplitting;
+}
+
+// The partition predicate center(prim bounds)[d] < split (BVHAccelerator.h:196-198) for every position of a splitting node.
+__global__ void __launch_bounds__(kBlock) k_flags(Build b, uint32_t level_begin)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < b.n; pos += stride) {
+        const uint32_t seg = b.seg_of[pos];
+        uint8_t        f   = 0;
+        if (seg != kInvalid && b.state[seg] == kSplitting) {
+            const uint32_t d = b.dim[seg - level_begin];
+            const float*   x = reinterpret_cast<const float*>(&b.bounds[b.perm[pos]]);
+            f                = __fdiv_rn(__fadd_rn(__ldg(x + d), __ldg(x + 3 + d)), 2.0f) < b.at[seg - level_begin];
+        }
+        b.flag[pos] = f;
+    }
+}
+
+// ---- exclusive prefix sum of bytes (three passes) ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sum_bytes(uint2 v)
+{
+    return __vsadu4(v.x, 0u) + __vsadu4(v.y, 0u);
+}
+
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* total)
+{
+    __shared__ uint32_t warp_sums[kBlock / 32];
+    const uint32_t      lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t            inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+        if (lane >= static_cast<uint32_t>(off)) {
+            inc += o;
+        }
+    }
+    __syncthreads(); // warp_sums may still be read by a previous call
+    if (lane == 31u) {
+        warp_sums[w] = inc;
+    }
+    __syncthreads();
+    uint32_t base = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < kBlock / 32; ++i) {
+        const uint32_t s = warp_sums[i];
+        base += static_cast<uint32_t>(i) < w ? s : 0u;
+        all += s;
+    }
+    *total = all;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kBlock) k_scan_reduce(const uint8_t* in, uint32_t* partials)
+{
+    const uint2 v = reinterpret_cast<const uint2*>(in)[static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x];
+    uint32_t    total;
+    block_exclusive(sum_bytes(v), &total);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = total;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_scan_partials(uint32_t* partials, uint32_t count)
+{
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < count; base += kBlock) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < count ? partials[i] : 0u;
+        uint32_t       total;
+        const uint32_t e = block_exclusive(v, &total);
+        if (i < count) {
+            partials[i] = running + e;
+        }
+        running += total;
+    }
+}
+
+// out[i] = sum of in[0 .. i) for i in [0, n]  (in[] is zero beyond n)
+__global__ void __launch_bounds__(kBlock) k_scan_apply(const uint8_t* in, const uint32_t* partials, uint32_t* out, uint32_t n)
+{
+    const size_t t = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+    const uint2  v = reinterpret_cast<const uint2*>(in)[t];
+    uint32_t     total;
+    uint32_t     run = partials[blockIdx.x] + block_exclusive(sum_bytes(v), &total);
+    const size_t i0  = t * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (i0 + j <= n) {
+            out[i0 + j] = run;
+        }
+        run += ((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFFu;
+    }
+}
+
+// std::partition's outcome for every splitting node: empty side -> leaf of any size (BVHAccelerator.h:200-203), else two children.
+__global__ void k_split(Build b, uint32_t level_begin, uint32_t level_count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= level_count) {
+        return;
+    }
+    const uint32_t node = level_begin + i;
+    if (b.state[node] != kSplitting) {
+        return;
+    }
+    const uint32_t first = b.first[node], last = b.last[node];
+    const uint32_t trues = b.prefix[last] - b.prefix[first];
+    if (trues == 0u || trues == last - first) {
+        b.state[node] = kLeaf;
+        return;
+    }
+    const uint32_t mid = first + trues;
+    const uint32_t c0  = atomicAdd(b.n_nodes, 2u);
+    b.state[node]      = kInternal;
+    b.child0[node]     = c0;
+    b.mid[i]           = mid;
+    b.first[c0] = first, b.last[c0] = mid, b.parent[c0] = node << 1, b.left_run[c0] = b.left_run[node] + 1u, b.state[c0] = kPending;
+    b.first[c0 + 1] = mid, b.last[c0 + 1] = last, b.parent[c0 + 1] = (node << 1) | 1u, b.left_run[c0 + 1] = 0u, b.state[c0 + 1] = kPending;
+}
+
+// Hoare partition as a permutation, step 1: list the misplaced elements of both sides in the order the two cursors of
+// libstdc++'s __partition (bits/stl_algo.h, bidirectional version) meet them.
+__global__ void __launch_bounds__(kBlock) k_scatter(Build b, uint32_t level_begin)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < b.n; pos += stride) {
+        const uint32_t seg = b.seg_of[pos];
+        if (seg == kInvalid || b.state[seg] != kInternal) {
+            continue;
+        }
+        const uint32_t first = b.first[seg], mid = b.mid[seg - level_begin];
+        const uint32_t before = b.prefix[pos] - b.prefix[first]; // trues in [first, pos)
+        const bool     f      = b.flag[pos] != 0;
+        if (pos < mid && !f) {
+            b.left_misplaced[first + (pos - first - before)] = pos; // rank among the falses, from the left
+        } else if (pos >= mid && f) {
+            b.right_misplaced[first + (mid - first - before - 1u)] = pos; // trues after pos = rank from the right
+        }
+    }
+}
+
+// step 2: swap the pairs, hand every position to its child (or retire it with its leaf).
+__global__ void __launch_bounds__(kBlock) k_apply(Build b, uint32_t level_begin)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < b.n; pos += stride) {
+        const uint32_t seg = b.seg_of[pos];
+        if (seg == kInvalid) {
+            continue;
+        }
+        if (b.state[seg] != kInternal) {
+            b.seg_of[pos] = kInvalid;
+            continue;
+        }
+        const uint32_t first = b.first[seg], mid = b.mid[seg - level_begin];
+        const uint32_t misplaced = (mid - first) - (b.prefix[mid] - b.prefix[first]); // falses in [first, mid)
+        const uint32_t j         = pos - first;
+        if (j < misplaced) {
+            const uint32_t p = b.left_misplaced[first + j], q = b.right_misplaced[first + j];
+            const uint32_t t = b.perm[p];
+            b.perm[p]        = b.perm[q];
+            b.perm[q]        = t;
+        }
+        b.seg_of[pos] = b.child0[seg] + (pos >= mid ? 1u : 0u);
+    }
+}
+
+// Numbering: internal nodes that start at the same position form a chain of left children; the chain's length goes to its
+// start position, and the prefix sum over positions is the pre-order index of each chain's head.
+__global__ void k_chain_counts(Build b, uint32_t n_nodes)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_nodes && b.state[v] == kInternal && b.state[b.child0[v]] != kInternal) {
+        b.flag[b.first[v]] = static_cast<uint8_t>(b.left_run[v] + 1u);
+    }
+}
+
+// Every node but the root fills its half of its parent's record (the flattener's layout, include/spcu.h spcu_bvh_node).
+__global__ void k_emit(Build b, uint32_t n_nodes, spcu_bvh_node* out, uint32_t first_id, const uint8_t* non_triangle)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0u || v >= n_nodes) {
+        return;
+    }
+    const uint32_t parent = b.parent[v] >> 1, which = b.parent[v] & 1u;
+    spcu_bvh_node* dst    = &out[b.prefix[b.first[parent]] + b.left_run[parent]];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        dst->box[6 * which + a] = b.box[6 * v + a];
+    }
+    if (b.state[v] == kInternal) {
+        dst->child[which] = static_cast<int32_t>(b.prefix[b.first[v]] + b.left_run[v]);
+        dst->count[which] = 0u;
+    } else {
+        uint32_t mixed = 0;
+        if (non_triangle) {
+            for (uint32_t p = b.first[v]; p < b.last[v]; ++p) {
+                mixed |= non_triangle[b.perm[p]];
+            }
+        }
+        dst->child[which] = ~static_cast<int32_t>(first_id + b.first[v]);
+        dst->count[which] = (b.last[v] - b.first[v]) | (mixed ? SPCU_LEAF_MIXED_FLAG : 0u);
+    }
+}
+
+// Triangle::get_world_bounds_impl (shapes/Triangle.h:228-237): BBox::extend(p) = { min(p, m_min), max(p, m_max) }
+// (math/BBox.h:42-46), _mm_min_ps / _mm_max_ps semantics (the running value is the second operand and wins a tie).
+__global__ void __launch_bounds__(kBlock) k_triangle_bounds(const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4* q  = reinterpret_cast<const float4*>(&tris[i]);
+        const float4  p0 = __ldg(q), p1 = __ldg(q + 1), p2 = __ldg(q + 2);
+        const float   v[3][3] = { { p0.x, p0.y, p0.z }, { p1.x, p1.y, p1.z }, { p2.x, p2.y, p2.z } };
+        float         lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = __int_as_float(0x7F800000), hi[a] = __int_as_float(0xFF800000);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                lo[a] = v[k][a] < lo[a] ? v[k][a] : lo[a];
+                hi[a] = v[k][a] > hi[a] ? v[k][a] : hi[a];
+            }
+        }
+        float2* o = reinterpret_cast<float2*>(&out[i]);
+        o[0]      = make_float2(lo[0], lo[1]);
+        o[1]      = make_float2(lo[2], hi[0]);
+        o[2]      = make_float2(hi[1], hi[2]);
+    }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+struct Scratch
+{
+    std::vector<DevBuf> bufs;
+    ~Scratch()
+    {
+        for (auto& b : bufs) {
+            b.release();
+        }
+    }
+    template <typename T>
+    cudaError_t get(T** out, size_t count)
+    {
+        bufs.emplace_back();
+        const cudaError_t e = bufs.back().reserve(std::max<size_t>(count * sizeof(T), 16));
+        *out                = bufs.back().as<T>();
+        return e;
+    }
+};
+
+unsigned grid_for(uint64_t n, int sm_count)
+{
+    const uint64_t want = (n + kBlock - 1) / kBlock;
+    return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(sm_count) * 8)));
+}
+
+void scan_bytes(const Build& b, uint32_t* partials, uint32_t n_tiles, cudaStream_t st)
+{
+    k_scan_reduce<<<n_tiles, kBlock, 0, st>>>(b.flag, partials);
+    k_scan_partials<<<1, kBlock, 0, st>>>(partials, n_tiles);
+    k_scan_apply<<<n_tiles, kBlock, 0, st>>>(b.flag, partials, b.prefix, b.n);
+}
+
+} // namespace
+
+extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id,
+                              uint32_t* order, spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* device_ms)
+{
+    if (!c) {
+        return SPCU_ERR_INVALID;
+    }
+    if (!accel || (n && (!bounds || !order)) || (capacity && !nodes)) {
+        return fail(c, SPCU_ERR_INVALID, "spcu_build_bvh: NULL argument");
+    }
+    if (n >= (1u << 30) || static_cast<uint64_t>(first_id) + n >= (1u << 30)) {
+        return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: more than 2^30 primitives");
+    }
+    CK(c, cudaSetDevice(c->device));
+    spcu_accel a{};
+    a.n_unbounded = first_id;
+    a.n_prims     = first_id + n;
+    a.nodes       = nodes;
+    if (device_ms) {
+        *device_ms = 0.0f;
+    }
+    if (n == 0) { // BVHAccelerator(first, first): one empty leaf (base/Scene.h:34-37)
+        a.root = ~static_cast<int32_t>(first_id);
+        *accel = a;
+        return SPCU_OK;
+    }
+
+    const cudaStream_t st        = c->stream;
+    const size_t       max_nodes = 2 * static_cast<size_t>(n);
+    // a node with children holds >= 5 primitives, so a level has at most n/5 of them and the next level 2n/5 nodes
+    const size_t       max_level = std::max<size_t>(2 * (static_cast<size_t>(n) / 5) + 2, 4);
+    const uint32_t     n_tiles   = n / kScanTile + 1; // covers index n
+    Scratch            mem;
+    Build              b{};
+    b.n = n;
+    spcu_bounds* d_bounds  = nullptr;
+    uint32_t*    partials  = nullptr;
+    uint8_t*     d_non_tri = nullptr;
+    CK(c, mem.get(&d_bounds, n));
+    CK(c, mem.get(&b.perm, n));
+    CK(c, mem.get(&b.seg_of, n));
+    CK(c, mem.get(&b.first, max_nodes));
+    CK(c, mem.get(&b.last, max_nodes));
+    CK(c, mem.get(&b.parent, max_nodes));
+    CK(c, mem.get(&b.left_run, max_nodes));
+    CK(c, mem.get(&b.state, max_nodes));
+    CK(c, mem.get(&b.child0, max_nodes));
+    CK(c, mem.get(&b.box, 6 * max_nodes));
+    CK(c, mem.get(&b.keys, max_level));
+    CK(c, mem.get(&b.dim, max_level));
+    CK(c, mem.get(&b.at, max_level));
+    CK(c, mem.get(&b.mid, max_level));
+    CK(c, mem.get(&b.flag, static_cast<size_t>(n_tiles) * kScanTile));
+    CK(c, mem.get(&b.prefix, static_cast<size_t>(n) + 1));
+    CK(c, mem.get(&b.left_misplaced, n));
+    CK(c, mem.get(&b.right_misplaced, n));
+    CK(c, mem.get(&b.n_nodes, 1));
+    CK(c, mem.get(&partials, n_tiles));
+    b.bounds = d_bounds;
+    CK(c, cudaMemcpyAsync(d_bounds, bounds, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyHostToDevice, st));
+    if (non_triangle) {
+        CK(c, mem.get(&d_non_tri, n));
+        CK(c, cudaMemcpyAsync(d_non_tri, non_triangle, n, cudaMemcpyHostToDevice, st));
+    }
+    CK(c, cudaMemsetAsync(b.flag, 0, static_cast<size_t>(n_tiles) * kScanTile, st));
+
+    const unsigned grid = grid_for(n, c->sm_count);
+    CK(c, cudaEventRecord(c->ev0, st));
+    k_init<<<grid, kBlock, 0, st>>>(b);
+    uint32_t level_begin = 0, level_end = 1, max_depth = 0;
+    for (uint32_t level = 0; level_begin < level_end; ++level) {
+        const uint32_t count = level_end - level_begin;
+        if (count > max_level) {
+            return fail(c, SPCU_ERR_INVALID, "spcu_build_bvh: level %u holds %u nodes (internal error)", level, count);
+        }
+        const unsigned node_grid = (count + kBlock - 1) / kBlock;
+        k_keys_init<<<node_grid, kBlock, 0, st>>>(b.keys, count);
+        k_bounds<<<grid, kBlock, 0, st>>>(b, level_begin);
+        k_decide<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
+        k_flags<<<grid, kBlock, 0, st>>>(b, level_begin);
+        scan_bytes(b, partials, n_tiles, st);
+        k_split<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
+        k_scatter<<<grid, kBlock, 0, st>>>(b, level_begin);
+        k_apply<<<grid, kBlock, 0, st>>>(b, level_begin);
+        uint32_t total = 0;
+        CK(c, cudaMemcpyAsync(&total, b.n_nodes, sizeof total, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        if (total > level_end) {
+            max_depth = level + 1;
+            if (max_depth > SPCU_MAX_BVH_DEPTH) {
+                return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: tree deeper than SPCU_MAX_BVH_DEPTH (%u)", SPCU_MAX_BVH_DEPTH);
+            }
+        }
+        level_begin = level_end;
+        level_end   = total;
+    }
+    const uint32_t n_nodes = level_end;
+
+    // numbering + emission
+    CK(c, cudaMemsetAsync(b.flag, 0, static_cast<size_t>(n_tiles) * kScanTile, st));
+    const unsigned all_grid = (n_nodes + kBlock - 1) / kBlock;
+    k_chain_counts<<<all_grid, kBlock, 0, st>>>(b, n_nodes);
+    scan_bytes(b, partials, n_tiles, st);
+    uint32_t n_internal = 0, root_state = 0;
+    CK(c, cudaMemcpyAsync(&n_internal, b.prefix + n, sizeof n_internal, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(&root_state, b.state, sizeof root_state, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (n_internal > capacity) {
+        return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: %u internal nodes, capacity %u", n_internal, capacity);
+    }
+    spcu_bvh_node* d_nodes = nullptr;
+    CK(c, mem.get(&d_nodes, n_internal));
+    k_emit<<<all_grid, kBlock, 0, st>>>(b, n_nodes, d_nodes, first_id, d_non_tri);
+    CK(c, cudaEventRecord(c->ev1, st));
+    CK(c, cudaGetLastError());
+    if (n_internal) {
+        CK(c, cudaMemcpyAsync(nodes, d_nodes, static_cast<size_t>(n_internal) * sizeof(spcu_bvh_node), cudaMemcpyDeviceToHost, st));
+    }
+    CK(c, cudaMemcpyAsync(order, b.perm, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (device_ms) {
+        CK(c, cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
+    }
+    a.n_nodes   = n_internal;
+    a.max_depth = max_depth;
+    if (root_state == kInternal) {
+        a.root = 0;
+    } else {
+        uint32_t mixed = 0;
+        for (uint32_t i = 0; non_triangle && i < n; ++i) {
+            mixed |= non_triangle[i];
+        }
+        a.root       = ~static_cast<int32_t>(first_id);
+        a.root_count = n | (mixed ? SPCU_LEAF_MIXED_FLAG : 0u);
+    }
+    *accel = a;
+    return SPCU_OK;
+}
+
+extern "C" int spcu_triangle_bounds(spcu_ctx* c, const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out)
+{
+    if (!c) {
+        return SPCU_ERR_INVALID;
+    }
+    if (n && (!tris || !out)) {
+        return fail(c, SPCU_ERR_INVALID, "spcu_triangle_bounds: NULL argument");
+    }
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) {
+        return SPCU_OK;
+    }
+    Scratch         mem;
+    spcu_prim_geom* d_tris = nullptr;
+    spcu_bounds*    d_out  = nullptr;
+    CK(c, mem.get(&d_tris, n));
+    CK(c, mem.get(&d_out, n));
+    CK(c, cudaMemcpyAsync(d_tris, tris, static_cast<size_t>(n) * sizeof(spcu_prim_geom), cudaMemcpyHostToDevice, c->stream));
+    k_triangle_bounds<<<grid_for(n, c->sm_count), kBlock, 0, c->stream>>>(d_tris, n, d_out);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d_out, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SPCU_OK;
+}

@@ -368,6 +368,19 @@ typedef struct spcu_bounds {
 int spcu_build_bvh(spcu_ctx* ctx, const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id,
                    uint32_t* order, spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* device_ms);
 
+/* spcu_upload_scene for a scene whose geometry accelerator has NOT been built: create_acceleration_structure + the
+ * flattener's walk (base/Scene.h:27-45; shapes/BVHAccelerator.h:123-209) happen on the device.  scene->geom_prims / geom_shade /
+ * geom_meta hold the primitives in PRE-construction order: [0, geom.n_unbounded) the top-level list (planes), then the bounded
+ * primitives as the reference holds them before BVHAccelerator(first, last); scene->geom.{n_prims, n_unbounded} are read, the
+ * other fields of scene->geom are ignored.  Triangle bounds are computed on the device; `bounds` ([n_prims - n_unbounded], may
+ * be NULL when every bounded primitive is a triangle) supplies the world bounds of the others (spheres:
+ * TransformableShape::get_world_bounds_impl, shapes/Shape.h:61-64).  order ([n_prims - n_unbounded], may be NULL): order[k] =
+ * pre-construction index (within the bounded range) of the primitive that received ID n_unbounded + k.  built (may be NULL):
+ * header of the accelerator now resident (nodes = NULL).  The resident scene is bit-identical to what spcu_upload_scene gets
+ * from the flattener for the tree the reference builds from the same sequence. */
+int spcu_upload_scene_build(spcu_ctx* ctx, const spcu_flat_scene* scene, const float* jitter, uint32_t spp,
+                            const spcu_bounds* bounds, uint32_t* order, spcu_accel* built);
+
 /* Triangle::get_world_bounds_impl (shapes/Triangle.h:228-237): BBox::extend over the three world-space vertices of
  * tris[i] (layout of spcu_prim_geom), in vertex order.  Host pointers. */
 int spcu_triangle_bounds(spcu_ctx* ctx, const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out);

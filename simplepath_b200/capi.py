@@ -111,7 +111,7 @@ EXPORTS = [
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
     "spcu_generate_rays", "spcu_render", "spcu_render_frame", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times", "spcu_resolved_pipeline",
-    "spcu_build_bvh", "spcu_triangle_bounds",
+    "spcu_build_bvh", "spcu_triangle_bounds", "spcu_upload_scene_build",
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
@@ -174,6 +174,8 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_build_bvh.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(Accel),
                                    C.POINTER(C.c_float)]
     lib.spcu_build_bvh.restype = C.c_int
+    lib.spcu_upload_scene_build.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(C.c_float), C.c_uint32, vp, vp, C.POINTER(Accel)]
+    lib.spcu_upload_scene_build.restype = C.c_int
     lib.spcu_triangle_bounds.argtypes = [vp, vp, C.c_uint32, vp]
     lib.spcu_triangle_bounds.restype = C.c_int
     if lib.spcu_abi_version() != ABI_VERSION:
@@ -220,6 +222,23 @@ class Context:
         self.width, self.height = fp.contents.width, fp.contents.height
         self.spp = jitter.shape[0]
         self._scene_keepalive = keepalive
+
+    def upload_scene_build(self, flat, jitter: np.ndarray, bounds=None, keepalive=None):
+        """spcu_upload_scene_build: geometry in pre-construction order, BVH built on the device.  Returns (order, accel head)."""
+        jitter = np.ascontiguousarray(jitter, dtype=np.float32).reshape(-1, 2)
+        fp = flat if isinstance(flat, C.POINTER(FlatScene)) else C.pointer(flat)
+        g = fp.contents.geom
+        order = np.zeros(max(g.n_prims - g.n_unbounded, 1), dtype=np.uint32)
+        b = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 6)
+        accel = Accel()
+        self._check(self.lib.spcu_upload_scene_build(self.h, fp, jitter.ctypes.data_as(C.POINTER(C.c_float)), jitter.shape[0],
+                                                     _ptr(b) if b is not None else None, _ptr(order), C.byref(accel)),
+                    "spcu_upload_scene_build")
+        self.width, self.height = fp.contents.width, fp.contents.height
+        self.spp = jitter.shape[0]
+        self._scene_keepalive = keepalive
+        head = {k: int(getattr(accel, k)) for k in ("n_prims", "n_unbounded", "n_nodes", "root", "root_count", "max_depth")}
+        return order[:g.n_prims - g.n_unbounded].copy(), head
 
     def _trace(self, fn, rays: np.ndarray, what: str) -> np.ndarray:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

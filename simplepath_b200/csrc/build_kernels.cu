@@ -136,73 +136,126 @@ __global__ void k_keys_init(NodeKeys* keys, uint32_t count)
     }
 }
 
+// Per-lane partial reduction of k_bounds: keys of the positions a lane has seen for node `seg`.
+struct Partial
+{
+    unsigned long long k[6];
+    uint32_t           fnz[3];
+    uint32_t           seg;
+};
+
+// Positions of one node are contiguous: reduce each run of equal `seg` across the warp towards its first lane, which adds the
+// run to the node's keys.  `start` = first position the lane's partial covers, `covered` = positions per lane-run element
+// (32 * iterations for a partial accumulated over several iterations of a warp-uniform node, else 1 per lane).
+__device__ __forceinline__ void flush_partial(const Build& b, uint32_t level_begin, Partial p, uint32_t start, uint32_t iterations)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, p.seg, off);
+        const bool     take  = lane + off < 32u && other == p.seg;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const unsigned long long lo = __shfl_down_sync(0xFFFFFFFFu, p.k[a], off);
+            const unsigned long long hi = __shfl_down_sync(0xFFFFFFFFu, p.k[3 + a], off);
+            const uint32_t           z  = __shfl_down_sync(0xFFFFFFFFu, p.fnz[a], off);
+            if (take) {
+                p.k[a]     = min(p.k[a], lo);
+                p.k[3 + a] = max(p.k[3 + a], hi);
+                p.fnz[a]   = min(p.fnz[a], z);
+            }
+        }
+    }
+    const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, p.seg, 1);
+    const bool     head   = lane == 0u || before != p.seg;
+    const uint32_t heads  = __ballot_sync(0xFFFFFFFFu, head);
+    if (head && p.seg != kInvalid) {
+        const uint32_t above   = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
+        const uint32_t run_len = ((above ? __ffs(above) - 1u : 32u) - lane) * iterations;
+        NodeKeys*      dst     = &b.keys[p.seg - level_begin];
+        if (start == b.first[p.seg] && start + run_len == b.last[p.seg]) {
+            // the run is the whole node: single writer
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                dst->k[a] = p.k[a];
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                dst->first_nonzero[a] = p.fnz[a];
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                atomicMin(&dst->k[a], p.k[a]);
+                atomicMax(&dst->k[3 + a], p.k[3 + a]);
+                if (p.fnz[a] != kInvalid) {
+                    atomicMin(&dst->first_nonzero[a], p.fnz[a]);
+                }
+            }
+        }
+    }
+}
+
 // bounds = merge(bounds, prim->get_world_bounds()) over the node's range (BVHAccelerator.h:181-185), as key reductions.
+// A warp walks kBoundsIterations x 32 consecutive positions.  While they all belong to one node (the upper levels of the
+// tree, where every warp of the grid would otherwise hit the same nine addresses) the lanes just keep accumulating; the
+// partial is flushed when the node changes.  Measured on 28 M boxes: the first levels took 5 ms each without this.
+constexpr int kBoundsIterations = 32;
+
 __global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin)
 {
-    const uint32_t lane   = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos - lane < b.n; pos += stride) {
-        const uint32_t seg = pos < b.n ? b.seg_of[pos] : kInvalid;
-        unsigned long long k[6];
-        uint32_t           fnz[3];
-        if (seg != kInvalid) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t base = warp * (32u * kBoundsIterations);
+    if (base >= b.n) {
+        return;
+    }
+    Partial  carry;
+    uint32_t carry_start = 0, carry_iterations = 0; // 0 iterations: nothing carried
+    bool     carry_uniform = false;
+    for (int it = 0; it < kBoundsIterations; ++it) {
+        const uint64_t pos64 = base + static_cast<uint64_t>(it) * 32u + lane;
+        if (pos64 - lane >= b.n) {
+            break;
+        }
+        const uint32_t pos = static_cast<uint32_t>(pos64);
+        Partial        cur;
+        cur.seg = pos < b.n ? b.seg_of[pos] : kInvalid;
+        if (cur.seg != kInvalid) {
             const spcu_bounds x = load_bounds(&b.bounds[b.perm[pos]]);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                k[a]     = min_key(x.lo[a], pos);
-                k[3 + a] = max_key(x.hi[a], pos);
-                fnz[a]   = (x.lo[a] == 0.0f && x.hi[a] == 0.0f) ? kInvalid : pos;
+                cur.k[a]     = min_key(x.lo[a], pos);
+                cur.k[3 + a] = max_key(x.hi[a], pos);
+                cur.fnz[a]   = (x.lo[a] == 0.0f && x.hi[a] == 0.0f) ? kInvalid : pos;
             }
         } else {
-            k[0] = k[1] = k[2] = ~0ull;
-            k[3] = k[4] = k[5] = 0ull;
-            fnz[0] = fnz[1] = fnz[2] = kInvalid;
+            cur.k[0] = cur.k[1] = cur.k[2] = ~0ull;
+            cur.k[3] = cur.k[4] = cur.k[5] = 0ull;
+            cur.fnz[0] = cur.fnz[1] = cur.fnz[2] = kInvalid;
         }
-        // positions of one node are contiguous: reduce each run of equal `seg` towards its first lane
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, seg, off);
-            const bool     take  = lane + off < 32u && other == seg;
+        const uint32_t seg0    = __shfl_sync(0xFFFFFFFFu, cur.seg, 0);
+        const bool     uniform = __all_sync(0xFFFFFFFFu, cur.seg == seg0);
+        if (carry_iterations && uniform && carry_uniform && seg0 == carry.seg) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const unsigned long long lo = __shfl_down_sync(0xFFFFFFFFu, k[a], off);
-                const unsigned long long hi = __shfl_down_sync(0xFFFFFFFFu, k[3 + a], off);
-                const uint32_t           z  = __shfl_down_sync(0xFFFFFFFFu, fnz[a], off);
-                if (take) {
-                    k[a]     = min(k[a], lo);
-                    k[3 + a] = max(k[3 + a], hi);
-                    fnz[a]   = min(fnz[a], z);
-                }
+                carry.k[a]     = min(carry.k[a], cur.k[a]);
+                carry.k[3 + a] = max(carry.k[3 + a], cur.k[3 + a]);
+                carry.fnz[a]   = min(carry.fnz[a], cur.fnz[a]);
             }
+            ++carry_iterations;
+            continue;
         }
-        const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, seg, 1);
-        const bool     head   = lane == 0u || before != seg;
-        const uint32_t heads  = __ballot_sync(0xFFFFFFFFu, head);
-        if (head && seg != kInvalid) {
-            const uint32_t above   = lane == 31u ? 0u : (heads >> (lane + 1u)) << (lane + 1u);
-            const uint32_t run_len = (above ? __ffs(above) - 1u : 32u) - lane;
-            NodeKeys*      dst     = &b.keys[seg - level_begin];
-            if (pos == b.first[seg] && pos + run_len == b.last[seg]) {
-                // the run is the whole node: single writer
-#pragma unroll
-                for (int a = 0; a < 6; ++a) {
-                    dst->k[a] = k[a];
-                }
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    dst->first_nonzero[a] = fnz[a];
-                }
-            } else {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    atomicMin(&dst->k[a], k[a]);
-                    atomicMax(&dst->k[3 + a], k[3 + a]);
-                    if (fnz[a] != kInvalid) {
-                        atomicMin(&dst->first_nonzero[a], fnz[a]);
-                    }
-                }
-            }
+        if (carry_iterations) {
+            flush_partial(b, level_begin, carry, carry_start, carry_uniform ? carry_iterations : 1u);
         }
+        carry            = cur;
+        carry_start      = pos;
+        carry_iterations = 1;
+        carry_uniform    = uniform;
+    }
+    if (carry_iterations) {
+        flush_partial(b, level_begin, carry, carry_start, carry_uniform ? carry_iterations : 1u);
     }
 }
 
@@ -526,46 +579,65 @@ void scan_bytes(const Build& b, uint32_t* partials, uint32_t n_tiles, cudaStream
     k_scan_apply<<<n_tiles, kBlock, 0, st>>>(b.flag, partials, b.prefix, b.n);
 }
 
-} // namespace
-
-extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id,
-                              uint32_t* order, spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* device_ms)
+// Gathers the primitive records of the bounded primitives into leaf order: dst[first_id + k] = src[first_id + order[k]].
+__global__ void __launch_bounds__(kBlock) k_gather_prims(const uint32_t* order, uint32_t n, uint32_t first_id, const float4* src_geom,
+                                                         const float4* src_shade, const uint32_t* src_meta, float4* dst_geom,
+                                                         float4* dst_shade, uint32_t* dst_meta)
 {
-    if (!c) {
-        return SPCU_ERR_INVALID;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const size_t from = first_id + order[k], to = first_id + k;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            dst_geom[3 * to + j]  = __ldg(&src_geom[3 * from + j]);
+            dst_shade[3 * to + j] = __ldg(&src_shade[3 * from + j]);
+        }
+        dst_meta[to] = __ldg(&src_meta[from]);
     }
-    if (!accel || (n && (!bounds || !order)) || (capacity && !nodes)) {
-        return fail(c, SPCU_ERR_INVALID, "spcu_build_bvh: NULL argument");
-    }
-    if (n >= (1u << 30) || static_cast<uint64_t>(first_id) + n >= (1u << 30)) {
-        return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: more than 2^30 primitives");
-    }
-    CK(c, cudaSetDevice(c->device));
-    spcu_accel a{};
-    a.n_unbounded = first_id;
-    a.n_prims     = first_id + n;
-    a.nodes       = nodes;
-    if (device_ms) {
-        *device_ms = 0.0f;
-    }
-    if (n == 0) { // BVHAccelerator(first, first): one empty leaf (base/Scene.h:34-37)
-        a.root = ~static_cast<int32_t>(first_id);
-        *accel = a;
-        return SPCU_OK;
-    }
+}
 
+// Triangle bounds for the bounded primitives of a scene; non-triangles (spheres) keep what the caller supplied.
+__global__ void __launch_bounds__(kBlock) k_scene_bounds(const spcu_prim_geom* prims, const uint32_t* meta, uint32_t n, spcu_bounds* out,
+                                                         uint8_t* non_triangle)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool tri  = SPCU_META_KIND(meta[i]) == SPCU_PRIM_TRIANGLE;
+        non_triangle[i] = tri ? 0 : 1;
+        if (!tri) {
+            continue;
+        }
+        const float4* q  = reinterpret_cast<const float4*>(&prims[i]);
+        const float4  p0 = __ldg(q), p1 = __ldg(q + 1), p2 = __ldg(q + 2);
+        const float   v[3][3] = { { p0.x, p0.y, p0.z }, { p1.x, p1.y, p1.z }, { p2.x, p2.y, p2.z } };
+        spcu_bounds   r;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            r.lo[a] = __int_as_float(0x7F800000), r.hi[a] = __int_as_float(0xFF800000);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                r.lo[a] = v[k][a] < r.lo[a] ? v[k][a] : r.lo[a];
+                r.hi[a] = v[k][a] > r.hi[a] ? v[k][a] : r.hi[a];
+            }
+        }
+        out[i] = r;
+    }
+}
+
+// The construction proper, on device-resident inputs.  Leaves the internal nodes in *d_nodes (allocated from `mem`), the
+// leaf order in b.perm and fills `a` (a.nodes stays untouched).  d_non_tri may be NULL.
+int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bounds, uint32_t n, const uint8_t* d_non_tri,
+                 uint32_t first_id, uint32_t capacity, spcu_bvh_node** d_nodes, spcu_accel& a)
+{
     const cudaStream_t st        = c->stream;
     const size_t       max_nodes = 2 * static_cast<size_t>(n);
     // a node with children holds >= 5 primitives, so a level has at most n/5 of them and the next level 2n/5 nodes
     const size_t       max_level = std::max<size_t>(2 * (static_cast<size_t>(n) / 5) + 2, 4);
     const uint32_t     n_tiles   = n / kScanTile + 1; // covers index n
-    Scratch            mem;
-    Build              b{};
-    b.n = n;
-    spcu_bounds* d_bounds  = nullptr;
-    uint32_t*    partials  = nullptr;
-    uint8_t*     d_non_tri = nullptr;
-    CK(c, mem.get(&d_bounds, n));
+    uint32_t*          partials  = nullptr;
+    b        = Build{};
+    b.n      = n;
+    b.bounds = d_bounds;
     CK(c, mem.get(&b.perm, n));
     CK(c, mem.get(&b.seg_of, n));
     CK(c, mem.get(&b.first, max_nodes));
@@ -585,16 +657,11 @@ extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n
     CK(c, mem.get(&b.right_misplaced, n));
     CK(c, mem.get(&b.n_nodes, 1));
     CK(c, mem.get(&partials, n_tiles));
-    b.bounds = d_bounds;
-    CK(c, cudaMemcpyAsync(d_bounds, bounds, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyHostToDevice, st));
-    if (non_triangle) {
-        CK(c, mem.get(&d_non_tri, n));
-        CK(c, cudaMemcpyAsync(d_non_tri, non_triangle, n, cudaMemcpyHostToDevice, st));
-    }
     CK(c, cudaMemsetAsync(b.flag, 0, static_cast<size_t>(n_tiles) * kScanTile, st));
 
-    const unsigned grid = grid_for(n, c->sm_count);
-    CK(c, cudaEventRecord(c->ev0, st));
+    const unsigned grid        = grid_for(n, c->sm_count);
+    const unsigned bounds_grid = static_cast<unsigned>((static_cast<uint64_t>(n) + kBlock * kBoundsIterations - 1) / (kBlock * kBoundsIterations));
+    CK(c, cudaEventRecord(c->ev0, st)); // ev0 .. ev1: the construction kernels (allocations above are outside)
     k_init<<<grid, kBlock, 0, st>>>(b);
     uint32_t level_begin = 0, level_end = 1, max_depth = 0;
     for (uint32_t level = 0; level_begin < level_end; ++level) {
@@ -604,7 +671,7 @@ extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n
         }
         const unsigned node_grid = (count + kBlock - 1) / kBlock;
         k_keys_init<<<node_grid, kBlock, 0, st>>>(b.keys, count);
-        k_bounds<<<grid, kBlock, 0, st>>>(b, level_begin);
+        k_bounds<<<bounds_grid, kBlock, 0, st>>>(b, level_begin);
         k_decide<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
         k_flags<<<grid, kBlock, 0, st>>>(b, level_begin);
         scan_bytes(b, partials, n_tiles, st);
@@ -637,30 +704,149 @@ extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n
     if (n_internal > capacity) {
         return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: %u internal nodes, capacity %u", n_internal, capacity);
     }
-    spcu_bvh_node* d_nodes = nullptr;
-    CK(c, mem.get(&d_nodes, n_internal));
-    k_emit<<<all_grid, kBlock, 0, st>>>(b, n_nodes, d_nodes, first_id, d_non_tri);
+    CK(c, mem.get(d_nodes, n_internal));
+    k_emit<<<all_grid, kBlock, 0, st>>>(b, n_nodes, *d_nodes, first_id, d_non_tri);
     CK(c, cudaEventRecord(c->ev1, st));
     CK(c, cudaGetLastError());
-    if (n_internal) {
-        CK(c, cudaMemcpyAsync(nodes, d_nodes, static_cast<size_t>(n_internal) * sizeof(spcu_bvh_node), cudaMemcpyDeviceToHost, st));
+    a.n_unbounded = first_id;
+    a.n_prims     = first_id + n;
+    a.n_nodes     = n_internal;
+    a.max_depth   = max_depth;
+    a.root_count  = 0;
+    if (root_state == kInternal) {
+        a.root = 0;
+    } else { // one leaf holds everything: its mixed flag is the OR over all primitives
+        uint32_t mixed = 0;
+        if (d_non_tri) {
+            std::vector<uint8_t> h(n);
+            CK(c, cudaMemcpyAsync(h.data(), d_non_tri, n, cudaMemcpyDeviceToHost, st));
+            CK(c, cudaStreamSynchronize(st));
+            for (const uint8_t f : h) {
+                mixed |= f;
+            }
+        }
+        a.root       = ~static_cast<int32_t>(first_id);
+        a.root_count = n | (mixed ? SPCU_LEAF_MIXED_FLAG : 0u);
+    }
+    return SPCU_OK;
+}
+
+} // namespace
+
+// The geometry half of spcu_upload_scene_build (spcu_api.cu): primitive records arrive in PRE-construction order
+// ([0, n_unbounded) the top-level list, then the bounded primitives as the reference holds them before
+// BVHAccelerator(first, last)); bounds, tree and the gather into leaf order all happen on the device, and the context's
+// geometry buffers end up exactly as spcu_upload_scene would have filled them from the flattener's output.
+int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu_bounds* extra_bounds, uint32_t* order_out,
+                               spcu_accel* built)
+{
+    const uint32_t n_prims = s->geom.n_prims, first_id = s->geom.n_unbounded, n = n_prims - first_id;
+    const cudaStream_t st  = c->stream;
+    Scratch            mem;
+    spcu_prim_geom*    src_geom  = nullptr;
+    spcu_prim_shade*   src_shade = nullptr;
+    uint32_t*          src_meta  = nullptr;
+    const size_t       np        = std::max<size_t>(n_prims, 1);
+    CK(c, mem.get(&src_geom, np));
+    CK(c, mem.get(&src_shade, np));
+    CK(c, mem.get(&src_meta, np));
+    CK(c, c->geom_prims.reserve(np * sizeof(spcu_prim_geom)));
+    CK(c, c->geom_shade.reserve(np * sizeof(spcu_prim_shade)));
+    CK(c, c->geom_meta.reserve(np * sizeof(uint32_t)));
+    if (n_prims) {
+        CK(c, cudaMemcpyAsync(src_geom, s->geom_prims, n_prims * sizeof(spcu_prim_geom), cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(src_shade, s->geom_shade, n_prims * sizeof(spcu_prim_shade), cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(src_meta, s->geom_meta, n_prims * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        c->scene_bytes += n_prims * (sizeof(spcu_prim_geom) + sizeof(spcu_prim_shade) + sizeof(uint32_t));
+    }
+    if (first_id) { // the top-level list keeps its order
+        CK(c, cudaMemcpyAsync(c->geom_prims.p, src_geom, first_id * sizeof(spcu_prim_geom), cudaMemcpyDeviceToDevice, st));
+        CK(c, cudaMemcpyAsync(c->geom_shade.p, src_shade, first_id * sizeof(spcu_prim_shade), cudaMemcpyDeviceToDevice, st));
+        CK(c, cudaMemcpyAsync(c->geom_meta.p, src_meta, first_id * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    spcu_accel a{};
+    a.n_unbounded = first_id;
+    a.n_prims     = n_prims;
+    a.root        = ~static_cast<int32_t>(first_id);
+    CK(c, c->geom_nodes.reserve(16));
+    if (n) {
+        spcu_bounds* d_bounds  = nullptr;
+        uint8_t*     d_non_tri = nullptr;
+        CK(c, mem.get(&d_bounds, n));
+        CK(c, mem.get(&d_non_tri, n));
+        if (extra_bounds) {
+            CK(c, cudaMemcpyAsync(d_bounds, extra_bounds, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyHostToDevice, st));
+        }
+        k_scene_bounds<<<grid_for(n, c->sm_count), kBlock, 0, st>>>(src_geom + first_id, src_meta + first_id, n, d_bounds, d_non_tri);
+        Build          b;
+        spcu_bvh_node* d_nodes = nullptr;
+        if (const int rc = device_build(c, mem, b, d_bounds, n, d_non_tri, first_id, n - 1, &d_nodes, a); rc != SPCU_OK) {
+            return rc;
+        }
+        CK(c, c->geom_nodes.reserve(std::max<size_t>(a.n_nodes, 1) * sizeof(spcu_bvh_node)));
+        if (a.n_nodes) {
+            CK(c, cudaMemcpyAsync(c->geom_nodes.p, d_nodes, a.n_nodes * sizeof(spcu_bvh_node), cudaMemcpyDeviceToDevice, st));
+        }
+        k_gather_prims<<<grid_for(n, c->sm_count), kBlock, 0, st>>>(
+            b.perm, n, first_id, reinterpret_cast<const float4*>(src_geom), reinterpret_cast<const float4*>(src_shade), src_meta,
+            c->geom_prims.as<float4>(), c->geom_shade.as<float4>(), c->geom_meta.as<uint32_t>());
+        CK(c, cudaGetLastError());
+        if (order_out) {
+            CK(c, cudaMemcpyAsync(order_out, b.perm, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        CK(c, cudaStreamSynchronize(st));
+    }
+    *built = a;
+    return SPCU_OK;
+}
+
+extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n, const uint8_t* non_triangle, uint32_t first_id,
+                              uint32_t* order, spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, float* device_ms)
+{
+    if (!c) {
+        return SPCU_ERR_INVALID;
+    }
+    if (!accel || (n && (!bounds || !order)) || (capacity && !nodes)) {
+        return fail(c, SPCU_ERR_INVALID, "spcu_build_bvh: NULL argument");
+    }
+    if (n >= (1u << 30) || static_cast<uint64_t>(first_id) + n >= (1u << 30)) {
+        return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: more than 2^30 primitives");
+    }
+    CK(c, cudaSetDevice(c->device));
+    spcu_accel a{};
+    a.n_unbounded = first_id;
+    a.n_prims     = first_id + n;
+    a.nodes       = nodes;
+    if (device_ms) {
+        *device_ms = 0.0f;
+    }
+    if (n == 0) { // BVHAccelerator(first, first): one empty leaf (base/Scene.h:34-37)
+        a.root = ~static_cast<int32_t>(first_id);
+        *accel = a;
+        return SPCU_OK;
+    }
+    const cudaStream_t st = c->stream;
+    Scratch            mem;
+    spcu_bounds*       d_bounds  = nullptr;
+    uint8_t*           d_non_tri = nullptr;
+    CK(c, mem.get(&d_bounds, n));
+    CK(c, cudaMemcpyAsync(d_bounds, bounds, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyHostToDevice, st));
+    if (non_triangle) {
+        CK(c, mem.get(&d_non_tri, n));
+        CK(c, cudaMemcpyAsync(d_non_tri, non_triangle, n, cudaMemcpyHostToDevice, st));
+    }
+    Build          b;
+    spcu_bvh_node* d_nodes = nullptr;
+    if (const int rc = device_build(c, mem, b, d_bounds, n, d_non_tri, first_id, capacity, &d_nodes, a); rc != SPCU_OK) {
+        return rc;
+    }
+    if (a.n_nodes) {
+        CK(c, cudaMemcpyAsync(nodes, d_nodes, static_cast<size_t>(a.n_nodes) * sizeof(spcu_bvh_node), cudaMemcpyDeviceToHost, st));
     }
     CK(c, cudaMemcpyAsync(order, b.perm, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (device_ms) {
         CK(c, cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
-    }
-    a.n_nodes   = n_internal;
-    a.max_depth = max_depth;
-    if (root_state == kInternal) {
-        a.root = 0;
-    } else {
-        uint32_t mixed = 0;
-        for (uint32_t i = 0; non_triangle && i < n; ++i) {
-            mixed |= non_triangle[i];
-        }
-        a.root       = ~static_cast<int32_t>(first_id);
-        a.root_count = n | (mixed ? SPCU_LEAF_MIXED_FLAG : 0u);
     }
     *accel = a;
     return SPCU_OK;

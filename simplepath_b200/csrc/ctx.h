@@ -71,6 +71,7 @@ struct spcu_ctx
     spcu::DevBuf geom_nodes, geom_prims, geom_shade, geom_meta, light_nodes, lights, light_order, materials, bxdfs, pool,
         jitter;
     uint64_t scene_bytes = 0;
+    spcu_accel built_geom{}; // geometry accelerator header of the resident scene (nodes = NULL: they live on the device)
 
     // batch-query scratch
     spcu::DevBuf q_rays, q_out, q_aux, q_cnt;
@@ -101,6 +102,9 @@ namespace spcu {
 
 int fail(spcu_ctx* c, int code, const char* fmt, ...);
 int need_scene(spcu_ctx* c);
+// build_kernels.cu: geometry of an UNBUILT scene -> bounds, BVH and leaf-order gather on the device (spcu_upload_scene_build)
+int build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu_bounds* extra_bounds, uint32_t* order_out,
+                         spcu_accel* built);
 
 #define CK(ctx, call)                                                                                                     \
     do {                                                                                                                  \

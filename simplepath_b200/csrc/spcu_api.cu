@@ -224,7 +224,9 @@ int spcu_set_wavefront_size(spcu_ctx* c, uint64_t n_paths)
     return SPCU_OK;
 }
 
-int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter, uint32_t spp)
+// spcu_upload_scene (build = false) and spcu_upload_scene_build (build = true: the geometry arrives unbuilt).
+static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter, uint32_t spp, bool build,
+                       const spcu_bounds* bounds, uint32_t* order)
 {
     if (!c) {
         return SPCU_ERR_INVALID;
@@ -238,7 +240,11 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     if (spp > 0 && !jitter) {
         return fail(c, SPCU_ERR_INVALID, "jitter table is NULL");
     }
-    if (int rc = validate_accel(c, s->geom, "geometry accelerator"); rc != SPCU_OK) return rc;
+    if (!build) {
+        if (int rc = validate_accel(c, s->geom, "geometry accelerator"); rc != SPCU_OK) return rc;
+    } else if (s->geom.n_unbounded > s->geom.n_prims || s->geom.n_prims >= (1u << 30)) {
+        return fail(c, SPCU_ERR_INVALID, "geometry: n_unbounded > n_prims, or more than 2^30 primitives");
+    }
     if (int rc = validate_accel(c, s->lights_accel, "lights accelerator"); rc != SPCU_OK) return rc;
     if (s->lights_accel.n_prims != s->n_lights) {
         return fail(c, SPCU_ERR_INVALID, "lights accelerator holds %u prims but n_lights is %u", s->lights_accel.n_prims,
@@ -247,6 +253,9 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     for (uint32_t i = 0; i < s->geom.n_prims; ++i) {
         if (SPCU_META_MATERIAL(s->geom_meta[i]) >= s->n_materials || SPCU_META_KIND(s->geom_meta[i]) > SPCU_PRIM_PLANE) {
             return fail(c, SPCU_ERR_INVALID, "primitive %u: bad kind or material index", i);
+        }
+        if (build && !bounds && i >= s->geom.n_unbounded && SPCU_META_KIND(s->geom_meta[i]) != SPCU_PRIM_TRIANGLE) {
+            return fail(c, SPCU_ERR_INVALID, "primitive %u is bounded and not a triangle: its world bounds must be supplied", i);
         }
     }
     for (uint32_t i = 0; i < s->n_materials; ++i) {
@@ -279,11 +288,16 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     CK(c, cudaSetDevice(c->device));
     c->have_scene  = false;
     c->scene_bytes = 0;
-    int rc;
-    if ((rc = upload(c, c->geom_nodes, s->geom.nodes, s->geom.n_nodes)) != SPCU_OK) return rc;
-    if ((rc = upload(c, c->geom_prims, s->geom_prims, s->geom.n_prims)) != SPCU_OK) return rc;
-    if ((rc = upload(c, c->geom_shade, s->geom_shade, s->geom.n_prims)) != SPCU_OK) return rc;
-    if ((rc = upload(c, c->geom_meta, s->geom_meta, s->geom.n_prims)) != SPCU_OK) return rc;
+    int        rc;
+    spcu_accel geom = s->geom;
+    if (build) {
+        if ((rc = build_scene_geometry(c, s, bounds, order, &geom)) != SPCU_OK) return rc;
+    } else {
+        if ((rc = upload(c, c->geom_nodes, s->geom.nodes, s->geom.n_nodes)) != SPCU_OK) return rc;
+        if ((rc = upload(c, c->geom_prims, s->geom_prims, s->geom.n_prims)) != SPCU_OK) return rc;
+        if ((rc = upload(c, c->geom_shade, s->geom_shade, s->geom.n_prims)) != SPCU_OK) return rc;
+        if ((rc = upload(c, c->geom_meta, s->geom_meta, s->geom.n_prims)) != SPCU_OK) return rc;
+    }
     if ((rc = upload(c, c->light_nodes, s->lights_accel.nodes, s->lights_accel.n_nodes)) != SPCU_OK) return rc;
     if ((rc = upload(c, c->lights, s->lights, s->n_lights)) != SPCU_OK) return rc;
     if ((rc = upload(c, c->light_order, s->light_order, s->n_lights)) != SPCU_OK) return rc;
@@ -299,7 +313,7 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     d.rr_depth  = s->rr_depth;
     d.max_depth = s->max_depth;
     std::memcpy(d.camera, s->camera, sizeof d.camera);
-    d.geom         = device_accel(s->geom, c->geom_nodes);
+    d.geom         = device_accel(geom, c->geom_nodes);
     d.geom_prims   = c->geom_prims.as<const float4>();
     d.geom_shade   = c->geom_shade.as<const float4>();
     d.geom_meta    = c->geom_meta.as<const uint32_t>();
@@ -313,10 +327,29 @@ int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter
     d.jitter       = c->jitter.as<const float>();
     d.spp          = spp;
     c->n_materials = s->n_materials;
-    c->features    = c->options[SPCU_OPT_GENERIC_KERNELS] ? FeatFull::id : scene_features(*s);
+    spcu_flat_scene as_built = *s;
+    as_built.geom            = geom;
+    c->features    = c->options[SPCU_OPT_GENERIC_KERNELS] ? FeatFull::id : scene_features(as_built);
+    c->built_geom  = geom;
+    c->built_geom.nodes = nullptr;
     c->have_scene      = true;
     c->pix_list_stride = 0; // invalidate the cached pixel list
     return SPCU_OK;
+}
+
+int spcu_upload_scene(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter, uint32_t spp)
+{
+    return upload_impl(c, s, jitter, spp, false, nullptr, nullptr);
+}
+
+int spcu_upload_scene_build(spcu_ctx* c, const spcu_flat_scene* s, const float* jitter, uint32_t spp, const spcu_bounds* bounds,
+                            uint32_t* order, spcu_accel* built)
+{
+    const int rc = upload_impl(c, s, jitter, spp, true, bounds, order);
+    if (rc == SPCU_OK && built) {
+        *built = c->built_geom;
+    }
+    return rc;
 }
 
 uint64_t spcu_scene_bytes(const spcu_ctx* c)

@@ -101,3 +101,84 @@ def test_build_full_size_properties(ctx):
         pb = b[order[first:first + cnt]]
         want = np.concatenate([pb[:, :3].min(0), pb[:, 3:].max(0)])
         assert np.array_equal(nodes["box"][i, 6 * k:6 * k + 6], want)
+
+
+def _clone(flat):
+    from simplepath_b200.flat import FlatSceneData
+    import copy
+    return FlatSceneData(copy.deepcopy(flat.head), {k: v.copy() for k, v in flat.arrays.items()})
+
+
+@pytest.mark.parametrize("name", ["g_bunny", "g_elf"])
+def test_upload_scene_build(ctx, oracle_port, name):
+    """spcu_upload_scene_build: primitives in a shuffled pre-construction order; bounds, tree and leaf-order gather on the
+    device.  Checked against the all-CPU pipeline (oracle bounds -> oracle construction -> oracle traversal), and, from
+    the reference's own leaf order, against the golden answers and a bitwise-equal render."""
+    from simplepath_b200 import capi
+    from simplepath_b200.flat import FlatSceneData
+    flat = FlatSceneData.load(GOLDEN / f"{name}.flat.npz")
+    vec = np.load(GOLDEN / f"{name}.vectors.npz")
+    nu, n = flat.head["geom"]["n_unbounded"], flat.head["geom"]["n_prims"] - flat.head["geom"]["n_unbounded"]
+    rays = np.concatenate([np.ascontiguousarray(vec[f"{b}.rays"]).view(capi.RAY_DTYPE).reshape(-1)
+                           for b in ("camera", "random", "segments", "axis", "grazing")])
+
+    perm = np.random.default_rng(9).permutation(n)
+    shuffled = _clone(flat)
+    for k in ("geom_prims", "geom_shade", "geom_meta"):
+        shuffled.arrays[k][nu:] = flat.arrays[k][nu + perm]
+    tris = shuffled.arrays["geom_prims"].view(np.float32).reshape(-1, 12)[nu:]
+    built = oracle_port.build_bvh(oracle_port.triangle_bounds(tris), None, nu)
+    cpu = _clone(shuffled)
+    for k in ("geom_prims", "geom_shade", "geom_meta"):
+        cpu.arrays[k][nu:] = shuffled.arrays[k][nu + built["order"]]
+    cpu.arrays["geom_nodes"] = built["nodes"].view(np.uint8).reshape(-1, 64).copy()
+    cpu.head["geom"] = built["head"]
+    want = oracle_port.trace_closest(cpu.pointer(), rays)
+    want_any = oracle_port.trace_any(cpu.pointer(), rays)
+
+    order, head = ctx.upload_scene_build(shuffled.pointer(), vec["jitter"], keepalive=shuffled)
+    assert head == built["head"]
+    assert np.array_equal(order, built["order"])
+    got = ctx.trace_closest(rays)
+    assert np.array_equal(got["id"], want["id"])
+    assert got["t"].tobytes() == want["t"].tobytes()
+    assert np.array_equal(ctx.trace_any(rays), want_any)
+    # same triangles as the reference's tree found (IDs differ: another order, another tree)
+    cam = np.ascontiguousarray(vec["camera.rays"]).view(capi.RAY_DTYPE).reshape(-1)
+    hit = ctx.trace_closest(cam)
+    ref_id = vec["camera.closest_id"]
+    assert np.array_equal(hit["id"] >= 0, ref_id >= 0)
+    bounded = hit["id"] >= nu
+    original = nu + perm[order[hit["id"][bounded] - nu]]          # device ID -> shuffled index -> golden leaf position
+    same = original == ref_id[bounded]
+    assert same.mean() > 0.999, same.mean()                        # equal-distance ties on shared edges may pick the neighbour
+    assert (hit["t"][bounded][same].view(np.uint32) == vec["camera.closest_t"][bounded][same].view(np.uint32)).all()
+
+    # from the reference's leaf order the construction is a fixed point: the golden answers, and the same image bit for bit
+    ctx.upload_scene(flat.pointer(), vec["jitter"], keepalive=flat)
+    part = ctx.partition(spp=int(vec["jitter"].shape[0]), seed=3)
+    rgb_flat, _, _ = ctx.render(part)
+    order, head = ctx.upload_scene_build(flat.pointer(), vec["jitter"], keepalive=flat)
+    assert head == flat.head["geom"] and np.array_equal(order, np.arange(n))
+    hit = ctx.trace_closest(cam)
+    assert np.array_equal(hit["id"], ref_id) and hit["t"].tobytes() == vec["camera.closest_t"].tobytes()
+    rgb_built, _, _ = ctx.render(part)
+    assert rgb_built.tobytes() == rgb_flat.tobytes()
+
+
+def test_upload_scene_build_analytic_and_errors(ctx):
+    """Scenes without a mesh: spheres need caller-supplied bounds; four spheres make one root leaf (material_spheres)."""
+    from simplepath_b200 import capi
+    from simplepath_b200.flat import FlatSceneData
+    flat = FlatSceneData.load(GOLDEN / "g_spheres.flat.npz")
+    vec = np.load(GOLDEN / "g_spheres.vectors.npz")
+    with pytest.raises(capi.SpcuError):
+        ctx.upload_scene_build(flat.pointer(), vec["jitter"], keepalive=flat)     # spheres, no bounds
+    g = flat.head["geom"]
+    n = g["n_prims"] - g["n_unbounded"]
+    bounds = bvhcases.boxes(np.random.default_rng(2), n)                          # <= 4 primitives: any bounds give a leaf
+    order, head = ctx.upload_scene_build(flat.pointer(), vec["jitter"], bounds=bounds, keepalive=flat)
+    assert head == g and np.array_equal(order, np.arange(n))
+    cam = np.ascontiguousarray(vec["camera.rays"]).view(capi.RAY_DTYPE).reshape(-1)
+    hit = ctx.trace_closest(cam)
+    assert np.array_equal(hit["id"], vec["camera.closest_id"]) and hit["t"].tobytes() == vec["camera.closest_t"].tobytes()

@@ -385,6 +385,20 @@ int spcu_upload_scene_build(spcu_ctx* ctx, const spcu_flat_scene* scene, const f
  * tris[i] (layout of spcu_prim_geom), in vertex order.  Host pointers. */
 int spcu_triangle_bounds(spcu_ctx* ctx, const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out);
 
+/* ---- output side on the device ------------------------------------------------------------- */
+/* What the reference writes after render(): image(x, y) /= num_pixel_samples (main.cpp:100-102), then sp::write
+ * (Image/Image.cpp:14-55).  Both formats store rows bottom-up (j = ny-1 .. 0).
+ *   SPCU_IMAGE_PFM : out = float[h][w][3], the payload of write_pfm (:40-55) on a little-endian host: sum / spp
+ *   SPCU_IMAGE_PPM : out = uint16_t[h][w][3], the numbers write_ppm prints (:14-29): int(255.99f * rgb_to_srgb(sum / spp))
+ *                    (Image/Image.h:38-50), clamped to [0, 65535]; a quarter of the device->host bytes of the float sums */
+#define SPCU_IMAGE_PFM 0u
+#define SPCU_IMAGE_PPM 1u
+/* Packs host-resident per-pixel sums (rgb_sum[(y*w+x)*3+c], as spcu_render returns them). */
+int spcu_pack_image(spcu_ctx* ctx, const float* rgb_sum, uint32_t width, uint32_t height, uint32_t spp, uint32_t format, void* out);
+/* spcu_render_frame + packing of the device-resident sums: only the packed image crosses to the host.  The divisor is the
+ * partition's sample count (sample_end - sample_begin). */
+int spcu_render_image(spcu_ctx* ctx, const spcu_partition* part, uint32_t format, void* out, spcu_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,3 +120,15 @@ def triangle_bounds(tris) -> np.ndarray:
     out = np.empty((tris.shape[0], 6), dtype=np.float32)
     l.spo_triangle_bounds(_p(tris), tris.shape[0], _p(out))
     return out
+
+
+def pack_image(rgb_sum, spp: int, fmt: int) -> np.ndarray:
+    """spo_pack_image: write_pfm payload (fmt 0, float32) / write_ppm numbers (fmt 1, uint16), rows bottom-up."""
+    l = lib()
+    l.spo_pack_image.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    l.spo_pack_image.restype = None
+    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+    h, w = rgb_sum.shape[:2]
+    out = np.empty((h, w, 3), dtype=np.float32 if fmt == 0 else np.uint16)
+    l.spo_pack_image(_p(rgb_sum), w, h, spp, fmt, _p(out))
+    return out

@@ -146,3 +146,15 @@ def build_bvh(bounds, non_triangle=None, first_id: int = 0, capacity: int | None
         if lib.spref_build_bvh(*a) != 0:
             raise RuntimeError(f"spref_build_bvh: {err.value.decode()}")
     return run_build(call, bounds, non_triangle, first_id, capacity, with_ms=False, extra=(err, 512))
+
+
+def write_image(rgb_sum, spp: int, path, lib_path: Path = STRICT) -> None:
+    """The reference's own sp::write (Image/Image.cpp) of sums divided as main.cpp:100-102 divides them; format by extension."""
+    lib = C.CDLL(str(lib_path))
+    lib.spref_write_image.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint, C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.spref_write_image.restype = C.c_int
+    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+    h, w = rgb_sum.shape[:2]
+    err = C.create_string_buffer(512)
+    if lib.spref_write_image(_p(rgb_sum), w, h, spp, str(path).encode(), err, 512) != 0:
+        raise RuntimeError(f"spref_write_image: {err.value.decode()}")

@@ -625,6 +625,23 @@ uint32_t spref_geom_bounds(spref_scene* s, float* out)
     return static_cast<uint32_t>(s->geom_ids.id.size());
 }
 
+// sp::write (Image/Image.cpp:66-76: write_pfm / write_ppm by extension) of an image whose pixels are per-pixel sums divided
+// the way render_thread divides them: image(p.x, p.y) /= num_pixel_samples with an unsigned divisor (main.cpp:100-102).
+int spref_write_image(const float* rgb_sum, uint32_t w, uint32_t h, unsigned spp, const char* path, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&] {
+        sp::Image image(w, h);
+        for (uint32_t y = 0; y < h; ++y) {
+            for (uint32_t x = 0; x < w; ++x) {
+                const float* c = rgb_sum + (static_cast<size_t>(y) * w + x) * 3;
+                image(x, y)    = sp::RGB{ c[0], c[1], c[2] };
+                image(x, y) /= spp;
+            }
+        }
+        sp::write(path, image);
+    });
+}
+
 int spref_width(spref_scene* s) { return s->scene->image_width; }
 int spref_height(spref_scene* s) { return s->scene->image_height; }
 } // extern "C"

@@ -634,4 +634,34 @@ void spo_triangle_bounds(const spcu_prim_geom* tris, uint32_t n, spcu_bounds* ou
     }
 }
 
+/* ===================================================================================================
+ * Output side (main.cpp:100-102, Image/Image.cpp:14-55, Image/Image.h:38-50)
+ * =================================================================================================== */
+static float pack_to_srgb(float u) /* rgb_to_srgb (Image/Image.h:38-45); std::pow(float, float) = powf */
+{
+    if (u <= 0.0031308f) return 12.92f * u;
+    return 1.055f * powf(u, 1.0f / 2.4f) - 0.055f;
+}
+
+void spo_pack_image(const float* rgb_sum, uint32_t width, uint32_t height, uint32_t spp, uint32_t format, void* out)
+{
+    const float n = (float)spp;
+    size_t      o = 0;
+    for (int j = (int)height - 1; j >= 0; --j) {
+        for (uint32_t i = 0; i < width; ++i, ++o) {
+            const float* c = rgb_sum + ((size_t)j * width + i) * 3;
+            for (int k = 0; k < 3; ++k) {
+                const float m = c[k] / n; /* RGB::operator/=(float) (math/RGB.h:126-132) */
+                if (format == SPCU_IMAGE_PFM) {
+                    ((float*)out)[3 * o + k] = m;
+                } else {
+                    int v = (int)(255.99f * pack_to_srgb(m)); /* write_ppm (Image/Image.cpp:22-24) */
+                    v     = v < 0 ? 0 : (v > 65535 ? 65535 : v);
+                    ((uint16_t*)out)[3 * o + k] = (uint16_t)v;
+                }
+            }
+        }
+    }
+}
+
 #include "sp_oracle_shade.inc"

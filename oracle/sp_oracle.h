@@ -67,6 +67,11 @@ int spo_build_bvh(const spcu_bounds* bounds, uint32_t n, const uint8_t* non_tria
 /* Triangle::get_world_bounds_impl (shapes/Triangle.h:228-237) */
 void spo_triangle_bounds(const spcu_prim_geom* tris, uint32_t n, spcu_bounds* out);
 
+/* image(x, y) /= spp (main.cpp:100-102), then write_pfm's payload (format SPCU_IMAGE_PFM: float[h][w][3]) or the numbers
+ * write_ppm prints (SPCU_IMAGE_PPM: uint16_t[h][w][3], clamped to [0, 65535]), rows bottom-up (Image/Image.cpp:14-55).
+ * Pinned against files the reference's own sp::write produced (tests/golden/image_pack.npz). */
+void spo_pack_image(const float* rgb_sum, uint32_t width, uint32_t height, uint32_t spp, uint32_t format, void* out);
+
 #ifdef __cplusplus
 }
 #endif

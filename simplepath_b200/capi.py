@@ -111,11 +111,13 @@ EXPORTS = [
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
     "spcu_generate_rays", "spcu_render", "spcu_render_frame", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times", "spcu_resolved_pipeline",
-    "spcu_build_bvh", "spcu_triangle_bounds", "spcu_upload_scene_build",
+    "spcu_build_bvh", "spcu_triangle_bounds", "spcu_upload_scene_build", "spcu_pack_image", "spcu_render_image",
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
 PIPELINE_WAVEFRONT, PIPELINE_PATHS, PIPELINE_SMWAVE, PIPELINE_AUTO = 0, 1, 2, 3
+IMAGE_PFM, IMAGE_PPM = 0, 1
+IMAGE_DTYPES = {IMAGE_PFM: np.float32, IMAGE_PPM: np.uint16}
 
 
 class SpcuError(RuntimeError):
@@ -176,6 +178,10 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_build_bvh.restype = C.c_int
     lib.spcu_upload_scene_build.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(C.c_float), C.c_uint32, vp, vp, C.POINTER(Accel)]
     lib.spcu_upload_scene_build.restype = C.c_int
+    lib.spcu_pack_image.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    lib.spcu_pack_image.restype = C.c_int
+    lib.spcu_render_image.argtypes = [vp, C.POINTER(Partition), C.c_uint32, vp, C.POINTER(Stats)]
+    lib.spcu_render_image.restype = C.c_int
     lib.spcu_triangle_bounds.argtypes = [vp, vp, C.c_uint32, vp]
     lib.spcu_triangle_bounds.restype = C.c_int
     if lib.spcu_abi_version() != ABI_VERSION:
@@ -361,6 +367,21 @@ class Context:
         out = np.empty((tris.shape[0], 6), dtype=np.float32)
         self._check(self.lib.spcu_triangle_bounds(self.h, _ptr(tris), tris.shape[0], _ptr(out)), "spcu_triangle_bounds")
         return out
+
+    def pack_image(self, rgb_sum, spp: int, fmt: int) -> np.ndarray:
+        """Host sums [H, W, 3] -> write_pfm payload (float32) / write_ppm numbers (uint16), rows bottom-up."""
+        rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+        h, w = rgb_sum.shape[:2]
+        out = np.empty((h, w, 3), dtype=IMAGE_DTYPES[fmt])
+        self._check(self.lib.spcu_pack_image(self.h, _ptr(rgb_sum), w, h, spp, fmt, _ptr(out)), "spcu_pack_image")
+        return out
+
+    def render_image(self, part: Partition, fmt: int):
+        """Render + pack on the device: (packed image [H, W, 3], stats)."""
+        out = np.empty((self.height, self.width, 3), dtype=IMAGE_DTYPES[fmt])
+        st = Stats()
+        self._check(self.lib.spcu_render_image(self.h, C.byref(part), fmt, _ptr(out), C.byref(st)), "spcu_render_image")
+        return out, st.as_dict()
 
     def set_wavefront_size(self, n: int) -> None:
         self._check(self.lib.spcu_set_wavefront_size(self.h, n), "spcu_set_wavefront_size")

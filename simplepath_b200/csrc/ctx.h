@@ -86,6 +86,7 @@ struct spcu_ctx
     spcu::DevBuf              pix_list;
     uint32_t                  pix_list_offset = ~0u, pix_list_stride = 0, pix_list_n = 0;
     spcu::DevBuf              host_rgb, host_sq; // device accumulators of the host-buffer entry point
+    spcu::DevBuf              packed;            // packed output image (spcu_render_image / spcu_pack_image)
     spcu::DevBuf              path_radiance;     // float4 per slot of a batch (SPCU_PIPELINE_PATHS)
     spcu::DevBuf              sorted_queue;      // material-sorted hand-over between extend and shade
     uint32_t                  n_materials = 0;
@@ -102,6 +103,8 @@ namespace spcu {
 
 int fail(spcu_ctx* c, int code, const char* fmt, ...);
 int need_scene(spcu_ctx* c);
+// image_kernels.cu: mean, row order and sRGB quantisation of device-resident sums, result copied to the host buffer `out`
+int pack_device_image(spcu_ctx* c, const float* d_rgb_sum, uint32_t w, uint32_t h, uint32_t spp, uint32_t format, void* out);
 // build_kernels.cu: geometry of an UNBUILT scene -> bounds, BVH and leaf-order gather on the device (spcu_upload_scene_build)
 int build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu_bounds* extra_bounds, uint32_t* order_out,
                          spcu_accel* built);

@@ -185,7 +185,7 @@ void spcu_destroy(spcu_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : { &c->geom_nodes, &c->geom_prims, &c->geom_shade, &c->geom_meta, &c->light_nodes, &c->lights,
                        &c->light_order, &c->materials, &c->bxdfs, &c->pool, &c->jitter, &c->q_rays, &c->q_out, &c->q_aux,
-                       &c->q_cnt, &c->queue_counts, &c->counters, &c->pix_list, &c->host_rgb, &c->host_sq, &c->path_radiance, &c->sorted_queue }) {
+                       &c->q_cnt, &c->queue_counts, &c->counters, &c->pix_list, &c->host_rgb, &c->host_sq, &c->path_radiance, &c->sorted_queue, &c->packed }) {
         b->release();
     }
     for (auto& b : c->wave_bufs) {

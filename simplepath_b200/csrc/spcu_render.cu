@@ -466,6 +466,19 @@ int spcu_render_frame(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, f
     return SPCU_OK;
 }
 
+int spcu_render_image(spcu_ctx* c, const spcu_partition* part, uint32_t format, void* out, spcu_stats* stats)
+{
+    if (int rc = need_scene(c); rc != SPCU_OK) return rc;
+    if (!part || part->sample_end <= part->sample_begin) {
+        return fail(c, SPCU_ERR_INVALID, "empty sample range");
+    }
+    const size_t n_pixels = static_cast<size_t>(c->ds.width) * c->ds.height;
+    CK(c, c->host_rgb.reserve(n_pixels * 3 * sizeof(float)));
+    CK(c, cudaMemsetAsync(c->host_rgb.p, 0, n_pixels * 3 * sizeof(float), c->stream));
+    if (int rc = render_impl(c, part, c->host_rgb.as<float>(), nullptr, stats, nullptr, false); rc != SPCU_OK) return rc;
+    return pack_device_image(c, c->host_rgb.as<float>(), c->ds.width, c->ds.height, part->sample_end - part->sample_begin, format, out);
+}
+
 int spcu_stage_times(spcu_ctx* c, spcu_stage_time* out, uint32_t capacity, uint32_t* n_out)
 {
     if (!c || !out || !n_out) {

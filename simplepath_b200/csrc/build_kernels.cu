@@ -46,9 +46,14 @@ static_assert(sizeof(NodeKeys) == 64, "NodeKeys");
 
 struct Build
 {
-    const spcu_bounds* bounds; // [n] initial order
+    // Position-ordered, double-buffered: bounds_in[position] / perm_in[position] describe the primitive at that position when
+    // the level starts (perm = its index in the caller's array); k_apply writes the permuted level into *_out and the host
+    // swaps.  Every pass over positions therefore reads contiguously; only the elements a partition moves are gathered.
+    const spcu_bounds* bounds_in;
+    spcu_bounds*       bounds_out;
+    const uint32_t*    perm_in;
+    uint32_t*          perm_out;
     uint32_t           n;
-    uint32_t*          perm;   // [n] perm[position] = index into bounds
     uint32_t*          seg_of; // [n] node (BFS numbering) the position belongs to at the current level; kInvalid once in a leaf
     // per node, BFS numbering, capacity 2n
     uint32_t* first;
@@ -114,8 +119,8 @@ __global__ void k_init(Build b)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += stride) {
-        b.perm[i]   = i;
-        b.seg_of[i] = 0;
+        b.perm_out[i] = i; // the host swaps in/out before the first level
+        b.seg_of[i]   = 0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         b.first[0] = 0, b.last[0] = b.n, b.parent[0] = kInvalid, b.left_run[0] = 0, b.state[0] = kPending;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin
         Partial        cur;
         cur.seg = pos < b.n ? b.seg_of[pos] : kInvalid;
         if (cur.seg != kInvalid) {
-            const spcu_bounds x = load_bounds(&b.bounds[b.perm[pos]]);
+            const spcu_bounds x = load_bounds(&b.bounds_in[pos]);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 cur.k[a]     = min_key(x.lo[a], pos);
@@ -274,7 +279,7 @@ __device__ void decode_bounds(const Build& b, const NodeKeys& nk, float lo[3], f
         if (l == 0.0f) {
             const uint32_t j = 0x7FFFFFFFu - (static_cast<uint32_t>(kl) >> 1);
             if (j < nk.first_nonzero[a]) {
-                l = b.bounds[b.perm[j]].hi[a];
+                l = b.bounds_in[j].hi[a];
             }
         }
         lo[a] = l;
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kBlock) k_flags(Build b, uint32_t level_begin)
         uint8_t        f   = 0;
         if (seg != kInvalid && b.state[seg] == kSplitting) {
             const uint32_t d = b.dim[seg - level_begin];
-            const float*   x = reinterpret_cast<const float*>(&b.bounds[b.perm[pos]]);
+            const float*   x = reinterpret_cast<const float*>(&b.bounds_in[pos]);
             f                = __fdiv_rn(__fadd_rn(__ldg(x + d), __ldg(x + 3 + d)), 2.0f) < b.at[seg - level_begin];
         }
         b.flag[pos] = f;
@@ -456,7 +461,9 @@ __global__ void __launch_bounds__(kBlock) k_scatter(Build b, uint32_t level_begi
     }
 }
 
-// step 2: swap the pairs, hand every position to its child (or retire it with its leaf).
+// step 2, as a gather: every position fetches the element the partition leaves there (its own, or its partner's when it
+// holds a misplaced one), writes it to the level's output buffers and joins its child — or retires with its leaf, whose
+// elements stay where they are in BOTH buffers from now on.
 __global__ void __launch_bounds__(kBlock) k_apply(Build b, uint32_t level_begin)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -465,20 +472,25 @@ __global__ void __launch_bounds__(kBlock) k_apply(Build b, uint32_t level_begin)
         if (seg == kInvalid) {
             continue;
         }
+        uint32_t src = pos;
         if (b.state[seg] != kInternal) {
             b.seg_of[pos] = kInvalid;
-            continue;
+        } else {
+            const uint32_t first = b.first[seg], mid = b.mid[seg - level_begin];
+            const uint32_t before = b.prefix[pos] - b.prefix[first]; // trues in [first, pos)
+            const bool     f      = b.flag[pos] != 0;
+            if (pos < mid && !f) {
+                src = b.right_misplaced[first + (pos - first - before)];
+            } else if (pos >= mid && f) {
+                src = b.left_misplaced[first + (mid - first - before - 1u)];
+            }
+            b.seg_of[pos] = b.child0[seg] + (pos >= mid ? 1u : 0u);
         }
-        const uint32_t first = b.first[seg], mid = b.mid[seg - level_begin];
-        const uint32_t misplaced = (mid - first) - (b.prefix[mid] - b.prefix[first]); // falses in [first, mid)
-        const uint32_t j         = pos - first;
-        if (j < misplaced) {
-            const uint32_t p = b.left_misplaced[first + j], q = b.right_misplaced[first + j];
-            const uint32_t t = b.perm[p];
-            b.perm[p]        = b.perm[q];
-            b.perm[q]        = t;
-        }
-        b.seg_of[pos] = b.child0[seg] + (pos >= mid ? 1u : 0u);
+        b.perm_out[pos] = b.perm_in[src];
+        const float2* q = reinterpret_cast<const float2*>(&b.bounds_in[src]);
+        float2*       o = reinterpret_cast<float2*>(&b.bounds_out[pos]);
+        const float2  v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+        o[0] = v0, o[1] = v1, o[2] = v2;
     }
 }
 
@@ -512,7 +524,7 @@ __global__ void k_emit(Build b, uint32_t n_nodes, spcu_bvh_node* out, uint32_t f
         uint32_t mixed = 0;
         if (non_triangle) {
             for (uint32_t p = b.first[v]; p < b.last[v]; ++p) {
-                mixed |= non_triangle[b.perm[p]];
+                mixed |= non_triangle[b.perm_in[p]];
             }
         }
         dst->child[which] = ~static_cast<int32_t>(first_id + b.first[v]);
@@ -625,8 +637,8 @@ __global__ void __launch_bounds__(kBlock) k_scene_bounds(const spcu_prim_geom* p
 }
 
 // The construction proper, on device-resident inputs.  Leaves the internal nodes in *d_nodes (allocated from `mem`), the
-// leaf order in b.perm and fills `a` (a.nodes stays untouched).  d_non_tri may be NULL.
-int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bounds, uint32_t n, const uint8_t* d_non_tri,
+// leaf order in b.perm_in and fills `a` (a.nodes stays untouched).  d_non_tri may be NULL.
+int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uint32_t n, const uint8_t* d_non_tri,
                  uint32_t first_id, uint32_t capacity, spcu_bvh_node** d_nodes, spcu_accel& a)
 {
     const cudaStream_t st        = c->stream;
@@ -635,10 +647,19 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bound
     const size_t       max_level = std::max<size_t>(2 * (static_cast<size_t>(n) / 5) + 2, 4);
     const uint32_t     n_tiles   = n / kScanTile + 1; // covers index n
     uint32_t*          partials  = nullptr;
-    b        = Build{};
-    b.n      = n;
-    b.bounds = d_bounds;
-    CK(c, mem.get(&b.perm, n));
+    b   = Build{};
+    b.n = n;
+    spcu_bounds* bounds_buf[2] = { d_bounds, nullptr };
+    uint32_t*    perm_buf[2]   = { nullptr, nullptr };
+    CK(c, mem.get(&bounds_buf[1], n));
+    CK(c, mem.get(&perm_buf[0], n));
+    CK(c, mem.get(&perm_buf[1], n));
+    int  cur     = 0; // buffers the current level reads
+    auto set_buf = [&] {
+        b.bounds_in = bounds_buf[cur], b.bounds_out = bounds_buf[cur ^ 1], b.perm_in = perm_buf[cur], b.perm_out = perm_buf[cur ^ 1];
+    };
+    cur = 1; // k_init writes perm_out = perm_buf[0]
+    set_buf();
     CK(c, mem.get(&b.seg_of, n));
     CK(c, mem.get(&b.first, max_nodes));
     CK(c, mem.get(&b.last, max_nodes));
@@ -663,6 +684,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bound
     const unsigned bounds_grid = static_cast<unsigned>((static_cast<uint64_t>(n) + kBlock * kBoundsIterations - 1) / (kBlock * kBoundsIterations));
     CK(c, cudaEventRecord(c->ev0, st)); // ev0 .. ev1: the construction kernels (allocations above are outside)
     k_init<<<grid, kBlock, 0, st>>>(b);
+    cur = 0;
     uint32_t level_begin = 0, level_end = 1, max_depth = 0;
     for (uint32_t level = 0; level_begin < level_end; ++level) {
         const uint32_t count = level_end - level_begin;
@@ -670,6 +692,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bound
             return fail(c, SPCU_ERR_INVALID, "spcu_build_bvh: level %u holds %u nodes (internal error)", level, count);
         }
         const unsigned node_grid = (count + kBlock - 1) / kBlock;
+        set_buf();
         k_keys_init<<<node_grid, kBlock, 0, st>>>(b.keys, count);
         k_bounds<<<bounds_grid, kBlock, 0, st>>>(b, level_begin);
         k_decide<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
@@ -678,6 +701,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bound
         k_split<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
         k_scatter<<<grid, kBlock, 0, st>>>(b, level_begin);
         k_apply<<<grid, kBlock, 0, st>>>(b, level_begin);
+        cur ^= 1;
         uint32_t total = 0;
         CK(c, cudaMemcpyAsync(&total, b.n_nodes, sizeof total, cudaMemcpyDeviceToHost, st));
         CK(c, cudaStreamSynchronize(st));
@@ -691,6 +715,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, const spcu_bounds* d_bound
         level_end   = total;
     }
     const uint32_t n_nodes = level_end;
+    set_buf(); // perm_in = the final order
 
     // numbering + emission
     CK(c, cudaMemsetAsync(b.flag, 0, static_cast<size_t>(n_tiles) * kScanTile, st));
@@ -788,11 +813,11 @@ int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu
             CK(c, cudaMemcpyAsync(c->geom_nodes.p, d_nodes, a.n_nodes * sizeof(spcu_bvh_node), cudaMemcpyDeviceToDevice, st));
         }
         k_gather_prims<<<grid_for(n, c->sm_count), kBlock, 0, st>>>(
-            b.perm, n, first_id, reinterpret_cast<const float4*>(src_geom), reinterpret_cast<const float4*>(src_shade), src_meta,
+            b.perm_in, n, first_id, reinterpret_cast<const float4*>(src_geom), reinterpret_cast<const float4*>(src_shade), src_meta,
             c->geom_prims.as<float4>(), c->geom_shade.as<float4>(), c->geom_meta.as<uint32_t>());
         CK(c, cudaGetLastError());
         if (order_out) {
-            CK(c, cudaMemcpyAsync(order_out, b.perm, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(c, cudaMemcpyAsync(order_out, b.perm_in, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
         CK(c, cudaStreamSynchronize(st));
     }
@@ -843,7 +868,7 @@ extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n
     if (a.n_nodes) {
         CK(c, cudaMemcpyAsync(nodes, d_nodes, static_cast<size_t>(a.n_nodes) * sizeof(spcu_bvh_node), cudaMemcpyDeviceToHost, st));
     }
-    CK(c, cudaMemcpyAsync(order, b.perm, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(order, b.perm_in, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     if (device_ms) {
         CK(c, cudaEventElapsedTime(device_ms, c->ev0, c->ev1));

@@ -399,6 +399,24 @@ int spcu_pack_image(spcu_ctx* ctx, const float* rgb_sum, uint32_t width, uint32_
  * partition's sample count (sample_end - sample_begin). */
 int spcu_render_image(spcu_ctx* ctx, const spcu_partition* part, uint32_t format, void* out, spcu_stats* stats);
 
+/* ---- mesh ingest on the device ------------------------------------------------------------- */
+/* What read_ply does once the vertex and face lists are read (base/PlyReader.cpp:487-531) followed by Mesh's constructor
+ * (shapes/Triangle.h:25-51): face normals by compensated cross product, zero-area faces dropped, vertex normals = normalised
+ * sum of the kept faces' normals in face order ((0,1,0) for an empty sum), vertices and normals to world space, and the
+ * pre-gathered triangle records of this header in face order — the pre-construction order spcu_upload_scene_build takes.
+ *   vertices[nv*3], faces[nf*3]   object-space positions and the indices of the triangular faces, as the parser read them
+ *   object_to_world[12]           AffineSpace, layout c0.xyz c1.xyz c2.xyz affine.xyz (as spcu_prim_geom's transform)
+ *   normal_xf[9]                  inverse(linear).transposed(), column major: what LinearSpace3x3::operator()(Normal3)
+ *                                 (math/LinearSpace3x3.h:163-167) builds on every call — computed once by the host
+ *   prims / shade / meta [nf]     out; the first *n_kept entries are valid (meta = triangle | material)
+ *   world_vertices / world_normals [nv*3]  out, may be NULL: Mesh::m_vertices / m_normals
+ * Positions, the set of kept faces and their order are bit-exact; normals agree with the reference to a few ulp because
+ * normalize() multiplies by an SSE rsqrtss estimate there (math/Math.h:205-227). */
+int spcu_ingest_mesh(spcu_ctx* ctx, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
+                     const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                     spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices, float* world_normals,
+                     float* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ from pathlib import Path
 
 import numpy as np
 
-from simplepath_b200.capi import Accel, FlatScene, HIT_DTYPE, RAY_DTYPE, Light, Partition, Stats, run_build
+from simplepath_b200.capi import Accel, FlatScene, HIT_DTYPE, RAY_DTYPE, Light, Partition, Stats, run_build, run_ingest
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libsp_oracle.so"
@@ -132,3 +132,12 @@ def pack_image(rgb_sum, spp: int, fmt: int) -> np.ndarray:
     out = np.empty((h, w, 3), dtype=np.float32 if fmt == 0 else np.uint16)
     l.spo_pack_image(_p(rgb_sum), w, h, spp, fmt, _p(out))
     return out
+
+
+def ingest_mesh(vertices, faces, object_to_world, normal_xf, material: int = 0) -> dict:
+    """spo_ingest_mesh (read_ply's normal passes + Mesh's constructor): same dict as capi.Context.ingest_mesh."""
+    l = lib()
+    vp = C.c_void_p
+    l.spo_ingest_mesh.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32), vp, vp]
+    l.spo_ingest_mesh.restype = None
+    return run_ingest(l.spo_ingest_mesh, vertices, faces, object_to_world, normal_xf, material, with_ms=False)

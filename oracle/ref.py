@@ -158,3 +158,23 @@ def write_image(rgb_sum, spp: int, path, lib_path: Path = STRICT) -> None:
     err = C.create_string_buffer(512)
     if lib.spref_write_image(_p(rgb_sum), w, h, spp, str(path).encode(), err, 512) != 0:
         raise RuntimeError(f"spref_write_image: {err.value.decode()}")
+
+
+def read_ply(path, object_to_world, cap_vertices: int, cap_triangles: int, lib_path: Path = STRICT) -> dict:
+    """The reference's own read_ply + Mesh constructor: {vertices, normals (world space), indices [t,3], normal_xf [9]}."""
+    lib = C.CDLL(str(lib_path))
+    u32p = C.POINTER(C.c_uint32)
+    lib.spref_read_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, u32p, u32p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.spref_read_ply.restype = C.c_int
+    xf = np.ascontiguousarray(object_to_world, dtype=np.float32).reshape(12)
+    v = np.zeros((max(cap_vertices, 1), 3), dtype=np.float32)
+    n = np.zeros((max(cap_vertices, 1), 3), dtype=np.float32)
+    idx = np.zeros((max(cap_triangles, 1), 3), dtype=np.uint32)
+    nxf = np.zeros(9, dtype=np.float32)
+    nv, nt = C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(512)
+    if lib.spref_read_ply(str(path).encode(), _p(xf), cap_vertices, cap_triangles, C.byref(nv), C.byref(nt), _p(v), _p(n), _p(idx),
+                          _p(nxf), err, 512) != 0:
+        raise RuntimeError(f"spref_read_ply: {err.value.decode()}")
+    return {"vertices": v[:nv.value].copy(), "normals": n[:nv.value].copy(), "indices": idx[:nt.value].copy(), "normal_xf": nxf}

@@ -17,6 +17,7 @@
 #include "flat_scene.h"
 
 #include "base/FileParser.h"
+#include "base/PlyReader.h"
 #include "base/Logger.h"
 #include "base/MemoryArena.h"
 #include "base/RunningStats.h"
@@ -303,6 +304,13 @@ static int guarded(char* err, size_t errlen, F&& f)
     }
 }
 
+
+void put3f(float* dst, const auto& v)
+{
+    dst[0] = v.x;
+    dst[1] = v.y;
+    dst[2] = v.z;
+}
 
 // ---- BVH construction by the reference's own BVHAccelerator (shapes/BVHAccelerator.h:123-209) ---------------------------
 // A bounded Hitable that is nothing but its world bounds: lets the reference build a tree over arbitrary boxes.
@@ -639,6 +647,38 @@ int spref_write_image(const float* rgb_sum, uint32_t w, uint32_t h, unsigned spp
             }
         }
         sp::write(path, image);
+    });
+}
+
+// The reference's own read_ply (base/PlyReader.cpp:326-531) with object_to_world = the given AffineSpace (12 floats:
+// c0.xyz c1.xyz c2.xyz affine.xyz): Mesh::m_vertices / m_normals (world space) and m_indices.  Also returns the normal
+// matrix the reference applies, inverse(linear).transposed() (math/LinearSpace3x3.h:163-167), column major.
+int spref_read_ply(const char* path, const float xf[12], uint32_t cap_vertices, uint32_t cap_triangles, uint32_t* n_vertices,
+                   uint32_t* n_triangles, float* vertices, float* normals, uint32_t* indices, float normal_xf[9], char* err,
+                   size_t errlen)
+{
+    return guarded(err, errlen, [&] {
+        sp::Logger::set_level(sp::Logger::LoggingLevel::error);
+        const sp::LinearSpace3x3 lin{ sp::Vector3{ xf[0], xf[1], xf[2] }, sp::Vector3{ xf[3], xf[4], xf[5] }, sp::Vector3{ xf[6], xf[7], xf[8] } };
+        const sp::AffineSpace    aff{ lin, sp::Vector3{ xf[9], xf[10], xf[11] } };
+        const auto               xform = sp::AffineTransformation::compute_inverse(aff);
+        const sp::Mesh           mesh  = sp::read_ply(path, xform);
+        arm_exit_guard();
+        const auto nm = aff.get_linear().inverse().transposed();
+        const float m9[9] = { nm.col0().x, nm.col0().y, nm.col0().z, nm.col1().x, nm.col1().y, nm.col1().z, nm.col2().x, nm.col2().y, nm.col2().z };
+        std::memcpy(normal_xf, m9, sizeof m9);
+        *n_vertices  = static_cast<uint32_t>(mesh.m_vertices.size());
+        *n_triangles = static_cast<uint32_t>(mesh.get_num_triangles());
+        if (*n_vertices > cap_vertices || *n_triangles > cap_triangles) {
+            throw std::runtime_error("spref_read_ply: output capacity too small");
+        }
+        for (uint32_t i = 0; i < *n_vertices; ++i) {
+            put3f(vertices + 3 * i, mesh.m_vertices[i]);
+            put3f(normals + 3 * i, mesh.m_normals[i]);
+        }
+        for (size_t i = 0; i < mesh.m_indices.size(); ++i) {
+            indices[i] = static_cast<uint32_t>(mesh.m_indices[i]);
+        }
     });
 }
 

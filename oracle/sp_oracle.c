@@ -664,4 +664,64 @@ void spo_pack_image(const float* rgb_sum, uint32_t width, uint32_t height, uint3
     }
 }
 
+/* ===================================================================================================
+ * Mesh ingest (base/PlyReader.cpp:487-531, shapes/Triangle.h:25-51)
+ * =================================================================================================== */
+/* difference_of_products (math/Vector3.h:489-498): cd = c*d; err = nmadd(c, d, cd); dop = msub(a, b, cd); dop + err */
+static inline float mesh_dop(float a, float b, float c, float d)
+{
+    const float cd  = c * d;
+    const float err = fmaf(-c, d, cd);
+    const float dop = fmaf(a, b, -cd);
+    return dop + err;
+}
+/* cross (math/Vector3.h:769-775) */
+static inline v3 mesh_cross(v3 a, v3 b)
+{
+    return V(mesh_dop(a.y, b.z, a.z, b.y), mesh_dop(a.z, b.x, a.x, b.z), mesh_dop(a.x, b.y, a.y, b.x));
+}
+
+void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float object_to_world[12],
+                     const float normal_xf[9], uint32_t material, spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta,
+                     uint32_t* n_kept, float* world_vertices, float* world_normals)
+{
+    v3*       vn   = (v3*)calloc(nv ? nv : 1, sizeof(v3)); /* vertex_normals(num_vertices, Normal3{0,0,0}) (PlyReader.cpp:510) */
+    v3*       wv   = (v3*)malloc((nv ? nv : 1) * sizeof(v3));
+    uint32_t* kept = (uint32_t*)malloc((nf ? nf : 1) * sizeof(uint32_t));
+    uint32_t  nk   = 0;
+#define VERT(i) V(vertices[3 * (size_t)(i)], vertices[3 * (size_t)(i) + 1], vertices[3 * (size_t)(i) + 2])
+    for (uint32_t f = 0; f < nf; ++f) {
+        const uint32_t* ix = faces + 3 * (size_t)f;
+        const v3        e0 = sub3(VERT(ix[1]), VERT(ix[0])), e1 = sub3(VERT(ix[2]), VERT(ix[0]));
+        v3              n  = mesh_cross(e0, e1);
+        if (dot3(n, n) == 0.0f) continue; /* zero-area face: skipped (PlyReader.cpp:497-500) */
+        n = normalize3(n);
+        for (int k = 0; k < 3; ++k) vn[ix[k]] = add3(vn[ix[k]], n); /* in face order (PlyReader.cpp:511-515) */
+        kept[nk++] = f;
+    }
+    for (uint32_t v = 0; v < nv; ++v) {
+        v3 n = vn[v];
+        n    = (n.x != 0.0f || n.y != 0.0f || n.z != 0.0f) ? normalize3(n) : V(0.0f, 1.0f, 0.0f); /* PlyReader.cpp:517-528 */
+        wv[v] = xf_point(object_to_world, VERT(v));                                                /* Triangle.h:37-41 */
+        vn[v] = xf_vector(normal_xf, n);                                                           /* Triangle.h:43-47 */
+        if (world_vertices) { world_vertices[3 * (size_t)v] = wv[v].x; world_vertices[3 * (size_t)v + 1] = wv[v].y; world_vertices[3 * (size_t)v + 2] = wv[v].z; }
+        if (world_normals)  { world_normals[3 * (size_t)v] = vn[v].x;  world_normals[3 * (size_t)v + 1] = vn[v].y;  world_normals[3 * (size_t)v + 2] = vn[v].z; }
+    }
+#undef VERT
+    for (uint32_t t = 0; t < nk; ++t) {
+        const uint32_t* ix = faces + 3 * (size_t)kept[t];
+        memset(&prims[t], 0, sizeof prims[t]);
+        memset(&shade[t], 0, sizeof shade[t]);
+        for (int k = 0; k < 3; ++k) {
+            prims[t].v[4 * k] = wv[ix[k]].x, prims[t].v[4 * k + 1] = wv[ix[k]].y, prims[t].v[4 * k + 2] = wv[ix[k]].z;
+            shade[t].v[4 * k] = vn[ix[k]].x, shade[t].v[4 * k + 1] = vn[ix[k]].y, shade[t].v[4 * k + 2] = vn[ix[k]].z;
+        }
+        meta[t] = SPCU_MAKE_META(SPCU_PRIM_TRIANGLE, material);
+    }
+    *n_kept = nk;
+    free(vn);
+    free(wv);
+    free(kept);
+}
+
 #include "sp_oracle_shade.inc"

@@ -72,6 +72,13 @@ void spo_triangle_bounds(const spcu_prim_geom* tris, uint32_t n, spcu_bounds* ou
  * Pinned against files the reference's own sp::write produced (tests/golden/image_pack.npz). */
 void spo_pack_image(const float* rgb_sum, uint32_t width, uint32_t height, uint32_t spp, uint32_t format, void* out);
 
+/* read_ply's face / vertex-normal passes + Mesh's constructor (base/PlyReader.cpp:487-531, shapes/Triangle.h:25-51); same
+ * arguments and outputs as spcu_ingest_mesh.  Pinned bit for bit (x86: same rsqrtss) against the reference's own read_ply
+ * (oracle/ref_harness.cpp spref_read_ply; tests/golden/mesh_ingest.npz). */
+void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float object_to_world[12],
+                     const float normal_xf[9], uint32_t material, spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta,
+                     uint32_t* n_kept, float* world_vertices, float* world_normals);
+
 #ifdef __cplusplus
 }
 #endif

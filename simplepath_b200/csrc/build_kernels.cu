@@ -20,15 +20,13 @@
 //     left children starting at the same position) — a prefix sum over range starts, no tree walk.
 //
 // Compiled WITHOUT fast-math and with --fmad=false (Makefile): (lo + hi) / 2 and hi - lo are IEEE operations.
-#include "ctx.h"
+#include "build_util.cuh"
 
 using namespace spcu;
 
 namespace {
 
 constexpr uint32_t kInvalid   = 0xFFFFFFFFu;
-constexpr int      kBlock     = 256;
-constexpr uint32_t kScanTile  = 2048; // bytes per block of the prefix sum: 256 threads x 8
 constexpr uint32_t kPending   = 0;    // node states
 constexpr uint32_t kLeaf      = 1;
 constexpr uint32_t kInternal  = 2;
@@ -338,82 +336,6 @@ __global__ void __launch_bounds__(kBlock) k_flags(Build b, uint32_t level_begin)
     }
 }
 
-// ---- exclusive prefix sum of bytes (three passes) ---------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sum_bytes(uint2 v)
-{
-    return __vsadu4(v.x, 0u) + __vsadu4(v.y, 0u);
-}
-
-__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* total)
-{
-    __shared__ uint32_t warp_sums[kBlock / 32];
-    const uint32_t      lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    uint32_t            inc = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, off);
-        if (lane >= static_cast<uint32_t>(off)) {
-            inc += o;
-        }
-    }
-    __syncthreads(); // warp_sums may still be read by a previous call
-    if (lane == 31u) {
-        warp_sums[w] = inc;
-    }
-    __syncthreads();
-    uint32_t base = 0, all = 0;
-#pragma unroll
-    for (int i = 0; i < kBlock / 32; ++i) {
-        const uint32_t s = warp_sums[i];
-        base += static_cast<uint32_t>(i) < w ? s : 0u;
-        all += s;
-    }
-    *total = all;
-    return base + inc - v;
-}
-
-__global__ void __launch_bounds__(kBlock) k_scan_reduce(const uint8_t* in, uint32_t* partials)
-{
-    const uint2 v = reinterpret_cast<const uint2*>(in)[static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x];
-    uint32_t    total;
-    block_exclusive(sum_bytes(v), &total);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = total;
-    }
-}
-
-__global__ void __launch_bounds__(kBlock) k_scan_partials(uint32_t* partials, uint32_t count)
-{
-    uint32_t running = 0;
-    for (uint32_t base = 0; base < count; base += kBlock) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < count ? partials[i] : 0u;
-        uint32_t       total;
-        const uint32_t e = block_exclusive(v, &total);
-        if (i < count) {
-            partials[i] = running + e;
-        }
-        running += total;
-    }
-}
-
-// out[i] = sum of in[0 .. i) for i in [0, n]  (in[] is zero beyond n)
-__global__ void __launch_bounds__(kBlock) k_scan_apply(const uint8_t* in, const uint32_t* partials, uint32_t* out, uint32_t n)
-{
-    const size_t t = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
-    const uint2  v = reinterpret_cast<const uint2*>(in)[t];
-    uint32_t     total;
-    uint32_t     run = partials[blockIdx.x] + block_exclusive(sum_bytes(v), &total);
-    const size_t i0  = t * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (i0 + j <= n) {
-            out[i0 + j] = run;
-        }
-        run += ((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFFu;
-    }
-}
-
 // std::partition's outcome for every splitting node: empty side -> leaf of any size (BVHAccelerator.h:200-203), else two children.
 __global__ void k_split(Build b, uint32_t level_begin, uint32_t level_count)
 {
@@ -558,39 +480,6 @@ __global__ void __launch_bounds__(kBlock) k_triangle_bounds(const spcu_prim_geom
     }
 }
 
-// ---- host -----------------------------------------------------------------------------------------------------------
-struct Scratch
-{
-    std::vector<DevBuf> bufs;
-    ~Scratch()
-    {
-        for (auto& b : bufs) {
-            b.release();
-        }
-    }
-    template <typename T>
-    cudaError_t get(T** out, size_t count)
-    {
-        bufs.emplace_back();
-        const cudaError_t e = bufs.back().reserve(std::max<size_t>(count * sizeof(T), 16));
-        *out                = bufs.back().as<T>();
-        return e;
-    }
-};
-
-unsigned grid_for(uint64_t n, int sm_count)
-{
-    const uint64_t want = (n + kBlock - 1) / kBlock;
-    return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(sm_count) * 8)));
-}
-
-void scan_bytes(const Build& b, uint32_t* partials, uint32_t n_tiles, cudaStream_t st)
-{
-    k_scan_reduce<<<n_tiles, kBlock, 0, st>>>(b.flag, partials);
-    k_scan_partials<<<1, kBlock, 0, st>>>(partials, n_tiles);
-    k_scan_apply<<<n_tiles, kBlock, 0, st>>>(b.flag, partials, b.prefix, b.n);
-}
-
 // Gathers the primitive records of the bounded primitives into leaf order: dst[first_id + k] = src[first_id + order[k]].
 __global__ void __launch_bounds__(kBlock) k_gather_prims(const uint32_t* order, uint32_t n, uint32_t first_id, const float4* src_geom,
                                                          const float4* src_shade, const uint32_t* src_meta, float4* dst_geom,
@@ -697,7 +586,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
         k_bounds<<<bounds_grid, kBlock, 0, st>>>(b, level_begin);
         k_decide<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
         k_flags<<<grid, kBlock, 0, st>>>(b, level_begin);
-        scan_bytes(b, partials, n_tiles, st);
+        exclusive_scan(b.flag, b.prefix, b.n, partials, st);
         k_split<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
         k_scatter<<<grid, kBlock, 0, st>>>(b, level_begin);
         k_apply<<<grid, kBlock, 0, st>>>(b, level_begin);
@@ -721,7 +610,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
     CK(c, cudaMemsetAsync(b.flag, 0, static_cast<size_t>(n_tiles) * kScanTile, st));
     const unsigned all_grid = (n_nodes + kBlock - 1) / kBlock;
     k_chain_counts<<<all_grid, kBlock, 0, st>>>(b, n_nodes);
-    scan_bytes(b, partials, n_tiles, st);
+    exclusive_scan(b.flag, b.prefix, b.n, partials, st);
     uint32_t n_internal = 0, root_state = 0;
     CK(c, cudaMemcpyAsync(&n_internal, b.prefix + n, sizeof n_internal, cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(&root_state, b.state, sizeof root_state, cudaMemcpyDeviceToHost, st));

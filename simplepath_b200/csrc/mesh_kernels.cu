@@ -1,0 +1,262 @@
+// Mesh ingest on the device: what read_ply does after it has read the vertex and face lists
+// (reference base/PlyReader.cpp:487-531) and what Mesh's constructor does with the result (shapes/Triangle.h:25-51):
+//
+//   per face      edge0 = v1 - v0, edge1 = v2 - v0, n = cross(edge0, edge1)  (compensated products, math/Vector3.h:489-498,769-775);
+//                 a face with sqr_length(n) == 0 is dropped; n = normalize(n)
+//   per vertex    normal = sum of the normals of the kept faces that use it, IN FACE ORDER (float addition does not commute
+//                 with reordering); normalize, or (0, 1, 0) when the sum is zero
+//   Mesh          vertex -> object_to_world(vertex) (fma chain, math/AffineSpace.h:79-86); normal -> object_to_world(normal)
+//                 = inverse(linear).transposed() * normal (math/LinearSpace3x3.h:163-167), NOT renormalised
+//   per triangle  the pre-gathered records of include/spcu.h (three world-space vertices / three normals), in face order =
+//                 the order the parser appends the mesh's triangles to the scene = the pre-construction order
+//                 spcu_upload_scene_build expects.
+//
+// Everything that decides geometry (which faces survive, vertex positions, hence bounds, tree and hits) is bit-exact: explicit
+// round-to-nearest intrinsics, fma exactly where the reference calls madd / msub / nmadd, --fmad=false.  normalize() is the
+// one operation that cannot be: the reference multiplies by an SSE rsqrtss estimate refined by one Newton step
+// (math/Math.h:205-227), a value no other hardware reproduces; the device uses the correctly rounded reciprocal square root,
+// so shading normals agree to a few ulp (stated and tested), as for camera directions.
+#include "build_util.cuh"
+
+using namespace spcu;
+
+namespace {
+
+struct F3
+{
+    float x, y, z;
+};
+
+__device__ __forceinline__ F3 ld3(const float* p, size_t i) { return F3{ __ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2) }; }
+__device__ __forceinline__ F3 sub(F3 a, F3 b) { return F3{ __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z) }; }
+
+// difference_of_products (math/Vector3.h:489-498): a*b - c*d with the rounding error of c*d recovered
+__device__ __forceinline__ float dop(float a, float b, float c, float d)
+{
+    const float cd  = __fmul_rn(c, d);
+    const float err = __fmaf_rn(-c, d, cd);
+    const float r   = __fmaf_rn(a, b, -cd);
+    return __fadd_rn(r, err);
+}
+// cross (math/Vector3.h:769-775)
+__device__ __forceinline__ F3 cross(F3 a, F3 b) { return F3{ dop(a.y, b.z, a.z, b.y), dop(a.z, b.x, a.x, b.z), dop(a.x, b.y, a.y, b.x) }; }
+// dot = _mm_dp_ps: (x + y) + (z + 0) (math/Vector3.h:742-746)
+__device__ __forceinline__ float dot(F3 a, F3 b)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.z, b.z), 0.0f));
+}
+__device__ __forceinline__ F3 normalize(F3 a)
+{
+    const float s = __frsqrt_rn(dot(a, a));
+    return F3{ __fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s) };
+}
+
+// face pass of read_ply (base/PlyReader.cpp:493-503)
+__global__ void __launch_bounds__(kBlock) k_face_normals(const float* verts, const uint32_t* faces, uint32_t nf, float* face_n, uint8_t* keep)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += stride) {
+        const uint32_t i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+        const F3       v0 = ld3(verts, i0);
+        F3             n  = cross(sub(ld3(verts, i1), v0), sub(ld3(verts, i2), v0));
+        const bool     ok = dot(n, n) != 0.0f;
+        keep[f]           = ok ? 1 : 0;
+        if (ok) {
+            n = normalize(n);
+        }
+        face_n[3 * f] = n.x, face_n[3 * f + 1] = n.y, face_n[3 * f + 2] = n.z;
+    }
+}
+
+// kept faces, compacted in order: kept_faces[rank] = face; and the vertex degrees over kept faces
+__global__ void __launch_bounds__(kBlock) k_compact_faces(const uint32_t* faces, const uint8_t* keep, const uint32_t* rank, uint32_t nf,
+                                                          uint32_t* kept, uint32_t* degree)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += stride) {
+        if (!keep[f]) {
+            continue;
+        }
+        kept[rank[f]] = f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicAdd(&degree[__ldg(faces + 3 * f + k)], 1u);
+        }
+    }
+}
+
+// adjacency lists (vertex -> kept faces that use it, one entry per corner), filled in arbitrary order
+__global__ void __launch_bounds__(kBlock) k_fill_adjacency(const uint32_t* faces, const uint8_t* keep, uint32_t nf, const uint32_t* offset,
+                                                           uint32_t* cursor, uint32_t* adjacency)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += stride) {
+        if (!keep[f]) {
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v                               = __ldg(faces + 3 * f + k);
+            adjacency[offset[v] + atomicAdd(&cursor[v], 1u)] = f;
+        }
+    }
+}
+
+// vertex normals (base/PlyReader.cpp:509-528) and Mesh's transforms (shapes/Triangle.h:37-47).  The sequential loop adds
+// face normals face by face, so a vertex sees its faces in ascending face index: sort the (short) list, then add in order.
+__global__ void __launch_bounds__(kBlock) k_vertices(const float* verts, uint32_t nv, const uint32_t* offset, uint32_t* adjacency,
+                                                     const float* face_n, const float* xf, const float* nxf, float* world_v,
+                                                     float* world_n)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
+        uint32_t*      list = adjacency + offset[v];
+        const uint32_t deg  = offset[v + 1] - offset[v];
+        for (uint32_t i = 1; i < deg; ++i) { // insertion sort: valence is a handful
+            const uint32_t key = list[i];
+            uint32_t       j   = i;
+            for (; j > 0 && list[j - 1] > key; --j) {
+                list[j] = list[j - 1];
+            }
+            list[j] = key;
+        }
+        F3 n{ 0.0f, 0.0f, 0.0f };
+        for (uint32_t i = 0; i < deg; ++i) {
+            const F3 f = ld3(face_n, list[i]);
+            n          = F3{ __fadd_rn(n.x, f.x), __fadd_rn(n.y, f.y), __fadd_rn(n.z, f.z) };
+        }
+        n = (n.x != 0.0f || n.y != 0.0f || n.z != 0.0f) ? normalize(n) : F3{ 0.0f, 1.0f, 0.0f };
+        // AffineSpace::operator()(Point3): madd(x, c0, madd(y, c1, madd(z, c2, affine)))
+        const F3 p = ld3(verts, v);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            world_v[3 * v + a] = __fmaf_rn(p.x, xf[a], __fmaf_rn(p.y, xf[3 + a], __fmaf_rn(p.z, xf[6 + a], xf[9 + a])));
+            // LinearSpace3x3::operator()(Normal3): madd(x, c0, madd(y, c1, z * c2)) with the inverse-transposed matrix
+            world_n[3 * v + a] = __fmaf_rn(n.x, nxf[a], __fmaf_rn(n.y, nxf[3 + a], __fmul_rn(n.z, nxf[6 + a])));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_triangle_records(const uint32_t* faces, const uint32_t* kept, uint32_t n_kept, const float* world_v,
+                                                             const float* world_n, uint32_t meta_word, float4* prims, float4* shade,
+                                                             uint32_t* meta)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_kept; t += stride) {
+        const uint32_t f = kept[t];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v = __ldg(faces + 3 * f + k);
+            const F3       p = ld3(world_v, v), n = ld3(world_n, v);
+            prims[3 * static_cast<size_t>(t) + k] = make_float4(p.x, p.y, p.z, 0.0f);
+            shade[3 * static_cast<size_t>(t) + k] = make_float4(n.x, n.y, n.z, 0.0f);
+        }
+        meta[t] = meta_word;
+    }
+}
+
+} // namespace
+
+extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
+                                const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                                spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept_out, float* world_vertices, float* world_normals,
+                                float* device_ms)
+{
+    if (!c) {
+        return SPCU_ERR_INVALID;
+    }
+    if (!n_kept_out || !object_to_world || !normal_xf || (nv && !vertices) || (nf && (!faces || !prims || !shade || !meta))) {
+        return fail(c, SPCU_ERR_INVALID, "spcu_ingest_mesh: NULL argument");
+    }
+    if (nf >= (1u << 30) || nv >= (1u << 30)) {
+        return fail(c, SPCU_ERR_LIMIT, "spcu_ingest_mesh: more than 2^30 vertices or faces");
+    }
+    for (uint32_t i = 0; i < 3 * nf; ++i) { // vertices.at(...) throws in the reference (base/PlyReader.cpp:493-494)
+        if (faces[i] >= nv) {
+            return fail(c, SPCU_ERR_INVALID, "spcu_ingest_mesh: face %u refers to vertex %u of %u", i / 3, faces[i], nv);
+        }
+    }
+    CK(c, cudaSetDevice(c->device));
+    *n_kept_out = 0;
+    if (device_ms) {
+        *device_ms = 0.0f;
+    }
+    const cudaStream_t st = c->stream;
+    Scratch            mem;
+    float *            d_v = nullptr, *d_face_n = nullptr, *d_xf = nullptr, *d_world_v = nullptr, *d_world_n = nullptr;
+    uint32_t *         d_f = nullptr, *d_rank = nullptr, *d_kept = nullptr, *d_degree = nullptr, *d_offset = nullptr, *d_cursor = nullptr,
+             *d_adj = nullptr, *d_partials = nullptr;
+    uint8_t* d_keep = nullptr;
+    const size_t f_pad = static_cast<size_t>(scan_tiles(nf)) * kScanTile, v_pad = static_cast<size_t>(scan_tiles(nv)) * kScanTile;
+    CK(c, mem.get(&d_v, 3 * static_cast<size_t>(nv)));
+    CK(c, mem.get(&d_f, 3 * static_cast<size_t>(nf)));
+    CK(c, mem.get(&d_face_n, 3 * static_cast<size_t>(nf)));
+    CK(c, mem.get(&d_keep, f_pad));
+    CK(c, mem.get(&d_rank, static_cast<size_t>(nf) + 1));
+    CK(c, mem.get(&d_kept, nf));
+    CK(c, mem.get(&d_degree, v_pad));
+    CK(c, mem.get(&d_offset, static_cast<size_t>(nv) + 1));
+    CK(c, mem.get(&d_cursor, nv));
+    CK(c, mem.get(&d_adj, 3 * static_cast<size_t>(nf)));
+    CK(c, mem.get(&d_partials, std::max(scan_tiles(nf), scan_tiles(nv))));
+    CK(c, mem.get(&d_xf, 24));
+    CK(c, mem.get(&d_world_v, 3 * static_cast<size_t>(nv)));
+    CK(c, mem.get(&d_world_n, 3 * static_cast<size_t>(nv)));
+    if (nv) {
+        CK(c, cudaMemcpyAsync(d_v, vertices, 3 * static_cast<size_t>(nv) * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (nf) {
+        CK(c, cudaMemcpyAsync(d_f, faces, 3 * static_cast<size_t>(nf) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    CK(c, cudaMemcpyAsync(d_xf, object_to_world, 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_xf + 12, normal_xf, 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemsetAsync(d_keep, 0, f_pad, st));
+    CK(c, cudaMemsetAsync(d_degree, 0, v_pad * sizeof(uint32_t), st));
+    CK(c, cudaMemsetAsync(d_cursor, 0, std::max<size_t>(nv, 1) * sizeof(uint32_t), st));
+
+    CK(c, cudaEventRecord(c->ev0, st));
+    uint32_t n_kept = 0;
+    if (nf) {
+        k_face_normals<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_v, d_f, nf, d_face_n, d_keep);
+        exclusive_scan(d_keep, d_rank, nf, d_partials, st);
+        k_compact_faces<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_f, d_keep, d_rank, nf, d_kept, d_degree);
+    }
+    exclusive_scan(d_degree, d_offset, nv, d_partials, st);
+    if (nf) {
+        k_fill_adjacency<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_f, d_keep, nf, d_offset, d_cursor, d_adj);
+        CK(c, cudaMemcpyAsync(&n_kept, d_rank + nf, sizeof n_kept, cudaMemcpyDeviceToHost, st));
+    }
+    if (nv) {
+        k_vertices<<<grid_for(nv, c->sm_count), kBlock, 0, st>>>(d_v, nv, d_offset, d_adj, d_face_n, d_xf, d_xf + 12, d_world_v, d_world_n);
+    }
+    CK(c, cudaStreamSynchronize(st));
+    float4 *  d_prims = nullptr, *d_shade = nullptr;
+    uint32_t* d_meta = nullptr;
+    CK(c, mem.get(&d_prims, 3 * static_cast<size_t>(n_kept)));
+    CK(c, mem.get(&d_shade, 3 * static_cast<size_t>(n_kept)));
+    CK(c, mem.get(&d_meta, n_kept));
+    if (n_kept) {
+        k_triangle_records<<<grid_for(n_kept, c->sm_count), kBlock, 0, st>>>(d_f, d_kept, n_kept, d_world_v, d_world_n,
+                                                                             SPCU_MAKE_META(SPCU_PRIM_TRIANGLE, material), d_prims, d_shade,
+                                                                             d_meta);
+    }
+    CK(c, cudaEventRecord(c->ev1, st));
+    CK(c, cudaGetLastError());
+    if (n_kept) {
+        CK(c, cudaMemcpyAsync(prims, d_prims, static_cast<size_t>(n_kept) * sizeof(spcu_prim_geom), cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(shade, d_shade, static_cast<size_t>(n_kept) * sizeof(spcu_prim_shade), cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(meta, d_meta, static_cast<size_t>(n_kept) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (world_vertices && nv) {
+        CK(c, cudaMemcpyAsync(world_vertices, d_world_v, 3 * static_cast<size_t>(nv) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (world_normals && nv) {
+        CK(c, cudaMemcpyAsync(world_normals, d_world_n, 3 * static_cast<size_t>(nv) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CK(c, cudaStreamSynchronize(st));
+    if (device_ms) {
+        CK(c, cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
+    }
+    *n_kept_out = n_kept;
+    return SPCU_OK;
+}

@@ -1,0 +1,51 @@
+"""Meshes and transforms for the mesh-ingest parity tests (read_ply's face / vertex-normal passes + Mesh's constructor,
+reference base/PlyReader.cpp:487-531, shapes/Triangle.h:25-51)."""
+from __future__ import annotations
+
+import numpy as np
+
+from simplepath_b200 import scenes
+
+
+def transform(seed: int = 3) -> np.ndarray:
+    """object_to_world as 12 floats c0.xyz c1.xyz c2.xyz affine.xyz: a rotation about a skew axis, non-uniform scale, offset."""
+    rng = np.random.default_rng(seed)
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    a = 0.7
+    k = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    rot = np.eye(3) + np.sin(a) * k + (1 - np.cos(a)) * (k @ k)
+    m = rot @ np.diag([10.0, 7.5, 12.0])
+    return np.concatenate([m[:, 0], m[:, 1], m[:, 2], [0.3, -1.25, 4.0]]).astype(np.float32)
+
+
+def mesh(n_tris: int = 3000, seed: int = 1) -> tuple[np.ndarray, np.ndarray]:
+    """A bumpy sphere plus what the reader has to cope with: zero-area faces (repeated index, collinear and coincident
+    vertices), vertices no face uses, one vertex shared by a large fan, faces in shuffled order."""
+    rng = np.random.default_rng(seed)
+    v, f = scenes.bumpy_sphere(n_tris, (-0.1, 0.03, -0.06), (0.06, 0.19, 0.06))
+    v = np.asarray(v, dtype=np.float32)
+    f = np.asarray(f, dtype=np.uint32)
+    nv = len(v)
+    extra_v = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0.5, 0.25, 0.125], [0.5, 0.25, 0.125], [9, 9, 9]], dtype=np.float32)
+    v = np.concatenate([v, extra_v])
+    degenerate = np.array([[nv, nv + 1, nv + 2],       # collinear
+                           [nv + 3, nv + 4, 0],        # two coincident vertices
+                           [5, 5, 9],                  # repeated index
+                           [7, 7, 7]], dtype=np.uint32)
+    hub = nv + 5                                       # a fan of 200 triangles around one vertex
+    ring = rng.integers(0, nv, 201).astype(np.uint32)
+    fan = np.stack([np.full(200, hub, dtype=np.uint32), ring[:-1], ring[1:]], axis=1)
+    fan = fan[(fan[:, 1] != fan[:, 2])]
+    f = np.concatenate([f, degenerate, fan])
+    f = f[rng.permutation(len(f))]
+    return v, f
+
+
+def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Distance in units of the last place between float32 arrays (same sign assumed where it matters)."""
+    ia = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    ib = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return np.abs(ia - ib)

@@ -1,0 +1,47 @@
+"""Mesh ingest (read_ply's face / vertex-normal passes + Mesh's constructor, reference base/PlyReader.cpp:487-531,
+shapes/Triangle.h:25-51): the oracle's restatement against what the reference's own read_ply produced for the committed mesh
+(tests/golden/mesh_ingest.npz, made by tests/golden/make_golden_mesh.py) — bit for bit on x86, normals included."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+import meshcases
+
+
+def golden():
+    return np.load(GOLDEN / "mesh_ingest.npz")
+
+
+def test_golden_inputs_are_the_generated_mesh():
+    z = golden()
+    v, f = meshcases.mesh()
+    assert np.array_equal(z["in_vertices"], v) and np.array_equal(z["in_faces"], f)
+    assert z["object_to_world"].tobytes() == meshcases.transform().tobytes()
+    assert len(z["indices"]) < len(f), "the case must contain zero-area faces"
+
+
+def test_oracle_ingest_matches_reference_mesh(oracle_port):
+    z = golden()
+    r = oracle_port.ingest_mesh(z["in_vertices"], z["in_faces"], z["object_to_world"], z["normal_xf"], material=3)
+    assert r["world_vertices"].tobytes() == z["vertices"].tobytes()
+    assert r["world_normals"].tobytes() == z["normals"].tobytes()
+    idx = z["indices"]
+    assert len(r["prims"]) == len(idx)
+    assert np.array_equal(r["prims"].reshape(-1, 3, 4)[:, :, :3], z["vertices"][idx])
+    assert np.array_equal(r["shade"].reshape(-1, 3, 4)[:, :, :3], z["normals"][idx])
+    assert (r["prims"].reshape(-1, 3, 4)[:, :, 3] == 0).all() and (r["meta"] == (3 << 2)).all()
+
+
+def test_oracle_ingest_on_live_reference(oracle_port, tmp_path):
+    from oracle import ref
+    from simplepath_b200 import scenes
+    if not ref.available():
+        pytest.skip("reference library not built (needs /root/reference)")
+    v, f = meshcases.mesh(n_tris=20000, seed=8)
+    xf = meshcases.transform(seed=12)
+    scenes.write_ply(tmp_path / "m.ply", v, f)
+    want = ref.read_ply(tmp_path / "m.ply", xf, len(v), len(f))
+    r = oracle_port.ingest_mesh(v, f, xf, want["normal_xf"])
+    assert r["world_vertices"].tobytes() == want["vertices"].tobytes()
+    assert r["world_normals"].tobytes() == want["normals"].tobytes()
+    assert np.array_equal(r["prims"].reshape(-1, 3, 4)[:, :, :3], want["vertices"][want["indices"]])

@@ -91,16 +91,17 @@ def test_file_to_hits_on_the_device(ctx, oracle_port):
     assert head == built["head"] and np.array_equal(order, built["order"])
 
     rng = np.random.default_rng(4)
-    lo, hi = z["vertices"].min(0), z["vertices"].max(0)
     n = 1 << 15
-    target = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    tri = z["vertices"][z["indices"][rng.integers(0, len(z["indices"]), n)]]           # aim at random triangles, from nearby
+    w = rng.random((n, 3, 1)).astype(np.float32)
+    target = (tri * (w / w.sum(axis=1, keepdims=True))).sum(axis=1).astype(np.float32)
     d = rng.normal(size=(n, 3)).astype(np.float32)
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     rays = np.zeros(n, dtype=capi.RAY_DTYPE)
-    rays["o"] = target - d * np.float32(2.0 * np.linalg.norm(hi - lo))
+    rays["o"] = target - d * np.float32(0.5)
     rays["d"] = d
     rays["t_min"] = 0.0
-    rays["t_max"] = np.finfo(np.float32).max
+    rays["t_max"] = 4.0
     got, want = ctx.trace_closest(rays), oracle_port.trace_closest(cpu.pointer(), rays)
-    assert (want["id"] >= nu).mean() > 0.3
+    assert (want["id"] >= nu).mean() > 0.2
     assert np.array_equal(got["id"], want["id"]) and got["t"].tobytes() == want["t"].tobytes()

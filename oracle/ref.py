@@ -178,3 +178,24 @@ def read_ply(path, object_to_world, cap_vertices: int, cap_triangles: int, lib_p
                           _p(nxf), err, 512) != 0:
         raise RuntimeError(f"spref_read_ply: {err.value.decode()}")
     return {"vertices": v[:nv.value].copy(), "normals": n[:nv.value].copy(), "indices": idx[:nt.value].copy(), "normal_xf": nxf}
+
+
+def accel_from_mesh(ply, object_to_world, unbounded, lib_path: Path = STRICT) -> dict:
+    """internal::create_acceleration_structure (base/Scene.h:27-45) by the reference over [triangles of the mesh it reads
+    itself | unbounded stand-ins where unbounded[i] != 0]: {order (ID -> list position), nodes, head}."""
+    from simplepath_b200.capi import NODE_DTYPE
+    lib = C.CDLL(str(lib_path))
+    lib.spref_accel_from_mesh.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                          C.POINTER(Accel), C.c_char_p, C.c_size_t]
+    lib.spref_accel_from_mesh.restype = C.c_int
+    xf = np.ascontiguousarray(object_to_world, dtype=np.float32).reshape(12)
+    ub = np.ascontiguousarray(unbounded, dtype=np.uint8)
+    n = ub.shape[0]
+    order = np.zeros(max(n, 1), dtype=np.uint32)
+    nodes = np.zeros(max(n, 1), dtype=NODE_DTYPE)
+    accel = Accel()
+    err = C.create_string_buffer(512)
+    if lib.spref_accel_from_mesh(str(ply).encode(), _p(xf), _p(ub), n, _p(order), _p(nodes), n, C.byref(accel), err, 512) != 0:
+        raise RuntimeError(f"spref_accel_from_mesh: {err.value.decode()}")
+    head = {k: int(getattr(accel, k)) for k in ("n_prims", "n_unbounded", "n_nodes", "root", "root_count", "max_depth")}
+    return {"order": order[:n].copy(), "nodes": nodes[:head["n_nodes"]].copy(), "head": head}

@@ -39,6 +39,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
+#include <functional>
 #include <fstream>
 #include <memory>
 #include <ranges>
@@ -325,6 +326,16 @@ struct BoxHitable final : Hitable
     bool                                 intersect_p_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return false; }
     sp::BBox3                            get_world_bounds_impl() const noexcept override { return box; }
     bool                                 is_bounded_impl() const noexcept override { return true; }
+};
+
+// An unbounded primitive that is nothing but that (a plane's stand-in for the partition of base/Scene.h:33).
+struct UnboundedStub final : Hitable
+{
+    std::optional<sp::LightIntersection> intersect_lights_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return {}; }
+    std::optional<sp::Intersection>      intersect_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return {}; }
+    bool                                 intersect_p_impl(const sp::Ray&, const sp::RayLimits&) const noexcept override { return false; }
+    sp::BBox3                            get_world_bounds_impl() const noexcept override { return {}; }
+    bool                                 is_bounded_impl() const noexcept override { return false; }
 };
 
 struct BuildWalker
@@ -679,6 +690,81 @@ int spref_read_ply(const char* path, const float xf[12], uint32_t cap_vertices, 
         for (size_t i = 0; i < mesh.m_indices.size(); ++i) {
             indices[i] = static_cast<uint32_t>(mesh.m_indices[i]);
         }
+    });
+}
+
+// internal::create_acceleration_structure (base/Scene.h:27-45) — what Scene's constructor runs on the parser's primitive
+// list — over a list made of the REAL triangles of a mesh the reference itself reads (read_ply + Mesh + Triangle, in face
+// order, as FileParser appends them: base/FileParser.cpp:589-598) and unbounded stand-ins: unbounded[i] != 0 puts a stand-in
+// at list position i, every other position takes the next triangle.  order[k] = list position of the primitive with ID k
+// (unbounded list first, then the BVH's leaves), nodes / accel as the flattener numbers them.
+int spref_accel_from_mesh(const char* ply, const float xf[12], const uint8_t* unbounded, uint32_t n_total, uint32_t* order,
+                          spcu_bvh_node* nodes, uint32_t capacity, spcu_accel* accel, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&] {
+        sp::Logger::set_level(sp::Logger::LoggingLevel::error);
+        const sp::LinearSpace3x3 lin{ sp::Vector3{ xf[0], xf[1], xf[2] }, sp::Vector3{ xf[3], xf[4], xf[5] }, sp::Vector3{ xf[6], xf[7], xf[8] } };
+        const sp::AffineSpace    aff{ lin, sp::Vector3{ xf[9], xf[10], xf[11] } };
+        auto mesh = std::make_shared<sp::Mesh>(sp::read_ply(ply, sp::AffineTransformation::compute_inverse(aff)));
+        arm_exit_guard();
+        std::vector<std::shared_ptr<const Hitable>>   list;
+        std::unordered_map<const Hitable*, uint32_t> position;
+        size_t                                        next_triangle = 0;
+        for (uint32_t i = 0; i < n_total; ++i) {
+            std::shared_ptr<const Hitable> p;
+            if (unbounded[i]) {
+                p = std::make_shared<UnboundedStub>();
+            } else {
+                if (next_triangle >= mesh->get_num_triangles()) {
+                    throw std::runtime_error("spref_accel_from_mesh: the list asks for more triangles than the mesh has");
+                }
+                p = std::make_shared<sp::Triangle>(mesh, next_triangle++);
+            }
+            position.emplace(p.get(), i);
+            list.push_back(std::move(p));
+        }
+        const sp::ListAccelerator top = sp::internal::create_acceleration_structure(list.begin(), list.end());
+        uint32_t                  n_prims = 0, n_nodes = 0, max_depth = 0;
+        spcu_accel                a{};
+        std::function<int32_t(const BVHAccelerator::NodeBase*, uint32_t&, uint32_t)> walk =
+            [&](const BVHAccelerator::NodeBase* node, uint32_t& count_word, uint32_t depth) -> int32_t {
+            if (const auto* leaf = dynamic_cast<const BVHAccelerator::NodeLeaf*>(node)) {
+                const uint32_t first = n_prims;
+                for (const auto& p : leaf->m_primitives.m_primitives) {
+                    order[n_prims++] = position.at(p.get());
+                }
+                count_word = n_prims - first;
+                return ~static_cast<int32_t>(first);
+            }
+            const auto* inner = static_cast<const BVHAccelerator::NodeInternal*>(node);
+            max_depth         = std::max(max_depth, depth + 1);
+            const uint32_t idx = n_nodes++;
+            if (idx >= capacity) {
+                throw std::runtime_error("spref_accel_from_mesh: node capacity exceeded");
+            }
+            spcu_bvh_node n{};
+            for (int k = 0; k < 2; ++k) {
+                put3f(n.box + 6 * k, inner->m_children[k]->m_bounds.get_lower());
+                put3f(n.box + 6 * k + 3, inner->m_children[k]->m_bounds.get_upper());
+                n.child[k] = walk(inner->m_children[k].get(), n.count[k], depth + 1);
+            }
+            nodes[idx] = n;
+            count_word = 0;
+            return static_cast<int32_t>(idx);
+        };
+        for (const auto& p : top.m_primitives) {
+            if (const auto* bvh = dynamic_cast<const BVHAccelerator*>(p.get())) {
+                a.n_unbounded = n_prims;
+                a.root        = walk(bvh->m_root.get(), a.root_count, 0);
+            } else {
+                order[n_prims++] = position.at(p.get());
+            }
+        }
+        a.n_prims   = n_prims;
+        a.n_nodes   = n_nodes;
+        a.max_depth = max_depth;
+        a.nodes     = nodes;
+        *accel      = a;
     });
 }
 

@@ -139,3 +139,20 @@ def _accel_struct(h: dict, nodes: np.ndarray) -> Accel:
         setattr(a, k, h[k])
     a.nodes = nodes.ctypes.data_as(C.POINTER(BvhNode))
     return a
+
+
+def pre_construction_order(is_bounded) -> tuple[np.ndarray, np.ndarray]:
+    """What `std::partition(first, last, is_bounded)` of internal::create_acceleration_structure (reference base/Scene.h:33)
+    leaves behind for a primitive list in parser order: (positions of the bounded primitives in the order
+    BVHAccelerator(first, part_it) receives them, positions of the unbounded ones in the order the top-level list keeps
+    them).  libstdc++'s bidirectional partition is Hoare's scheme — the first misplaced element from the left trades places
+    with the first from the right — so the result is NOT the parser order once a plane precedes a mesh.  This is the order
+    `spcu_upload_scene_build` expects its primitive records in: unbounded first, then bounded."""
+    flags = np.asarray(is_bounded, dtype=bool)
+    pos = np.arange(flags.shape[0], dtype=np.uint32)
+    k = int(flags.sum())
+    left_false = np.flatnonzero(~flags[:k])          # misplaced in [0, k), ascending
+    right_true = np.flatnonzero(flags[k:])[::-1] + k  # misplaced in [k, n), from the right
+    assert left_false.shape == right_true.shape
+    pos[left_false], pos[right_true] = right_true.astype(np.uint32), left_false.astype(np.uint32)
+    return pos[:k].copy(), pos[k:].copy()

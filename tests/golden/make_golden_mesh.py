@@ -35,3 +35,35 @@ def main() -> None:
 
 if __name__ == "__main__":
     main()
+
+
+def accel_cases(n_triangles: int) -> dict:
+    """Positions of the unbounded stand-ins (planes) in the parser's primitive list, per case."""
+    return {"plane_first": [0], "planes_around": [0, n_triangles + 1], "planes_inside": [5, 100, n_triangles + 2], "no_plane": []}
+
+
+def main_accel() -> None:
+    """tests/golden/scene_accel.npz: internal::create_acceleration_structure (base/Scene.h:27-45) run by the reference over
+    the real triangles of the mesh above (read by its own read_ply) and unbounded stand-ins at the positions of accel_cases."""
+    v, f = meshcases.mesh()
+    xf = meshcases.transform()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        path = Path(d) / "m.ply"
+        scenes.write_ply(path, v, f)
+        nt = len(ref.read_ply(path, xf, len(v), len(f))["indices"])
+        for name, where in accel_cases(nt).items():
+            ub = np.zeros(nt + len(where), dtype=np.uint8)
+            ub[where] = 1
+            r = ref.accel_from_mesh(path, xf, ub)
+            out[f"{name}.unbounded"] = ub
+            out[f"{name}.order"] = r["order"]
+            out[f"{name}.nodes"] = r["nodes"].view(np.uint8).reshape(-1, 64)
+            out[f"{name}.head"] = np.array([r["head"][k] for k in ("n_prims", "n_unbounded", "n_nodes", "root", "root_count", "max_depth")],
+                                           dtype=np.int64)
+            print(name, r["head"])
+    np.savez_compressed(Path(__file__).resolve().parent / "scene_accel.npz", **out)
+
+
+if __name__ == "__main__":
+    main_accel()

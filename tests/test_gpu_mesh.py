@@ -105,3 +105,33 @@ def test_file_to_hits_on_the_device(ctx, oracle_port):
     got, want = ctx.trace_closest(rays), oracle_port.trace_closest(cpu.pointer(), rays)
     assert (want["id"] >= nu).mean() > 0.2
     assert np.array_equal(got["id"], want["id"]) and got["t"].tobytes() == want["t"].tobytes()
+
+
+@pytest.mark.parametrize("name", ["plane_first", "planes_around", "planes_inside", "no_plane"])
+def test_device_pipeline_reproduces_the_reference_scene_accelerator(ctx, name):
+    """vertex / face lists -> spcu_ingest_mesh -> std::partition(is_bounded) order -> spcu_upload_scene_build, against what the
+    reference's own create_acceleration_structure built over the triangles of the mesh it read itself (scene_accel.npz): the
+    same primitive behind every ID and the same header; and spcu_build_bvh on the same bounds gives the same nodes."""
+    from simplepath_b200.flat import FlatSceneData
+    from test_gpu_build import _clone
+    from test_oracle_mesh import golden_accel, list_order
+    z, g = golden(), golden_accel(name)
+    shell = FlatSceneData.load(GOLDEN / "g_bunny.flat.npz")
+    vec = np.load(GOLDEN / "g_bunny.vectors.npz")
+    material = int(shell.arrays["geom_meta"].view(np.uint32).reshape(-1)[1] >> 2)
+    ing = ctx.ingest_mesh(z["in_vertices"], z["in_faces"], z["object_to_world"], z["normal_xf"], material)
+    bounded, unb, rec = list_order(ing, g["unbounded"])
+    s = _clone(shell)
+    plane = {k: shell.arrays[k][:1] for k in ("geom_prims", "geom_shade", "geom_meta")}   # g_bunny's plane, once per stand-in
+    for key, width in (("geom_prims", 48), ("geom_shade", 48), ("geom_meta", 4)):
+        short = key.split("_")[1]
+        s.arrays[key] = np.concatenate([np.repeat(plane[key], len(unb), axis=0),
+                                        np.ascontiguousarray(rec[short]).view(np.uint8).reshape(len(bounded), width)])
+    s.head["geom"] = dict(shell.head["geom"], n_prims=len(unb) + len(bounded), n_unbounded=len(unb), n_nodes=0, root=~len(unb),
+                          root_count=0, max_depth=0)
+    s.arrays["geom_nodes"] = np.zeros((0, 64), dtype=np.uint8)
+    order, head = ctx.upload_scene_build(s.pointer(), vec["jitter"], keepalive=s)
+    assert head == g["head"]
+    assert np.array_equal(np.concatenate([unb, bounded[order]]), g["order"])
+    built = ctx.build_bvh(ctx.triangle_bounds(rec["prims"]), None, len(unb))
+    assert built["nodes"].tobytes() == g["nodes"].tobytes()

@@ -45,3 +45,37 @@ def test_oracle_ingest_on_live_reference(oracle_port, tmp_path):
     assert r["world_vertices"].tobytes() == want["vertices"].tobytes()
     assert r["world_normals"].tobytes() == want["normals"].tobytes()
     assert np.array_equal(r["prims"].reshape(-1, 3, 4)[:, :, :3], want["vertices"][want["indices"]])
+
+
+ACCEL_CASES = ("plane_first", "planes_around", "planes_inside", "no_plane")
+HEAD_KEYS = ("n_prims", "n_unbounded", "n_nodes", "root", "root_count", "max_depth")
+
+
+def golden_accel(name):
+    from simplepath_b200.capi import NODE_DTYPE
+    z = np.load(GOLDEN / "scene_accel.npz")
+    return {"unbounded": z[f"{name}.unbounded"], "order": z[f"{name}.order"], "nodes": z[f"{name}.nodes"].reshape(-1).view(NODE_DTYPE),
+            "head": dict(zip(HEAD_KEYS, (int(x) for x in z[f"{name}.head"])))}
+
+
+def list_order(ingested, unbounded):
+    """Parser-order list [unbounded stand-ins | the mesh's triangles in face order] -> (bounded list positions in
+    pre-construction order, unbounded list positions, triangle records in pre-construction order)."""
+    from simplepath_b200.flat import pre_construction_order
+    bounded, unb = pre_construction_order(unbounded == 0)
+    triangle_of_position = np.cumsum(unbounded == 0) - 1
+    return bounded, unb, {k: ingested[k][triangle_of_position[bounded]] for k in ("prims", "shade", "meta")}
+
+
+@pytest.mark.parametrize("name", ACCEL_CASES)
+def test_cpu_pipeline_reproduces_the_reference_scene_accelerator(oracle_port, name):
+    """vertex / face lists -> oracle ingest -> std::partition(is_bounded) order -> oracle bounds + construction, against what
+    the reference's own create_acceleration_structure (base/Scene.h:27-45) built over the triangles of the mesh IT read:
+    the same primitive behind every ID, the same nodes, the same header."""
+    z, g = golden(), golden_accel(name)
+    ing = oracle_port.ingest_mesh(z["in_vertices"], z["in_faces"], z["object_to_world"], z["normal_xf"])
+    bounded, unb, rec = list_order(ing, g["unbounded"])
+    built = oracle_port.build_bvh(oracle_port.triangle_bounds(rec["prims"]), None, len(unb))
+    assert built["head"] == g["head"]
+    assert np.array_equal(np.concatenate([unb, bounded[built["order"]]]), g["order"])
+    assert built["nodes"].tobytes() == g["nodes"].tobytes()

@@ -102,6 +102,50 @@ __global__ void __launch_bounds__(kBlock) k_fill_adjacency(const uint32_t* faces
     }
 }
 
+// In-place ascending sort of a vertex's face list: insertion sort for the usual handful of entries, heap sort beyond (a
+// vertex shared by a huge fan must not turn into a quadratic loop on one thread).
+__device__ void sort_ascending(uint32_t* list, uint32_t n)
+{
+    if (n <= 32u) {
+        for (uint32_t i = 1; i < n; ++i) {
+            const uint32_t key = list[i];
+            uint32_t       j   = i;
+            for (; j > 0 && list[j - 1] > key; --j) {
+                list[j] = list[j - 1];
+            }
+            list[j] = key;
+        }
+        return;
+    }
+    auto sift = [list](uint32_t root, uint32_t end) { // max-heap on [0, end)
+        const uint32_t key = list[root];
+        for (;;) {
+            uint32_t child = 2u * root + 1u;
+            if (child >= end) {
+                break;
+            }
+            if (child + 1u < end && list[child + 1u] > list[child]) {
+                ++child;
+            }
+            if (list[child] <= key) {
+                break;
+            }
+            list[root] = list[child];
+            root       = child;
+        }
+        list[root] = key;
+    };
+    for (uint32_t i = n / 2u; i-- > 0u;) {
+        sift(i, n);
+    }
+    for (uint32_t end = n - 1u; end > 0u; --end) {
+        const uint32_t t = list[0];
+        list[0]          = list[end];
+        list[end]        = t;
+        sift(0u, end);
+    }
+}
+
 // vertex normals (base/PlyReader.cpp:509-528) and Mesh's transforms (shapes/Triangle.h:37-47).  The sequential loop adds
 // face normals face by face, so a vertex sees its faces in ascending face index: sort the (short) list, then add in order.
 __global__ void __launch_bounds__(kBlock) k_vertices(const float* verts, uint32_t nv, const uint32_t* offset, uint32_t* adjacency,
@@ -112,14 +156,7 @@ __global__ void __launch_bounds__(kBlock) k_vertices(const float* verts, uint32_
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
         uint32_t*      list = adjacency + offset[v];
         const uint32_t deg  = offset[v + 1] - offset[v];
-        for (uint32_t i = 1; i < deg; ++i) { // insertion sort: valence is a handful
-            const uint32_t key = list[i];
-            uint32_t       j   = i;
-            for (; j > 0 && list[j - 1] > key; --j) {
-                list[j] = list[j - 1];
-            }
-            list[j] = key;
-        }
+        sort_ascending(list, deg);
         F3 n{ 0.0f, 0.0f, 0.0f };
         for (uint32_t i = 0; i < deg; ++i) {
             const F3 f = ld3(face_n, list[i]);

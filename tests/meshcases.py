@@ -19,7 +19,7 @@ def transform(seed: int = 3) -> np.ndarray:
     return np.concatenate([m[:, 0], m[:, 1], m[:, 2], [0.3, -1.25, 4.0]]).astype(np.float32)
 
 
-def mesh(n_tris: int = 3000, seed: int = 1) -> tuple[np.ndarray, np.ndarray]:
+def mesh(n_tris: int = 3000, seed: int = 1, fan: int = 200) -> tuple[np.ndarray, np.ndarray]:
     """A bumpy sphere plus what the reader has to cope with: zero-area faces (repeated index, collinear and coincident
     vertices), vertices no face uses, one vertex shared by a large fan, faces in shuffled order."""
     rng = np.random.default_rng(seed)
@@ -34,10 +34,10 @@ def mesh(n_tris: int = 3000, seed: int = 1) -> tuple[np.ndarray, np.ndarray]:
                            [5, 5, 9],                  # repeated index
                            [7, 7, 7]], dtype=np.uint32)
     hub = nv + 5                                       # a fan of 200 triangles around one vertex
-    ring = rng.integers(0, nv, 201).astype(np.uint32)
-    fan = np.stack([np.full(200, hub, dtype=np.uint32), ring[:-1], ring[1:]], axis=1)
-    fan = fan[(fan[:, 1] != fan[:, 2])]
-    f = np.concatenate([f, degenerate, fan])
+    ring = rng.integers(0, nv, fan + 1).astype(np.uint32)
+    fan_faces = np.stack([np.full(fan, hub, dtype=np.uint32), ring[:-1], ring[1:]], axis=1)
+    fan_faces = fan_faces[(fan_faces[:, 1] != fan_faces[:, 2])]
+    f = np.concatenate([f, degenerate, fan_faces])
     f = f[rng.permutation(len(f))]
     return v, f
 

@@ -33,7 +33,7 @@ def test_ingest_matches_reference_mesh(ctx):
 
 @pytest.mark.parametrize("n_tris", [12, 2048, 300_000])
 def test_ingest_matches_oracle(ctx, oracle_port, n_tris):
-    v, f = meshcases.mesh(n_tris=n_tris, seed=n_tris)
+    v, f = meshcases.mesh(n_tris=n_tris, seed=n_tris, fan=200 if n_tris < 300_000 else 100_000)  # one vertex in 100 K faces
     xf = meshcases.transform(seed=n_tris)
     m = xf[:9].reshape(3, 3).T.astype(np.float64)               # columns c0 c1 c2
     nxf = np.linalg.inv(m).T.T.reshape(9).astype(np.float32)    # inverse-transposed, column major (= inverse, row major)

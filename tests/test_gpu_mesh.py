@@ -13,10 +13,16 @@ pytestmark = pytest.mark.gpu
 NORMAL_TOLERANCE = 4.0 * 2.0 ** -23
 
 
-def normals_close(got, want):
+def normals_close(got, want, ill_conditioned=None):
+    """ill_conditioned: normals of vertices whose face normals nearly cancel (the hub of a 100 K-face fan sums 10^5 unit
+    vectors to a length of a few hundred): the last-bit differences of the summands are amplified by that ratio, so those get
+    the tolerance times 1000."""
     scale = np.linalg.norm(want.astype(np.float64), axis=-1, keepdims=True)
-    err = np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale
-    assert err.max() <= NORMAL_TOLERANCE, float(err.max())
+    err = (np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale).max(axis=-1)
+    tol = np.full(err.shape, NORMAL_TOLERANCE)
+    if ill_conditioned is not None:
+        tol[ill_conditioned] *= 1000.0
+    assert (err <= tol).all(), float((err / tol).max())
 
 
 def test_ingest_matches_reference_mesh(ctx):
@@ -41,8 +47,11 @@ def test_ingest_matches_oracle(ctx, oracle_port, n_tris):
     assert got["world_vertices"].tobytes() == want["world_vertices"].tobytes()
     assert got["prims"].tobytes() == want["prims"].tobytes()
     assert np.array_equal(got["meta"], want["meta"])
-    normals_close(got["world_normals"], want["world_normals"])
-    normals_close(got["shade"].reshape(-1, 3, 4)[:, :, :3], want["shade"].reshape(-1, 3, 4)[:, :, :3])
+    hub = np.bincount(f.ravel(), minlength=len(v)) > 1000
+    normals_close(got["world_normals"], want["world_normals"], hub)
+    corner_normals = want["shade"].reshape(-1, 3, 4)[:, :, :3]
+    at_hub = (corner_normals[:, :, None, :] == want["world_normals"][hub][None, None, :, :]).all(axis=-1).any(axis=-1)
+    normals_close(got["shade"].reshape(-1, 3, 4)[:, :, :3], corner_normals, at_hub)
 
 
 def test_ingest_edge_cases(ctx, oracle_port):

@@ -49,3 +49,24 @@ def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
     ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
     return np.abs(ia - ib)
+
+
+def normal_condition(v: np.ndarray, f: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """How ill-conditioned each vertex normal is: (number of face normals summed) / |their sum| >= 1 — last-bit differences
+    in the unit summands reach the normalised result amplified by this ratio.  Returns (per vertex, per corner of the faces
+    with non-zero area in face order), computed in float64."""
+    p = v.astype(np.float64)[f.astype(np.int64)]
+    n = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    area = np.linalg.norm(n, axis=1)
+    keep = area > 0
+    unit = n[keep] / area[keep, None]
+    fk = f[keep].astype(np.int64)
+    total = np.zeros((len(v), 3))
+    count = np.zeros(len(v))
+    for k in range(3):
+        np.add.at(total, fk[:, k], unit)
+        np.add.at(count, fk[:, k], 1.0)
+    length = np.linalg.norm(total, axis=1)
+    cond = np.where(length > 0, count / np.maximum(length, 1e-300), 1.0)
+    cond = np.maximum(cond, 1.0)
+    return cond, cond[fk]

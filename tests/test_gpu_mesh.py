@@ -1,7 +1,8 @@
 """spcu_ingest_mesh (include/spcu.h) through the C-ABI.  Bit-exact: which faces survive, their order, every vertex position
 (hence bounds, tree and hits downstream).  Tolerance, stated: shading normals, because normalize() in the reference multiplies
 by an SSE rsqrtss estimate (math/Math.h:205-227) that only x86 reproduces — every component within 4 * 2^-23 of the normal's
-length of the reference's value."""
+length of the reference's value, times the conditioning of that vertex's sum (meshcases.normal_condition; 1 for ordinary
+vertices, hundreds where opposing face normals nearly cancel)."""
 import numpy as np
 import pytest
 
@@ -13,15 +14,13 @@ pytestmark = pytest.mark.gpu
 NORMAL_TOLERANCE = 4.0 * 2.0 ** -23
 
 
-def normals_close(got, want, ill_conditioned=None):
-    """ill_conditioned: normals of vertices whose face normals nearly cancel (the hub of a 100 K-face fan sums 10^5 unit
-    vectors to a length of a few hundred): the last-bit differences of the summands are amplified by that ratio, so those get
-    the tolerance times 1000."""
+def normals_close(got, want, condition=None):
+    """condition (meshcases.normal_condition): faces summed / |sum of their unit normals| per normal.  Where a vertex's face
+    normals nearly cancel (the hub of a 100 K-face fan sums 10^5 unit vectors to a length of a few hundred) the last-bit
+    differences of the summands are amplified by that ratio, and so is the tolerance."""
     scale = np.linalg.norm(want.astype(np.float64), axis=-1, keepdims=True)
     err = (np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale).max(axis=-1)
-    tol = np.full(err.shape, NORMAL_TOLERANCE)
-    if ill_conditioned is not None:
-        tol[ill_conditioned] *= 1000.0
+    tol = NORMAL_TOLERANCE * (np.ones(err.shape) if condition is None else condition)
     assert (err <= tol).all(), float((err / tol).max())
 
 
@@ -33,8 +32,9 @@ def test_ingest_matches_reference_mesh(ctx):
     assert len(r["prims"]) == len(idx)
     assert np.array_equal(r["prims"].reshape(-1, 3, 4)[:, :, :3], z["vertices"][idx])
     assert (r["prims"].reshape(-1, 3, 4)[:, :, 3] == 0).all() and (r["meta"] == (3 << 2)).all()
-    normals_close(r["world_normals"], z["normals"])
-    normals_close(r["shade"].reshape(-1, 3, 4)[:, :, :3], z["normals"][idx])
+    cond_vertex, cond_corner = meshcases.normal_condition(z["in_vertices"], z["in_faces"])
+    normals_close(r["world_normals"], z["normals"], cond_vertex)
+    normals_close(r["shade"].reshape(-1, 3, 4)[:, :, :3], z["normals"][idx], cond_corner)
 
 
 @pytest.mark.parametrize("n_tris", [12, 2048, 300_000])
@@ -47,11 +47,10 @@ def test_ingest_matches_oracle(ctx, oracle_port, n_tris):
     assert got["world_vertices"].tobytes() == want["world_vertices"].tobytes()
     assert got["prims"].tobytes() == want["prims"].tobytes()
     assert np.array_equal(got["meta"], want["meta"])
-    hub = np.bincount(f.ravel(), minlength=len(v)) > 1000
-    normals_close(got["world_normals"], want["world_normals"], hub)
-    corner_normals = want["shade"].reshape(-1, 3, 4)[:, :, :3]
-    at_hub = (corner_normals[:, :, None, :] == want["world_normals"][hub][None, None, :, :]).all(axis=-1).any(axis=-1)
-    normals_close(got["shade"].reshape(-1, 3, 4)[:, :, :3], corner_normals, at_hub)
+    cond_vertex, cond_corner = meshcases.normal_condition(v, f)
+    assert cond_corner.shape[0] == len(want["prims"])
+    normals_close(got["world_normals"], want["world_normals"], cond_vertex)
+    normals_close(got["shade"].reshape(-1, 3, 4)[:, :, :3], want["shade"].reshape(-1, 3, 4)[:, :, :3], cond_corner)
 
 
 def test_ingest_edge_cases(ctx, oracle_port):

@@ -182,3 +182,54 @@ def test_upload_scene_build_analytic_and_errors(ctx):
     cam = np.ascontiguousarray(vec["camera.rays"]).view(capi.RAY_DTYPE).reshape(-1)
     hit = ctx.trace_closest(cam)
     assert np.array_equal(hit["id"], vec["camera.closest_id"]) and hit["t"].tobytes() == vec["camera.closest_t"].tobytes()
+
+
+def test_upload_scene_build_with_spheres_inside_the_tree(ctx, oracle_port):
+    """Forty spheres (copies of material_spheres' four, moved apart) and their caller-supplied bounds: a real tree whose leaves
+    carry the mixed flag.  Same tree from the oracle, same hits from the oracle's traversal of it."""
+    from simplepath_b200 import capi
+    from simplepath_b200.flat import FlatSceneData
+    flat = FlatSceneData.load(GOLDEN / "g_spheres.flat.npz")
+    vec = np.load(GOLDEN / "g_spheres.vectors.npz")
+    g = flat.head["geom"]
+    nu, n0 = g["n_unbounded"], g["n_prims"] - g["n_unbounded"]
+    rng = np.random.default_rng(6)
+    prims0 = flat.arrays["geom_prims"].view(np.float32).reshape(-1, 12)
+    recs, bounds = {k: [flat.arrays[k][:nu]] for k in ("geom_prims", "geom_shade", "geom_meta")}, []
+    for copy in range(10):
+        shift = (rng.uniform(-6, 6, 3) * np.array([1.0, 0.2, 1.0])).astype(np.float64) if copy else np.zeros(3)
+        for i in range(nu, nu + n0):
+            w2o = prims0[i].astype(np.float64)                      # c0.xyz c1.xyz c2.xyz affine.xyz
+            lin = w2o[:9].reshape(3, 3).T
+            moved = prims0[i].copy()
+            moved[9:12] = (w2o[9:12] - lin @ shift).astype(np.float32)
+            o2w = np.linalg.inv(lin)
+            centre = -o2w @ moved[9:12].astype(np.float64)
+            reach = np.abs(o2w).sum(axis=1) * 1.001                 # the unit sphere's box through object_to_world, padded
+            bounds.append(np.concatenate([centre - reach, centre + reach]).astype(np.float32))
+            recs["geom_prims"].append(moved.view(np.uint8).reshape(1, 48))
+            recs["geom_shade"].append(flat.arrays["geom_shade"][i:i + 1])
+            recs["geom_meta"].append(flat.arrays["geom_meta"][i:i + 1])
+    s = _clone(flat)
+    for k in recs:
+        s.arrays[k] = np.concatenate(recs[k])
+    n = 10 * n0
+    s.head["geom"] = dict(g, n_prims=nu + n, n_nodes=0, root=~nu, root_count=0, max_depth=0)
+    bounds = np.stack(bounds)
+    kinds = s.arrays["geom_meta"].view(np.uint32).reshape(-1)[nu:] & 3
+    built = oracle_port.build_bvh(bounds, (kinds != 0).astype(np.uint8), nu)
+    assert built["head"]["n_nodes"] > 3
+    leaf = built["nodes"]["child"] < 0
+    assert ((built["nodes"]["count"][leaf] & 0x80000000) != 0).all()          # every leaf holds spheres
+    order, head = ctx.upload_scene_build(s.pointer(), vec["jitter"], bounds=bounds, keepalive=s)
+    assert head == built["head"] and np.array_equal(order, built["order"])
+    cpu = _clone(s)
+    for k in ("geom_prims", "geom_shade", "geom_meta"):
+        cpu.arrays[k][nu:] = s.arrays[k][nu + built["order"]]
+    cpu.arrays["geom_nodes"] = built["nodes"].view(np.uint8).reshape(-1, 64).copy()
+    cpu.head["geom"] = built["head"]
+    rays = np.concatenate([np.ascontiguousarray(vec[f"{b}.rays"]).view(capi.RAY_DTYPE).reshape(-1) for b in ("camera", "random", "segments")])
+    want, got = oracle_port.trace_closest(cpu.pointer(), rays), ctx.trace_closest(rays)
+    assert (want["id"] >= nu).sum() > 1000
+    assert np.array_equal(got["id"], want["id"]) and got["t"].tobytes() == want["t"].tobytes()
+    assert np.array_equal(ctx.trace_any(rays), oracle_port.trace_any(cpu.pointer(), rays))

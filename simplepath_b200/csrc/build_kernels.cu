@@ -8,6 +8,7 @@
 //
 //   * level-synchronous: all nodes of one depth are processed by a handful of passes over the n primitive positions
 //     (every position knows the node it currently belongs to), ~10 launches per level, no recursion, no per-node launch;
+//     the pass that applies a level's partition also reduces the bounds of the next level's nodes (k_bounds<true>);
 //   * the bounds fold is order-dependent only through ties (_mm_min_ps / _mm_max_ps return their SECOND operand on a tie,
 //     which shows in +0 / -0): "the last position among the equal minima wins".  A 64-bit key (ordered float | position |
 //     sign) under atomicMin / atomicMax reproduces that with no ordered traversal; warps reduce their contiguous runs with
@@ -45,7 +46,7 @@ static_assert(sizeof(NodeKeys) == 64, "NodeKeys");
 struct Build
 {
     // Position-ordered, double-buffered: bounds_in[position] / perm_in[position] describe the primitive at that position when
-    // the level starts (perm = its index in the caller's array); k_apply writes the permuted level into *_out and the host
+    // the level starts (perm = its index in the caller's array); k_bounds<true> writes the permuted level into *_out and the host
     // swaps.  Every pass over positions therefore reads contiguously; only the elements a partition moves are gathered.
     const spcu_bounds* bounds_in;
     spcu_bounds*       bounds_out;
@@ -205,7 +206,20 @@ __device__ __forceinline__ void flush_partial(const Build& b, uint32_t level_beg
 // partial is flushed when the node changes.  Measured on 28 M boxes: the first levels took 5 ms each without this.
 constexpr int kBoundsIterations = 32;
 
-__global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin)
+__device__ __forceinline__ void store_bounds(spcu_bounds* p, const spcu_bounds& x)
+{
+    float2* o = reinterpret_cast<float2*>(p);
+    o[0] = make_float2(x.lo[0], x.lo[1]), o[1] = make_float2(x.lo[2], x.hi[0]), o[2] = make_float2(x.hi[1], x.hi[2]);
+}
+
+// kApply = false: the bounds of the level's nodes from the elements where they are (the root).
+// kApply = true : FUSED with the end of the previous level — every position first fetches the element the partition leaves
+// there (its own, or its partner's when it holds a misplaced one: Hoare's partition as a gather), writes it to the level's
+// output buffers and joins its child, or retires with its leaf (whose elements stay put in BOTH buffers from then on); the
+// element it has just moved then goes straight into the CHILD's keys.  One pass over the bounds instead of two.
+// level_begin: first node of the level being partitioned; keys_begin: first node of the level whose keys are reduced.
+template <bool kApply>
+__global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin, uint32_t keys_begin)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -223,9 +237,33 @@ __global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin
         }
         const uint32_t pos = static_cast<uint32_t>(pos64);
         Partial        cur;
-        cur.seg = pos < b.n ? b.seg_of[pos] : kInvalid;
+        spcu_bounds    x{};
+        cur.seg = kInvalid;
+        const uint32_t seg = pos < b.n ? b.seg_of[pos] : kInvalid;
+        if (seg != kInvalid) {
+            if (!kApply) {
+                cur.seg = seg;
+                x       = load_bounds(&b.bounds_in[pos]);
+            } else {
+                uint32_t src = pos;
+                if (b.state[seg] == kInternal) {
+                    const uint32_t first = b.first[seg], mid = b.mid[seg - level_begin];
+                    const uint32_t before = b.prefix[pos] - b.prefix[first]; // trues in [first, pos)
+                    const bool     f      = b.flag[pos] != 0;
+                    if (pos < mid && !f) {
+                        src = b.right_misplaced[first + (pos - first - before)];
+                    } else if (pos >= mid && f) {
+                        src = b.left_misplaced[first + (mid - first - before - 1u)];
+                    }
+                    cur.seg = b.child0[seg] + (pos >= mid ? 1u : 0u);
+                }
+                b.seg_of[pos]   = cur.seg;
+                b.perm_out[pos] = b.perm_in[src];
+                x               = load_bounds(&b.bounds_in[src]);
+                store_bounds(&b.bounds_out[pos], x);
+            }
+        }
         if (cur.seg != kInvalid) {
-            const spcu_bounds x = load_bounds(&b.bounds_in[pos]);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 cur.k[a]     = min_key(x.lo[a], pos);
@@ -250,7 +288,7 @@ __global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin
             continue;
         }
         if (carry_iterations) {
-            flush_partial(b, level_begin, carry, carry_start, carry_uniform ? carry_iterations : 1u);
+            flush_partial(b, keys_begin, carry, carry_start, carry_uniform ? carry_iterations : 1u);
         }
         carry            = cur;
         carry_start      = pos;
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(kBlock) k_bounds(Build b, uint32_t level_begin
         carry_uniform    = uniform;
     }
     if (carry_iterations) {
-        flush_partial(b, level_begin, carry, carry_start, carry_uniform ? carry_iterations : 1u);
+        flush_partial(b, keys_begin, carry, carry_start, carry_uniform ? carry_iterations : 1u);
     }
 }
 
@@ -380,39 +418,6 @@ __global__ void __launch_bounds__(kBlock) k_scatter(Build b, uint32_t level_begi
         } else if (pos >= mid && f) {
             b.right_misplaced[first + (mid - first - before - 1u)] = pos; // trues after pos = rank from the right
         }
-    }
-}
-
-// step 2, as a gather: every position fetches the element the partition leaves there (its own, or its partner's when it
-// holds a misplaced one), writes it to the level's output buffers and joins its child — or retires with its leaf, whose
-// elements stay where they are in BOTH buffers from now on.
-__global__ void __launch_bounds__(kBlock) k_apply(Build b, uint32_t level_begin)
-{
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < b.n; pos += stride) {
-        const uint32_t seg = b.seg_of[pos];
-        if (seg == kInvalid) {
-            continue;
-        }
-        uint32_t src = pos;
-        if (b.state[seg] != kInternal) {
-            b.seg_of[pos] = kInvalid;
-        } else {
-            const uint32_t first = b.first[seg], mid = b.mid[seg - level_begin];
-            const uint32_t before = b.prefix[pos] - b.prefix[first]; // trues in [first, pos)
-            const bool     f      = b.flag[pos] != 0;
-            if (pos < mid && !f) {
-                src = b.right_misplaced[first + (pos - first - before)];
-            } else if (pos >= mid && f) {
-                src = b.left_misplaced[first + (mid - first - before - 1u)];
-            }
-            b.seg_of[pos] = b.child0[seg] + (pos >= mid ? 1u : 0u);
-        }
-        b.perm_out[pos] = b.perm_in[src];
-        const float2* q = reinterpret_cast<const float2*>(&b.bounds_in[src]);
-        float2*       o = reinterpret_cast<float2*>(&b.bounds_out[pos]);
-        const float2  v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
-        o[0] = v0, o[1] = v1, o[2] = v2;
     }
 }
 
@@ -582,14 +587,19 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
         }
         const unsigned node_grid = (count + kBlock - 1) / kBlock;
         set_buf();
-        k_keys_init<<<node_grid, kBlock, 0, st>>>(b.keys, count);
-        k_bounds<<<bounds_grid, kBlock, 0, st>>>(b, level_begin);
+        if (level == 0) {
+            k_keys_init<<<1, kBlock, 0, st>>>(b.keys, 1);
+            k_bounds<false><<<bounds_grid, kBlock, 0, st>>>(b, 0, 0);
+        }
         k_decide<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
         k_flags<<<grid, kBlock, 0, st>>>(b, level_begin);
         exclusive_scan(b.flag, b.prefix, b.n, partials, st);
         k_split<<<node_grid, kBlock, 0, st>>>(b, level_begin, count);
+        // the children's keys (k_decide has consumed this level's): at most two per node of this level
+        const uint32_t next_max = static_cast<uint32_t>(std::min<size_t>(2 * static_cast<size_t>(count), max_level));
+        k_keys_init<<<(next_max + kBlock - 1) / kBlock, kBlock, 0, st>>>(b.keys, next_max);
         k_scatter<<<grid, kBlock, 0, st>>>(b, level_begin);
-        k_apply<<<grid, kBlock, 0, st>>>(b, level_begin);
+        k_bounds<true><<<bounds_grid, kBlock, 0, st>>>(b, level_begin, level_end); // apply the partition + the children's bounds
         cur ^= 1;
         uint32_t total = 0;
         CK(c, cudaMemcpyAsync(&total, b.n_nodes, sizeof total, cudaMemcpyDeviceToHost, st));

@@ -84,6 +84,42 @@ def peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def construction_side(ctx) -> dict:
+    """Outside the timed region and not part of `value`: the steps either side of the path on a bounded
+    synthetic input, device-timed — BVHAccelerator::construct (spcu_build_bvh), read_ply's normal passes + Mesh's constructor
+    (spcu_ingest_mesh) — and the same inputs through the oracle's sequential restatement on one host core."""
+    from oracle import port
+    from simplepath_b200 import scenes
+    n = 1_000_000
+    rng = np.random.default_rng(5)
+    c = rng.random((n, 3), dtype=np.float32) * np.float32(100.0)
+    h = rng.random((n, 3), dtype=np.float32) * np.float32(0.05)
+    boxes = np.concatenate([c - h, c + h], axis=1)
+    ctx.build_bvh(boxes)  # warm-up (allocations, kernel load)
+    built = ctx.build_bvh(boxes)
+    t0 = time.perf_counter()
+    want = port.build_bvh(boxes)
+    cpu_build_ms = (time.perf_counter() - t0) * 1e3
+    v, f = scenes.bumpy_sphere(n, (-0.1, 0.03, -0.06), (0.06, 0.19, 0.06))
+    v, f = np.asarray(v, dtype=np.float32), np.asarray(f, dtype=np.uint32)
+    xf = np.array([10, 0, 0, 0, 10, 0, 0, 0, 10, 0, 0, 0], dtype=np.float32)
+    nxf = np.array([0.1, 0, 0, 0, 0.1, 0, 0, 0, 0.1], dtype=np.float32)
+    ctx.ingest_mesh(v, f, xf, nxf)
+    ingested = ctx.ingest_mesh(v, f, xf, nxf)
+    t0 = time.perf_counter()
+    want_mesh = port.ingest_mesh(v, f, xf, nxf)
+    cpu_ingest_ms = (time.perf_counter() - t0) * 1e3
+    return {
+        "bvh_build": {"primitives": n, "device_ms": built["device_ms"], "internal_nodes": built["head"]["n_nodes"],
+                      "oracle_port_ms_1_core": cpu_build_ms,
+                      "identical_to_oracle": bool(built["nodes"].tobytes() == want["nodes"].tobytes()
+                                                  and np.array_equal(built["order"], want["order"]))},
+        "mesh_ingest": {"faces": int(len(f)), "vertices": int(len(v)), "device_ms": ingested["device_ms"],
+                        "oracle_port_ms_1_core": cpu_ingest_ms,
+                        "positions_identical_to_oracle": bool(ingested["prims"].tobytes() == want_mesh["prims"].tobytes())},
+    }
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -270,6 +306,7 @@ def run_cuda(args) -> None:
     traffic_item, traffic_src = measured_traffic_per_item(dominant, args.workload, ctx.resolved_pipeline())
 
     cpu = cpu_baseline(scene_name, flat) if world == 1 and not args.no_cpu else None
+    construction = construction_side(ctx) if world == 1 and not args.no_cpu else None
 
     steps_s = total_ms / 1e3
     line = {
@@ -298,6 +335,7 @@ def run_cuda(args) -> None:
                      "note": "shading stages are instruction-issue bound, not HBM bound (profiles/)"},
         "stages_ms_per_step": {k: v / stage_steps for k, v in stage_ms.items() if stage_launches.get(k)},
         "cpu_baseline": cpu,
+        "construction_side": construction,
     }
     emit(line)
     ctx.close()

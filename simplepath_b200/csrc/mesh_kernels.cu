@@ -239,6 +239,11 @@ extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv,
     CK(c, mem.get(&d_xf, 24));
     CK(c, mem.get(&d_world_v, 3 * static_cast<size_t>(nv)));
     CK(c, mem.get(&d_world_n, 3 * static_cast<size_t>(nv)));
+    float4 *  d_prims = nullptr, *d_shade = nullptr; // sized for every face: no allocation between the timed kernels
+    uint32_t* d_meta = nullptr;
+    CK(c, mem.get(&d_prims, 3 * static_cast<size_t>(nf)));
+    CK(c, mem.get(&d_shade, 3 * static_cast<size_t>(nf)));
+    CK(c, mem.get(&d_meta, nf));
     if (nv) {
         CK(c, cudaMemcpyAsync(d_v, vertices, 3 * static_cast<size_t>(nv) * sizeof(float), cudaMemcpyHostToDevice, st));
     }
@@ -266,12 +271,7 @@ extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv,
     if (nv) {
         k_vertices<<<grid_for(nv, c->sm_count), kBlock, 0, st>>>(d_v, nv, d_offset, d_adj, d_face_n, d_xf, d_xf + 12, d_world_v, d_world_n);
     }
-    CK(c, cudaStreamSynchronize(st));
-    float4 *  d_prims = nullptr, *d_shade = nullptr;
-    uint32_t* d_meta = nullptr;
-    CK(c, mem.get(&d_prims, 3 * static_cast<size_t>(n_kept)));
-    CK(c, mem.get(&d_shade, 3 * static_cast<size_t>(n_kept)));
-    CK(c, mem.get(&d_meta, n_kept));
+    CK(c, cudaStreamSynchronize(st)); // n_kept
     if (n_kept) {
         k_triangle_records<<<grid_for(n_kept, c->sm_count), kBlock, 0, st>>>(d_f, d_kept, n_kept, d_world_v, d_world_n,
                                                                              SPCU_MAKE_META(SPCU_PRIM_TRIANGLE, material), d_prims, d_shade,

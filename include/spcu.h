@@ -390,7 +390,7 @@ int spcu_triangle_bounds(spcu_ctx* ctx, const spcu_prim_geom* tris, uint32_t n, 
  * (Image/Image.cpp:14-55).  Both formats store rows bottom-up (j = ny-1 .. 0).
  *   SPCU_IMAGE_PFM : out = float[h][w][3], the payload of write_pfm (:40-55) on a little-endian host: sum / spp
  *   SPCU_IMAGE_PPM : out = uint16_t[h][w][3], the numbers write_ppm prints (:14-29): int(255.99f * rgb_to_srgb(sum / spp))
- *                    (Image/Image.h:38-50), clamped to [0, 65535]; a quarter of the device->host bytes of the float sums */
+ *                    (Image/Image.h:38-50), clamped to [0, 65535]; half the device->host bytes of the float sums */
 #define SPCU_IMAGE_PFM 0u
 #define SPCU_IMAGE_PPM 1u
 /* Packs host-resident per-pixel sums (rgb_sum[(y*w+x)*3+c], as spcu_render returns them). */

@@ -52,8 +52,10 @@ namespace sp {
 struct CudaIntegrator::Device
 {
     spcu_ctx* ctx = nullptr;
+    int       index;
 
-    explicit Device(int index)
+    explicit Device(int index_)
+    : index(index_)
     {
         if (spcu_create(index, &ctx) != SPCU_OK) {
             throw std::runtime_error(std::string("CudaIntegrator: ") + spcu_last_error(nullptr));
@@ -125,8 +127,31 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
         // The flattened copy only lives for the duration of the upload: nothing of `scene` is retained.
         const spb200::FlatScene  flat   = spb200::flatten_scene(scene);
         const std::vector<float> jitter = spb200::jitter_table(spp);
+        // SPCU_BUILD_ON_DEVICE=1: hand the geometry over UNBUILT and let the device construct the acceleration structure
+        // (spcu_upload_scene_build).  The flattener lists the bounded primitives in leaf order, and construction from the
+        // leaf order is a fixed point of BVHAccelerator::construct (Hoare's partition does not move a partitioned range),
+        // so the device must arrive at exactly the tree the reference built: checked, header and primitive order.
+        const bool build_on_device = env_unsigned("SPCU_BUILD_ON_DEVICE", 0) != 0;
         for (const auto& d : m_devices) {
-            d->check(spcu_upload_scene(d->ctx, &flat.view, jitter.data(), spp), "spcu_upload_scene");
+            if (!build_on_device) {
+                d->check(spcu_upload_scene(d->ctx, &flat.view, jitter.data(), spp), "spcu_upload_scene");
+                continue;
+            }
+            const spcu_accel&     want = flat.view.geom;
+            std::vector<uint32_t> order(want.n_prims - want.n_unbounded);
+            spcu_accel            built{};
+            d->check(spcu_upload_scene_build(d->ctx, &flat.view, jitter.data(), spp, nullptr, order.data(), &built),
+                     "spcu_upload_scene_build");
+            bool same = built.n_prims == want.n_prims && built.n_unbounded == want.n_unbounded && built.n_nodes == want.n_nodes &&
+                        built.root == want.root && built.root_count == want.root_count && built.max_depth == want.max_depth;
+            for (uint32_t k = 0; same && k < order.size(); ++k) {
+                same = order[k] == k;
+            }
+            if (!same) {
+                throw std::runtime_error("CudaIntegrator: the device-built acceleration structure differs from the reference's");
+            }
+            std::fprintf(stderr, "CudaIntegrator: acceleration structure built on device %d: %u primitives, %u nodes, depth %u\n",
+                         d->index, built.n_prims, built.n_nodes, built.max_depth);
         }
         m_uploaded_scene = &scene;
         m_uploaded_spp   = spp;

@@ -56,3 +56,19 @@ def test_driver_over_two_devices_is_bit_identical(tmp_path):
         assert proc.returncode == 0, proc.stdout[-2000:]
         images.append(scenes.read_pfm(tmp_path / "image.pfm"))
     assert images[0].tobytes() == images[1].tobytes()
+
+
+@pytest.mark.skipif(not host.DRIVER.exists() or not host.available(), reason="host plugin not built (needs the reference sources)")
+def test_driver_with_the_tree_built_on_the_device(tmp_path):
+    """SPCU_BUILD_ON_DEVICE=1: the plugin hands the geometry over unbuilt (spcu_upload_scene_build); the device must arrive at
+    the reference's own tree (checked inside the plugin) and the image is the same, bit for bit."""
+    sp = scenes.ensure("g_bunny", tmp_path)
+    images = []
+    for build in ("0", "1"):
+        env = dict(os.environ, SPCU_SEED="5", SPCU_BUILD_ON_DEVICE=build)
+        proc = subprocess.run([str(host.DRIVER), "--samples", "4", "--integrator", "cuda", sp.name], cwd=tmp_path, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+        assert proc.returncode == 0, proc.stdout[-2000:]
+        assert ("acceleration structure built on device" in proc.stdout) == (build == "1")
+        images.append(scenes.read_pfm(tmp_path / "image.pfm"))
+    assert images[0].tobytes() == images[1].tobytes()

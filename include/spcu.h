@@ -417,6 +417,15 @@ int spcu_ingest_mesh(spcu_ctx* ctx, const float* vertices, uint32_t nv, const ui
                      spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices, float* world_normals,
                      float* device_ms);
 
+/* The STL flavour (base/STLReader.cpp:60-137): vertices[] is the parser's de-duplicated vertex list (VertexIndexer, :18-36, host
+ * side), faces[] its index triples, face_normals[nf*3] the normals stored in the file.  A stored normal is used unless it
+ * is_zero (every component within 1e-5 of 0: math/Vector3.h:644-647), then the cross product; a face whose normal still is_zero
+ * adds nothing to the vertex normals but — its indices were pushed before the test (:95-96) — STAYS in the mesh: *n_kept = nf. */
+int spcu_ingest_mesh_stl(spcu_ctx* ctx, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
+                         const float* face_normals, const float object_to_world[12], const float normal_xf[9], uint32_t material,
+                         spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices,
+                         float* world_normals, float* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,13 @@ def ingest_mesh(vertices, faces, object_to_world, normal_xf, material: int = 0) 
     l.spo_ingest_mesh.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32), vp, vp]
     l.spo_ingest_mesh.restype = None
     return run_ingest(l.spo_ingest_mesh, vertices, faces, object_to_world, normal_xf, material, with_ms=False)
+
+
+def ingest_mesh_stl(vertices, faces, face_normals, object_to_world, normal_xf, material: int = 0) -> dict:
+    """spo_ingest_mesh_stl (read_binary_stl's normal passes + Mesh's constructor)."""
+    l = lib()
+    vp = C.c_void_p
+    l.spo_ingest_mesh_stl.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32), vp, vp]
+    l.spo_ingest_mesh_stl.restype = None
+    return run_ingest(l.spo_ingest_mesh_stl, vertices, faces, object_to_world, normal_xf, material, with_ms=False,
+                      face_normals=face_normals)

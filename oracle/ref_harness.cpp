@@ -18,6 +18,7 @@
 
 #include "base/FileParser.h"
 #include "base/PlyReader.h"
+#include "base/STLReader.h"
 #include "base/Logger.h"
 #include "base/MemoryArena.h"
 #include "base/RunningStats.h"
@@ -661,7 +662,7 @@ int spref_write_image(const float* rgb_sum, uint32_t w, uint32_t h, unsigned spp
     });
 }
 
-// The reference's own read_ply (base/PlyReader.cpp:326-531) with object_to_world = the given AffineSpace (12 floats:
+// The reference's own read_ply (base/PlyReader.cpp:326-531) — or read_stl (base/STLReader.cpp:139-156) for a ".stl" path — with object_to_world = the given AffineSpace (12 floats:
 // c0.xyz c1.xyz c2.xyz affine.xyz): Mesh::m_vertices / m_normals (world space) and m_indices.  Also returns the normal
 // matrix the reference applies, inverse(linear).transposed() (math/LinearSpace3x3.h:163-167), column major.
 int spref_read_ply(const char* path, const float xf[12], uint32_t cap_vertices, uint32_t cap_triangles, uint32_t* n_vertices,
@@ -673,7 +674,8 @@ int spref_read_ply(const char* path, const float xf[12], uint32_t cap_vertices, 
         const sp::LinearSpace3x3 lin{ sp::Vector3{ xf[0], xf[1], xf[2] }, sp::Vector3{ xf[3], xf[4], xf[5] }, sp::Vector3{ xf[6], xf[7], xf[8] } };
         const sp::AffineSpace    aff{ lin, sp::Vector3{ xf[9], xf[10], xf[11] } };
         const auto               xform = sp::AffineTransformation::compute_inverse(aff);
-        const sp::Mesh           mesh  = sp::read_ply(path, xform);
+        const bool               stl   = std::filesystem::path(path).extension() == ".stl"; // FileParser.cpp:577-581
+        const sp::Mesh           mesh  = stl ? sp::read_stl(path, xform) : sp::read_ply(path, xform);
         arm_exit_guard();
         const auto nm = aff.get_linear().inverse().transposed();
         const float m9[9] = { nm.col0().x, nm.col0().y, nm.col0().z, nm.col1().x, nm.col1().y, nm.col1().z, nm.col2().x, nm.col2().y, nm.col2().z };

@@ -681,9 +681,14 @@ static inline v3 mesh_cross(v3 a, v3 b)
     return V(mesh_dop(a.y, b.z, a.z, b.y), mesh_dop(a.z, b.x, a.x, b.z), mesh_dop(a.x, b.y, a.y, b.x));
 }
 
-void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float object_to_world[12],
-                     const float normal_xf[9], uint32_t material, spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta,
-                     uint32_t* n_kept, float* world_vertices, float* world_normals)
+/* is_zero (math/Vector3.h:644-647) = float_compare(c, 0) per component (math/Math.h:265-272): |c| <= 1e-5 */
+static int mesh_is_zero(v3 a) { return fabsf(a.x) <= 1.0e-05f && fabsf(a.y) <= 1.0e-05f && fabsf(a.z) <= 1.0e-05f; }
+
+/* file_normals == NULL: read_ply; else read_binary_stl (base/STLReader.cpp:107-118: stored normal unless is_zero, then the
+ * cross product; still is_zero: no contribution to the vertex normals, but the triangle stays — its indices were pushed at :96) */
+static void mesh_ingest(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float* file_normals,
+                        const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                        spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices, float* world_normals)
 {
     v3*       vn   = (v3*)calloc(nv ? nv : 1, sizeof(v3)); /* vertex_normals(num_vertices, Normal3{0,0,0}) (PlyReader.cpp:510) */
     v3*       wv   = (v3*)malloc((nv ? nv : 1) * sizeof(v3));
@@ -693,11 +698,19 @@ void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, 
     for (uint32_t f = 0; f < nf; ++f) {
         const uint32_t* ix = faces + 3 * (size_t)f;
         const v3        e0 = sub3(VERT(ix[1]), VERT(ix[0])), e1 = sub3(VERT(ix[2]), VERT(ix[0]));
-        v3              n  = mesh_cross(e0, e1);
-        if (dot3(n, n) == 0.0f) continue; /* zero-area face: skipped (PlyReader.cpp:497-500) */
+        v3              n;
+        if (file_normals) {
+            n = V(file_normals[3 * (size_t)f], file_normals[3 * (size_t)f + 1], file_normals[3 * (size_t)f + 2]);
+            if (mesh_is_zero(n)) n = mesh_cross(e0, e1);
+            kept[nk++] = f; /* the indices are already in the mesh (STLReader.cpp:95-96) */
+            if (mesh_is_zero(n)) continue;
+        } else {
+            n = mesh_cross(e0, e1);
+            if (dot3(n, n) == 0.0f) continue; /* zero-area face: skipped (PlyReader.cpp:497-500) */
+            kept[nk++] = f;
+        }
         n = normalize3(n);
         for (int k = 0; k < 3; ++k) vn[ix[k]] = add3(vn[ix[k]], n); /* in face order (PlyReader.cpp:511-515) */
-        kept[nk++] = f;
     }
     for (uint32_t v = 0; v < nv; ++v) {
         v3 n = vn[v];
@@ -722,6 +735,22 @@ void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, 
     free(vn);
     free(wv);
     free(kept);
+}
+
+void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float object_to_world[12],
+                     const float normal_xf[9], uint32_t material, spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta,
+                     uint32_t* n_kept, float* world_vertices, float* world_normals)
+{
+    mesh_ingest(vertices, nv, faces, nf, NULL, object_to_world, normal_xf, material, prims, shade, meta, n_kept, world_vertices,
+                world_normals);
+}
+
+void spo_ingest_mesh_stl(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float* face_normals,
+                         const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                         spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices, float* world_normals)
+{
+    mesh_ingest(vertices, nv, faces, nf, face_normals, object_to_world, normal_xf, material, prims, shade, meta, n_kept,
+                world_vertices, world_normals);
 }
 
 #include "sp_oracle_shade.inc"

@@ -78,6 +78,11 @@ void spo_pack_image(const float* rgb_sum, uint32_t width, uint32_t height, uint3
 void spo_ingest_mesh(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float object_to_world[12],
                      const float normal_xf[9], uint32_t material, spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta,
                      uint32_t* n_kept, float* world_vertices, float* world_normals);
+/* read_binary_stl's face / vertex-normal passes (base/STLReader.cpp:107-137) + Mesh's constructor; as spcu_ingest_mesh_stl.
+ * Pinned against the reference's own read_stl (spref_read_stl; tests/golden/mesh_ingest_stl.npz). */
+void spo_ingest_mesh_stl(const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float* face_normals,
+                         const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                         spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices, float* world_normals);
 
 #ifdef __cplusplus
 }

@@ -111,7 +111,7 @@ EXPORTS = [
     "spcu_trace_closest", "spcu_trace_any", "spcu_trace_lights", "spcu_trace_closest_fast",
     "spcu_generate_rays", "spcu_render", "spcu_render_frame", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times", "spcu_resolved_pipeline",
-    "spcu_build_bvh", "spcu_triangle_bounds", "spcu_upload_scene_build", "spcu_pack_image", "spcu_render_image", "spcu_ingest_mesh",
+    "spcu_build_bvh", "spcu_triangle_bounds", "spcu_upload_scene_build", "spcu_pack_image", "spcu_render_image", "spcu_ingest_mesh", "spcu_ingest_mesh_stl",
 ]
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
@@ -181,6 +181,9 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_ingest_mesh.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32), vp, vp,
                                      C.POINTER(C.c_float)]
     lib.spcu_ingest_mesh.restype = C.c_int
+    lib.spcu_ingest_mesh_stl.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32),
+                                         vp, vp, C.POINTER(C.c_float)]
+    lib.spcu_ingest_mesh_stl.restype = C.c_int
     lib.spcu_pack_image.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     lib.spcu_pack_image.restype = C.c_int
     lib.spcu_render_image.argtypes = [vp, C.POINTER(Partition), C.c_uint32, vp, C.POINTER(Stats)]
@@ -376,6 +379,11 @@ class Context:
         return run_ingest(lambda *a: self._check(self.lib.spcu_ingest_mesh(self.h, *a), "spcu_ingest_mesh"),
                           vertices, faces, object_to_world, normal_xf, material, with_ms=True)
 
+    def ingest_mesh_stl(self, vertices, faces, face_normals, object_to_world, normal_xf, material: int = 0) -> dict:
+        """spcu_ingest_mesh_stl: as ingest_mesh, with the normals stored in the STL file."""
+        return run_ingest(lambda *a: self._check(self.lib.spcu_ingest_mesh_stl(self.h, *a), "spcu_ingest_mesh_stl"),
+                          vertices, faces, object_to_world, normal_xf, material, with_ms=True, face_normals=face_normals)
+
     def pack_image(self, rgb_sum, spp: int, fmt: int) -> np.ndarray:
         """Host sums [H, W, 3] -> write_pfm payload (float32) / write_ppm numbers (uint16), rows bottom-up."""
         rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
@@ -418,7 +426,7 @@ def run_build(call, bounds: np.ndarray, non_triangle, first_id: int, capacity: i
     return {"nodes": nodes[:head["n_nodes"]].copy(), "order": order[:n].copy(), "head": head, **tail_out}
 
 
-def run_ingest(call, vertices, faces, object_to_world, normal_xf, material: int, with_ms: bool) -> dict:
+def run_ingest(call, vertices, faces, object_to_world, normal_xf, material: int, with_ms: bool, face_normals=None) -> dict:
     """Shared marshalling of the mesh-ingest entry points (CUDA, oracle): call(vertices, nv, faces, nf, xf, nxf, material,
     prims, shade, meta, n_kept, world_vertices, world_normals[, device_ms])."""
     v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
@@ -432,8 +440,12 @@ def run_ingest(call, vertices, faces, object_to_world, normal_xf, material: int,
     wv = np.zeros((max(nv, 1), 3), dtype=np.float32)
     wn = np.zeros((max(nv, 1), 3), dtype=np.float32)
     kept = C.c_uint32()
-    args = [_ptr(v), nv, _ptr(f), nf, _ptr(xf), _ptr(nxf), material, _ptr(prims), _ptr(shade), _ptr(meta), C.byref(kept),
-            _ptr(wv), _ptr(wn)]
+    args = [_ptr(v), nv, _ptr(f), nf]
+    if face_normals is not None:  # the STL flavour takes the file's normals after the faces
+        fn = np.ascontiguousarray(face_normals, dtype=np.float32).reshape(-1, 3)
+        assert fn.shape[0] == nf
+        args.append(_ptr(fn))
+    args += [_ptr(xf), _ptr(nxf), material, _ptr(prims), _ptr(shade), _ptr(meta), C.byref(kept), _ptr(wv), _ptr(wn)]
     ms = C.c_float()
     if with_ms:
         args.append(C.byref(ms))

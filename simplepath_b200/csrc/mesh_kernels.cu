@@ -51,16 +51,36 @@ __device__ __forceinline__ F3 normalize(F3 a)
     return F3{ __fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s) };
 }
 
-// face pass of read_ply (base/PlyReader.cpp:493-503)
-__global__ void __launch_bounds__(kBlock) k_face_normals(const float* verts, const uint32_t* faces, uint32_t nf, float* face_n, uint8_t* keep)
+// is_zero (math/Vector3.h:644-647) through float_compare(a, 0) (math/Math.h:265-272): |a| <= 1e-5 (the relative branch can
+// never hold against zero)
+__device__ __forceinline__ bool is_zero_eps(F3 a) { return fabsf(a.x) <= 1.0e-05f && fabsf(a.y) <= 1.0e-05f && fabsf(a.z) <= 1.0e-05f; }
+
+// face pass.  PLY (file_normals == NULL; base/PlyReader.cpp:493-503): the normal is the cross product, a face whose normal
+// has sqr_length == 0 exactly is dropped altogether.  STL (base/STLReader.cpp:107-118): the normal comes from the file unless
+// it is_zero (then the cross product); a face whose normal still is_zero adds nothing to the vertex normals — but its indices
+// were pushed before the test (:95-96), so the triangle STAYS in the mesh.  contributes: adds to vertex normals; keep: emitted.
+__global__ void __launch_bounds__(kBlock) k_face_normals(const float* verts, const uint32_t* faces, uint32_t nf, const float* file_normals,
+                                                         float* face_n, uint8_t* keep, uint8_t* contributes)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += stride) {
         const uint32_t i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
         const F3       v0 = ld3(verts, i0);
-        F3             n  = cross(sub(ld3(verts, i1), v0), sub(ld3(verts, i2), v0));
-        const bool     ok = dot(n, n) != 0.0f;
-        keep[f]           = ok ? 1 : 0;
+        F3             n;
+        bool           ok;
+        if (file_normals) {
+            n = ld3(file_normals, f);
+            if (is_zero_eps(n)) {
+                n = cross(sub(ld3(verts, i1), v0), sub(ld3(verts, i2), v0));
+            }
+            ok      = !is_zero_eps(n);
+            keep[f] = 1;
+        } else {
+            n       = cross(sub(ld3(verts, i1), v0), sub(ld3(verts, i2), v0));
+            ok      = dot(n, n) != 0.0f;
+            keep[f] = ok ? 1 : 0;
+        }
+        contributes[f] = ok ? 1 : 0;
         if (ok) {
             n = normalize(n);
         }
@@ -69,15 +89,17 @@ __global__ void __launch_bounds__(kBlock) k_face_normals(const float* verts, con
 }
 
 // kept faces, compacted in order: kept_faces[rank] = face; and the vertex degrees over kept faces
-__global__ void __launch_bounds__(kBlock) k_compact_faces(const uint32_t* faces, const uint8_t* keep, const uint32_t* rank, uint32_t nf,
-                                                          uint32_t* kept, uint32_t* degree)
+__global__ void __launch_bounds__(kBlock) k_compact_faces(const uint32_t* faces, const uint8_t* keep, const uint8_t* contributes,
+                                                          const uint32_t* rank, uint32_t nf, uint32_t* kept, uint32_t* degree)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += stride) {
-        if (!keep[f]) {
+        if (keep[f]) {
+            kept[rank[f]] = f;
+        }
+        if (!contributes[f]) {
             continue;
         }
-        kept[rank[f]] = f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             atomicAdd(&degree[__ldg(faces + 3 * f + k)], 1u);
@@ -86,12 +108,12 @@ __global__ void __launch_bounds__(kBlock) k_compact_faces(const uint32_t* faces,
 }
 
 // adjacency lists (vertex -> kept faces that use it, one entry per corner), filled in arbitrary order
-__global__ void __launch_bounds__(kBlock) k_fill_adjacency(const uint32_t* faces, const uint8_t* keep, uint32_t nf, const uint32_t* offset,
-                                                           uint32_t* cursor, uint32_t* adjacency)
+__global__ void __launch_bounds__(kBlock) k_fill_adjacency(const uint32_t* faces, const uint8_t* contributes, uint32_t nf,
+                                                           const uint32_t* offset, uint32_t* cursor, uint32_t* adjacency)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += stride) {
-        if (!keep[f]) {
+        if (!contributes[f]) {
             continue;
         }
 #pragma unroll
@@ -194,10 +216,10 @@ __global__ void __launch_bounds__(kBlock) k_triangle_records(const uint32_t* fac
 
 } // namespace
 
-extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
-                                const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
-                                spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept_out, float* world_vertices, float* world_normals,
-                                float* device_ms)
+static int ingest(spcu_ctx* c, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const float* file_normals,
+                  const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                  spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept_out, float* world_vertices, float* world_normals,
+                  float* device_ms)
 {
     if (!c) {
         return SPCU_ERR_INVALID;
@@ -223,12 +245,18 @@ extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv,
     float *            d_v = nullptr, *d_face_n = nullptr, *d_xf = nullptr, *d_world_v = nullptr, *d_world_n = nullptr;
     uint32_t *         d_f = nullptr, *d_rank = nullptr, *d_kept = nullptr, *d_degree = nullptr, *d_offset = nullptr, *d_cursor = nullptr,
              *d_adj = nullptr, *d_partials = nullptr;
-    uint8_t* d_keep = nullptr;
+    uint8_t *d_keep = nullptr, *d_contributes = nullptr;
+    float*   d_file_n = nullptr;
     const size_t f_pad = static_cast<size_t>(scan_tiles(nf)) * kScanTile, v_pad = static_cast<size_t>(scan_tiles(nv)) * kScanTile;
     CK(c, mem.get(&d_v, 3 * static_cast<size_t>(nv)));
     CK(c, mem.get(&d_f, 3 * static_cast<size_t>(nf)));
     CK(c, mem.get(&d_face_n, 3 * static_cast<size_t>(nf)));
     CK(c, mem.get(&d_keep, f_pad));
+    CK(c, mem.get(&d_contributes, std::max<size_t>(nf, 1)));
+    if (file_normals && nf) {
+        CK(c, mem.get(&d_file_n, 3 * static_cast<size_t>(nf)));
+        CK(c, cudaMemcpyAsync(d_file_n, file_normals, 3 * static_cast<size_t>(nf) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
     CK(c, mem.get(&d_rank, static_cast<size_t>(nf) + 1));
     CK(c, mem.get(&d_kept, nf));
     CK(c, mem.get(&d_degree, v_pad));
@@ -259,13 +287,13 @@ extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv,
     CK(c, cudaEventRecord(c->ev0, st));
     uint32_t n_kept = 0;
     if (nf) {
-        k_face_normals<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_v, d_f, nf, d_face_n, d_keep);
+        k_face_normals<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_v, d_f, nf, d_file_n, d_face_n, d_keep, d_contributes);
         exclusive_scan(d_keep, d_rank, nf, d_partials, st);
-        k_compact_faces<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_f, d_keep, d_rank, nf, d_kept, d_degree);
+        k_compact_faces<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_f, d_keep, d_contributes, d_rank, nf, d_kept, d_degree);
     }
     exclusive_scan(d_degree, d_offset, nv, d_partials, st);
     if (nf) {
-        k_fill_adjacency<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_f, d_keep, nf, d_offset, d_cursor, d_adj);
+        k_fill_adjacency<<<grid_for(nf, c->sm_count), kBlock, 0, st>>>(d_f, d_contributes, nf, d_offset, d_cursor, d_adj);
         CK(c, cudaMemcpyAsync(&n_kept, d_rank + nf, sizeof n_kept, cudaMemcpyDeviceToHost, st));
     }
     if (nv) {
@@ -296,4 +324,25 @@ extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv,
     }
     *n_kept_out = n_kept;
     return SPCU_OK;
+}
+
+extern "C" int spcu_ingest_mesh(spcu_ctx* c, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
+                                const float object_to_world[12], const float normal_xf[9], uint32_t material, spcu_prim_geom* prims,
+                                spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept, float* world_vertices, float* world_normals,
+                                float* device_ms)
+{
+    return ingest(c, vertices, nv, faces, nf, nullptr, object_to_world, normal_xf, material, prims, shade, meta, n_kept, world_vertices,
+                  world_normals, device_ms);
+}
+
+extern "C" int spcu_ingest_mesh_stl(spcu_ctx* c, const float* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
+                                    const float* face_normals, const float object_to_world[12], const float normal_xf[9],
+                                    uint32_t material, spcu_prim_geom* prims, spcu_prim_shade* shade, uint32_t* meta, uint32_t* n_kept,
+                                    float* world_vertices, float* world_normals, float* device_ms)
+{
+    if (c && nf && !face_normals) {
+        return fail(c, SPCU_ERR_INVALID, "spcu_ingest_mesh_stl: face_normals is NULL");
+    }
+    return ingest(c, vertices, nv, faces, nf, face_normals, object_to_world, normal_xf, material, prims, shade, meta, n_kept,
+                  world_vertices, world_normals, device_ms);
 }

@@ -65,5 +65,20 @@ def main_accel() -> None:
     np.savez_compressed(Path(__file__).resolve().parent / "scene_accel.npz", **out)
 
 
+def main_stl() -> None:
+    """tests/golden/mesh_ingest_stl.npz: the reference's own read_stl (base/STLReader.cpp) + Mesh on the binary STL of
+    meshcases.stl_soup()."""
+    corners, stored = meshcases.stl_soup()
+    xf = meshcases.transform(seed=4)
+    with tempfile.TemporaryDirectory() as d:
+        path = Path(d) / "m.stl"
+        meshcases.write_stl(path, corners, stored)
+        r = ref.read_ply(path, xf, 3 * len(corners), len(corners))
+    np.savez_compressed(Path(__file__).resolve().parent / "mesh_ingest_stl.npz", corners=corners, stored_normals=stored,
+                        object_to_world=xf, vertices=r["vertices"], normals=r["normals"], indices=r["indices"], normal_xf=r["normal_xf"])
+    print("stl:", len(corners), "triangles ->", len(r["vertices"]), "vertices,", len(r["indices"]), "triangles in the mesh")
+
+
 if __name__ == "__main__":
     main_accel()
+    main_stl()

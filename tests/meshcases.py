@@ -70,3 +70,49 @@ def normal_condition(v: np.ndarray, f: np.ndarray) -> tuple[np.ndarray, np.ndarr
     cond = np.where(length > 0, count / np.maximum(length, 1e-300), 1.0)
     cond = np.maximum(cond, 1.0)
     return cond, cond[fk]
+
+
+def stl_soup(n_tris: int = 3000, seed: int = 2) -> tuple[np.ndarray, np.ndarray]:
+    """Triangle soup + stored normals as a binary STL holds them: (corners [t, 3, 3], normals [t, 3]).  Stored normals are a
+    mix of unit normals, zero vectors (the reader falls back to the cross product), arbitrary non-unit vectors (the reader
+    trusts them) — and some triangles are tiny, so that their cross product is_zero by the reader's 1e-5 epsilon: they stay
+    in the mesh but add nothing to the vertex normals (base/STLReader.cpp:95-118)."""
+    rng = np.random.default_rng(seed)
+    v, f = mesh(n_tris, seed)
+    corners = v[f.astype(np.int64)].astype(np.float32)
+    n = np.cross(corners[:, 1] - corners[:, 0], corners[:, 2] - corners[:, 0]).astype(np.float64)
+    length = np.linalg.norm(n, axis=1, keepdims=True)
+    stored = np.where(length > 0, n / np.maximum(length, 1e-300), 0.0).astype(np.float32)
+    kind = rng.integers(0, 4, len(f))
+    stored[kind == 1] = 0.0                                                   # no normal in the file
+    stored[kind == 2] = rng.normal(size=(int((kind == 2).sum()), 3)).astype(np.float32) * np.float32(3.0)
+    tiny = rng.random(len(f)) < 0.05                                          # edges ~1e-3: cross ~1e-6 "is zero"
+    centre = corners[tiny].mean(axis=1, keepdims=True)
+    corners[tiny] = (centre + (corners[tiny] - centre) * np.float32(0.02)).astype(np.float32)
+    stored[tiny & (kind != 2)] = 0.0
+    return corners, stored
+
+
+def write_stl(path, corners: np.ndarray, normals: np.ndarray) -> None:
+    rec = np.zeros(len(corners), dtype=[("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")])
+    rec["n"], rec["v"] = normals, corners
+    with open(path, "wb") as fh:
+        fh.write(b"binary stl written by tests/meshcases.py".ljust(80, b" "))
+        fh.write(np.uint32(len(corners)).tobytes())
+        fh.write(rec.tobytes())
+
+
+def stl_index(corners: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """VertexIndexer (base/STLReader.cpp:18-36): a vertex gets the index of its first appearance; equality is exact
+    (operator<=> on the three floats, math/Vector3.h:619-628)."""
+    seen, verts = {}, []
+    faces = np.zeros((len(corners), 3), dtype=np.uint32)
+    for t, tri in enumerate(corners):
+        for k in range(3):
+            key = (float(tri[k, 0]), float(tri[k, 1]), float(tri[k, 2]))
+            i = seen.get(key)
+            if i is None:
+                i = seen[key] = len(verts)
+                verts.append(tri[k])
+            faces[t, k] = i
+    return np.asarray(verts, dtype=np.float32), faces

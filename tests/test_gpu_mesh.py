@@ -143,3 +143,30 @@ def test_device_pipeline_reproduces_the_reference_scene_accelerator(ctx, name):
     assert np.array_equal(np.concatenate([unb, bounded[order]]), g["order"])
     built = ctx.build_bvh(ctx.triangle_bounds(rec["prims"]), None, len(unb))
     assert built["nodes"].tobytes() == g["nodes"].tobytes()
+
+
+def test_stl_ingest_matches_reference_mesh(ctx, oracle_port):
+    """spcu_ingest_mesh_stl against the reference's own read_stl (tests/golden/mesh_ingest_stl.npz) and the oracle."""
+    from test_oracle_mesh import golden_stl
+    z, v, f = golden_stl()
+    r = ctx.ingest_mesh_stl(v, f, z["stored_normals"], z["object_to_world"], z["normal_xf"], material=2)
+    w = oracle_port.ingest_mesh_stl(v, f, z["stored_normals"], z["object_to_world"], z["normal_xf"], material=2)
+    assert len(r["prims"]) == len(f)
+    assert r["world_vertices"].tobytes() == z["vertices"].tobytes()
+    assert r["prims"].tobytes() == w["prims"].tobytes() and np.array_equal(r["meta"], w["meta"])
+    # conditioning of each vertex sum, from the normals that actually contribute
+    tri = z["corners"].astype(np.float64)
+    n = z["stored_normals"].astype(np.float64)
+    cross = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    zero = (np.abs(n) <= 1e-5).all(axis=1)
+    n[zero] = cross[zero]
+    used = ~(np.abs(n) <= 1e-5).all(axis=1)
+    unit = n[used] / np.linalg.norm(n[used], axis=1, keepdims=True)
+    total, count = np.zeros((len(v), 3)), np.zeros(len(v))
+    for k in range(3):
+        np.add.at(total, f[used][:, k].astype(np.int64), unit)
+        np.add.at(count, f[used][:, k].astype(np.int64), 1.0)
+    length = np.linalg.norm(total, axis=1)
+    cond = np.maximum(np.where(length > 0, count / np.maximum(length, 1e-300), 1.0), 1.0)
+    normals_close(r["world_normals"], z["normals"], cond)
+    normals_close(r["shade"].reshape(-1, 3, 4)[:, :, :3], z["normals"][z["indices"]], cond[f.astype(np.int64)])

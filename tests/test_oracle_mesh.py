@@ -79,3 +79,32 @@ def test_cpu_pipeline_reproduces_the_reference_scene_accelerator(oracle_port, na
     assert built["head"] == g["head"]
     assert np.array_equal(np.concatenate([unb, bounded[built["order"]]]), g["order"])
     assert built["nodes"].tobytes() == g["nodes"].tobytes()
+
+
+def golden_stl():
+    z = np.load(GOLDEN / "mesh_ingest_stl.npz")
+    v, f = meshcases.stl_index(z["corners"])
+    return z, v, f
+
+
+def test_stl_vertex_indexer_matches_reference():
+    z, v, f = golden_stl()
+    corners, stored = meshcases.stl_soup()
+    assert np.array_equal(z["corners"], corners) and np.array_equal(z["stored_normals"], stored)
+    assert np.array_equal(f, z["indices"]) and len(v) == len(z["vertices"])
+
+
+def test_oracle_stl_ingest_matches_reference_mesh(oracle_port):
+    """read_binary_stl (base/STLReader.cpp:60-137): stored normals, zero normals replaced by the cross product, faces whose
+    normal is_zero by the 1e-5 epsilon kept in the mesh without a contribution."""
+    z, v, f = golden_stl()
+    r = oracle_port.ingest_mesh_stl(v, f, z["stored_normals"], z["object_to_world"], z["normal_xf"], material=2)
+    assert len(r["prims"]) == len(f) == len(z["indices"])            # nothing is dropped on the STL path
+    assert r["world_vertices"].tobytes() == z["vertices"].tobytes()
+    assert r["world_normals"].tobytes() == z["normals"].tobytes()
+    assert np.array_equal(r["shade"].reshape(-1, 3, 4)[:, :, :3], z["normals"][z["indices"]])
+    # the case exercises the epsilon: some faces contribute nothing although their area is not exactly zero
+    tri = z["corners"].astype(np.float64)
+    cross = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    silent = (np.abs(z["stored_normals"]) <= 1e-5).all(axis=1) & (np.abs(cross) <= 1e-5).all(axis=1)
+    assert silent.sum() > 20 and (np.linalg.norm(cross[silent], axis=1) > 0).any()

@@ -678,9 +678,10 @@ int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu
     CK(c, c->geom_shade.reserve(np * sizeof(spcu_prim_shade)));
     CK(c, c->geom_meta.reserve(np * sizeof(uint32_t)));
     if (n_prims) {
-        CK(c, cudaMemcpyAsync(src_geom, s->geom_prims, n_prims * sizeof(spcu_prim_geom), cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemcpyAsync(src_shade, s->geom_shade, n_prims * sizeof(spcu_prim_shade), cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemcpyAsync(src_meta, s->geom_meta, n_prims * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        int rc;
+        if ((rc = copy_to_device(c, src_geom, s->geom_prims, n_prims * sizeof(spcu_prim_geom))) != SPCU_OK) return rc;
+        if ((rc = copy_to_device(c, src_shade, s->geom_shade, n_prims * sizeof(spcu_prim_shade))) != SPCU_OK) return rc;
+        if ((rc = copy_to_device(c, src_meta, s->geom_meta, n_prims * sizeof(uint32_t))) != SPCU_OK) return rc;
         c->scene_bytes += n_prims * (sizeof(spcu_prim_geom) + sizeof(spcu_prim_shade) + sizeof(uint32_t));
     }
     if (first_id) { // the top-level list keeps its order
@@ -754,7 +755,9 @@ extern "C" int spcu_build_bvh(spcu_ctx* c, const spcu_bounds* bounds, uint32_t n
     spcu_bounds*       d_bounds  = nullptr;
     uint8_t*           d_non_tri = nullptr;
     CK(c, mem.get(&d_bounds, n));
-    CK(c, cudaMemcpyAsync(d_bounds, bounds, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyHostToDevice, st));
+    if (const int rc = copy_to_device(c, d_bounds, bounds, static_cast<size_t>(n) * sizeof(spcu_bounds)); rc != SPCU_OK) {
+        return rc;
+    }
     if (non_triangle) {
         CK(c, mem.get(&d_non_tri, n));
         CK(c, cudaMemcpyAsync(d_non_tri, non_triangle, n, cudaMemcpyHostToDevice, st));

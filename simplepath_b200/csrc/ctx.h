@@ -87,6 +87,9 @@ struct spcu_ctx
     uint32_t                  pix_list_offset = ~0u, pix_list_stride = 0, pix_list_n = 0;
     spcu::DevBuf              host_rgb, host_sq; // device accumulators of the host-buffer entry point
     spcu::DevBuf              packed;            // packed output image (spcu_render_image / spcu_pack_image)
+    void*                     stage[2]    = { nullptr, nullptr }; // page-locked staging of large host->device copies
+    cudaEvent_t               stage_ev[2] = { nullptr, nullptr };
+    bool                      stage_busy[2] = { false, false };
     spcu::DevBuf              path_radiance;     // float4 per slot of a batch (SPCU_PIPELINE_PATHS)
     spcu::DevBuf              sorted_queue;      // material-sorted hand-over between extend and shade
     uint32_t                  n_materials = 0;
@@ -103,6 +106,9 @@ namespace spcu {
 
 int fail(spcu_ctx* c, int code, const char* fmt, ...);
 int need_scene(spcu_ctx* c);
+// spcu_api.cu: host->device copy on the context's stream.  Large copies from pageable memory go through two page-locked
+// staging buffers (CPU memcpy of chunk k+1 overlaps the DMA of chunk k); the source is fully consumed when the call returns.
+int copy_to_device(spcu_ctx* c, void* dst, const void* src, size_t bytes);
 // image_kernels.cu: mean, row order and sRGB quantisation of device-resident sums, result copied to the host buffer `out`
 int pack_device_image(spcu_ctx* c, const float* d_rgb_sum, uint32_t w, uint32_t h, uint32_t spp, uint32_t format, void* out);
 // build_kernels.cu: geometry of an UNBUILT scene -> bounds, BVH and leaf-order gather on the device (spcu_upload_scene_build)

@@ -273,10 +273,10 @@ static int ingest(spcu_ctx* c, const float* vertices, uint32_t nv, const uint32_
     CK(c, mem.get(&d_shade, 3 * static_cast<size_t>(nf)));
     CK(c, mem.get(&d_meta, nf));
     if (nv) {
-        CK(c, cudaMemcpyAsync(d_v, vertices, 3 * static_cast<size_t>(nv) * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (const int rc = copy_to_device(c, d_v, vertices, 3 * static_cast<size_t>(nv) * sizeof(float)); rc != SPCU_OK) return rc;
     }
     if (nf) {
-        CK(c, cudaMemcpyAsync(d_f, faces, 3 * static_cast<size_t>(nf) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (const int rc = copy_to_device(c, d_f, faces, 3 * static_cast<size_t>(nf) * sizeof(uint32_t)); rc != SPCU_OK) return rc;
     }
     CK(c, cudaMemcpyAsync(d_xf, object_to_world, 12 * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(d_xf + 12, normal_xf, 9 * sizeof(float), cudaMemcpyHostToDevice, st));

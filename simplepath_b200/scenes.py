@@ -91,7 +91,7 @@ def write_ply(path: Path, verts: np.ndarray, faces: np.ndarray) -> None:
     rec = np.empty(len(faces), dtype=[("n", "u1"), ("i", "<i4", (3,))])
     rec["n"] = 3
     rec["i"] = faces
-    tmp = path.with_suffix(path.suffix + ".tmp")
+    tmp = path.with_suffix(path.suffix + f".{os.getpid()}.tmp")  # one per process: ranks of a torchrun job generate concurrently
     with open(tmp, "wb") as f:
         f.write(header)
         f.write(np.ascontiguousarray(verts, dtype="<f4").tobytes())
@@ -121,7 +121,7 @@ def sky_image(w: int, h: int) -> np.ndarray:
 def write_pfm(path: Path, img: np.ndarray) -> None:
     """Image(x, y) = img[y, x]; the file stores rows j = ny-1 .. 0 (Image/Image.cpp:40-55)."""
     h, w, _ = img.shape
-    tmp = path.with_suffix(path.suffix + ".tmp")
+    tmp = path.with_suffix(path.suffix + f".{os.getpid()}.tmp")
     with open(tmp, "wb") as f:
         f.write(f"PF\n{w} {h}\n-1\n".encode("ascii"))
         f.write(np.ascontiguousarray(img[::-1], dtype="<f4").tobytes())
@@ -345,7 +345,9 @@ def ensure(name: str, out: Path | str = DEFAULT_OUT) -> Path:
     path = out / f"{name}.sp"
     text = build(out)
     if not path.exists() or path.read_text() != text:
-        path.write_text(text)
+        tmp = out / f"{name}.sp.{os.getpid()}.tmp"
+        tmp.write_text(text)
+        os.replace(tmp, path)  # atomic: a concurrent rank never reads a half-written file
     return path
 
 

@@ -60,3 +60,20 @@ def test_generated_scenes_are_deterministic(tmp_path):
     assert pa == pb
     v, f = scenes.bumpy_sphere(scenes.BUNNY_TRIS, scenes.BUNNY_LO, scenes.BUNNY_HI)
     assert f.shape == (scenes.BUNNY_TRIS, 3)
+
+
+def test_scene_assets_can_be_generated_by_concurrent_ranks(tmp_path):
+    """Every rank of a torchrun job calls scenes.ensure() on a fresh box: writers must not trip over each other's files."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(6) as pool:
+        texts = pool.starmap(_ensure_text, [("g_bunny", str(tmp_path))] * 6)
+    assert len(set(texts)) == 1
+    assert not [p for p in tmp_path.iterdir() if p.name.endswith(".tmp")]
+
+
+def _ensure_text(name, out):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from simplepath_b200 import scenes
+    return scenes.ensure(name, out).read_text()

@@ -108,3 +108,37 @@ def test_oracle_stl_ingest_matches_reference_mesh(oracle_port):
     cross = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
     silent = (np.abs(z["stored_normals"]) <= 1e-5).all(axis=1) & (np.abs(cross) <= 1e-5).all(axis=1)
     assert silent.sum() > 20 and (np.linalg.norm(cross[silent], axis=1) > 0).any()
+
+
+def test_small_degenerate_meshes_on_live_reference(oracle_port, tmp_path):
+    """Vertex coordinates from a handful of values: collinear, coincident and repeated corners in most meshes, vertices
+    whose face normals cancel exactly, vertices no face uses — PLY and STL readers of the live reference against the oracle."""
+    from oracle import ref
+    from simplepath_b200 import scenes
+    if not ref.available():
+        pytest.skip("reference library not built (needs /root/reference)")
+    rng = np.random.default_rng(123)
+    values = np.array([0.0, 1.0, -1.0, 0.5, 2.0], dtype=np.float32)
+    xf = meshcases.transform(seed=21)
+    for trial in range(60):
+        nv, nf = int(rng.integers(3, 12)), int(rng.integers(1, 30))
+        v = values[rng.integers(0, len(values), (nv, 3))]
+        f = rng.integers(0, nv, (nf, 3)).astype(np.uint32)
+        scenes.write_ply(tmp_path / "m.ply", v, f)
+        want = ref.read_ply(tmp_path / "m.ply", xf, nv, nf)
+        got = oracle_port.ingest_mesh(v, f, xf, want["normal_xf"])
+        assert len(got["prims"]) == len(want["indices"]), trial
+        assert got["world_vertices"].tobytes() == want["vertices"].tobytes(), trial
+        assert got["world_normals"].tobytes() == want["normals"].tobytes(), trial
+        assert np.array_equal(got["prims"].reshape(-1, 3, 4)[:, :, :3], want["vertices"][want["indices"]]), trial
+        # the same triangles as an STL: soup + stored normals (a third of them zero)
+        corners = v[f.astype(np.int64)]
+        stored = rng.normal(size=(nf, 3)).astype(np.float32)
+        stored[rng.random(nf) < 0.34] = 0.0
+        meshcases.write_stl(tmp_path / "m.stl", corners, stored)
+        want = ref.read_ply(tmp_path / "m.stl", xf, 3 * nf, nf)
+        sv, sf = meshcases.stl_index(corners)
+        assert np.array_equal(sf, want["indices"]), trial
+        got = oracle_port.ingest_mesh_stl(sv, sf, stored, xf, want["normal_xf"])
+        assert got["world_vertices"].tobytes() == want["vertices"].tobytes(), trial
+        assert got["world_normals"].tobytes() == want["normals"].tobytes(), trial

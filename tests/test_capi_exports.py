@@ -34,9 +34,10 @@ def test_python_mirror_matches_header_sizes(built):
     probe = r'''
     #include "spcu.h"
     #include <stdio.h>
-    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(spcu_ray), sizeof(spcu_hit),
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(spcu_ray), sizeof(spcu_hit),
         sizeof(spcu_bvh_node), sizeof(spcu_prim_geom), sizeof(spcu_accel), sizeof(spcu_bxdf), sizeof(spcu_material),
-        sizeof(spcu_light), sizeof(spcu_flat_scene), sizeof(spcu_partition), sizeof(spcu_stats)); return 0; }
+        sizeof(spcu_light), sizeof(spcu_flat_scene), sizeof(spcu_partition), sizeof(spcu_stats), sizeof(spcu_bounds),
+        sizeof(spcu_prim_shade)); return 0; }
     '''
     with tempfile.TemporaryDirectory() as d:
         src = f"{d}/p.c"
@@ -45,7 +46,9 @@ def test_python_mirror_matches_header_sizes(built):
         sizes = [int(x) for x in subprocess.check_output([f"{d}/p"]).split()]
     mine = [ctypes.sizeof(t) for t in (capi.Ray, capi.Hit, capi.BvhNode, capi.PrimGeom, capi.Accel, capi.Bxdf,
                                        capi.Material, capi.Light, capi.FlatScene, capi.Partition, capi.Stats)]
+    mine += [capi.BOUNDS_DTYPE.itemsize, ctypes.sizeof(capi.PrimShade)]
     assert sizes == mine
+    assert capi.NODE_DTYPE.itemsize == ctypes.sizeof(capi.BvhNode) and capi.RAY_DTYPE.itemsize == ctypes.sizeof(capi.Ray)
 
 
 def test_no_device_is_an_error_not_a_fallback(built):

@@ -33,6 +33,7 @@ extern "C" {
 #define SPCU_ERR_CUDA (-2)      /* CUDA runtime error (no CPU fallback exists)                 */
 #define SPCU_ERR_NO_SCENE (-3)  /* call needs spcu_upload_scene first                          */
 #define SPCU_ERR_LIMIT (-4)     /* scene exceeds a compiled-in limit (stack depth, bxdfs, ...) */
+#define SPCU_ERR_INTERNAL (-5)  /* a kernel's bounded wait / iteration cap ran out (protocol fault); the result is void */
 
 /* ---- primitive / light / material kinds -------------------------------------------------- */
 #define SPCU_PRIM_TRIANGLE 0u /* shapes/Triangle.h:69-246 (vertices pre-transformed to world) */

@@ -64,6 +64,8 @@ struct spcu_ctx
     cudaStream_t stream = nullptr;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     int          sm_count = 148;
+    bool         scratch_in_use = false;   // a render has been enqueued: its last event is ev1 on scratch_stream
+    cudaStream_t scratch_stream = nullptr;
 
     // scene
     bool         have_scene = false;

@@ -139,6 +139,7 @@ enum Counter : int
     kCntRaysAny,
     kCntRaysLights,
     kCntShadeCalls,
+    kCntErrors, // protocol faults a kernel detected instead of hanging (bounded spins / iteration caps): must stay 0
     kNumCounters
 };
 

@@ -153,7 +153,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         ps.rng.ctr       = 0u;
         const MSample ms = material_sample<F>(s, material, wo, normal, ps.rng);
         ++pc.shade_calls;
-        if (ms.pdf == 0.0f || is_black(ms.color) || !ms.specular) {
+        if (!ms.specular) { // is_specular(properties) alone decides (:359)
             return false;
         }
         ps.o     = point;

@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_whitted_advance(const __grid_co
             const VertexRec vx = w.vertex[slot];
             Rng             rng = make_rng(w.path[slot], p.seed, p.depth, kSiteBsdf, 0u);
             const MSample   ms  = material_sample<F>(s, __float_as_uint(vx.p.w), -xyz(w.ray[slot].d), xyz(vx.n), rng);
-            if (!(ms.pdf == 0.0f || is_black(ms.color)) && ms.specular) {
+            if (ms.specular) { // is_specular(properties) alone decides (:359); a black or pdf-0 specular sample is followed too
                 w.ray[slot] = RayRec{ make_float4(vx.p.x, vx.p.y, vx.p.z, kEps), f4(ms.dir, kFltMax) };
                 alive       = true;
             }

@@ -69,7 +69,10 @@ struct SmQueues
     uint32_t next_slot; // next camera sample of this CTA's range
     uint32_t live;      // state slots that still carry, or may still draw, a path
     int      preferred; // the stage the CTA ran last
+    uint32_t error;     // a bounded wait ran out: every warp leaves, the kernel reports kCntErrors (never a hung GPU)
 };
+constexpr uint32_t kSpinCap = 1u << 22; // polls of a slot whose publication is in flight (normally a handful)
+constexpr uint32_t kIdleCap = 1u << 22; // consecutive empty scans (x 64 ns sleep) of a warp while paths are still live
 
 struct PathCounters
 {
@@ -117,7 +120,12 @@ __device__ __forceinline__ int q_pop(SmQueues& q, int stage, int lane)
     }
     volatile uint8_t* e = reinterpret_cast<volatile uint8_t*>(&q.ring[stage][h & (kRing - 1)][lane]);
     uint32_t          v;
+    uint32_t          spins = 0;
     while ((v = *e) == 0u) {
+        if (++spins > kSpinCap) { // a lost publication: fail the render, do not hang the device
+            *reinterpret_cast<volatile uint32_t*>(&q.error) = 1u;
+            return -1;
+        }
     }
     *e = 0u;
     __threadfence_block();
@@ -181,7 +189,7 @@ __device__ __forceinline__ void finish_vertex(const Shared& sh, const State& x, 
         Rng           rng = state_rng(sh, x, depth, kSiteBsdf, 0u);
         const MSample ms  = material_sample<F>(sh.s, x.u(kFMat), -x.get3(kFD), x.get3(kFN), rng);
         ++sh.pc.shade_calls;
-        if (ms.pdf == 0.0f || is_black(ms.color) || !ms.specular || depth + 1u >= sh.s.max_depth) {
+        if (!ms.specular || depth + 1u >= sh.s.max_depth) { // is_specular(properties) alone decides (:359)
             terminate(sh, x, lane, x.get3(kFL));
             return;
         }
@@ -492,8 +500,10 @@ __global__ void __launch_bounds__(kSmBlock, 1)
         q.next_slot = begin;
         q.live      = P;
         q.preferred = kQExtend;
+        q.error     = 0u;
     }
     __syncthreads();
+    uint32_t idle = 0;
 
     PathCounters  pc;
     TraceCounters tc{ 0, 0, 0 };
@@ -527,7 +537,11 @@ __global__ void __launch_bounds__(kSmBlock, 1)
                 }
             }
             if (best == 0) {
-                if (*reinterpret_cast<volatile uint32_t*>(&q.live) == 0u) {
+                if (*reinterpret_cast<volatile uint32_t*>(&q.live) == 0u || *reinterpret_cast<volatile uint32_t*>(&q.error) != 0u) {
+                    break;
+                }
+                if (++idle > kIdleCap) { // live paths but no queue ever fills again: a protocol fault, not a reason to hang
+                    *reinterpret_cast<volatile uint32_t*>(&q.error) = 1u;
                     break;
                 }
                 __nanosleep(64);
@@ -537,6 +551,7 @@ __global__ void __launch_bounds__(kSmBlock, 1)
                 *reinterpret_cast<volatile int*>(&q.preferred) = stage;
             }
         }
+        idle            = 0;
         const int   idx = q_pop(q, stage, lane);
         const State x{ st, P, static_cast<uint32_t>(max(idx, 0)) * 32u + static_cast<uint32_t>(lane) };
         if (stage == kQExtend) {
@@ -553,6 +568,9 @@ __global__ void __launch_bounds__(kSmBlock, 1)
         __syncwarp();
     }
 
+    if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(&q.error) != 0u) {
+        atomicAdd(counters + kCntErrors, 1ull);
+    }
     // ---- counters: one atomic per warp and counter ----------------------------------------------------------------------
     unsigned  v[5]   = { pc.paths, pc.rays_closest, pc.rays_any, pc.rays_lights, pc.shade_calls };
     const int idx[5] = { kCntPaths, kCntRaysClosest, kCntRaysAny, kCntRaysLights, kCntShadeCalls };

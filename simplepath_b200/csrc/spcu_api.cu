@@ -104,12 +104,22 @@ int validate_accel(spcu_ctx* c, const spcu_accel& a, const char* what)
     if (a.root >= 0 && static_cast<uint32_t>(a.root) >= a.n_nodes) {
         return fail(c, SPCU_ERR_INVALID, "%s: root out of range", what);
     }
+    if (a.n_nodes > 0 && !a.nodes) {
+        return fail(c, SPCU_ERR_INVALID, "%s: nodes is NULL but n_nodes is %u", what, a.n_nodes);
+    }
     auto leaf_ok = [&](int32_t link, uint32_t count) {
         const uint64_t first = static_cast<uint32_t>(~link);
         return first + (count & SPCU_LEAF_COUNT_MASK) <= a.n_prims;
     };
     if (a.root < 0 && !leaf_ok(a.root, a.root_count)) {
         return fail(c, SPCU_ERR_INVALID, "%s: root leaf out of range", what);
+    }
+    // The traversal stacks (trace.cuh) push without a bound check, so the depth they are sized for is DERIVED here, not
+    // taken from the header: children always follow their parent, one forward pass gives every node its nesting level.
+    std::vector<uint8_t> level(a.n_nodes, 0);
+    uint32_t             depth = 0;
+    if (a.root >= 0) {
+        level[a.root] = 1;
     }
     for (uint32_t i = 0; i < a.n_nodes; ++i) {
         for (int k = 0; k < 2; ++k) {
@@ -118,7 +128,18 @@ int validate_accel(spcu_ctx* c, const spcu_accel& a, const char* what)
                           : !leaf_ok(link, a.nodes[i].count[k])) {
                 return fail(c, SPCU_ERR_INVALID, "%s: node %u child %d out of range", what, i, k);
             }
+            if (link >= 0 && level[i]) {
+                if (level[i] >= SPCU_MAX_BVH_DEPTH) {
+                    return fail(c, SPCU_ERR_LIMIT, "%s: BVH deeper than SPCU_MAX_BVH_DEPTH (%u) at node %d", what,
+                                SPCU_MAX_BVH_DEPTH, link);
+                }
+                level[link] = std::max<uint8_t>(level[link], static_cast<uint8_t>(level[i] + 1));
+            }
         }
+        depth = std::max<uint32_t>(depth, level[i]);
+    }
+    if (depth != a.max_depth) {
+        return fail(c, SPCU_ERR_INVALID, "%s: header says max_depth %u but the nodes nest %u deep", what, a.max_depth, depth);
     }
     return SPCU_OK;
 }
@@ -202,6 +223,9 @@ int spcu_create(int device, spcu_ctx** out)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         const int rc = fail(nullptr, SPCU_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->stream) cudaStreamDestroy(c->stream);
         delete c;
         return rc;
     }
@@ -284,6 +308,11 @@ static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitte
     } else if (s->geom.n_unbounded > s->geom.n_prims || s->geom.n_prims >= (1u << 30)) {
         return fail(c, SPCU_ERR_INVALID, "geometry: n_unbounded > n_prims, or more than 2^30 primitives");
     }
+    // every array with a non-zero count must be there BEFORE the loops below read it
+    if ((s->geom.n_prims && (!s->geom_meta || !s->geom_prims || !s->geom_shade)) || (s->n_materials && !s->materials) ||
+        (s->n_bxdfs && !s->bxdfs) || (s->n_lights && (!s->lights || !s->light_order)) || (s->n_pool && !s->float_pool)) {
+        return fail(c, SPCU_ERR_INVALID, "a scene array is NULL but its count is not 0");
+    }
     if (int rc = validate_accel(c, s->lights_accel, "lights accelerator"); rc != SPCU_OK) return rc;
     if (s->lights_accel.n_prims != s->n_lights) {
         return fail(c, SPCU_ERR_INVALID, "lights accelerator holds %u prims but n_lights is %u", s->lights_accel.n_prims,
@@ -319,10 +348,12 @@ static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitte
             return fail(c, SPCU_ERR_INVALID, "material %u: unknown kind", i);
         }
     }
+    std::vector<bool> light_seen(s->n_lights, false); // light_order is a permutation: every light sampled exactly once
     for (uint32_t i = 0; i < s->n_lights; ++i) {
-        if (s->lights[i].kind > SPCU_LIGHT_ENV_IBL || s->light_order[i] >= s->n_lights) {
-            return fail(c, SPCU_ERR_INVALID, "light %u: bad kind or order entry", i);
+        if (s->lights[i].kind > SPCU_LIGHT_ENV_IBL || s->light_order[i] >= s->n_lights || light_seen[s->light_order[i]]) {
+            return fail(c, SPCU_ERR_INVALID, "light %u: bad kind, or light_order is not a permutation", i);
         }
+        light_seen[s->light_order[i]] = true;
     }
     CK(c, cudaSetDevice(c->device));
     c->have_scene  = false;

@@ -148,6 +148,10 @@ int read_back_stats(spcu_ctx* c, cudaStream_t st, spcu_stats* stats, uint64_t la
     stats->prims_tested    = tc.tris;
     stats->xf_prims_tested = tc.xf;
     stats->kernel_launches = launches;
+    if (h[kCntErrors]) {
+        return fail(c, SPCU_ERR_INTERNAL, "%llu kernel(s) gave up on a bounded wait (queue protocol fault); the image is void",
+                    h[kCntErrors]);
+    }
     CK(c, cudaEventElapsedTime(&stats->device_ms, c->ev0, c->ev1));
     for (int i = 0; i < kNumStages; ++i) {
         spcu_stage_time& r = c->stage_report[i];
@@ -247,6 +251,13 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     }
     // The caller's stream (spcu_render_device) orders this call after the caller's earlier work on that stream.
     const cudaStream_t st = have_caller_stream ? caller_stream : c->stream;
+    // The wavefront state, queues and counters are context-owned scratch: a render on ANOTHER stream than the previous one
+    // must not start before that one has finished with them (ev1 is recorded at the end of every render).
+    if (c->scratch_in_use && c->scratch_stream != st) {
+        CK(c, cudaStreamWaitEvent(st, c->ev1, 0));
+    }
+    c->scratch_in_use = true;
+    c->scratch_stream = st;
 
     if (int rc = ensure_pixel_list(c, *part); rc != SPCU_OK) return rc;
     const uint32_t n_pix     = c->pix_list_n;
@@ -402,6 +413,22 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     return SPCU_OK;
 }
 
+// The host-buffer entry points synchronise anyway: they also read the fault counter (kCntErrors) when no stats were asked
+// for, so a kernel that gave up on a bounded wait fails the call instead of returning a void image.
+int sync_and_check_faults(spcu_ctx* c, bool already_checked)
+{
+    unsigned long long faults = 0;
+    if (!already_checked && c->counters.p) {
+        CK(c, cudaMemcpyAsync(&faults, c->counters.as<unsigned long long>() + kCntErrors, sizeof faults, cudaMemcpyDeviceToHost,
+                              c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (faults) {
+        return fail(c, SPCU_ERR_INTERNAL, "%llu kernel(s) gave up on a bounded wait (queue protocol fault); the image is void", faults);
+    }
+    return SPCU_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -433,8 +460,7 @@ int spcu_render(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, float* 
     if (lum_sumsq) {
         CK(c, cudaMemcpyAsync(lum_sumsq, c->host_sq.p, n_pixels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
-    CK(c, cudaStreamSynchronize(c->stream));
-    return SPCU_OK;
+    return sync_and_check_faults(c, stats != nullptr);
 }
 
 int spcu_resolved_pipeline(const spcu_ctx* c)
@@ -462,8 +488,7 @@ int spcu_render_frame(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, f
     if (lum_sumsq) {
         CK(c, cudaMemcpyAsync(lum_sumsq, c->host_sq.p, n_pixels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
-    CK(c, cudaStreamSynchronize(c->stream));
-    return SPCU_OK;
+    return sync_and_check_faults(c, stats != nullptr);
 }
 
 int spcu_render_image(spcu_ctx* c, const spcu_partition* part, uint32_t format, void* out, spcu_stats* stats)
@@ -476,6 +501,7 @@ int spcu_render_image(spcu_ctx* c, const spcu_partition* part, uint32_t format, 
     CK(c, c->host_rgb.reserve(n_pixels * 3 * sizeof(float)));
     CK(c, cudaMemsetAsync(c->host_rgb.p, 0, n_pixels * 3 * sizeof(float), c->stream));
     if (int rc = render_impl(c, part, c->host_rgb.as<float>(), nullptr, stats, nullptr, false); rc != SPCU_OK) return rc;
+    if (int rc = sync_and_check_faults(c, stats != nullptr); rc != SPCU_OK) return rc;
     return pack_device_image(c, c->host_rgb.as<float>(), c->ds.width, c->ds.height, part->sample_end - part->sample_begin, format, out);
 }
 

@@ -268,6 +268,17 @@ int spcu_trace_lights(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit*
  * NULL) = { internal nodes visited, triangle tests, sphere/plane tests }. */
 int spcu_trace_closest_fast(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, spcu_hit* hits, uint64_t counters[3]);
 
+/* The same queries through the RENDERER's traversal stages — the kernels a frame actually runs (the two-kernel extend / shadow
+ * stages: set-up + root for all rays, then the persistent walk with lane refill and warp-wide leaf steps) — so that the parity
+ * tests can hold them to the oracle on arbitrary ray batches.
+ *   spcu_extend_batch: Integrator.cpp:558-563 — Scene::intersect_lights with the ray's limits, then Scene::intersect with t_max
+ *     shrunk to the light's distance.  hits[i] = closest geometry primitive under that limit (id -1, t = the shrunk limit on a
+ *     miss); light_hits[i] (may be NULL) = the light (id -1, t = the ray's t_max when none).  traversal = SPCU_TRAVERSAL_EXACT
+ *     (reference order: bit-exact IDs and distances) or SPCU_TRAVERSAL_ORDERED (the render default: epsilon ties may differ).
+ *   spcu_shadow_batch: Integrator.cpp:503 — Scene::intersect_p of a light sample's visibility ray. out[i] = 0/1. */
+int spcu_extend_batch(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, uint32_t traversal, spcu_hit* hits, spcu_hit* light_hits);
+int spcu_shadow_batch(spcu_ctx* ctx, const spcu_ray* rays, uint64_t n, uint8_t* occluded);
+
 /* Camera::generate_ray for (pixel, sample) pairs (Cameras/Camera.h:119-129 + main.cpp:96-98):
  * rays[i] for pixel index pix[i] (= y*width+x) and sample index smp[i]. host pointers. */
 int spcu_generate_rays(spcu_ctx* ctx, const uint32_t* pix, const uint32_t* smp, uint64_t n, spcu_ray* rays);
@@ -287,6 +298,29 @@ int spcu_render_frame(spcu_ctx* ctx, const spcu_partition* part, float* rgb_sum,
 int spcu_render_device(spcu_ctx* ctx, const spcu_partition* part, float* d_rgb_sum, float* d_lum_sumsq,
                        spcu_stats* stats, void* stream);
 
+/* ---- multi-GPU: accumulators summed into rank 0 with NCCL over NVLink ------------------------------------
+ * The scene is replicated (every rank uploads it), the work is partitioned by spcu_partition (tiles or sample ranges), there
+ * is no exchange during tracing; ONE ncclReduce(sum, root 0) per accumulator ends a frame.  Replaces nothing in the reference
+ * (its image is one process's Array2D, main.cpp:100-102).
+ *   one process per GPU : rank 0 calls spcu_comm_unique_id, the launcher hands the bytes to every rank (MPI / torchrun /
+ *                         a file), every rank calls spcu_comm_init_rank(ctx, nranks, rank, id) — a collective.
+ *   one process, n GPUs : spcu_comm_init_all over n contexts (rank i = ctxs[i]); afterwards every context is driven from its
+ *                         own host thread (what sp::CudaIntegrator does with SPCU_DEVICES=n).
+ * spcu_reduce_to_root: in place on DEVICE buffers of the image's size, on `stream`; every rank calls it, rank 0's buffers hold
+ * the sums afterwards.  A context without a communicator is a world of one rank (no-op).
+ * spcu_render_frame_reduced = spcu_render_frame of this rank's partition + the reduction + the single device->host copy on
+ * rank 0 (the other ranks may pass NULL host pointers); with_sumsq must agree on all ranks. */
+#define SPCU_NCCL_ID_BYTES 128
+int  spcu_comm_unique_id(uint8_t id[SPCU_NCCL_ID_BYTES]);
+int  spcu_comm_init_rank(spcu_ctx* ctx, int nranks, int rank, const uint8_t id[SPCU_NCCL_ID_BYTES]);
+int  spcu_comm_init_all(spcu_ctx** ctxs, int n);
+void spcu_comm_destroy(spcu_ctx* ctx);
+int  spcu_comm_rank(const spcu_ctx* ctx);
+int  spcu_comm_size(const spcu_ctx* ctx);
+int  spcu_reduce_to_root(spcu_ctx* ctx, float* d_rgb_sum, float* d_lum_sumsq, void* stream);
+int  spcu_render_frame_reduced(spcu_ctx* ctx, const spcu_partition* part, int with_sumsq, float* rgb_sum, float* lum_sumsq,
+                               spcu_stats* stats);
+
 /* Upper bound of paths kept in flight per wavefront batch (0 = default). */
 int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 
@@ -305,8 +339,12 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
  *                          faster for the uploaded scene's feature set (profiles/): SMWAVE for analytic
  *                          scenes, WAVEFRONT for scenes with a BVH. */
 #define SPCU_OPT_PIPELINE 2u
-/*   SPCU_OPT_TRAVERSAL   : closest-hit walk of the extend stage: SPCU_TRAVERSAL_EXACT (default) = the reference's own
- *                          order, bit-exact IDs; SPCU_TRAVERSAL_ORDERED = nearer child first (see spcu_trace_closest_fast). */
+/*   SPCU_OPT_TRAVERSAL   : closest-hit walk of the RENDERER's extend stage: SPCU_TRAVERSAL_ORDERED (default) = nearer child
+ *                          first (see spcu_trace_closest_fast): about half the node visits, answers differ from the
+ *                          reference-order walk on epsilon ties only (counted by tests/test_gpu_trace.py and by bench.py's
+ *                          `ordered_walk` object, stated in DESIGN.md); SPCU_TRAVERSAL_EXACT = the reference's own order,
+ *                          bit-exact IDs.  spcu_trace_closest is always the exact walk; with SPCU_OPT_COUNT_NODES the
+ *                          renderer also walks in reference order (the counters are defined on that walk). */
 #define SPCU_OPT_TRAVERSAL 3u
 /*   SPCU_OPT_GENERIC_KERNELS : 1 = always run the kernels compiled for every scene feature (default 0: spcu_upload_scene picks
  *                          the smallest compiled feature set that covers the scene).  Takes effect at the next upload. */

@@ -439,18 +439,29 @@ static isect_t make_isect(const spcu_flat_scene* s, const ray_t* r, const closes
 void spo_trace_closest(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, spcu_hit* hits, spo_counters* cnt)
 {
     spo_counters local = { 0, 0, 0 };
+    if (!cnt) { /* rays are independent: the 2^20-ray parity batches of tests/test_gpu_scale.py use every host core */
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            const ray_t     r = load_ray(&rays[i]);
+            const closest_t c = scene_intersect(s, &r, NULL);
+            hits[i].id        = c.id;
+            hits[i].t         = c.t;
+        }
+        return;
+    }
     for (uint64_t i = 0; i < n; ++i) {
         const ray_t     r = load_ray(&rays[i]);
-        const closest_t c = scene_intersect(s, &r, cnt ? &local : NULL);
+        const closest_t c = scene_intersect(s, &r, &local);
         hits[i].id        = c.id;
         hits[i].t         = c.t;
     }
-    if (cnt) *cnt = local;
+    *cnt = local;
 }
 
 void spo_trace_any(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, uint8_t* out)
 {
-    for (uint64_t i = 0; i < n; ++i) {
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
         const ray_t r = load_ray(&rays[i]);
         out[i]        = (uint8_t)scene_intersect_p(s, &r, NULL);
     }
@@ -458,7 +469,8 @@ void spo_trace_any(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, u
 
 void spo_trace_lights(const spcu_flat_scene* s, const spcu_ray* rays, uint64_t n, spcu_hit* hits)
 {
-    for (uint64_t i = 0; i < n; ++i) {
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
         const ray_t     r = load_ray(&rays[i]);
         const closest_t c = scene_intersect_lights(s, &r);
         hits[i].id        = c.id;

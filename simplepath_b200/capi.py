@@ -112,7 +112,11 @@ EXPORTS = [
     "spcu_generate_rays", "spcu_render", "spcu_render_frame", "spcu_render_device", "spcu_set_wavefront_size", "spcu_set_option",
     "spcu_scene_bytes", "spcu_trace_closest_counted", "spcu_stage_times", "spcu_resolved_pipeline",
     "spcu_build_bvh", "spcu_triangle_bounds", "spcu_upload_scene_build", "spcu_pack_image", "spcu_render_image", "spcu_ingest_mesh", "spcu_ingest_mesh_stl",
+    "spcu_extend_batch", "spcu_shadow_batch",
+    "spcu_comm_unique_id", "spcu_comm_init_rank", "spcu_comm_init_all", "spcu_comm_destroy", "spcu_comm_rank", "spcu_comm_size",
+    "spcu_reduce_to_root", "spcu_render_frame_reduced",
 ]
+NCCL_ID_BYTES = 128
 OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
 PIPELINE_WAVEFRONT, PIPELINE_PATHS, PIPELINE_SMWAVE, PIPELINE_AUTO = 0, 1, 2, 3
@@ -155,6 +159,22 @@ def load(path: Path | str | None = None) -> C.CDLL:
     lib.spcu_trace_closest_fast.restype = C.c_int
     lib.spcu_trace_any.argtypes = [vp, vp, C.c_uint64, vp]
     lib.spcu_trace_any.restype = C.c_int
+    lib.spcu_comm_unique_id.argtypes = [vp]
+    lib.spcu_comm_unique_id.restype = C.c_int
+    lib.spcu_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.spcu_comm_init_rank.restype = C.c_int
+    lib.spcu_comm_destroy.argtypes = [vp]
+    lib.spcu_comm_destroy.restype = None
+    lib.spcu_comm_rank.argtypes = [vp]
+    lib.spcu_comm_size.argtypes = [vp]
+    lib.spcu_reduce_to_root.argtypes = [vp, vp, vp, vp]
+    lib.spcu_reduce_to_root.restype = C.c_int
+    lib.spcu_render_frame_reduced.argtypes = [vp, C.POINTER(Partition), C.c_int, vp, vp, C.POINTER(Stats)]
+    lib.spcu_render_frame_reduced.restype = C.c_int
+    lib.spcu_extend_batch.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp, vp]
+    lib.spcu_extend_batch.restype = C.c_int
+    lib.spcu_shadow_batch.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.spcu_shadow_batch.restype = C.c_int
     lib.spcu_generate_rays.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.spcu_generate_rays.restype = C.c_int
     lib.spcu_render.argtypes = [vp, C.POINTER(Partition), vp, vp, C.POINTER(Stats)]
@@ -302,6 +322,23 @@ class Context:
         self._check(self.lib.spcu_trace_any(self.h, _ptr(rays), rays.shape[0], _ptr(out)), "spcu_trace_any")
         return out
 
+    def extend_batch(self, rays, traversal: int = TRAVERSAL_EXACT):
+        """The render's extend stage on a ray batch (Integrator.cpp:558-563): (geometry hits under the light-shrunk limit,
+        light hits)."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        lights = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        self._check(self.lib.spcu_extend_batch(self.h, _ptr(rays), rays.shape[0], traversal, _ptr(hits), _ptr(lights)),
+                    "spcu_extend_batch")
+        return hits, lights
+
+    def shadow_batch(self, rays) -> np.ndarray:
+        """The render's shadow stage on a ray batch (Scene::intersect_p): uint8 occlusion flags."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.empty(rays.shape[0], dtype=np.uint8)
+        self._check(self.lib.spcu_shadow_batch(self.h, _ptr(rays), rays.shape[0], _ptr(out)), "spcu_shadow_batch")
+        return out
+
     def generate_rays(self, pix, smp) -> np.ndarray:
         pix = np.ascontiguousarray(pix, dtype=np.uint32)
         smp = np.ascontiguousarray(smp, dtype=np.uint32)
@@ -353,6 +390,40 @@ class Context:
                                                 C.byref(st) if want_stats else None,
                                                 C.c_void_p(stream) if stream else None), "spcu_render_device")
         return st.as_dict() if want_stats else None
+
+    # ---- multi-GPU (one process per GPU): NCCL communicator of the product library ------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """ncclGetUniqueId (rank 0 calls; the launcher hands the bytes to every rank)."""
+        buf = (C.c_uint8 * NCCL_ID_BYTES)()
+        self._check(self.lib.spcu_comm_unique_id(buf), "spcu_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes) -> None:
+        assert len(unique_id) == NCCL_ID_BYTES
+        buf = (C.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self.lib.spcu_comm_init_rank(self.h, nranks, rank, buf), "spcu_comm_init_rank")
+
+    def reduce_to_root(self, d_rgb_sum: int, d_lum_sumsq: int | None, stream: int | None = None) -> None:
+        """ncclReduce(sum, root 0) of the device accumulators, in place, on `stream` (enqueue only)."""
+        self._check(self.lib.spcu_reduce_to_root(self.h, C.c_void_p(d_rgb_sum), C.c_void_p(d_lum_sumsq) if d_lum_sumsq else None,
+                                                 C.c_void_p(stream) if stream else None), "spcu_reduce_to_root")
+
+    def render_frame_reduced(self, part: Partition, out=None, want_sumsq: bool = True, want_stats: bool = True):
+        """This rank's partition + NCCL reduction + (rank 0 only) the device->host copy: (rgb_sum, lum_sumsq, stats) on rank 0,
+        (None, None, stats) elsewhere."""
+        root = self.lib.spcu_comm_rank(self.h) == 0
+        rgb = sq = None
+        if root:
+            if out is not None:
+                rgb, sq = out
+            else:
+                rgb = np.empty((self.height, self.width, 3), dtype=np.float32)
+                sq = np.empty((self.height, self.width), dtype=np.float32) if want_sumsq else None
+        st = Stats()
+        self._check(self.lib.spcu_render_frame_reduced(self.h, C.byref(part), 1 if want_sumsq else 0,
+                                                       _ptr(rgb) if root else None, _ptr(sq) if root and want_sumsq else None,
+                                                       C.byref(st) if want_stats else None), "spcu_render_frame_reduced")
+        return rgb, sq, (st.as_dict() if want_stats else None)
 
     def resolved_pipeline(self) -> str:
         """The kernel organisation the next render runs (PIPELINE_AUTO resolved for the uploaded scene)."""

@@ -661,9 +661,25 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
 // ([0, n_unbounded) the top-level list, then the bounded primitives as the reference holds them before
 // BVHAccelerator(first, last)); bounds, tree and the gather into leaf order all happen on the device, and the context's
 // geometry buffers end up exactly as spcu_upload_scene would have filled them from the flattener's output.
-int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu_bounds* extra_bounds, uint32_t* order_out,
-                               spcu_accel* built)
+// 0 into *flag when a primitive's bounds are not finite with lo <= hi (then the tree's boxes are not either)
+__global__ void k_bounds_proper(const spcu_bounds* bounds, uint32_t n, int* flag)
 {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const spcu_bounds b  = bounds[i];
+        bool              ok = true;
+        for (int d = 0; d < 3; ++d) {
+            ok = ok && fabsf(b.lo[d]) < __int_as_float(0x7f800000) && fabsf(b.hi[d]) < __int_as_float(0x7f800000) && b.lo[d] <= b.hi[d];
+        }
+        if (!ok) {
+            *flag = 0;
+        }
+    }
+}
+
+int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu_bounds* extra_bounds, uint32_t* order_out,
+                               spcu_accel* built, bool* proper_boxes)
+{
+    *proper_boxes = true;
     const uint32_t n_prims = s->geom.n_prims, first_id = s->geom.n_unbounded, n = n_prims - first_id;
     const cudaStream_t st  = c->stream;
     Scratch            mem;
@@ -703,6 +719,12 @@ int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu
             CK(c, cudaMemcpyAsync(d_bounds, extra_bounds, static_cast<size_t>(n) * sizeof(spcu_bounds), cudaMemcpyHostToDevice, st));
         }
         k_scene_bounds<<<grid_for(n, c->sm_count), kBlock, 0, st>>>(src_geom + first_id, src_meta + first_id, n, d_bounds, d_non_tri);
+        int* d_proper = nullptr;
+        int  h_proper = 1;
+        CK(c, mem.get(&d_proper, 1));
+        CK(c, cudaMemcpyAsync(d_proper, &h_proper, sizeof(int), cudaMemcpyHostToDevice, st));
+        k_bounds_proper<<<grid_for(n, c->sm_count), kBlock, 0, st>>>(d_bounds, n, d_proper);
+        CK(c, cudaMemcpyAsync(&h_proper, d_proper, sizeof(int), cudaMemcpyDeviceToHost, st));
         Build          b;
         spcu_bvh_node* d_nodes = nullptr;
         if (const int rc = device_build(c, mem, b, d_bounds, n, d_non_tri, first_id, n - 1, &d_nodes, a); rc != SPCU_OK) {
@@ -720,6 +742,7 @@ int spcu::build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu
             CK(c, cudaMemcpyAsync(order_out, b.perm_in, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
         CK(c, cudaStreamSynchronize(st));
+        *proper_boxes = h_proper != 0;
     }
     *built = a;
     return SPCU_OK;

@@ -64,6 +64,9 @@ struct spcu_ctx
     cudaStream_t stream = nullptr;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     int          sm_count = 148;
+    void*        nccl_comm   = nullptr; // ncclComm_t of this context's rank (comm.cu); NULL: single GPU
+    int          comm_rank   = 0;
+    int          comm_nranks = 1;
     bool         scratch_in_use = false;   // a render has been enqueued: its last event is ev1 on scratch_stream
     cudaStream_t scratch_stream = nullptr;
 
@@ -115,7 +118,7 @@ int copy_to_device(spcu_ctx* c, void* dst, const void* src, size_t bytes);
 int pack_device_image(spcu_ctx* c, const float* d_rgb_sum, uint32_t w, uint32_t h, uint32_t spp, uint32_t format, void* out);
 // build_kernels.cu: geometry of an UNBUILT scene -> bounds, BVH and leaf-order gather on the device (spcu_upload_scene_build)
 int build_scene_geometry(spcu_ctx* c, const spcu_flat_scene* s, const spcu_bounds* extra_bounds, uint32_t* order_out,
-                         spcu_accel* built);
+                         spcu_accel* built, bool* proper_boxes);
 
 #define CK(ctx, call)                                                                                                     \
     do {                                                                                                                  \

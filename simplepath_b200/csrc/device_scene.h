@@ -16,6 +16,7 @@ struct DAccel
     uint32_t      root_count;
     uint32_t      n_unbounded;
     uint32_t      n_prims;
+    uint32_t      proper_boxes; // every child box is finite with lo <= hi: the slab test may take its NaN-free form (trace.cuh)
 };
 
 struct DScene

@@ -16,6 +16,11 @@ void launch_trace_closest_ordered(const DScene& s, const spcu_ray* d_rays, uint6
 void launch_trace_any(const DScene& s, const spcu_ray* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t st);
 void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, cudaStream_t st);
 
+// Ray batches through the wavefront's own traversal stages (spcu_extend_batch / spcu_shadow_batch): slot i <- ray i.
+void launch_batch_fill(const DWave& w, const spcu_ray* d_rays, uint32_t n, uint32_t* queue, uint32_t* d_n_queue, bool shadow,
+                       cudaStream_t st);
+void launch_batch_gather_extend(const DWave& w, uint32_t n, spcu_hit* d_hits, spcu_hit* d_light_hits, cudaStream_t st);
+
 // Wavefront stages that traverse.  `queue` holds path slots; n_queue is read on the device (no host sync).
 // d_cursor (extend, shadow): a zeroed uint32 in device memory, the stage's global work cursor.
 // extend: Scene::intersect_lights then Scene::intersect for every queued path (Integrator.cpp:558-563).

@@ -126,8 +126,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         for (uint32_t k = 0; k < s.n_lights; ++k) {
             const spcu_light& light = s.lights[__ldg(s.light_order + k)];
             float             u0, u1;
-            ps.rng.stream = rng_stream(ps.depth, kSiteLight0 + k);
-            ps.rng.ctr    = 0u;
+            rng_seek(ps.rng, rng_stream(ps.depth, kSiteLight0 + k), 0u);
             rng_next2(ps.rng, u0, u1);
             const LSample ls = light_sample<F>(s, light, point, normal, u0, u1);
             if (ls.pdf == 0.0f || is_black(ls.L)) {
@@ -149,8 +148,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         }
         // WhittedIntegrator (Integrator.cpp:357-363): follow the BSDF sample only when it is specular, default limits,
         // radiance of the reflected ray added unweighted
-        ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);
-        ps.rng.ctr       = 0u;
+        rng_seek(ps.rng, rng_stream(ps.depth, kSiteBsdf), 0u);
         const MSample ms = material_sample<F>(s, material, wo, normal, ps.rng);
         ++pc.shade_calls;
         if (!ms.specular) { // is_specular(properties) alone decides (:359)
@@ -163,8 +161,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         return ps.depth < s.max_depth;
     }
 
-    ps.rng.stream    = rng_stream(ps.depth, kSiteBsdf);
-    ps.rng.ctr       = 0u;
+    rng_seek(ps.rng, rng_stream(ps.depth, kSiteBsdf), 0u);
     const MSample sr = material_sample<F>(s, material, wo, normal, ps.rng);
     ++pc.shade_calls;
     if (sr.pdf == 0.0f || is_black(sr.color)) {
@@ -173,8 +170,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
     if (integrator == SPCU_INTEGRATOR_ITERATIVE_RRNEE) {
         for (uint32_t k = 0; k < s.n_lights; ++k) {
             const spcu_light& light = s.lights[__ldg(s.light_order + k)];
-            ps.rng.stream = rng_stream(ps.depth, kSiteLight0 + k);
-            ps.rng.ctr    = 0u;
+            rng_seek(ps.rng, rng_stream(ps.depth, kSiteLight0 + k), 0u);
             ps.L = ps.L + ps.throughput * estimate_direct_mis<kCount, F>(s, light, point, normal, material, wo, ps.rng, stack, pc, tc);
         }
     }
@@ -184,8 +180,7 @@ __device__ __forceinline__ bool path_vertex(const DScene& s, uint32_t integrator
         const float lum = luminance(ps.throughput);
         if (lum < 0.1f) {
             const float q = max_std(0.05f, lum / 0.1f);
-            ps.rng.stream = rng_stream(ps.depth, kSiteRoulette);
-            ps.rng.ctr    = 0u;
+            rng_seek(ps.rng, rng_stream(ps.depth, kSiteRoulette), 0u);
             if (rng_next1(ps.rng) < q) {
                 ps.throughput = ps.throughput / q;
             } else {

@@ -6,14 +6,17 @@
 // A sub-stream belongs to one call site of the integrator at one path depth, s = depth << 16 | site:
 //     site 0      the vertex's primary BSDF sample            (Integrator.cpp:569 / :228)
 //     site 1      Russian roulette                            (Integrator.cpp:615 / :246)
-//     site 2 + l  next-event estimation for light l: block 0 = the light sample (Integrator.cpp:497 / :289), blocks 1.. =
+//     site 2 + l  next-event estimation for light l: draw 0 = the light sample (Integrator.cpp:497 / :289), draws 1.. =
 //                 Material::eval, pdf and the second sample, in the reference's order (:508-518 / :296)
-// Within a sub-stream every *draw call* of the reference (Sampler::get_next_1D or get_next_2D, math/Sampler.h:76-94)
-// consumes ONE block, in call order: 1D uses word 0, 2D uses words 0 and 1; the two get_next_1D() arguments of
-// beckmann_sample (materials/Material.cpp:150) are served by one block (U1 = word 0, U2 = word 1).  A word w maps to the
-// float (w >> 8) * 2^-24 in [0, 1).  No stage has to carry a draw counter to the next one, and the lights of a vertex
-// are independent of each other.  oracle/sp_oracle_shade.inc restates the same contract, so both sides draw identical
-// numbers.
+// Within a sub-stream the *draw calls* of the reference (Sampler::get_next_1D or get_next_2D, math/Sampler.h:76-94) are
+// numbered in call order, and draw d is served by HALF a block: block d >> 1, words (0, 1) when d is even and (2, 3) when it
+// is odd; a 1D draw uses the first word of its pair, a 2D draw both; the two get_next_1D() arguments of beckmann_sample
+// (materials/Material.cpp:150) are one draw (U1, U2 = the pair).  (Round 1 spent a whole block per draw: the ten rounds
+// are ~70 instructions and a microfacet vertex draws ~50 times per light — 40 % of the NEE stage's instructions.)  A word w
+// maps to the float (w >> 8) * 2^-24 in [0, 1).  The mapping is a pure function of (path, sub-stream, d): no stage has to
+// carry generator state to the next one — a stage that starts at an odd draw recomputes that block —, and the lights of a
+// vertex are independent of each other.  oracle/sp_oracle_shade.inc restates the same contract, so both sides draw
+// identical numbers.
 #pragma once
 
 #include <stdint.h>
@@ -25,8 +28,19 @@ struct Rng
     uint32_t pixel, sample;
     uint32_t seed_lo, seed_hi;
     uint32_t stream; // depth << 16 | site
-    uint32_t ctr;    // next block of the sub-stream
+    uint32_t ctr;    // next draw of the sub-stream
+    // words 2 and 3 of block ctr >> 1, kept from the even draw for the odd one that follows (`fresh`); not part of the contract
+    uint32_t w2 = 0u, w3 = 0u;
+    bool     fresh = false;
 };
+
+// continue at draw `ctr` of another sub-stream
+__host__ __device__ __forceinline__ void rng_seek(Rng& r, uint32_t stream, uint32_t ctr)
+{
+    r.stream = stream;
+    r.ctr    = ctr;
+    r.fresh  = false;
+}
 
 constexpr uint32_t kSiteBsdf = 0u, kSiteRoulette = 1u, kSiteLight0 = 2u;
 __host__ __device__ __forceinline__ uint32_t rng_stream(uint32_t depth, uint32_t site) { return (depth << 16) | site; }
@@ -69,29 +83,40 @@ __host__ __device__ __forceinline__ float word_to_unit(uint32_t w)
 #ifdef __CUDACC__
 // Words 0 and 1 of a block as ONE out-of-line copy per kernel: the ten rounds are ~70 instructions and a kernel draws
 // at some twenty-five call sites; inlined they were 11 % of the path kernels' SASS, whose limiter is instruction fetch.
-static __device__ __noinline__ uint2 philox_block01(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+static __device__ __noinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
     uint32_t o[4];
     philox4x32_10(c0, c1, c2, c3, k0, k1, o);
-    return make_uint2(o[0], o[1]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 #endif
 
-// One draw call: returns words 0 and 1 as floats in [0,1) and advances the path's counter.
+// One draw call: returns its pair of words as floats in [0,1) and advances the path's draw counter.
 __host__ __device__ __forceinline__ void rng_next2(Rng& r, float& u0, float& u1)
 {
+    const bool odd = (r.ctr & 1u) != 0u;
+    uint32_t   a, b;
+    if (odd && r.fresh) {
+        a       = r.w2;
+        b       = r.w3;
+        r.fresh = false;
+    } else {
 #ifdef __CUDA_ARCH__
-    const uint2 w = philox_block01(r.ctr, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample);
-    ++r.ctr;
-    u0 = word_to_unit(w.x);
-    u1 = word_to_unit(w.y);
+        const uint4 w = philox_block(r.ctr >> 1, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample);
 #else
-    uint32_t o[4];
-    philox4x32_10(r.ctr, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample, o);
-    ++r.ctr;
-    u0 = word_to_unit(o[0]);
-    u1 = word_to_unit(o[1]);
+        uint32_t o[4];
+        philox4x32_10(r.ctr >> 1, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample, o);
+        const struct { uint32_t x, y, z, w; } w = { o[0], o[1], o[2], o[3] };
 #endif
+        a       = odd ? w.z : w.x;
+        b       = odd ? w.w : w.y;
+        r.w2    = w.z;
+        r.w3    = w.w;
+        r.fresh = !odd;
+    }
+    ++r.ctr;
+    u0 = word_to_unit(a);
+    u1 = word_to_unit(b);
 }
 
 __host__ __device__ __forceinline__ float rng_next1(Rng& r)

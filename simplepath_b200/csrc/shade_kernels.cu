@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kShadeBlock, SPCU_NEE_MIN_BLOCKS) k_nee_bsdf(c
             const V3        wi       = xyz(lr.wi);
             const float     lpdf_s   = lr.aux.y;
             const V3        lL       = light_sample_L<F>(s, light, lr);
-            Rng             rng      = make_rng(pr, p.seed, p.depth, kSiteLight0 + p.light_index, 1u); // block 0 was the light sample
+            Rng             rng      = make_rng(pr, p.seed, p.depth, kSiteLight0 + p.light_index, 1u); // draw 0 was the light sample
 
             // Material::eval / pdf (materials/Material.h:475-490) rebuild the ONB on every call; it is the same basis
             const Onb onb = onb_from_v(nn);

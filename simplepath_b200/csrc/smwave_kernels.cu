@@ -421,7 +421,7 @@ __device__ __forceinline__ void stage_mis(const Shared& sh, State x, int lane)
     const uint32_t    material = x.u(kFMat);
     const V3          wo = -x.get3(kFD), wi = x.get3(kFLwi);
     const float       lpdf_s = x.f(kFLpdf);
-    Rng               rng    = state_rng(sh, x, depth, kSiteLight0 + k, 1u); // block 0 was the light sample
+    Rng               rng    = state_rng(sh, x, depth, kSiteLight0 + k, 1u); // draw 0 was the light sample
 
     V3        L   = v3(0, 0, 0);
     const Onb onb = onb_from_v(n);

@@ -90,6 +90,23 @@ int upload(spcu_ctx* c, DevBuf& buf, const T* src, size_t n)
     return SPCU_OK;
 }
 
+// every child box finite with lo <= hi (what the reference's construction always produces: bounds are folded min / max)
+bool boxes_are_proper(const spcu_accel& a)
+{
+    for (uint32_t i = 0; i < a.n_nodes; ++i) {
+        const float* b = a.nodes[i].box;
+        for (int k = 0; k < 2; ++k) {
+            for (int d = 0; d < 3; ++d) {
+                const float lo = b[6 * k + d], hi = b[6 * k + 3 + d];
+                if (!(std::isfinite(lo) && std::isfinite(hi) && lo <= hi)) {
+                    return false;
+                }
+            }
+        }
+    }
+    return true;
+}
+
 int validate_accel(spcu_ctx* c, const spcu_accel& a, const char* what)
 {
     if (a.n_unbounded > a.n_prims) {
@@ -169,9 +186,10 @@ int scene_features(const spcu_flat_scene& s)
     return analytic ? FeatAnalytic::id : FeatFull::id;
 }
 
-DAccel device_accel(const spcu_accel& a, const DevBuf& nodes)
+DAccel device_accel(const spcu_accel& a, const DevBuf& nodes, bool proper_boxes)
 {
     DAccel d;
+    d.proper_boxes = proper_boxes ? 1u : 0u;
     d.nodes       = nodes.as<const float4>();
     d.root        = a.root;
     d.root_count  = a.root_count;
@@ -217,7 +235,8 @@ int spcu_create(int device, spcu_ctx** out)
                     prop.minor);
     }
     auto* c     = new spcu_ctx;
-    c->options[SPCU_OPT_PIPELINE] = SPCU_PIPELINE_AUTO;
+    c->options[SPCU_OPT_PIPELINE]  = SPCU_PIPELINE_AUTO;
+    c->options[SPCU_OPT_TRAVERSAL] = SPCU_TRAVERSAL_ORDERED;
     c->device   = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -240,6 +259,7 @@ void spcu_destroy(spcu_ctx* c)
     }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    spcu_comm_destroy(c);
     for (DevBuf* b : { &c->geom_nodes, &c->geom_prims, &c->geom_shade, &c->geom_meta, &c->light_nodes, &c->lights,
                        &c->light_order, &c->materials, &c->bxdfs, &c->pool, &c->jitter, &c->q_rays, &c->q_out, &c->q_aux,
                        &c->q_cnt, &c->queue_counts, &c->counters, &c->pix_list, &c->host_rgb, &c->host_sq, &c->path_radiance, &c->sorted_queue, &c->packed }) {
@@ -359,10 +379,12 @@ static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitte
     c->have_scene  = false;
     c->scene_bytes = 0;
     int        rc;
-    spcu_accel geom = s->geom;
+    spcu_accel geom        = s->geom;
+    bool       geom_proper = true;
     if (build) {
-        if ((rc = build_scene_geometry(c, s, bounds, order, &geom)) != SPCU_OK) return rc;
+        if ((rc = build_scene_geometry(c, s, bounds, order, &geom, &geom_proper)) != SPCU_OK) return rc;
     } else {
+        geom_proper = boxes_are_proper(s->geom);
         if ((rc = upload(c, c->geom_nodes, s->geom.nodes, s->geom.n_nodes)) != SPCU_OK) return rc;
         if ((rc = upload(c, c->geom_prims, s->geom_prims, s->geom.n_prims)) != SPCU_OK) return rc;
         if ((rc = upload(c, c->geom_shade, s->geom_shade, s->geom.n_prims)) != SPCU_OK) return rc;
@@ -383,11 +405,11 @@ static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitte
     d.rr_depth  = s->rr_depth;
     d.max_depth = s->max_depth;
     std::memcpy(d.camera, s->camera, sizeof d.camera);
-    d.geom         = device_accel(geom, c->geom_nodes);
+    d.geom         = device_accel(geom, c->geom_nodes, geom_proper);
     d.geom_prims   = c->geom_prims.as<const float4>();
     d.geom_shade   = c->geom_shade.as<const float4>();
     d.geom_meta    = c->geom_meta.as<const uint32_t>();
-    d.lights_accel = device_accel(s->lights_accel, c->light_nodes);
+    d.lights_accel = device_accel(s->lights_accel, c->light_nodes, boxes_are_proper(s->lights_accel));
     d.n_lights     = s->n_lights;
     d.lights       = c->lights.as<const spcu_light>();
     d.light_order  = c->light_order.as<const uint32_t>();

@@ -342,7 +342,8 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 timer.begin(kStExtend);
                 uint32_t* cursor = new_count();
                 launches += launch_extend(L, s, c->wave, q_cur, n_cur, max_n, cursor, sorted,
-                                          c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED, q[kQWalk], new_count(),
+                                          // (node counting is DEFINED on the reference-order walk: DESIGN.md byte model)
+                                          c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED && !d_cnt, q[kQWalk], new_count(),
                                           d_counters, d_cnt);
                 timer.end();
                 uint32_t* n_live   = new_count();
@@ -491,6 +492,34 @@ int spcu_render_frame(spcu_ctx* c, const spcu_partition* part, float* rgb_sum, f
     return sync_and_check_faults(c, stats != nullptr);
 }
 
+int spcu_render_frame_reduced(spcu_ctx* c, const spcu_partition* part, int with_sumsq, float* rgb_sum, float* lum_sumsq,
+                              spcu_stats* stats)
+{
+    if (int rc = need_scene(c); rc != SPCU_OK) return rc;
+    const bool root = c->comm_rank == 0;
+    if (root && (!rgb_sum || (with_sumsq && !lum_sumsq))) {
+        return fail(c, SPCU_ERR_INVALID, "rank 0 needs the host buffers");
+    }
+    const size_t n_pixels = static_cast<size_t>(c->ds.width) * c->ds.height;
+    CK(c, c->host_rgb.reserve(n_pixels * 3 * sizeof(float)));
+    CK(c, cudaMemsetAsync(c->host_rgb.p, 0, n_pixels * 3 * sizeof(float), c->stream));
+    float* d_sq = nullptr;
+    if (with_sumsq) {
+        CK(c, c->host_sq.reserve(n_pixels * sizeof(float)));
+        CK(c, cudaMemsetAsync(c->host_sq.p, 0, n_pixels * sizeof(float), c->stream));
+        d_sq = c->host_sq.as<float>();
+    }
+    if (int rc = render_impl(c, part, c->host_rgb.as<float>(), d_sq, stats, nullptr, false); rc != SPCU_OK) return rc;
+    if (int rc = spcu_reduce_to_root(c, c->host_rgb.as<float>(), d_sq, c->stream); rc != SPCU_OK) return rc;
+    if (root) {
+        CK(c, cudaMemcpyAsync(rgb_sum, c->host_rgb.p, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (with_sumsq) {
+            CK(c, cudaMemcpyAsync(lum_sumsq, c->host_sq.p, n_pixels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    return sync_and_check_faults(c, stats != nullptr);
+}
+
 int spcu_render_image(spcu_ctx* c, const spcu_partition* part, uint32_t format, void* out, spcu_stats* stats)
 {
     if (int rc = need_scene(c); rc != SPCU_OK) return rc;
@@ -503,6 +532,78 @@ int spcu_render_image(spcu_ctx* c, const spcu_partition* part, uint32_t format, 
     if (int rc = render_impl(c, part, c->host_rgb.as<float>(), nullptr, stats, nullptr, false); rc != SPCU_OK) return rc;
     if (int rc = sync_and_check_faults(c, stats != nullptr); rc != SPCU_OK) return rc;
     return pack_device_image(c, c->host_rgb.as<float>(), c->ds.width, c->ds.height, part->sample_end - part->sample_begin, format, out);
+}
+
+// Ray batches through the renderer's own traversal stages: the kernels a frame runs (begin + persistent walk, lane refill,
+// pair leaf steps), not the one-thread-per-ray kernels behind spcu_trace_*.
+static int stage_batch(spcu_ctx* c, const spcu_ray* rays, uint64_t n, uint32_t traversal, spcu_hit* hits, spcu_hit* light_hits,
+                       uint8_t* occluded)
+{
+    if (int rc = need_scene(c); rc != SPCU_OK) return rc;
+    const bool shadow = occluded != nullptr;
+    if (n && (!rays || (!shadow && !hits))) {
+        return fail(c, SPCU_ERR_INVALID, "NULL ray or result buffer");
+    }
+    if (traversal > SPCU_TRAVERSAL_ORDERED) {
+        return fail(c, SPCU_ERR_INVALID, "unknown traversal %u", traversal);
+    }
+    const cudaStream_t st = c->stream;
+    if (c->scratch_in_use && c->scratch_stream != st) {
+        CK(c, cudaStreamWaitEvent(st, c->ev1, 0));
+    }
+    const uint32_t chunk = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(n, 1), kBatchRays));
+    // the batch borrows the render's wavefront state: keep its capacity when it is already large enough (capacity is also the
+    // stride of the per-light planes, and shadow rays use plane 0)
+    const uint32_t capacity = (c->wave.capacity >= chunk && c->wave_lights == c->ds.n_lights) ? c->wave.capacity : chunk;
+    if (int rc = ensure_wave(c, capacity); rc != SPCU_OK) return rc;
+    const uint32_t n_segments = std::min<uint32_t>(c->n_materials, kMaxMaterialSegments) + 1u;
+    CK(c, c->sorted_queue.reserve(static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)));
+    CK(c, c->q_rays.reserve(static_cast<size_t>(chunk) * sizeof(spcu_ray)));
+    CK(c, c->q_out.reserve(static_cast<size_t>(chunk) * sizeof(spcu_hit)));
+    CK(c, c->q_aux.reserve(static_cast<size_t>(chunk) * sizeof(spcu_hit)));
+    auto*        d_counters = c->counters.as<unsigned long long>();
+    uint32_t*    d_counts   = c->queue_counts.as<uint32_t>();
+    const Launch L{ c->sm_count, st, c->features };
+    for (uint64_t done = 0; done < n; done += chunk) {
+        const uint32_t m = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - done));
+        CK(c, cudaMemcpyAsync(c->q_rays.p, rays + done, static_cast<size_t>(m) * sizeof(spcu_ray), cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemsetAsync(d_counts, 0, (8 + n_segments) * sizeof(uint32_t), st));
+        CK(c, cudaMemsetAsync(d_counters, 0, kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters), st));
+        uint32_t* n_cur = d_counts + 0;
+        launch_batch_fill(c->wave, c->q_rays.as<spcu_ray>(), m, c->queues[kQCur].as<uint32_t>(), n_cur, shadow, st);
+        if (shadow) {
+            launch_shadow(L, c->ds, c->wave, c->queues[kQCur].as<uint32_t>(), n_cur, m, 0, d_counts + 1, nullptr, nullptr,
+                          c->queues[kQWalk].as<uint32_t>(), d_counts + 2, d_counters, nullptr);
+            CK(c, cudaGetLastError());
+            CK(c, cudaMemcpyAsync(occluded + done, c->wave.occluded, m, cudaMemcpyDeviceToHost, st));
+        } else {
+            SortedQueue sorted{ c->sorted_queue.as<uint32_t>(), d_counts + 8, n_segments, capacity };
+            launch_extend(L, c->ds, c->wave, c->queues[kQCur].as<uint32_t>(), n_cur, m, d_counts + 1, sorted,
+                          traversal == SPCU_TRAVERSAL_ORDERED, c->queues[kQWalk].as<uint32_t>(), d_counts + 2, d_counters, nullptr);
+            launch_batch_gather_extend(c->wave, m, c->q_out.as<spcu_hit>(), light_hits ? c->q_aux.as<spcu_hit>() : nullptr, st);
+            CK(c, cudaGetLastError());
+            CK(c, cudaMemcpyAsync(hits + done, c->q_out.p, static_cast<size_t>(m) * sizeof(spcu_hit), cudaMemcpyDeviceToHost, st));
+            if (light_hits) {
+                CK(c, cudaMemcpyAsync(light_hits + done, c->q_aux.p, static_cast<size_t>(m) * sizeof(spcu_hit), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (int rc = sync_and_check_faults(c, false); rc != SPCU_OK) return rc;
+    }
+    return SPCU_OK;
+}
+
+int spcu_extend_batch(spcu_ctx* c, const spcu_ray* rays, uint64_t n, uint32_t traversal, spcu_hit* hits, spcu_hit* light_hits)
+{
+    return stage_batch(c, rays, n, traversal, hits, light_hits, nullptr);
+}
+
+int spcu_shadow_batch(spcu_ctx* c, const spcu_ray* rays, uint64_t n, uint8_t* occluded)
+{
+    if (n && !occluded) {
+        return fail(c, SPCU_ERR_INVALID, "NULL result buffer");
+    }
+    uint8_t dummy = 0;
+    return stage_batch(c, rays, n, SPCU_TRAVERSAL_EXACT, nullptr, nullptr, occluded ? occluded : &dummy);
 }
 
 int spcu_stage_times(spcu_ctx* c, spcu_stage_time* out, uint32_t capacity, uint32_t* n_out)

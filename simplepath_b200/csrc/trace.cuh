@@ -30,11 +30,18 @@ struct Ray
 struct RayInv
 {
     float x, y, z; // 1.0f / d, IEEE division: the value BBox.h:130 recomputes at every box
+    bool  generic; // the slab test must run with the reference's literal swap / NaN rules (see slab_fast)
 };
 
-__device__ __forceinline__ RayInv make_inv(const Ray& r)
+__device__ __forceinline__ bool is_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
+
+// `proper_boxes`: every child box of the accelerator is finite with lo <= hi (checked at upload).
+__device__ __forceinline__ RayInv make_inv(const Ray& r, bool proper_boxes)
 {
-    return { __fdiv_rn(1.0f, r.dx), __fdiv_rn(1.0f, r.dy), __fdiv_rn(1.0f, r.dz) };
+    RayInv inv{ __fdiv_rn(1.0f, r.dx), __fdiv_rn(1.0f, r.dy), __fdiv_rn(1.0f, r.dz), false };
+    inv.generic = !(proper_boxes && is_finite(inv.x) && is_finite(inv.y) && is_finite(inv.z) && is_finite(r.ox) &&
+                    is_finite(r.oy) && is_finite(r.oz));
+    return inv;
 }
 
 // _mm_dp_ps(a, b, 0x7F) (math/Vector3.h:742-746): (x*x' + y*y') + (z*z' + 0)
@@ -59,23 +66,46 @@ __device__ __forceinline__ bool slab_axis(float lo, float hi, float o, float inv
     return !(t0 > t1);
 }
 
-__device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
-                                     const RayInv& inv, float t_max)
-{
-    float t0 = r.t_min, t1 = t_max;
-    return slab_axis(lox, hix, r.ox, inv.x, t0, t1) && slab_axis(loy, hiy, r.oy, inv.y, t0, t1) &&
-           slab_axis(loz, hiz, r.oz, inv.z, t0, t1);
-}
-
-// Same test, also returning the entry distance t0 (used by the ordered traversal to visit the nearer child first).
-__device__ __forceinline__ bool slab_t0(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
-                                        const RayInv& inv, float t_max, float& t0_out)
+__device__ __forceinline__ bool slab_literal(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
+                                             const RayInv& inv, float t_max, float& t0_out)
 {
     float      t0 = r.t_min, t1 = t_max;
     const bool ok = slab_axis(lox, hix, r.ox, inv.x, t0, t1) && slab_axis(loy, hiy, r.oy, inv.y, t0, t1) &&
                     slab_axis(loz, hiz, r.oz, inv.z, t0, t1);
     t0_out = t0;
     return ok;
+}
+
+// The same test in 8 instead of 11 instructions per axis, for the rays and boxes that cannot produce a NaN: a finite box
+// with lo <= hi, a finite origin and three finite reciprocals (0 * inf is the only NaN source of (b - o) * inv).  Without
+// NaNs the swap is min/max of the two products (equal products: nothing to swap), and the running bounds are max / min:
+// fmaxf / fminf return the non-NaN operand, which is also what the reference's ternaries do with a NaN t_min / t_max on the
+// first axis.  Results are the same VALUES (a zero may carry the other sign; t0 / t1 are only ever compared).  The three
+// axes are evaluated without the reference's early exit: each axis only tightens [t0, t1], so the final test decides the same.
+__device__ __forceinline__ bool slab_fast(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
+                                          const RayInv& inv, float t_max, float& t0_out)
+{
+    const float ax = __fmul_rn(__fsub_rn(lox, r.ox), inv.x), bx = __fmul_rn(__fsub_rn(hix, r.ox), inv.x);
+    const float ay = __fmul_rn(__fsub_rn(loy, r.oy), inv.y), by = __fmul_rn(__fsub_rn(hiy, r.oy), inv.y);
+    const float az = __fmul_rn(__fsub_rn(loz, r.oz), inv.z), bz = __fmul_rn(__fsub_rn(hiz, r.oz), inv.z);
+    const float t0 = fmaxf(fmaxf(fmaxf(r.t_min, fminf(ax, bx)), fminf(ay, by)), fminf(az, bz));
+    const float t1 = fminf(fminf(fminf(t_max, fmaxf(ax, bx)), fmaxf(ay, by)), fmaxf(az, bz));
+    t0_out         = t0;
+    return !(t0 > t1);
+}
+
+__device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
+                                     const RayInv& inv, float t_max)
+{
+    float t0;
+    return slab_literal(lox, loy, loz, hix, hiy, hiz, r, inv, t_max, t0);
+}
+
+// Same test, also returning the entry distance t0 (used by the ordered traversal to visit the nearer child first).
+__device__ __forceinline__ bool slab_t0(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray& r,
+                                        const RayInv& inv, float t_max, float& t0_out)
+{
+    return slab_literal(lox, loy, loz, hix, hiy, hiz, r, inv, t_max, t0_out);
 }
 
 // Early outs of the triangle test that decide `q <= 0` / `q >= 1` for q = fl(num / den) WITHOUT dividing.  They only
@@ -339,6 +369,31 @@ __device__ __forceinline__ void load_right(const float4* nodes, int32_t idx, Nod
     c1 = { v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, __float_as_int(v3.y), __float_as_uint(v3.w) };
 }
 
+// Both child boxes of node `idx` against the current limits; e0 / e1 = entry distances (valid where the box is hit).
+// The literal form lives out of line and reloads the node: it runs for axis-parallel rays and improper boxes only.
+static __device__ __noinline__ unsigned slab_pair_literal(const float4* nodes, int32_t idx, const Ray r, const RayInv inv,
+                                                          float t_max, float& e0, float& e1)
+{
+    NodeHalf c0, c1;
+    load_node(nodes, idx, c0, c1);
+    const bool h0 = slab_literal(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max, e0);
+    const bool h1 = slab_literal(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max, e1);
+    return (h0 ? 1u : 0u) | (h1 ? 2u : 0u);
+}
+
+__device__ __forceinline__ void slab_pair(const float4* nodes, int32_t idx, const NodeHalf& c0, const NodeHalf& c1, const Ray& r,
+                                          const RayInv& inv, float t_max, bool& h0, bool& h1, float& e0, float& e1)
+{
+    if (inv.generic) {
+        const unsigned m = slab_pair_literal(nodes, idx, r, inv, t_max, e0, e1);
+        h0               = (m & 1u) != 0u;
+        h1               = (m & 2u) != 0u;
+    } else {
+        h0 = slab_fast(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max, e0);
+        h1 = slab_fast(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max, e1);
+    }
+}
+
 constexpr int32_t kDone      = 0x7fffffff; // traversal cursor: no work left
 constexpr int     kAllLeaves = 0x7fffffff; // "run to completion"
 
@@ -421,8 +476,10 @@ __device__ __forceinline__ void closest_run(const DAccel& acc, const Prims& prim
                 NodeHalf c0, c1;
                 load_node(acc.nodes, w.link, c0, c1);
                 if (kCount && !w.retest) ++cnt->nodes;
-                const bool h0 = !w.retest && slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, w.t_max);
-                const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, w.t_max);
+                bool  h0, h1;
+                float e0, e1;
+                slab_pair(acc.nodes, w.link, c0, c1, r, inv, w.t_max, h0, h1, e0, e1);
+                h0 = h0 && !w.retest;
                 if (h0) {
                     if (h1) {
                         stack.push(w.link); // right child pending: re-tested against the t_max of that moment
@@ -483,8 +540,10 @@ __device__ __forceinline__ void closest_node_step(const DAccel& acc, const Ray& 
     NodeHalf c0, c1;
     load_node(acc.nodes, w.link, c0, c1);
     if (kCount && !w.retest) ++cnt->nodes;
-    const bool h0 = !w.retest && slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, w.t_max);
-    const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, w.t_max);
+    bool  h0, h1;
+    float e0, e1;
+    slab_pair(acc.nodes, w.link, c0, c1, r, inv, w.t_max, h0, h1, e0, e1);
+    h0 = h0 && !w.retest;
     if (h0) {
         if (h1) {
             stack.push(w.link); // right child pending: re-tested against the t_max of that moment
@@ -539,7 +598,7 @@ __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& p
     ClosestWalk w;
     w.t_max = t_max;
     closest_begin<kCount>(acc, prims, r, w, cnt);
-    const RayInv inv = make_inv(r);
+    const RayInv inv = make_inv(r, acc.proper_boxes != 0u);
     Stack        stack;
     stack.sh = stack_smem;
     closest_run<kCount>(acc, prims, r, inv, w, stack, kAllLeaves, cnt, __activemask());
@@ -605,6 +664,33 @@ __device__ __forceinline__ void ordered_pop(const DAccel& acc, OrderedStack& sta
     }
 }
 
+// one step of the ordered walk at an internal node (closest_run_ordered's node loop body)
+template <bool kCount>
+__device__ __forceinline__ void closest_node_step_ordered(const DAccel& acc, const Ray& r, const RayInv& inv, ClosestWalk& w,
+                                                          OrderedStack& stack, TraceCounters* cnt)
+{
+    NodeHalf c0, c1;
+    load_node(acc.nodes, w.link, c0, c1);
+    if (kCount) ++cnt->nodes;
+    bool  h0, h1;
+    float e0, e1;
+    slab_pair(acc.nodes, w.link, c0, c1, r, inv, w.t_max, h0, h1, e0, e1);
+    if (h0 && h1) {
+        const bool left_first = !(e1 < e0); // equal entries: the reference's order, left first
+        stack.push((w.link << 1) | (left_first ? 1 : 0), left_first ? e1 : e0);
+        w.link  = left_first ? c0.child : c1.child;
+        w.count = left_first ? c0.count : c1.count;
+    } else if (h0) {
+        w.link  = c0.child;
+        w.count = c0.count;
+    } else if (h1) {
+        w.link  = c1.child;
+        w.count = c1.count;
+    } else {
+        ordered_pop(acc, stack, w);
+    }
+}
+
 template <bool kCount, typename Prims>
 __device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Prims& prims, const Ray& r, const RayInv& inv,
                                                     ClosestWalk& w, OrderedStack& stack, int max_leaves, TraceCounters* cnt,
@@ -634,9 +720,9 @@ __device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Pri
                 NodeHalf c0, c1;
                 load_node(acc.nodes, w.link, c0, c1);
                 if (kCount) ++cnt->nodes;
-                float      e0, e1;
-                const bool h0 = slab_t0(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, w.t_max, e0);
-                const bool h1 = slab_t0(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, w.t_max, e1);
+                bool  h0, h1;
+                float e0, e1;
+                slab_pair(acc.nodes, w.link, c0, c1, r, inv, w.t_max, h0, h1, e0, e1);
                 if (h0 && h1) {
                     const bool left_first = !(e1 < e0); // equal entries: the reference's order, left first
                     stack.push((w.link << 1) | (left_first ? 1 : 0), left_first ? e1 : e0);
@@ -682,7 +768,7 @@ __device__ __forceinline__ int32_t closest_hit_ordered(const DAccel& acc, const 
     ClosestWalk w;
     w.t_max = t_max;
     closest_begin<kCount>(acc, prims, r, w, cnt); // the unbounded list is scanned first, in order, as in the reference
-    const RayInv inv = make_inv(r);
+    const RayInv inv = make_inv(r, acc.proper_boxes != 0u);
     OrderedStack stack;
     stack.attach(stack_smem);
     closest_run_ordered<kCount>(acc, prims, r, inv, w, stack, kAllLeaves, cnt, __activemask());
@@ -739,8 +825,9 @@ __device__ __forceinline__ int any_run(const DAccel& acc, const AnyTest& test, c
                 NodeHalf c0, c1;
                 load_node(acc.nodes, w.link, c0, c1);
                 if (kCount) ++cnt->nodes;
-                const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
-                const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
+                bool  h0, h1;
+                float e0, e1;
+                slab_pair(acc.nodes, w.link, c0, c1, r, inv, t_max, h0, h1, e0, e1);
                 if (h0) {
                     if (h1) {
                         stack.push(w.link);
@@ -785,7 +872,7 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
             return true;
         }
     }
-    const RayInv inv = make_inv(r);
+    const RayInv inv = make_inv(r, acc.proper_boxes != 0u);
     Stack        stack;
     stack.sh = stack_smem;
     AnyWalk w{ acc.root, acc.root_count };
@@ -803,8 +890,9 @@ __device__ __forceinline__ void any_node_step(const DAccel& acc, const Ray& r, c
     NodeHalf c0, c1;
     load_node(acc.nodes, w.link, c0, c1);
     if (kCount) ++cnt->nodes;
-    const bool h0 = slab(c0.lox, c0.loy, c0.loz, c0.hix, c0.hiy, c0.hiz, r, inv, t_max);
-    const bool h1 = slab(c1.lox, c1.loy, c1.loz, c1.hix, c1.hiy, c1.hiz, r, inv, t_max);
+    bool  h0, h1;
+    float e0, e1;
+    slab_pair(acc.nodes, w.link, c0, c1, r, inv, t_max, h0, h1, e0, e1);
     if (h0) {
         if (h1) {
             stack.push(w.link);

@@ -7,6 +7,8 @@
 #include "kernels.h"
 #include "trace.cuh"
 
+#include <algorithm>
+
 namespace spcu {
 namespace {
 
@@ -143,6 +145,13 @@ constexpr int      kRefillMin      = SPCU_REFILL_MIN; // idle lanes that make a 
 #define SPCU_WALK_REFILL_MIN 4
 #endif
 constexpr int      kWalkRefillMin  = SPCU_WALK_REFILL_MIN; // ... when the set-up is three loads (the begin / walk kernels)
+// phase vote of the walk kernels: a pair leaf step runs when  pairs * NUM > lanes_at_a_node * DEN  (tuned on the GPU: profiles/)
+#ifndef SPCU_LEAF_VOTE_NUM
+#define SPCU_LEAF_VOTE_NUM 1
+#endif
+#ifndef SPCU_LEAF_VOTE_DEN
+#define SPCU_LEAF_VOTE_DEN 1
+#endif
 
 struct LaneFeed
 {
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
                 const RayRec rr = w.ray[slot];
                 const float4 o = rr.o, d = rr.d;
                 r               = Ray{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
-                inv            = make_inv(r);
+                inv            = make_inv(r, s.geom.proper_boxes != 0u);
                 float t_max = d.w, beta, gamma;
                 // Scene::intersect_lights (a handful of lights: walked in one go)
                 const LightPrimsT<F> lp{ s.lights };
@@ -323,7 +332,7 @@ __device__ __forceinline__ int32_t unpark_link(int32_t parked, bool& root_pendin
     return root_pending ? (parked ^ kPendingBit) : parked;
 }
 
-template <bool kCount, typename F>
+template <bool kCount, bool kOrdered, typename F>
 __global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                               const uint32_t* queue, const uint32_t* n_queue,
                                                               uint32_t* q_walk, uint32_t* n_walk,
@@ -355,18 +364,28 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_const
             ClosestWalk walk;
             walk.t_max = t_max;
             closest_begin<kCount>(s.geom, gp, r, walk, &local); // unbounded primitives; cursor at the root
-            Stack stack;
+            Stack        stack;
+            OrderedStack ostack;
             stack.sh = stack_smem + threadIdx.x;
-            const RayInv inv = make_inv(r);
-            if (at_node(walk)) {
-                closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local); // the root's two child boxes
-            } else if (at_leaf(walk)) {
-                closest_run<kCount>(s.geom, gp, r, inv, walk, stack, kAllLeaves, &local, __activemask()); // the root is a leaf
+            ostack.attach(stack_smem + threadIdx.x);
+            const RayInv inv = make_inv(r, s.geom.proper_boxes != 0u);
+            if (at_node(walk)) { // the root's two child boxes
+                if (kOrdered) {
+                    closest_node_step_ordered<kCount>(s.geom, r, inv, walk, ostack, &local);
+                } else {
+                    closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
+                }
+            } else if (at_leaf(walk)) { // the root is a leaf
+                if (kOrdered) {
+                    closest_run_ordered<kCount>(s.geom, gp, r, inv, walk, ostack, kAllLeaves, &local, __activemask());
+                } else {
+                    closest_run<kCount>(s.geom, gp, r, inv, walk, stack, kAllLeaves, &local, __activemask());
+                }
             }
             ex.hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
             done   = walk.link == kDone;
             parked = !done;
-            ex.pad[0] = __int_as_float(park_link(walk.link, stack.n > 0));
+            ex.pad[0] = __int_as_float(park_link(walk.link, (kOrdered ? ostack.n : stack.n) > 0));
             ex.pad[1] = __uint_as_float(walk.count);
             w.extend[slot] = ex;
             // finished vertices go to the shading stage sorted by material: misses in the last segment
@@ -383,12 +402,189 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_const
     }
 }
 
-template <bool kCount, typename F>
+// ---------------------------------------------------------------------------------------------------------------------
+// Leaf step with the warp's (ray, triangle) tests spread over all 32 lanes.
+//
+// In the per-lane leaf step a lane walks through its own leaf's triangles while every lane that is not at a leaf waits, and
+// the loop runs to the LARGEST leaf among them: ncu on the bunny scene showed the triangle test at 5-9 of 32 lanes.  Here the
+// lanes at a triangle leaf of up to kPairLeafMax primitives publish their (ray, triangle) PAIRS — an exclusive prefix sum of
+// the leaf sizes gives every pair a lane —, every lane fetches the ray of its pair's owner by shuffle and runs ONE triangle
+// test, and the owners then fold their results in list order.  The fold is the reference's sequence: ListAccelerator tests a
+// leaf's primitives in order and a hit shrinks t_max for the next one (shapes/ListAccelerator.h:50-62); the triangle test
+// depends on t_max only through its final `t > t_max` rejection (Triangle.h:141), so testing all of a leaf's triangles
+// against the t_max of ENTRY and re-applying that one comparison in order gives the same accepted hit, bit for bit.
+// Leaves that do not fit this round (more than 32 pairs in the warp) stay where they are and go first in the next one; mixed
+// leaves (spheres among the bounded primitives) and leaves of more than kPairLeafMax primitives run the per-lane loop.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPairLeafMax = 4; // k_max_leaf_elements (shapes/BVHAccelerator.h:211)
+
+struct PairPlan
+{
+    unsigned part_mask; // lanes whose leaf is tested in this round
+    uint32_t offset;    // participant: the lane that runs its first pair
+    uint32_t my_n;      // participant: primitives of its leaf; 0 otherwise
+    uint32_t total;     // pairs of this round, <= 32
+};
+
+__device__ __forceinline__ PairPlan plan_pairs(bool candidate, uint32_t n)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t  incl = candidate ? n : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) {
+            incl += v;
+        }
+    }
+    PairPlan   p;
+    const bool part = candidate && incl <= 32u; // a prefix of the candidates, in lane order
+    p.part_mask     = __ballot_sync(0xffffffffu, part);
+    p.my_n          = part ? n : 0u;
+    p.offset        = incl - (candidate ? n : 0u);
+    p.total         = p.part_mask ? __shfl_sync(0xffffffffu, incl, 31 - __clz(p.part_mask)) : 0u;
+    return p;
+}
+
+// owner lane and index within the owner's leaf of the pair this lane runs (lanes >= total: garbage, not used)
+__device__ __forceinline__ void pair_assignment(const PairPlan& p, uint8_t* tbl /* this warp's 32 bytes */, int& owner, uint32_t& k)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (uint32_t j = 0; j < kPairLeafMax; ++j) {
+        if (j < p.my_n) {
+            tbl[p.offset + j] = static_cast<uint8_t>(lane | (j << 5));
+        }
+    }
+    __syncwarp();
+    const uint8_t e = tbl[lane];
+    __syncwarp();
+    owner = e & 31;
+    k     = e >> 5;
+}
+
+__device__ __forceinline__ Ray fetch_ray(const Ray& r, int owner)
+{
+    Ray o;
+    o.ox    = __shfl_sync(0xffffffffu, r.ox, owner);
+    o.oy    = __shfl_sync(0xffffffffu, r.oy, owner);
+    o.oz    = __shfl_sync(0xffffffffu, r.oz, owner);
+    o.dx    = __shfl_sync(0xffffffffu, r.dx, owner);
+    o.dy    = __shfl_sync(0xffffffffu, r.dy, owner);
+    o.dz    = __shfl_sync(0xffffffffu, r.dz, owner);
+    o.t_min = __shfl_sync(0xffffffffu, r.t_min, owner);
+    return o;
+}
+
+// the walk's next cursor after a leaf: the pending right child (exact walk, re-tested there) / the nearest deferred child
+template <bool kOrdered, typename StackT>
+__device__ __forceinline__ void leaf_pop(const DAccel& acc, StackT& stack, ClosestWalk& w)
+{
+    if constexpr (kOrdered) {
+        ordered_pop(acc, stack, w);
+    } else {
+        if (stack.n > 0) {
+            w.link   = stack.pop();
+            w.retest = true;
+        } else {
+            w.link = kDone;
+        }
+    }
+}
+
+// All 32 lanes call.  `mine` = this lane holds a ray whose cursor is at a leaf.
+template <bool kCount, bool kOrdered, typename Prims, typename StackT>
+__device__ __forceinline__ void closest_leaf_step_pairs(const DAccel& acc, const Prims& prims, const Ray& r, ClosestWalk& w, StackT& stack,
+                                                        bool mine, uint8_t* tbl, TraceCounters* cnt)
+{
+    const int      lane      = threadIdx.x & 31;
+    const uint32_t n         = w.count & SPCU_LEAF_COUNT_MASK;
+    const bool     candidate = mine && !(w.count & SPCU_LEAF_MIXED_FLAG) && n <= kPairLeafMax;
+    const PairPlan p         = plan_pairs(candidate, n);
+    if (p.part_mask) {
+        int      owner;
+        uint32_t k;
+        pair_assignment(p, tbl, owner, k);
+        const Ray      pr    = fetch_ray(r, owner);
+        const float    ptmax = __shfl_sync(0xffffffffu, w.t_max, owner);
+        const uint32_t first = __shfl_sync(0xffffffffu, static_cast<uint32_t>(~w.link), owner);
+        float          t = 0.0f, beta = 0.0f, gamma = 0.0f;
+        bool           hit = false;
+        if (static_cast<uint32_t>(lane) < p.total) {
+            const uint32_t id = first + k;
+            const float4   a  = __ldg(prims.prims + 3 * id + 0);
+            const float4   b  = __ldg(prims.prims + 3 * id + 1);
+            const float4   c  = __ldg(prims.prims + 3 * id + 2);
+            if (kCount) ++cnt->tris;
+            hit = tri_hit(a, b, c, pr, ptmax, t, beta, gamma);
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        int            win  = -1;
+#pragma unroll
+        for (uint32_t j = 0; j < kPairLeafMax; ++j) { // the owners fold their leaf's results in list order
+            const int   src = min(static_cast<int>(p.offset + j), 31);
+            const float tj  = __shfl_sync(0xffffffffu, t, src);
+            if (j < p.my_n && ((hits >> src) & 1u) && !(tj > w.t_max)) {
+                const int32_t id = static_cast<int32_t>(static_cast<uint32_t>(~w.link) + j);
+                if (!kOrdered || tj < w.t_max || id > w.hit_id) {
+                    w.t_max  = tj;
+                    w.hit_id = id;
+                    win      = src;
+                }
+            }
+        }
+        const int   from = win >= 0 ? win : lane;
+        const float bw = __shfl_sync(0xffffffffu, beta, from), gw = __shfl_sync(0xffffffffu, gamma, from);
+        if (win >= 0) {
+            w.beta  = bw;
+            w.gamma = gw;
+        }
+        if ((p.part_mask >> lane) & 1u) { // participants (also those with an empty leaf) move on
+            leaf_pop<kOrdered>(acc, stack, w);
+        }
+    }
+    // leaves the pair scheme does not take: mixed or oversized (the per-lane loop, reference order)
+    const bool     other      = mine && !candidate;
+    const unsigned other_mask = __ballot_sync(0xffffffffu, other);
+    if (other) {
+        float          t, b, g;
+        const uint32_t first = static_cast<uint32_t>(~w.link);
+        const bool     mixed = (w.count & SPCU_LEAF_MIXED_FLAG) != 0u;
+        const uint32_t n_max = __reduce_max_sync(other_mask, n);
+#pragma unroll 1
+        for (uint32_t i = 0; i < n_max; ++i) {
+            const int32_t id = static_cast<int32_t>(first + i);
+            if (i < n && prims.template test<kCount>(first + i, mixed, r, w.t_max, t, b, g, cnt) &&
+                (!kOrdered || t < w.t_max || id > w.hit_id)) {
+                w.t_max  = t;
+                w.hit_id = id;
+                w.beta   = b;
+                w.gamma  = g;
+            }
+        }
+        leaf_pop<kOrdered>(acc, stack, w);
+    }
+}
+
+// Which phase the warp runs next: the one that puts more lanes to work.  A node step employs the lanes at a node, a pair
+// leaf step min(32, triangles of the waiting leaves) lanes.
+__device__ __forceinline__ bool vote_leaf_step(int n_node, bool at_leaf_lane, uint32_t leaf_n)
+{
+    const uint32_t pairs = __reduce_add_sync(0xffffffffu, at_leaf_lane ? min(leaf_n, kPairLeafMax) : 0u);
+    return static_cast<int>(min(pairs, 32u)) * SPCU_LEAF_VOTE_NUM > n_node * SPCU_LEAF_VOTE_DEN;
+}
+
+// Persistent kernels give up (kCntErrors -> SPCU_ERR_INTERNAL on the host) instead of spinning for ever on a corrupted cursor.
+constexpr uint32_t kWalkIterCap = 1u << 27;
+
+template <bool kCount, bool kOrdered, typename F>
 __global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                              const uint32_t* q_walk, const uint32_t* n_walk, uint32_t* cursor,
-                                                             const __grid_constant__ SortedQueue sorted, TraceCounters* cnt)
+                                                             const __grid_constant__ SortedQueue sorted,
+                                                             unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    __shared__ uint8_t pair_tbl[kTraceBlock];
     LaneFeed           feed;
     feed.cursor = cursor;
     feed.n      = *n_walk;
@@ -396,17 +592,24 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_consta
     TraceCounters       local{ 0, 0, 0 };
     const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     Stack               stack;
+    OrderedStack        ostack;
     stack.sh = stack_smem + threadIdx.x;
+    ostack.attach(stack_smem + threadIdx.x);
+    uint8_t*    tbl = pair_tbl + (threadIdx.x & ~31);
     Ray         r{};
     RayInv      inv{};
     ClosestWalk walk{};
     walk.link     = kDone;
-    uint32_t slot = 0;
+    uint32_t slot = 0, iters = 0;
     bool     have = false, drained = false;
 
     for (;;) {
         const int n_node = __popc(__ballot_sync(0xffffffffu, have && at_node(walk)));
         const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && at_leaf(walk)));
+        if (++iters > kWalkIterCap) {
+            if ((threadIdx.x & 31) == 0) atomicAdd(counters + kCntErrors, 1ull);
+            break;
+        }
         if (!drained && (32 - n_node - n_leaf >= kWalkRefillMin || n_node + n_leaf == 0)) {
             const uint32_t i = feed.draw(!have);
             drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
@@ -415,7 +618,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_consta
                 const RayRec    rr = w.ray[slot];
                 const ExtendRec ex = w.extend[slot];
                 r                  = Ray{ rr.o.x, rr.o.y, rr.o.z, rr.d.x, rr.d.y, rr.d.z, rr.o.w };
-                inv                = make_inv(r);
+                inv                = make_inv(r, s.geom.proper_boxes != 0u);
                 bool root_pending;
                 walk.link   = unpark_link(__float_as_int(ex.pad[0]), root_pending);
                 walk.count  = __float_as_uint(ex.pad[1]);
@@ -424,23 +627,38 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_consta
                 walk.t_max  = ex.hit.t;
                 walk.beta   = ex.hit.beta;
                 walk.gamma  = ex.hit.gamma;
-                stack.n     = 0;
+                stack.n = ostack.n = 0;
                 if (root_pending) {
-                    stack.push(s.geom.root);
+                    if (kOrdered) {
+                        // the root's other child waits with its entry distance: recomputed here (nothing has changed since
+                        // `begin` tested it) instead of travelling through the parked record
+                        NodeHalf c0, c1;
+                        load_node(s.geom.nodes, s.geom.root, c0, c1);
+                        bool  h0, h1;
+                        float e0, e1;
+                        slab_pair(s.geom.nodes, s.geom.root, c0, c1, r, inv, walk.t_max, h0, h1, e0, e1);
+                        const bool right_pending = walk.link == c0.child && walk.count == c0.count;
+                        ostack.push((s.geom.root << 1) | (right_pending ? 1 : 0), right_pending ? e1 : e0);
+                    } else {
+                        stack.push(s.geom.root);
+                    }
                 }
                 have = true;
             }
         } else if (n_node + n_leaf == 0) {
             break;
-        } else if (n_node >= n_leaf) {
+        } else if (!vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK) && n_node > 0) {
             if (have && at_node(walk)) {
-                closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
+                if (kOrdered) {
+                    closest_node_step_ordered<kCount>(s.geom, r, inv, walk, ostack, &local);
+                } else {
+                    closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
+                }
             }
+        } else if (kOrdered) {
+            closest_leaf_step_pairs<kCount, true>(s.geom, gp, r, walk, ostack, have && at_leaf(walk), tbl, &local);
         } else {
-            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
-            if (have && at_leaf(walk)) {
-                closest_leaf_step<kCount>(gp, r, walk, stack, &local, leaf_mask);
-            }
+            closest_leaf_step_pairs<kCount, false>(s.geom, gp, r, walk, stack, have && at_leaf(walk), tbl, &local);
         }
         if (have && walk.link == kDone) {
             w.extend[slot].hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
@@ -493,7 +711,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
             stack.sh = stack_smem + threadIdx.x;
             if (!hit) {
                 walk = AnyWalk{ s.geom.root, s.geom.root_count };
-                const RayInv inv = make_inv(r);
+                const RayInv inv = make_inv(r, s.geom.proper_boxes != 0u);
                 if (at_node(walk)) {
                     any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
                 } else if (at_leaf(walk)) {
@@ -525,12 +743,66 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
     }
 }
 
+// Any-hit leaf step with the pairs spread over the warp (see closest_leaf_step_pairs): the limits of an any-hit query never
+// change and its answer is "some primitive of a reachable leaf accepts", so the order of the tests is free.  Returns true
+// for the lanes whose leaf holds an accepted primitive (their query is over).
+template <bool kCount, typename Prims>
+__device__ __forceinline__ bool any_leaf_step_pairs(const DAccel& acc, const Prims& prims, const Ray& r, float t_max, AnyWalk& w,
+                                                    Stack& stack, bool mine, uint8_t* tbl, TraceCounters* cnt)
+{
+    const int      lane      = threadIdx.x & 31;
+    const uint32_t n         = w.count & SPCU_LEAF_COUNT_MASK;
+    const bool     candidate = mine && !(w.count & SPCU_LEAF_MIXED_FLAG) && n <= kPairLeafMax;
+    const PairPlan p         = plan_pairs(candidate, n);
+    bool           found     = false;
+    if (p.part_mask) {
+        int      owner;
+        uint32_t k;
+        pair_assignment(p, tbl, owner, k);
+        const Ray      pr    = fetch_ray(r, owner);
+        const float    ptmax = __shfl_sync(0xffffffffu, t_max, owner);
+        const uint32_t first = __shfl_sync(0xffffffffu, static_cast<uint32_t>(~w.link), owner);
+        bool           hit   = false;
+        if (static_cast<uint32_t>(lane) < p.total) {
+            const uint32_t id = first + k;
+            const float4   a  = __ldg(prims.prims + 3 * id + 0);
+            const float4   b  = __ldg(prims.prims + 3 * id + 1);
+            const float4   c  = __ldg(prims.prims + 3 * id + 2);
+            float          t, beta, gamma;
+            if (kCount) ++cnt->tris;
+            hit = tri_hit(a, b, c, pr, ptmax, t, beta, gamma);
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        if ((p.part_mask >> lane) & 1u) {
+            const unsigned my_lanes = p.my_n ? (((1u << p.my_n) - 1u) << p.offset) : 0u; // my_n <= 4, offset + my_n <= 32
+            found                   = (hits & my_lanes) != 0u;
+            if (found) {
+                w.link = kDone;
+            } else {
+                any_pop(acc, stack, w);
+            }
+        }
+    }
+    const bool     other      = mine && !candidate;
+    const unsigned other_mask = __ballot_sync(0xffffffffu, other);
+    if (other) {
+        auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
+            float t, b, g;
+            return prims.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
+        };
+        found = any_leaf_step(acc, geom_test, w, stack, cnt, other_mask);
+    }
+    return found;
+}
+
 template <bool kCount, typename F>
 __global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                              const uint32_t* q_walk, const uint32_t* n_walk, uint32_t light_index,
-                                                             uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit, TraceCounters* cnt)
+                                                             uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit,
+                                                             unsigned long long* counters, TraceCounters* cnt)
 {
     __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    __shared__ uint8_t pair_tbl[kTraceBlock];
     LaneFeed           feed;
     feed.cursor = cursor;
     feed.n      = *n_walk;
@@ -539,20 +811,21 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_consta
     const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     Stack               stack;
     stack.sh = stack_smem + threadIdx.x;
+    uint8_t* tbl = pair_tbl + (threadIdx.x & ~31);
     Ray      r{};
     RayInv   inv{};
     AnyWalk  walk{ kDone, 0 };
     float    t_max = 0.0f;
-    uint32_t slot  = 0;
+    uint32_t slot = 0, iters = 0;
     bool     have = false, drained = false, hit = false;
-    auto     geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
-        float t, b, g;
-        return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
-    };
 
     for (;;) {
         const int n_node = __popc(__ballot_sync(0xffffffffu, have && at_node(walk)));
         const int n_leaf = __popc(__ballot_sync(0xffffffffu, have && at_leaf(walk)));
+        if (++iters > kWalkIterCap) {
+            if ((threadIdx.x & 31) == 0) atomicAdd(counters + kCntErrors, 1ull);
+            break;
+        }
         if (!drained && (32 - n_node - n_leaf >= kWalkRefillMin || n_node + n_leaf == 0)) {
             const uint32_t i = feed.draw(!have);
             drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
@@ -562,7 +835,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_consta
                 const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
                 const ExtendRec ex = w.extend[slot];
                 r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
-                inv               = make_inv(r);
+                inv               = make_inv(r, s.geom.proper_boxes != 0u);
                 t_max             = lr.wi.w;
                 bool root_pending;
                 walk.link  = unpark_link(__float_as_int(ex.pad[0]), root_pending);
@@ -576,15 +849,13 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_consta
             }
         } else if (n_node + n_leaf == 0) {
             break;
-        } else if (n_node >= n_leaf) {
+        } else if (!vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK) && n_node > 0) {
             if (have && at_node(walk)) {
                 any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
             }
         } else {
-            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
-            if (have && at_leaf(walk)) {
-                hit = any_leaf_step(s.geom, geom_test, walk, stack, &local, leaf_mask);
-            }
+            const bool found = any_leaf_step_pairs<kCount>(s.geom, gp, r, t_max, walk, stack, have && at_leaf(walk), tbl, &local);
+            hit              = hit || found;
         }
         if (have && walk.link == kDone) {
             if (!q_lit) {
@@ -652,7 +923,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow(const __grid_constant__ 
                 const float4   p  = w.vertex[slot].p;
                 const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
                 r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
-                inv               = make_inv(r);
+                inv               = make_inv(r, s.geom.proper_boxes != 0u);
                 t_max             = lr.wi.w;
                 stack.n        = 0;
                 walk           = AnyWalk{ s.geom.root, s.geom.root_count };
@@ -769,7 +1040,54 @@ inline unsigned grid_for(uint64_t n)
     return static_cast<unsigned>((n + kTraceBlock - 1) / kTraceBlock);
 }
 
+// ---- ray batches through the wavefront's own stage kernels (spcu_extend_batch / spcu_shadow_batch) -------------------------
+// slot i of the wavefront state <- ray i; queue = 0 .. n-1
+__global__ void __launch_bounds__(kTraceBlock) k_batch_fill(const __grid_constant__ DWave w, const spcu_ray* rays, uint32_t n,
+                                                            uint32_t* queue, uint32_t* n_queue, bool shadow)
+{
+    const uint32_t i = blockIdx.x * kTraceBlock + threadIdx.x;
+    if (i == 0) {
+        *n_queue = n;
+    }
+    if (i < n) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 0); // o, t_min
+        const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1); // d, t_max
+        queue[i]       = i;
+        if (shadow) { // what shade leaves behind for a light sample: VertexRec::p, LightRec (light plane 0)
+            w.vertex[i].p = make_float4(a.x, a.y, a.z, 0.0f);
+            w.light[i]    = LightRec{ b, make_float4(a.w, 0.0f, 0.0f, 0.0f) };
+        } else {
+            w.ray[i] = RayRec{ a, b };
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTraceBlock) k_batch_gather_extend(const __grid_constant__ DWave w, uint32_t n, spcu_hit* hits,
+                                                                     spcu_hit* light_hits)
+{
+    const uint32_t i = blockIdx.x * kTraceBlock + threadIdx.x;
+    if (i < n) {
+        const ExtendRec ex = w.extend[i];
+        hits[i]            = spcu_hit{ ex.hit.id, ex.hit.t };
+        if (light_hits) {
+            light_hits[i] = spcu_hit{ ex.light, ex.light_t };
+        }
+    }
+}
+
 } // namespace
+
+void launch_batch_fill(const DWave& w, const spcu_ray* d_rays, uint32_t n, uint32_t* queue, uint32_t* d_n_queue, bool shadow,
+                       cudaStream_t st)
+{
+    k_batch_fill<<<std::max(1u, grid_for(n)), kTraceBlock, 0, st>>>(w, d_rays, n, queue, d_n_queue, shadow);
+}
+
+void launch_batch_gather_extend(const DWave& w, uint32_t n, spcu_hit* d_hits, spcu_hit* d_light_hits, cudaStream_t st)
+{
+    if (n == 0) return;
+    k_batch_gather_extend<<<grid_for(n), kTraceBlock, 0, st>>>(w, n, d_hits, d_light_hits);
+}
 
 void launch_trace_closest(const DScene& s, const spcu_ray* d_rays, uint64_t n, spcu_hit* d_hits, TraceCounters* d_cnt,
                           cudaStream_t st)
@@ -841,17 +1159,17 @@ static void launch_extend_features(const Launch& l, const DScene& s, const DWave
 }
 
 // begin + walk (scenes with a BVH, exact walk)
-template <bool kCount>
+template <bool kCount, bool kOrdered>
 static void launch_extend_split(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
                                 uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, uint32_t* q_walk, uint32_t* d_n_walk,
                                 unsigned long long* d_counters, TraceCounters* d_cnt)
 {
-    static const int occ_b = trace_ctas_per_sm(k_extend_begin<kCount, FeatFull>);
-    static const int occ_w = trace_ctas_per_sm(k_extend_walk<kCount, FeatFull>);
-    k_extend_begin<kCount, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
+    static const int occ_b = trace_ctas_per_sm(k_extend_begin<kCount, kOrdered, FeatFull>);
+    static const int occ_w = trace_ctas_per_sm(k_extend_walk<kCount, kOrdered, FeatFull>);
+    k_extend_begin<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
         s, w, queue, d_n_queue, q_walk, d_n_walk, sorted, d_counters, d_cnt);
-    k_extend_walk<kCount, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
-        s, w, q_walk, d_n_walk, d_cursor, sorted, d_cnt);
+    k_extend_walk<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
+        s, w, q_walk, d_n_walk, d_cursor, sorted, d_counters, d_cnt);
 }
 
 int launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
@@ -863,14 +1181,16 @@ int launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32
         launch_extend_features<FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
         return 1;
     }
-    if (ordered || !q_walk) {
+    if (!q_walk) {
         launch_extend_features<FeatFull>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, ordered, d_counters, d_cnt);
         return 1;
     }
     if (d_cnt) {
-        launch_extend_split<true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt);
+        ordered ? launch_extend_split<true, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt)
+                : launch_extend_split<true, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt);
     } else {
-        launch_extend_split<false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr);
+        ordered ? launch_extend_split<false, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr)
+                : launch_extend_split<false, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr);
     }
     return 2;
 }
@@ -899,7 +1219,7 @@ int launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32
         k_shadow_begin<false, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
             s, w, queue, d_n_queue, light_index, q_walk, d_n_walk, q_lit, d_n_lit, d_counters, nullptr);
         k_shadow_walk<false, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
-            s, w, q_walk, d_n_walk, light_index, d_cursor, q_lit, d_n_lit, nullptr);
+            s, w, q_walk, d_n_walk, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
         return 2;
     }
     if (d_cnt) {

@@ -23,6 +23,19 @@ def tile_partition(rank: int, world: int, spp: int, integrator: str = "iterative
     return Partition(rank, world, 0, spp, spp, INTEGRATORS[integrator], seed)
 
 
+def init_product_comm(ctx) -> None:
+    """Form the product library's own NCCL communicator over the ranks of the torch.distributed job: rank 0 draws the
+    ncclUniqueId (spcu_comm_unique_id), torch.distributed only CARRIES its 128 bytes to the other ranks (what mpirun or a
+    shared file would do), every rank joins with spcu_comm_init_rank.  The frame's reduction then runs inside libspcu.so
+    (spcu_reduce_to_root / spcu_render_frame_reduced), not in Python."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    box = [ctx.comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init_rank(dist.get_world_size(), dist.get_rank(), box[0])
+
+
 def reduce_to_root(*tensors) -> None:
     """Sum the accumulators of all ranks into rank 0 (NCCL over NVLink for CUDA tensors, gloo for CPU tensors)."""
     import torch.distributed as dist

@@ -78,6 +78,21 @@ def bumpy_sphere(n_tris: int, lo, hi) -> tuple[np.ndarray, np.ndarray]:
     return v.astype("<f4"), faces.astype("<i4")
 
 
+def chain_mesh(n_tris: int = 58) -> tuple[np.ndarray, np.ndarray]:
+    """A mesh whose spatial-median BVH is a CHAIN: triangle i lies in the plane x = 1e10 * 0.45^i (object space; the scene
+    scales it by 1e-10) with a size proportional to its distance from the origin (a self-similar cone).
+    BVHAccelerator::construct (shapes/BVHAccelerator.h:175-209) splits at the centre of the node's bounds along x, which
+    peels ONE triangle off per level: depth = n_tris - 4, far beyond the 24 traversal-stack levels the kernels keep in shared
+    memory.  A ray aimed at the apex crosses every triangle, so the reference-order walk leaves a pending right child at
+    every level.  (The object-space scale keeps sqr_length(face normal) of the smallest triangle above float underflow:
+    read_ply drops faces where it is exactly 0, base/PlyReader.cpp:497.)"""
+    x = 1e10 * 0.45 ** np.arange(n_tris, dtype=np.float64)
+    s = 0.2 * x
+    v = np.stack([np.stack([x, -s, -s], 1), np.stack([x, s, -s], 1), np.stack([x, 0 * s, s], 1)], axis=1).reshape(-1, 3)
+    f = np.arange(3 * n_tris, dtype=np.int64).reshape(-1, 3)
+    return v.astype("<f4"), f.astype("<i4")
+
+
 def write_ply(path: Path, verts: np.ndarray, faces: np.ndarray) -> None:
     header = (
         "ply\n"
@@ -277,6 +292,36 @@ def sp_lucy(w: int, h: int, ply: str) -> str:
             "environment_light {\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 1.0 1.0 1.3\n}\n")
 
 
+def sp_chain(w: int, h: int, ply: str) -> str:
+    """The chain mesh (deep BVH) seen from outside the cone, on a plane, under one sphere light."""
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: 3.0 0.12 0.06\n    look_at: 0.0 0.0 0.0\n    fov: 30\n}\n\n" +
+            _MATERIALS_SPHERES + "\n" +
+            f"mesh {{\n    file: \"{ply}\"\n    scale: 1e-10 1e-10 1e-10\n    material: \"material_glossy\"\n}}\n\n"
+            "plane {\n    material: \"material_lambertian\"\n    translate: 0.0 -0.25 0.0\n}\n\n"
+            "sphere_light {\n    translate: 1.0 2.0 1.0\n    scale: 0.3 0.3 0.3\n    radiance: 10.0 10.0 10.0\n}\n")
+
+
+def sp_many_lights(w: int, h: int) -> str:
+    """Seven sphere lights + a constant environment: Scene's lights accelerator (base/Scene.h:29-45) becomes
+    [environment, BVH(7 sphere lights)] with INTERNAL nodes (k_max_leaf_elements = 4), so Scene::intersect_lights walks
+    NodeInternal::intersect_lights (shapes/BVHAccelerator.h:45-60).  Geometry: three spheres on a plane."""
+    lights = ""
+    for i, (x, y, z, r) in enumerate(((-3.0, 3.0, 1.0, 0.35), (-2.0, 4.0, -1.0, 0.25), (-0.8, 3.5, 2.0, 0.3), (0.5, 4.5, 0.0, 0.4),
+                                      (1.6, 3.2, -2.0, 0.3), (2.6, 3.8, 1.5, 0.25), (3.4, 2.8, -0.5, 0.35))):
+        c = (6.0 + 2.0 * (i % 3), 6.0 + 1.5 * ((i + 1) % 3), 6.0 + 2.5 * ((i + 2) % 3))
+        lights += (f"sphere_light {{\n    translate: {x} {y} {z}\n    scale: {r} {r} {r}\n"
+                   f"    radiance: {c[0]} {c[1]} {c[2]}\n}}\n\n")
+    return (_head(w, h) +
+            "perspective_camera {\n    origin: 0.0 2.5 9.0\n    look_at: 0.0 1.5 0.0\n    fov: 45\n}\n\n" +
+            _MATERIALS_SPHERES + "\n" +
+            "sphere {\n    translate: -2.0 1.0 0.0\n    material: \"material_glossy_clearcoat\"\n}\n\n"
+            "sphere {\n    translate: 0.0 1.0 0.0\n    material: \"material_lambertian\"\n}\n\n"
+            "sphere {\n    translate: 2.0 1.0 0.0\n    material: \"material_glossy\"\n}\n\n"
+            "plane {\n    material: \"material_glossy_plane\"\n}\n\n" + lights +
+            "environment_light {\n    rotate: 0.0 1.0 0.0 45.0\n    radiance: 0.2 0.2 0.25\n}\n")
+
+
 # Stanford-bunny object-space bounds (public figures; consistent with the plane at y = 0.329874 after x10).
 BUNNY_LO, BUNNY_HI = (-0.0947, 0.0329874, -0.0619), (0.0610, 0.1873, 0.0588)
 # elf: stands on the plane at y = -42.7188, centred on the camera axis x = -1.795, z ~ 13.8
@@ -304,12 +349,16 @@ def _specs():
         "t_bunny_full": (480, 270, 4, lambda o: sp_bunny(480, 270, _ply(o, "bunny", BUNNY_TRIS, BUNNY_LO, BUNNY_HI))),
         "t_elf": (120, 90, 4, lambda o: sp_elf(120, 90, _ply(o, "elf_small", 20_000, ELF_LO, ELF_HI))),
         "t_lucy": (128, 72, 4, lambda o: sp_lucy(128, 72, _ply(o, "lucy_small", 40_002, LUCY_LO, LUCY_HI))),
+        # a million-triangle statue at the lucy framing: the >= 10^6-primitive parity case (tests/test_gpu_scale.py)
+        "t_lucy_1m": (256, 144, 4, lambda o: sp_lucy(256, 144, _ply(o, "lucy_1m", 1_000_002, LUCY_LO, LUCY_HI))),
         # tiny versions whose flattened form is committed under tests/golden/ (tests/golden/make_golden.py)
         "g_spheres": (32, 32, 4, lambda o: sp_material_spheres(32, 32, "const")),
         "g_spheres_ibl": (32, 32, 4, lambda o: sp_material_spheres(32, 32, _pfm(o, 32, 16))),
         "g_example": (48, 27, 4, lambda o: sp_example_scene(48, 27)),
         "g_bunny": (48, 27, 4, lambda o: sp_bunny(48, 27, _ply(o, "bunny_tiny", 420, BUNNY_LO, BUNNY_HI))),
         "g_elf": (32, 24, 4, lambda o: sp_elf(32, 24, _ply(o, "elf_tiny", 1_500, ELF_LO, ELF_HI))),
+        "g_chain": (32, 24, 4, lambda o: sp_chain(32, 24, _chain_ply(o, 58))),
+        "g_lights": (32, 24, 4, lambda o: sp_many_lights(32, 24)),
     }
 
 
@@ -317,6 +366,14 @@ def _ply(out: Path, stem: str, n_tris: int, lo, hi) -> str:
     path = out / f"{stem}_{n_tris}.ply"
     if not path.exists():
         v, f = bumpy_sphere(n_tris, lo, hi)
+        write_ply(path, v, f)
+    return path.name
+
+
+def _chain_ply(out: Path, n_tris: int) -> str:
+    path = out / f"chain_{n_tris}.ply"
+    if not path.exists():
+        v, f = chain_mesh(n_tris)
         write_ply(path, v, f)
     return path.name
 

@@ -28,15 +28,16 @@ from simplepath_b200.flat import FlatSceneData  # noqa: E402
 import raybatches  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
-NAMES = ["g_spheres", "g_spheres_ibl", "g_example", "g_bunny", "g_elf"]
-RENDERS = {"g_spheres": 1024, "g_spheres_ibl": 1024, "g_example": 1024, "g_bunny": 1024, "g_elf": 1024}
+NAMES = ["g_spheres", "g_spheres_ibl", "g_example", "g_bunny", "g_elf", "g_chain", "g_lights"]
+RENDERS = {"g_spheres": 1024, "g_spheres_ibl": 1024, "g_example": 1024, "g_bunny": 1024, "g_elf": 1024, "g_chain": 1024,
+           "g_lights": 1024}
 N_EACH = 4096
 
 
 def main() -> None:
     if not ref.available():
         raise SystemExit("oracle/_ref/libsp_ref.so missing: run `make -C oracle` where /root/reference exists")
-    for name in NAMES:
+    for name in (sys.argv[1:] or NAMES):   # python tests/golden/make_golden.py [scene ...]
         path = scenes.ensure(name)
         w, h, spp = scenes.info(name)
         rs = ref.RefScene(path)
@@ -49,6 +50,8 @@ def main() -> None:
         out["cam_pix"], out["cam_smp"] = pix, smp
         cam = rs.generate_rays(pix, smp, spp)
         batches = {"camera": cam, **raybatches.all_batches(flat, N_EACH)}
+        if name == "g_chain":   # deep-stack rays through the chain BVH (depth 54 > the 24 shared-memory stack levels)
+            batches["cone"] = raybatches.cone_rays(N_EACH)
         for bname, rays in batches.items():
             hits, cnt = rs.trace_closest(rays, counters=True)
             out[f"{bname}.rays"] = rays.view(np.float32).reshape(-1, 8)

@@ -105,6 +105,28 @@ def grazing_rays(flat_data, n: int, seed: int = 999) -> np.ndarray:
     return _pack(o, d, 1e-3, FLT_MAX)
 
 
+def cone_rays(n: int, seed: int = 31337) -> np.ndarray:
+    """For the chain mesh of simplepath_b200.scenes.chain_mesh (a self-similar cone of triangles around the +x axis with
+    its apex at the origin): rays that cross MANY of its nested node boxes — from outside towards the apex (the
+    reference-order walk then leaves a pending right child at every level: the deepest traversal stack) and from next to
+    the apex outwards, starting between two triangles at a random level (the ordered walk's deepest stack)."""
+    rng = np.random.default_rng(seed)
+    half = n // 2
+    m = rng.uniform(-0.12, 0.12, size=(n, 2))                   # slopes inside the cone (its half-width is 0.2 x)
+    o = np.empty((n, 3))
+    d = np.empty((n, 3))
+    x_out = rng.uniform(1.2, 3.0, size=half)
+    o[:half] = np.stack([x_out, m[:half, 0] * x_out, m[:half, 1] * x_out], axis=1)
+    aim = rng.normal(scale=1e-3, size=(half, 3)) * rng.choice([0.0, 1.0], size=(half, 1))   # half of them exactly at the apex
+    d[:half] = aim - o[:half]
+    k = rng.integers(0, 57, size=n - half)
+    x_in = 0.45 ** k * rng.uniform(0.5, 0.95, size=n - half)    # between triangle k and k + 1
+    o[half:] = np.stack([x_in, m[half:, 0] * x_in, m[half:, 1] * x_in], axis=1)
+    m2 = rng.uniform(-0.12, 0.12, size=(n - half, 2))
+    d[half:] = np.stack([np.ones(n - half), m2[:, 0], m2[:, 1]], axis=1)
+    return _pack(o.astype(np.float32), _unit(d), 0.0, FLT_MAX)
+
+
 def all_batches(flat_data, n_each: int) -> dict[str, np.ndarray]:
     return {
         "random": random_rays(flat_data, n_each),

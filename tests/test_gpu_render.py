@@ -15,7 +15,7 @@ from simplepath_b200 import capi
 from simplepath_b200.flat import FlatSceneData
 
 pytestmark = pytest.mark.gpu
-SCENES = ["g_spheres", "g_spheres_ibl", "g_example", "g_bunny", "g_elf"]
+SCENES = ["g_spheres", "g_spheres_ibl", "g_example", "g_bunny", "g_elf", "g_chain", "g_lights"]
 INTEGRATORS = ["iterative_rrnee", "brute_force_iterative_rr", "direct_lighting", "whitted"]
 
 
@@ -108,9 +108,11 @@ def test_pipelines_agree(ctx, scene):
         ctx.set_option(capi.OPT_PIPELINE, code)
         imgs[pname], _, _ = ctx.render(ctx.partition(seed=77))
     ctx.set_option(capi.OPT_PIPELINE, CURRENT["pipeline"])
-    a, b = imgs["paths"], imgs["wavefront"]
-    bad = (np.abs(a - b) > 2e-3 * (1.0 + np.abs(b))).any(axis=-1)
-    assert bad.mean() < 0.02
+    b = imgs["wavefront"]
+    for other in ("paths", "smwave"):
+        a   = imgs[other]
+        bad = (np.abs(a - b) > 2e-3 * (1.0 + np.abs(b))).any(axis=-1)
+        assert bad.mean() < 0.02, f"{name}: {other} differs from the queue wavefront on {bad.mean():.2%} of the pixels"
 
 
 def test_ordered_traversal_renders_the_same_image(ctx, scene):
@@ -120,12 +122,12 @@ def test_ordered_traversal_renders_the_same_image(ctx, scene):
         pytest.skip("the ordered walk is an option of the wavefront's extend stage")
     jitter = vec["jitter"]
     upload(ctx, flat, jitter)
-    exact, _, st_e = ctx.render(ctx.partition(seed=123))
-    ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_ORDERED)
+    ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_EXACT)
     try:
-        fast, _, st_f = ctx.render(ctx.partition(seed=123))
+        exact, _, st_e = ctx.render(ctx.partition(seed=123))
     finally:
-        ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_EXACT)
+        ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_ORDERED)  # the render default
+    fast, _, st_f = ctx.render(ctx.partition(seed=123))
     differing = (exact != fast).any(axis=-1).mean()
     assert differing < 0.002, f"{name}: {differing:.3%} of pixels differ between the exact and the ordered walk"
     assert abs(st_e["rays_closest"] - st_f["rays_closest"]) <= 0.001 * st_e["rays_closest"] + 4

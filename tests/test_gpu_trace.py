@@ -5,12 +5,16 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, golden_names
-from simplepath_b200.capi import RAY_DTYPE, HIT_DTYPE
+from simplepath_b200.capi import RAY_DTYPE, HIT_DTYPE, TRAVERSAL_EXACT, TRAVERSAL_ORDERED
 from simplepath_b200.flat import FlatSceneData
 import raybatches
 
 pytestmark = pytest.mark.gpu
-BATCHES = ["camera", "random", "segments", "axis", "grazing"]
+BATCHES = ["camera", "random", "segments", "axis", "grazing", "cone"]  # "cone": g_chain only (deep traversal stacks)
+
+
+def batches_of(vec):
+    return [b for b in BATCHES if f"{b}.rays" in vec]
 
 
 def ulp_diff(a, b):
@@ -32,6 +36,8 @@ def scene(request, ctx):
 @pytest.mark.parametrize("batch", BATCHES)
 def test_golden_batches(ctx, scene, batch):
     name, flat, vec = scene
+    if f"{batch}.rays" not in vec:
+        pytest.skip(f"{name} has no {batch} batch")
     rays = np.ascontiguousarray(vec[f"{batch}.rays"]).view(RAY_DTYPE).reshape(-1)
     hits, cnt = ctx.trace_closest_counted(rays)
     mism = int((hits["id"] != vec[f"{batch}.closest_id"]).sum())
@@ -100,7 +106,7 @@ def test_ordered_walk_mismatches_are_epsilon_ties(ctx, scene, oracle_port):
     name, flat, vec = scene
     total = differ = 0
     saved_nodes = saved_tris = 0
-    for bname, rays in {**{b: np.ascontiguousarray(vec[f"{b}.rays"]).view(RAY_DTYPE).reshape(-1) for b in BATCHES},
+    for bname, rays in {**{b: np.ascontiguousarray(vec[f"{b}.rays"]).view(RAY_DTYPE).reshape(-1) for b in batches_of(vec)},
                         **{f"fresh_{k}": v for k, v in raybatches.all_batches(flat, 1 << 15).items()}}.items():
         rays = rays.copy()
         exact, c_exact = ctx.trace_closest_counted(rays)
@@ -119,6 +125,76 @@ def test_ordered_walk_mismatches_are_epsilon_ties(ctx, scene, oracle_port):
         saved_tris += int(c_exact[1]) - int(c_fast[1])
     print(f"\n{name}: ordered walk differs from the reference-order walk on {differ} of {total} rays; "
           f"{saved_nodes} node visits and {saved_tris} triangle tests saved")
+    assert differ <= max(1, total // 5_000)
+
+
+# ---- the renderer's own traversal stages (begin + persistent walk, lane refill, warp-wide leaf steps) on ray batches ---------
+def extend_reference(flat, rays, lights_id, lights_t, oracle_port):
+    """Integrator.cpp:558-563 from the oracle's pieces: intersect_lights, then intersect with t_max shrunk to the light."""
+    shrunk = rays.copy()
+    hit = lights_id >= 0
+    shrunk["t_max"][hit] = lights_t[hit]
+    return oracle_port.trace_closest(flat.pointer(), shrunk)
+
+
+@pytest.mark.parametrize("batch", BATCHES)
+def test_extend_and_shadow_stages_on_golden_batches(ctx, scene, oracle_port, batch):
+    """spcu_extend_batch (exact walk) and spcu_shadow_batch run the kernels a frame runs; they must give the reference's
+    answers bit for bit: light hits and any-hit flags straight from the golden vectors, geometry hits from the oracle under
+    the light-shrunk limit."""
+    name, flat, vec = scene
+    if f"{batch}.rays" not in vec:
+        pytest.skip(f"{name} has no {batch} batch")
+    rays = np.ascontiguousarray(vec[f"{batch}.rays"]).view(RAY_DTYPE).reshape(-1).copy()
+    hits, lights = ctx.extend_batch(rays, TRAVERSAL_EXACT)
+    assert np.array_equal(lights["id"], vec[f"{batch}.lights_id"])
+    assert lights["t"].tobytes() == vec[f"{batch}.lights_t"].tobytes()
+    want = extend_reference(flat, rays, vec[f"{batch}.lights_id"], vec[f"{batch}.lights_t"], oracle_port)
+    assert int((hits["id"] != want["id"]).sum()) == 0, f"{name}/{batch}"
+    assert hits["t"].tobytes() == want["t"].tobytes()
+    assert np.array_equal(ctx.shadow_batch(rays), vec[f"{batch}.any"])
+
+
+def test_stage_batches_fresh_and_ragged(ctx, scene, oracle_port):
+    """Fresh 2^16-ray batches (every lane-refill / leaf-pair pattern the persistent walk can get into) and ragged sizes."""
+    name, flat, vec = scene
+    for bname, rays in raybatches.all_batches(flat, 1 << 16).items():
+        rays = rays.copy()
+        hits, lights = ctx.extend_batch(rays, TRAVERSAL_EXACT)
+        wl = oracle_port.trace_lights(flat.pointer(), rays)
+        assert np.array_equal(lights["id"], wl["id"]) and lights["t"].tobytes() == wl["t"].tobytes(), f"{name}/{bname}"
+        want = extend_reference(flat, rays, wl["id"], wl["t"], oracle_port)
+        assert int((hits["id"] != want["id"]).sum()) == 0, f"{name}/{bname}"
+        assert hits["t"].tobytes() == want["t"].tobytes()
+        assert np.array_equal(ctx.shadow_batch(rays), oracle_port.trace_any(flat.pointer(), rays)), f"{name}/{bname}"
+    rays = np.ascontiguousarray(vec["random.rays"]).view(RAY_DTYPE).reshape(-1)
+    for n in (0, 1, 31, 33, 127, 129):
+        hits, _ = ctx.extend_batch(rays[:n], TRAVERSAL_EXACT)
+        assert hits.shape == (n,)
+        assert ctx.shadow_batch(rays[:n]).shape == (n,)
+
+
+def test_ordered_extend_stage_mismatches_are_epsilon_ties(ctx, scene, oracle_port):
+    """The render's DEFAULT extend stage (ordered walk + warp-wide leaf steps) against the exact one: same bar as
+    test_ordered_walk_mismatches_are_epsilon_ties, and it must agree with the one-thread-per-ray ordered kernel exactly."""
+    name, flat, vec = scene
+    total = differ = 0
+    for bname, rays in {**{b: np.ascontiguousarray(vec[f"{b}.rays"]).view(RAY_DTYPE).reshape(-1) for b in batches_of(vec)},
+                        **{f"fresh_{k}": v for k, v in raybatches.all_batches(flat, 1 << 15).items()}}.items():
+        rays = rays.copy()
+        exact, lights = ctx.extend_batch(rays, TRAVERSAL_EXACT)
+        fast, lights2 = ctx.extend_batch(rays, TRAVERSAL_ORDERED)
+        assert lights.tobytes() == lights2.tobytes()
+        shrunk = rays.copy()
+        shrunk["t_max"][lights["id"] >= 0] = lights["t"][lights["id"] >= 0]
+        per_ray, _ = ctx.trace_closest_fast(shrunk)
+        assert fast.tobytes() == per_ray.tobytes(), f"{name}/{bname}: stage kernel and per-ray ordered kernel disagree"
+        bad = exact["id"] != fast["id"]
+        tied = bad & (exact["id"] >= 0) & (fast["id"] >= 0)
+        assert ulp_diff(exact["t"][tied], fast["t"][tied]).max(initial=0) <= 4, f"{name}/{bname}"
+        total += rays.shape[0]
+        differ += int(bad.sum())
+    print(f"\n{name}: ordered extend stage differs from the exact one on {differ} of {total} rays")
     assert differ <= max(1, total // 5_000)
 
 

@@ -661,6 +661,60 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
 // ([0, n_unbounded) the top-level list, then the bounded primitives as the reference holds them before
 // BVHAccelerator(first, last)); bounds, tree and the gather into leaf order all happen on the device, and the context's
 // geometry buffers end up exactly as spcu_upload_scene would have filled them from the flattener's output.
+// ---- 4-wide nodes (trace.cuh): wide node i = the grandchildren of binary node i (a child that is a leaf stands for itself) ----
+__global__ void k_build_wide(const float4* nodes, uint32_t n, float4* wide)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float    box[4][6];
+        int32_t  link[4];
+        uint32_t count[4];
+        int      m = 0;
+        const float4 v0 = nodes[4 * i + 0], v1 = nodes[4 * i + 1], v2 = nodes[4 * i + 2], v3 = nodes[4 * i + 3];
+        const float  own[2][6] = { { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y }, { v1.z, v1.w, v2.x, v2.y, v2.z, v2.w } };
+        const int32_t  cl[2]   = { __float_as_int(v3.x), __float_as_int(v3.y) };
+        const uint32_t cc[2]   = { __float_as_uint(v3.z), __float_as_uint(v3.w) };
+        for (int k = 0; k < 2; ++k) {
+            if (cl[k] < 0) { // a leaf child keeps its own box
+                for (int d = 0; d < 6; ++d) box[m][d] = own[k][d];
+                link[m]  = cl[k];
+                count[m] = cc[k];
+                ++m;
+                continue;
+            }
+            const float4* c  = nodes + 4 * static_cast<size_t>(cl[k]);
+            const float4  w0 = c[0], w1 = c[1], w2 = c[2], w3 = c[3];
+            const float   g[2][6] = { { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y }, { w1.z, w1.w, w2.x, w2.y, w2.z, w2.w } };
+            for (int j = 0; j < 2; ++j) {
+                for (int d = 0; d < 6; ++d) box[m][d] = g[j][d];
+                link[m]  = j == 0 ? __float_as_int(w3.x) : __float_as_int(w3.y);
+                count[m] = j == 0 ? __float_as_uint(w3.z) : __float_as_uint(w3.w);
+                ++m;
+            }
+        }
+        for (; m < 4; ++m) { // unused slot: a point box no ray of the NaN-free form enters, an empty leaf behind it
+            for (int d = 0; d < 6; ++d) box[m][d] = 3.0e38f;
+            link[m]  = ~0;
+            count[m] = 0u;
+        }
+        float4* o = wide + 8 * static_cast<size_t>(i);
+        o[0] = make_float4(box[0][0], box[0][1], box[0][2], box[0][3]);
+        o[1] = make_float4(box[0][4], box[0][5], box[1][0], box[1][1]);
+        o[2] = make_float4(box[1][2], box[1][3], box[1][4], box[1][5]);
+        o[3] = make_float4(box[2][0], box[2][1], box[2][2], box[2][3]);
+        o[4] = make_float4(box[2][4], box[2][5], box[3][0], box[3][1]);
+        o[5] = make_float4(box[3][2], box[3][3], box[3][4], box[3][5]);
+        o[6] = make_float4(__int_as_float(link[0]), __uint_as_float(count[0]), __int_as_float(link[1]), __uint_as_float(count[1]));
+        o[7] = make_float4(__int_as_float(link[2]), __uint_as_float(count[2]), __int_as_float(link[3]), __uint_as_float(count[3]));
+    }
+}
+
+void spcu::launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int sm_count, cudaStream_t st)
+{
+    if (n) {
+        k_build_wide<<<grid_for(n, sm_count), kBlock, 0, st>>>(d_nodes, n, d_wide);
+    }
+}
+
 // 0 into *flag when a primitive's bounds are not finite with lo <= hi (then the tree's boxes are not either)
 __global__ void k_bounds_proper(const spcu_bounds* bounds, uint32_t n, int* flag)
 {

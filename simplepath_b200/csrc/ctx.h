@@ -73,6 +73,7 @@ struct spcu_ctx
     // scene
     bool         have_scene = false;
     spcu::DScene ds{};
+    spcu::DevBuf geom_wide; // 4-wide copy of geom_nodes (built at upload)
     spcu::DevBuf geom_nodes, geom_prims, geom_shade, geom_meta, light_nodes, lights, light_order, materials, bxdfs, pool,
         jitter;
     uint64_t scene_bytes = 0;

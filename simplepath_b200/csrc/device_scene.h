@@ -12,6 +12,7 @@ namespace spcu {
 struct DAccel
 {
     const float4* nodes; // 4 x float4 per node (spcu_bvh_node)
+    const float4* wide;  // 8 x float4 per node: the 4-wide node of binary node i (trace.cuh); NULL without internal nodes
     int32_t       root;
     uint32_t      root_count;
     uint32_t      n_unbounded;

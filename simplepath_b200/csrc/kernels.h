@@ -38,6 +38,9 @@ int launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const
 void launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
                       const uint32_t* d_n_queue, uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
 
+// ---- build_kernels.cu: the 4-wide copy of the resident binary nodes (8 x float4 per node, trace.cuh) ------------------------
+void launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int sm_count, cudaStream_t st);
+
 // ---- shade_kernels.cu ------------------------------------------------------------------------------------------
 struct RenderParams
 {

@@ -94,6 +94,15 @@ static __device__ __noinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint
 // One draw call: returns its pair of words as floats in [0,1) and advances the path's draw counter.
 __host__ __device__ __forceinline__ void rng_next2(Rng& r, float& u0, float& u1)
 {
+#if defined(SPCU_RNG_WHOLE_BLOCK) && defined(__CUDA_ARCH__) // A/B only (profiles/): round 1's contract, a whole block per draw — NOT what the oracle draws
+    {
+        const uint4 w = philox_block(r.ctr, r.stream, r.seed_lo, r.seed_hi, r.pixel, r.sample);
+        ++r.ctr;
+        u0 = word_to_unit(w.x);
+        u1 = word_to_unit(w.y);
+        return;
+    }
+#endif
     const bool odd = (r.ctr & 1u) != 0u;
     uint32_t   a, b;
     if (odd && r.fresh) {

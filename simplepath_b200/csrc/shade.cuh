@@ -148,10 +148,36 @@ __device__ __forceinline__ float erfinv_sp(float a)
 }
 
 // ---- Beckmann distribution (materials/Material.h:213-267, materials/Material.cpp:14-157) --------------------------------
-// beckmann_sample11 (Material.cpp:14-92): Newton iteration with bisection safeguard, at most 9 rounds.
-__device__ __forceinline__ void beckmann_sample11(float cos_i, float U1, float U2, float& slope_x, float& slope_y)
+// beckmann_sample11 (Material.cpp:14-92): Newton iteration with bisection safeguard, at most 9 rounds.  What depends on the
+// incident direction alone — a third of the function, with erf, acos and exp in it — is split off (Sample11Setup): the
+// 16-sample albedo estimates of OneSampleMaterial call this 16 times with the SAME direction (bxdf_rho_microfacet).
+struct Sample11Setup
 {
-    if (cos_i > .9999f) {
+    bool  normal_incidence; // cos_i > .9999: the closed-form branch
+    float tan_i, c0, fit, normalization;
+};
+
+__device__ __forceinline__ Sample11Setup beckmann_sample11_setup(float cos_i)
+{
+    Sample11Setup s{};
+    s.normal_incidence = cos_i > .9999f;
+    if (s.normal_incidence) {
+        return s;
+    }
+    const float sin_i = sqrtf(max_std(0.0f, 1.0f - sqr(cos_i)));
+    s.tan_i           = sin_i / cos_i;
+    const float cot_i = 1.0f / s.tan_i;
+    s.c0              = erff(cot_i);
+    const float theta_i     = acosf(cos_i);
+    s.fit                   = 1.0f + theta_i * (-0.876f + theta_i * (0.4265f - 0.0594f * theta_i));
+    const float sqrt_pi_inv = 1.0f / sqrtf(kPi);
+    s.normalization         = 1.0f / (1.0f + s.c0 + sqrt_pi_inv * s.tan_i * expf(-cot_i * cot_i));
+    return s;
+}
+
+__device__ __forceinline__ void beckmann_sample11_draw(const Sample11Setup& st, float U1, float U2, float& slope_x, float& slope_y)
+{
+    if (st.normal_incidence) {
         const float r = sqrtf(-logf(1.0f - U1));
         float       s, c;
         sincosf(2.0f * kPi * U2, &s, &c);
@@ -159,20 +185,16 @@ __device__ __forceinline__ void beckmann_sample11(float cos_i, float U1, float U
         slope_y = r * s;
         return;
     }
-    const float sin_i = sqrtf(max_std(0.0f, 1.0f - sqr(cos_i)));
-    const float tan_i = sin_i / cos_i;
-    const float cot_i = 1.0f / tan_i;
+    const float tan_i = st.tan_i;
 
     float       a        = -1.0f;
-    float       c        = erff(cot_i);
+    float       c        = st.c0;
     const float sample_x = max_std(U1, 1e-6f);
 
-    const float theta_i = acosf(cos_i);
-    const float fit     = 1.0f + theta_i * (-0.876f + theta_i * (0.4265f - 0.0594f * theta_i));
-    float       b       = c - (1.0f + c) * powf(1.0f - sample_x, fit);
+    float b = c - (1.0f + c) * powf(1.0f - sample_x, st.fit);
 
     const float sqrt_pi_inv   = 1.0f / sqrtf(kPi);
-    const float normalization = 1.0f / (1.0f + c + sqrt_pi_inv * tan_i * expf(-cot_i * cot_i));
+    const float normalization = st.normalization;
 
     for (int it = 0; it < 9; ++it) {
         if (!(b >= a && b <= c)) {
@@ -193,6 +215,11 @@ __device__ __forceinline__ void beckmann_sample11(float cos_i, float U1, float U
     }
     slope_x = erfinv_sp(b);
     slope_y = erfinv_sp(2.0f * max_std(U2, 1e-6f) - 1.0f);
+}
+
+__device__ __forceinline__ void beckmann_sample11(float cos_i, float U1, float U2, float& slope_x, float& slope_y)
+{
+    beckmann_sample11_draw(beckmann_sample11_setup(cos_i), U1, U2, slope_x, slope_y);
 }
 
 // beckmann_sample (Material.cpp:94-114)
@@ -389,6 +416,59 @@ __device__ __forceinline__ MSample bxdf_sample(const spcu_bxdf& bx, V3 wo, Rng& 
     return s;
 }
 
+// BRDF::rho_impl (:299-310) for a MicrofacetReflection over a Beckmann distribution that samples visible normals — the
+// 16-sample albedo estimate behind every OneSampleMaterial::sample / eval / pdf of a glossy material, i.e. where the NEE stage
+// spends its time (ncu, profiles/r02b_*: 58 K thread instructions per vertex and light, nearly all of it in these loops).
+// The same samples from the same random numbers, with two algebraic facts used:
+//  * everything that depends on wo alone is computed once, not 16 times: the stretched direction and its azimuth
+//    (beckmann_sample, Material.cpp:94-114), the incidence-dependent third of beckmann_sample11, Lambda(wo);
+//  * a sample's term is  f * |cos wi| / pdf  with  f = r D G F / (4 ci co)  (MicrofacetReflection::eval, :424-440) and
+//    pdf = D G1(wo) |wo.wh| / co / (4 wo.wh)  (:442-449 over MicrofacetDistribution::pdf :185-192): D, ci and co cancel and
+//    the term is  r F (1 + Lambda(wo)) / (1 + Lambda(wo) + Lambda(wi)),  with F at wo.wh (= wi.wh for a mirror direction).
+// The rejections of bxdf_sample (wo.wh < 0, wi below the horizon) are kept; what the cancellation drops is the case D == 0
+// (the exponential underflowing for a SAMPLED normal: probability below e^-87) and rounding in the last digits — parity of this
+// stage with the oracle is per pixel up to rounding (tests/test_gpu_render.py), parity with the reference statistical.
+static __device__ __noinline__ V3 bxdf_rho_microfacet(const spcu_bxdf& bx, V3 wo, Rng& rng)
+{
+    if (wo.y == 0.0f) {
+        return v3(0, 0, 0); // bxdf_sample returns before it draws (:400): no random numbers consumed
+    }
+    const bool  flip = wo.y < 0.0f;
+    const V3    wv   = flip ? -wo : wo;
+    const float ax = bx.alpha_x, ay = bx.alpha_y;
+    const V3    ws = normalize(v3(ax * wv.x, wv.y, ay * wv.z));
+    float       cp, sp;
+    cos_sin_phi(ws, cp, sp);
+    const Sample11Setup st        = beckmann_sample11_setup(cos_theta(ws));
+    const float         one_lo    = 1.0f + beckmann_lambda(wo, ax, ay);
+    float               sum       = 0.0f;
+#pragma unroll 1
+    for (unsigned i = 0; i < kRhoEvals; ++i) {
+        float U1, U2, sx, sy;
+        rng_next2(rng, U1, U2);
+        beckmann_sample11_draw(st, U1, U2, sx, sy);
+        const float tmp = cp * sx - sp * sy;
+        sy              = sp * sx + cp * sy;
+        sx              = ax * tmp;
+        sy              = ay * sy;
+        V3 wh = normalize(v3(-sx, 1.0f, -sy));
+        if (flip) {
+            wh = -wh;
+        }
+        const float dp = dot(wo, wh);
+        if (!(dp > 0.0f) || wh.y == 0.0f) { // dp < 0: rejected; dp == 0: pdf = 0 / 0, rejected by `pdf > 0`; wh.y == 0: D = 0
+            continue;
+        }
+        const V3 wi = -wo + 2.0f * dp * wh;
+        if (!same_hemisphere(wo, wi)) {
+            continue;
+        }
+        const float f = fresnel_dielectric(dp, 1.0f, bx.ior);
+        sum += f * one_lo / (one_lo + beckmann_lambda(wi, ax, ay));
+    }
+    return bxdf_r(bx) * (sum / static_cast<float>(kRhoEvals));
+}
+
 // BRDF::rho: LambertianBRDF overrides it (:344-347, no random numbers); the others run BRDF::rho_impl (:299-310)
 template <typename F>
 __device__ __forceinline__ V3 bxdf_rho(const spcu_bxdf& bx, V3 wo, Rng& rng)
@@ -396,6 +476,11 @@ __device__ __forceinline__ V3 bxdf_rho(const spcu_bxdf& bx, V3 wo, Rng& rng)
     if (!(F::microfacet || F::specular_bxdf) || bx.kind == SPCU_BXDF_LAMBERT) {
         return bxdf_r(bx) * kPi;
     }
+#ifndef SPCU_RHO_LITERAL // (A/B switch: the literal loop below for every BxDF)
+    if (F::microfacet && bx.kind == SPCU_BXDF_MICROFACET && bx.sample_visible) {
+        return bxdf_rho_microfacet(bx, wo, rng);
+    }
+#endif
     V3 r = v3(0, 0, 0);
 #pragma unroll 1
     for (unsigned i = 0; i < kRhoEvals; ++i) {

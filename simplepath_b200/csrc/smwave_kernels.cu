@@ -71,6 +71,9 @@ struct SmQueues
     int      preferred; // the stage the CTA ran last
     uint32_t error;     // a bounded wait ran out: every warp leaves, the kernel reports kCntErrors (never a hung GPU)
 };
+#ifndef SPCU_SMWAVE_CAPS
+#define SPCU_SMWAVE_CAPS 1 // 0: A/B builds without the bounded waits
+#endif
 constexpr uint32_t kSpinCap = 1u << 22; // polls of a slot whose publication is in flight (normally a handful)
 constexpr uint32_t kIdleCap = 1u << 22; // consecutive empty scans (x 64 ns sleep) of a warp while paths are still live
 
@@ -122,7 +125,7 @@ __device__ __forceinline__ int q_pop(SmQueues& q, int stage, int lane)
     uint32_t          v;
     uint32_t          spins = 0;
     while ((v = *e) == 0u) {
-        if (++spins > kSpinCap) { // a lost publication: fail the render, do not hang the device
+        if (SPCU_SMWAVE_CAPS && ++spins > kSpinCap) { // a lost publication: fail the render, do not hang the device
             *reinterpret_cast<volatile uint32_t*>(&q.error) = 1u;
             return -1;
         }
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(kSmBlock, 1)
                 if (*reinterpret_cast<volatile uint32_t*>(&q.live) == 0u || *reinterpret_cast<volatile uint32_t*>(&q.error) != 0u) {
                     break;
                 }
-                if (++idle > kIdleCap) { // live paths but no queue ever fills again: a protocol fault, not a reason to hang
+                if (SPCU_SMWAVE_CAPS && ++idle > kIdleCap) { // live paths but no queue ever fills again: a protocol fault, not a reason to hang
                     *reinterpret_cast<volatile uint32_t*>(&q.error) = 1u;
                     break;
                 }

@@ -17,7 +17,6 @@ namespace spcu {
 
 constexpr int   kTraceBlock   = 128; // threads per CTA of every traversal kernel
 constexpr int   kStackShared  = 24;  // stack entries per thread kept in shared memory (bank-conflict free)
-constexpr int   kStackLocal   = SPCU_MAX_BVH_DEPTH + 2 - kStackShared; // overflow, thread-local
 constexpr float kInfinite     = FLT_MAX; // k_infinite_distance (base/Constants.h:16)
 constexpr float kRayEpsilon   = 0.001f;  // k_ray_epsilon (math/Ray.h:11)
 
@@ -43,6 +42,10 @@ __device__ __forceinline__ RayInv make_inv(const Ray& r, bool proper_boxes)
                     is_finite(r.oy) && is_finite(r.oz));
     return inv;
 }
+
+// for the walks that use 4-wide nodes where they can: `generic` also when the accelerator has none
+struct DAccel;
+__device__ __forceinline__ RayInv make_inv_wide(const Ray& r, const DAccel& acc);
 
 // _mm_dp_ps(a, b, 0x7F) (math/Vector3.h:742-746): (x*x' + y*y') + (z*z' + 0)
 __device__ __forceinline__ float dot_dpps(float ax, float ay, float az, float bx, float by, float bz)
@@ -321,18 +324,19 @@ using LightPrims = LightPrimsT<FeatFull>;
 // An entry is the index of an internal node whose RIGHT child is still to be tested (the reference tests it only
 // after the left subtree returned, with the t_max the left subtree left behind; BVHAccelerator.h:62-77).
 // ---------------------------------------------------------------------------------------------------------------
-struct Stack
+template <int kShared, int kCapacity>
+struct StackT
 {
     int32_t* sh; // &smem[threadIdx.x]
-    int32_t  loc[kStackLocal];
+    int32_t  loc[kCapacity - kShared];
     int      n = 0;
 
     __device__ __forceinline__ void push(int32_t v)
     {
-        if (n < kStackShared) {
+        if (n < kShared) {
             sh[n * kTraceBlock] = v;
         } else {
-            loc[n - kStackShared] = v;
+            loc[n - kShared] = v;
         }
         ++n;
     }
@@ -340,9 +344,10 @@ struct Stack
     __device__ __forceinline__ int32_t pop()
     {
         --n;
-        return (n < kStackShared) ? sh[n * kTraceBlock] : loc[n - kStackShared];
+        return (n < kShared) ? sh[n * kTraceBlock] : loc[n - kShared];
     }
 };
+using Stack = StackT<kStackShared, SPCU_MAX_BVH_DEPTH + 2>;
 
 struct NodeHalf
 {
@@ -351,14 +356,41 @@ struct NodeHalf
     uint32_t count;
 };
 
+// 256-bit read-only global load (sm_100+: LDG.E.256): 32-byte aligned address, ONE 32-byte sector per lane.  A walk's loads
+// are scattered — every lane of a warp reads another node — so the L1's cost is per (lane, sector) tag look-up, not per byte:
+// ncu on the bunny scene showed l1tex at 69 % of its peak with four 128-bit loads per 64-byte node, i.e. every sector looked
+// up twice.  Two 256-bit loads read the same node with half the look-ups.
+struct Float8
+{
+    float4 lo, hi;
+};
+
+__device__ __forceinline__ Float8 ldg256(const void* p)
+{
+    unsigned long long a, b, c, d; // (four 64-bit registers: cicc 12.9 crashes on eight float outputs in these kernels)
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    Float8 r;
+    r.lo = make_float4(__uint_as_float(static_cast<unsigned>(a)), __uint_as_float(static_cast<unsigned>(a >> 32)),
+                       __uint_as_float(static_cast<unsigned>(b)), __uint_as_float(static_cast<unsigned>(b >> 32)));
+    r.hi = make_float4(__uint_as_float(static_cast<unsigned>(c)), __uint_as_float(static_cast<unsigned>(c >> 32)),
+                       __uint_as_float(static_cast<unsigned>(d)), __uint_as_float(static_cast<unsigned>(d >> 32)));
+    return r;
+}
+
 __device__ __forceinline__ void load_node(const float4* nodes, int32_t idx, NodeHalf& c0, NodeHalf& c1)
 {
+#ifndef SPCU_NODE_LOAD_128 // (A/B switch: four 128-bit loads, as in round 1)
+    const Float8 a = ldg256(nodes + 4 * idx), b = ldg256(nodes + 4 * idx + 2);
+    c0 = { a.lo.x, a.lo.y, a.lo.z, a.lo.w, a.hi.x, a.hi.y, __float_as_int(b.hi.x), __float_as_uint(b.hi.z) };
+    c1 = { a.hi.z, a.hi.w, b.lo.x, b.lo.y, b.lo.z, b.lo.w, __float_as_int(b.hi.y), __float_as_uint(b.hi.w) };
+#else
     const float4 v0 = __ldg(nodes + 4 * idx + 0);
     const float4 v1 = __ldg(nodes + 4 * idx + 1);
     const float4 v2 = __ldg(nodes + 4 * idx + 2);
     const float4 v3 = __ldg(nodes + 4 * idx + 3);
     c0 = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, __float_as_int(v3.x), __float_as_uint(v3.z) };
     c1 = { v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, __float_as_int(v3.y), __float_as_uint(v3.w) };
+#endif
 }
 
 __device__ __forceinline__ void load_right(const float4* nodes, int32_t idx, NodeHalf& c1)
@@ -384,7 +416,10 @@ static __device__ __noinline__ unsigned slab_pair_literal(const float4* nodes, i
 __device__ __forceinline__ void slab_pair(const float4* nodes, int32_t idx, const NodeHalf& c0, const NodeHalf& c1, const Ray& r,
                                           const RayInv& inv, float t_max, bool& h0, bool& h1, float& e0, float& e1)
 {
-    if (inv.generic) {
+#ifndef SPCU_FAST_SLAB
+#define SPCU_FAST_SLAB 1 // 0: always the literal form (A/B builds)
+#endif
+    if (!SPCU_FAST_SLAB || inv.generic) {
         const unsigned m = slab_pair_literal(nodes, idx, r, inv, t_max, e0, e1);
         h0               = (m & 1u) != 0u;
         h1               = (m & 2u) != 0u;
@@ -533,9 +568,9 @@ __device__ __forceinline__ bool at_node(const ClosestWalk& w) { return w.link >=
 __device__ __forceinline__ bool at_leaf(const ClosestWalk& w) { return w.link < 0; }
 
 // precondition: at_node(w)
-template <bool kCount>
+template <bool kCount, typename StackS>
 __device__ __forceinline__ void closest_node_step(const DAccel& acc, const Ray& r, const RayInv& inv, ClosestWalk& w,
-                                                  Stack& stack, TraceCounters* cnt)
+                                                  StackS& stack, TraceCounters* cnt)
 {
     NodeHalf c0, c1;
     load_node(acc.nodes, w.link, c0, c1);
@@ -564,8 +599,8 @@ __device__ __forceinline__ void closest_node_step(const DAccel& acc, const Ray& 
 }
 
 // precondition: at_leaf(w) for every lane of `mask`, the lanes that call together
-template <bool kCount, typename Prims>
-__device__ __forceinline__ void closest_leaf_step(const Prims& prims, const Ray& r, ClosestWalk& w, Stack& stack,
+template <bool kCount, typename Prims, typename StackS>
+__device__ __forceinline__ void closest_leaf_step(const Prims& prims, const Ray& r, ClosestWalk& w, StackS& stack,
                                                   TraceCounters* cnt, unsigned mask)
 {
     float          t, b, g;
@@ -622,35 +657,38 @@ __device__ __forceinline__ int32_t closest_hit(const DAccel& acc, const Prims& p
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kStackSharedOrdered = 12; // 12 levels x 128 threads x 8 B = 12 KB, the same footprint as the exact walk
 
-struct OrderedStack
+template <int kShared, int kCapacity>
+struct OrderedStackT
 {
     int2* sh; // &smem[threadIdx.x]
-    int2  loc[SPCU_MAX_BVH_DEPTH + 2 - kStackSharedOrdered];
+    int2  loc[kCapacity - kShared];
     int   n = 0;
 
     __device__ __forceinline__ void attach(int32_t* stack_smem)
     {
-        sh = reinterpret_cast<int2*>(stack_smem - threadIdx.x) + threadIdx.x; // same 12 KB block, 8-byte entries
+        sh = reinterpret_cast<int2*>(stack_smem - threadIdx.x) + threadIdx.x; // the same shared block, 8-byte entries
     }
     __device__ __forceinline__ void push(int32_t key, float t0)
     {
         const int2 v = make_int2(key, __float_as_int(t0));
-        if (n < kStackSharedOrdered) {
+        if (n < kShared) {
             sh[n * kTraceBlock] = v;
         } else {
-            loc[n - kStackSharedOrdered] = v;
+            loc[n - kShared] = v;
         }
         ++n;
     }
     __device__ __forceinline__ int2 pop()
     {
         --n;
-        return (n < kStackSharedOrdered) ? sh[n * kTraceBlock] : loc[n - kStackSharedOrdered];
+        return (n < kShared) ? sh[n * kTraceBlock] : loc[n - kShared];
     }
 };
+using OrderedStack = OrderedStackT<kStackSharedOrdered, SPCU_MAX_BVH_DEPTH + 2>;
 
 // next deferred child that is still reachable, or kDone
-__device__ __forceinline__ void ordered_pop(const DAccel& acc, OrderedStack& stack, ClosestWalk& w)
+template <typename StackS>
+__device__ __forceinline__ void ordered_pop(const DAccel& acc, StackS& stack, ClosestWalk& w)
 {
     w.link = kDone;
     while (stack.n > 0) {
@@ -665,9 +703,9 @@ __device__ __forceinline__ void ordered_pop(const DAccel& acc, OrderedStack& sta
 }
 
 // one step of the ordered walk at an internal node (closest_run_ordered's node loop body)
-template <bool kCount>
+template <bool kCount, typename StackS>
 __device__ __forceinline__ void closest_node_step_ordered(const DAccel& acc, const Ray& r, const RayInv& inv, ClosestWalk& w,
-                                                          OrderedStack& stack, TraceCounters* cnt)
+                                                          StackS& stack, TraceCounters* cnt)
 {
     NodeHalf c0, c1;
     load_node(acc.nodes, w.link, c0, c1);
@@ -691,9 +729,9 @@ __device__ __forceinline__ void closest_node_step_ordered(const DAccel& acc, con
     }
 }
 
-template <bool kCount, typename Prims>
+template <bool kCount, typename Prims, typename StackS>
 __device__ __forceinline__ void closest_run_ordered(const DAccel& acc, const Prims& prims, const Ray& r, const RayInv& inv,
-                                                    ClosestWalk& w, OrderedStack& stack, int max_leaves, TraceCounters* cnt,
+                                                    ClosestWalk& w, StackS& stack, int max_leaves, TraceCounters* cnt,
                                                     unsigned mask)
 {
     float t, b, g;
@@ -791,7 +829,8 @@ struct AnyWalk
 };
 constexpr int kAnyRunning = 0, kAnyHit = 1, kAnyMiss = 2;
 
-__device__ __forceinline__ void any_pop(const DAccel& acc, Stack& stack, AnyWalk& w)
+template <typename StackS>
+__device__ __forceinline__ void any_pop(const DAccel& acc, StackS& stack, AnyWalk& w)
 {
     if (stack.n > 0) {
         const float4 v3 = __ldg(acc.nodes + 4 * stack.pop() + 3);
@@ -883,9 +922,9 @@ __device__ __forceinline__ bool any_hit(const DAccel& acc, const AnyTest& test, 
 __device__ __forceinline__ bool at_node(const AnyWalk& w) { return w.link >= 0 && w.link != kDone; }
 __device__ __forceinline__ bool at_leaf(const AnyWalk& w) { return w.link < 0; }
 
-template <bool kCount>
+template <bool kCount, typename StackS>
 __device__ __forceinline__ void any_node_step(const DAccel& acc, const Ray& r, const RayInv& inv, float t_max, AnyWalk& w,
-                                              Stack& stack, TraceCounters* cnt)
+                                              StackS& stack, TraceCounters* cnt)
 {
     NodeHalf c0, c1;
     load_node(acc.nodes, w.link, c0, c1);
@@ -908,9 +947,12 @@ __device__ __forceinline__ void any_node_step(const DAccel& acc, const Ray& r, c
 }
 
 // returns true when a primitive of the leaf is hit (the query is over); otherwise the walk moves on
-template <typename AnyTest>
-__device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& test, AnyWalk& w, Stack& stack,
-                                              TraceCounters* cnt, unsigned mask)
+__device__ __forceinline__ void wide_child_of_key(const float4* wide, int32_t key, int32_t& link, uint32_t& count);
+
+// (`wide_keys`: the stack holds keys of 4-wide nodes — see "4-wide nodes" below — instead of binary node indices)
+template <typename AnyTest, typename StackS>
+__device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& test, AnyWalk& w, StackS& stack,
+                                              TraceCounters* cnt, unsigned mask, bool wide_keys = false)
 {
     const uint32_t first = static_cast<uint32_t>(~w.link);
     const uint32_t n     = w.count & SPCU_LEAF_COUNT_MASK;
@@ -925,10 +967,174 @@ __device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& 
     }
     if (hit) {
         w.link = kDone;
-    } else {
+    } else if (!wide_keys) {
         any_pop(acc, stack, w);
+    } else if (stack.n > 0) {
+        wide_child_of_key(acc.wide, stack.pop(), w.link, w.count);
+    } else {
+        w.link = kDone;
     }
     return hit;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 4-wide nodes: the reference topology with every other level folded away (device_scene.h DAccel::wide, built at upload
+// by k_build_wide, build_kernels.cu).  Wide node i belongs to binary node i and holds the boxes of its GRANDCHILDREN — or of
+// a child where that child is a leaf —, in the reference's left-to-right order:
+//     floats  0..23  four boxes  { lo.xyz hi.xyz }            (an unused slot is a point box at +3e38: never entered)
+//     words  24..31  four { link, count } pairs               (link / count as in spcu_bvh_node; unused: leaf of 0 primitives)
+// 128 bytes = four 256-bit loads.  The walks of the render's traversal stages are bound by the LATENCY of one dependent node
+// fetch per step and by the L1's look-up rate for scattered sectors, not by arithmetic (ncu, profiles/r02b_*: long-scoreboard
+// and fixed-latency stalls 7.4 of 11.4 cycles per issued instruction, l1tex at 69 % of peak); a wide step does the work of
+// two binary levels behind ONE fetch, and its four slab tests are independent instruction streams.
+// Skipping the child's own box is exact wherever the slab test is monotone under box inclusion — the child's box contains
+// its children's, so it passes whenever one of them does — i.e. for every ray and box of the NaN-free form (slab_fast);
+// rays with an infinite reciprocal take the binary walk over the reference's nodes (the `generic` flag).
+// Only the ORDERED closest-hit walk and the any-hit walk use wide nodes: their answers do not depend on the visiting order
+// (up to the epsilon ties stated for the ordered walk).  The exact walk stays on the binary nodes.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kWideStackCapacity = 3 * (SPCU_MAX_BVH_DEPTH / 2 + 1) + 2; // up to three deferred children per wide level
+constexpr int kWideSharedAny     = 24;                                    // 4-byte keys: [24][128] = the 12 KB block
+constexpr int kWideSharedOrdered = 16;                                    // 8-byte (key, entry distance): needs [32][128] words
+using WideStack        = StackT<kWideSharedAny, kWideStackCapacity>;
+using WideOrderedStack = OrderedStackT<kWideSharedOrdered, kWideStackCapacity>;
+
+struct WideNode
+{
+    Float8 q0, q1, q2, q3;
+};
+
+__device__ __forceinline__ WideNode load_wide(const float4* wide, int32_t idx)
+{
+    const float4* p = wide + 8 * static_cast<size_t>(idx);
+    return WideNode{ ldg256(p), ldg256(p + 2), ldg256(p + 4), ldg256(p + 6) };
+}
+
+// the four slab tests of a wide node (NaN-free form); h = hit mask, e[k] = entry distance of box k (valid where hit)
+__device__ __forceinline__ unsigned wide_slabs(const WideNode& n, const Ray& r, const RayInv& inv, float t_max, float (&e)[4])
+{
+    const bool h0 = slab_fast(n.q0.lo.x, n.q0.lo.y, n.q0.lo.z, n.q0.lo.w, n.q0.hi.x, n.q0.hi.y, r, inv, t_max, e[0]);
+    const bool h1 = slab_fast(n.q0.hi.z, n.q0.hi.w, n.q1.lo.x, n.q1.lo.y, n.q1.lo.z, n.q1.lo.w, r, inv, t_max, e[1]);
+    const bool h2 = slab_fast(n.q1.hi.x, n.q1.hi.y, n.q1.hi.z, n.q1.hi.w, n.q2.lo.x, n.q2.lo.y, r, inv, t_max, e[2]);
+    const bool h3 = slab_fast(n.q2.lo.z, n.q2.lo.w, n.q2.hi.x, n.q2.hi.y, n.q2.hi.z, n.q2.hi.w, r, inv, t_max, e[3]);
+    return (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
+}
+
+__device__ __forceinline__ void wide_child(const WideNode& n, unsigned slot, int32_t& link, uint32_t& count)
+{
+    const float l = slot == 0u ? n.q3.lo.x : slot == 1u ? n.q3.lo.z : slot == 2u ? n.q3.hi.x : n.q3.hi.z;
+    const float c = slot == 0u ? n.q3.lo.y : slot == 1u ? n.q3.lo.w : slot == 2u ? n.q3.hi.y : n.q3.hi.w;
+    link  = __float_as_int(l);
+    count = __float_as_uint(c);
+}
+
+// { link, count } of child `key & 3` of wide node `key >> 2`: one 8-byte load
+__device__ __forceinline__ void wide_child_of_key(const float4* wide, int32_t key, int32_t& link, uint32_t& count)
+{
+    const float2 lc = __ldg(reinterpret_cast<const float2*>(wide + 8 * static_cast<size_t>(key >> 2) + 6) + (key & 3));
+    link  = __float_as_int(lc.x);
+    count = __float_as_uint(lc.y);
+}
+
+// next deferred child that is still reachable, or kDone (wide keys)
+__device__ __forceinline__ void wide_ordered_pop(const DAccel& acc, WideOrderedStack& stack, ClosestWalk& w)
+{
+    w.link = kDone;
+    while (stack.n > 0) {
+        const int2 e = stack.pop();
+        if (!(__int_as_float(e.y) > w.t_max)) { // entry not beyond the current hit
+            wide_child_of_key(acc.wide, e.x, w.link, w.count);
+            return;
+        }
+    }
+}
+
+// One step of the ordered walk at an internal node, over its wide node: the nearest of the (up to four) boxes the ray enters
+// becomes the cursor, the others wait on the stack, farthest first (so the nearest of them is popped first).  Equal entry
+// distances keep the reference's left-to-right order.
+template <bool kCount>
+__device__ __forceinline__ void closest_wide_step_ordered(const DAccel& acc, const Ray& r, const RayInv& inv, ClosestWalk& w,
+                                                          WideOrderedStack& stack, TraceCounters* cnt)
+{
+    const int32_t  idx = w.link;
+    const WideNode n   = load_wide(acc.wide, idx);
+    if (kCount) ++cnt->nodes;
+    float          e[4];
+    const unsigned h = wide_slabs(n, r, inv, w.t_max, e);
+    if (h == 0u) {
+        wide_ordered_pop(acc, stack, w);
+        return;
+    }
+    // sort (distance, slot) ascending; a box that is not entered sorts last (+inf)
+    const float inf = __int_as_float(0x7f800000);
+    float    k0 = (h & 1u) ? e[0] : inf, k1 = (h & 2u) ? e[1] : inf, k2 = (h & 4u) ? e[2] : inf, k3 = (h & 8u) ? e[3] : inf;
+    unsigned s0 = 0u, s1 = 1u, s2 = 2u, s3 = 3u;
+#define SPCU_CSWAP(ka, sa, kb, sb)        \
+    {                                     \
+        const bool     sw = kb < ka;      \
+        const float    tk = sw ? kb : ka; \
+        const unsigned ts = sw ? sb : sa; \
+        kb                = sw ? ka : kb; \
+        sb                = sw ? sa : sb; \
+        ka                = tk;           \
+        sa                = ts;           \
+    }
+    SPCU_CSWAP(k0, s0, k1, s1)
+    SPCU_CSWAP(k2, s2, k3, s3)
+    SPCU_CSWAP(k0, s0, k2, s2)
+    SPCU_CSWAP(k1, s1, k3, s3)
+    SPCU_CSWAP(k1, s1, k2, s2)
+#undef SPCU_CSWAP
+    if (k3 < inf) stack.push((idx << 2) | static_cast<int32_t>(s3), k3);
+    if (k2 < inf) stack.push((idx << 2) | static_cast<int32_t>(s2), k2);
+    if (k1 < inf) stack.push((idx << 2) | static_cast<int32_t>(s1), k1);
+    wide_child(n, s0, w.link, w.count);
+}
+
+__device__ __forceinline__ void wide_any_pop(const DAccel& acc, WideStack& stack, AnyWalk& w)
+{
+    if (stack.n > 0) {
+        wide_child_of_key(acc.wide, stack.pop(), w.link, w.count);
+    } else {
+        w.link = kDone;
+    }
+}
+
+// One step of the any-hit walk over a wide node: the limits never change, so the order is free — the first entered box
+// becomes the cursor, the others wait.
+template <bool kCount>
+__device__ __forceinline__ void any_wide_step(const DAccel& acc, const Ray& r, const RayInv& inv, float t_max, AnyWalk& w,
+                                              WideStack& stack, TraceCounters* cnt)
+{
+    const int32_t  idx = w.link;
+    const WideNode n   = load_wide(acc.wide, idx);
+    if (kCount) ++cnt->nodes;
+    float    e[4];
+    unsigned h = wide_slabs(n, r, inv, t_max, e);
+    if (h == 0u) {
+        wide_any_pop(acc, stack, w);
+        return;
+    }
+    const unsigned first = __ffs(h) - 1u;
+    h &= h - 1u;
+    while (h) {
+        const unsigned k = __ffs(h) - 1u;
+        h &= h - 1u;
+        stack.push((idx << 2) | static_cast<int32_t>(k));
+    }
+    wide_child(n, first, w.link, w.count);
+}
+
+__device__ __forceinline__ RayInv make_inv_wide(const Ray& r, const DAccel& acc)
+{
+    return make_inv(r, acc.proper_boxes != 0u && acc.wide != nullptr);
+}
+
+// does the ray enter ANY box of the root's wide node?  (what the `begin` kernels ask before they park a ray for the walk)
+__device__ __forceinline__ bool wide_root_entered(const DAccel& acc, const Ray& r, const RayInv& inv, float t_max)
+{
+    float e[4];
+    return wide_slabs(load_wide(acc.wide, acc.root), r, inv, t_max, e) != 0u;
 }
 
 // Lights half of Scene::intersect_p: only sphere lights occlude.

@@ -146,6 +146,13 @@ constexpr int      kRefillMin      = SPCU_REFILL_MIN; // idle lanes that make a 
 #endif
 constexpr int      kWalkRefillMin  = SPCU_WALK_REFILL_MIN; // ... when the set-up is three loads (the begin / walk kernels)
 // phase vote of the walk kernels: a pair leaf step runs when  pairs * NUM > lanes_at_a_node * DEN  (tuned on the GPU: profiles/)
+// tuning / A-B switches of the walk kernels (make EXTRA=-D...; defaults are what measured best, profiles/r02*)
+#ifndef SPCU_WALK_MIN_BLOCKS
+#define SPCU_WALK_MIN_BLOCKS 8 // resident CTAs per SM the walk kernels are compiled for (register cap = 65536 / (128 * this))
+#endif
+#ifndef SPCU_PAIR_LEAVES
+#define SPCU_PAIR_LEAVES 1 // 0: per-lane leaf loops (round 1's leaf step)
+#endif
 #ifndef SPCU_LEAF_VOTE_NUM
 #define SPCU_LEAF_VOTE_NUM 1
 #endif
@@ -578,7 +585,7 @@ __device__ __forceinline__ bool vote_leaf_step(int n_node, bool at_leaf_lane, ui
 constexpr uint32_t kWalkIterCap = 1u << 27;
 
 template <bool kCount, bool kOrdered, typename F>
-__global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+__global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                              const uint32_t* q_walk, const uint32_t* n_walk, uint32_t* cursor,
                                                              const __grid_constant__ SortedQueue sorted,
                                                              unsigned long long* counters, TraceCounters* cnt)
@@ -647,15 +654,25 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_walk(const __grid_consta
             }
         } else if (n_node + n_leaf == 0) {
             break;
-        } else if (!vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK) && n_node > 0) {
+        } else if (n_node > 0 && (SPCU_PAIR_LEAVES ? !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)
+                                                    : n_node >= n_leaf)) {
             if (have && at_node(walk)) {
-                if (kOrdered) {
+                if constexpr (kOrdered) {
                     closest_node_step_ordered<kCount>(s.geom, r, inv, walk, ostack, &local);
                 } else {
                     closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
                 }
             }
-        } else if (kOrdered) {
+        } else if (!SPCU_PAIR_LEAVES) {
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
+            if (have && at_leaf(walk)) {
+                if constexpr (kOrdered) {
+                    closest_run_ordered<kCount>(s.geom, gp, r, inv, walk, ostack, 1, &local, leaf_mask); // at a leaf: exactly that leaf
+                } else {
+                    closest_leaf_step<kCount>(gp, r, walk, stack, &local, leaf_mask);
+                }
+            }
+        } else if constexpr (kOrdered) {
             closest_leaf_step_pairs<kCount, true>(s.geom, gp, r, walk, ostack, have && at_leaf(walk), tbl, &local);
         } else {
             closest_leaf_step_pairs<kCount, false>(s.geom, gp, r, walk, stack, have && at_leaf(walk), tbl, &local);
@@ -796,7 +813,7 @@ __device__ __forceinline__ bool any_leaf_step_pairs(const DAccel& acc, const Pri
 }
 
 template <bool kCount, typename F>
-__global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+__global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                              const uint32_t* q_walk, const uint32_t* n_walk, uint32_t light_index,
                                                              uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit,
                                                              unsigned long long* counters, TraceCounters* cnt)
@@ -849,9 +866,19 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_walk(const __grid_consta
             }
         } else if (n_node + n_leaf == 0) {
             break;
-        } else if (!vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK) && n_node > 0) {
+        } else if (n_node > 0 && (SPCU_PAIR_LEAVES ? !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)
+                                                    : n_node >= n_leaf)) {
             if (have && at_node(walk)) {
                 any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+            }
+        } else if (!SPCU_PAIR_LEAVES) {
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
+            if (have && at_leaf(walk)) {
+                auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
+                    float t, b, g;
+                    return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
+                };
+                hit = any_leaf_step(s.geom, geom_test, walk, stack, &local, leaf_mask) || hit;
             }
         } else {
             const bool found = any_leaf_step_pairs<kCount>(s.geom, gp, r, t_max, walk, stack, have && at_leaf(walk), tbl, &local);

@@ -156,3 +156,29 @@ def pre_construction_order(is_bounded) -> tuple[np.ndarray, np.ndarray]:
     assert left_false.shape == right_true.shape
     pos[left_false], pos[right_true] = right_true.astype(np.uint32), left_false.astype(np.uint32)
     return pos[:k].copy(), pos[k:].copy()
+
+
+def unbuilt_scene_with_mesh(ctx, standin: FlatSceneData, vertices, faces, object_to_world, normal_xf) -> FlatSceneData:
+    """A scene whose geometry arrives UNBUILT (spcu_upload_scene_build): camera, materials, lights and the top-level
+    unbounded primitives of `standin` (a flattened scene holding ONE mesh), with that mesh replaced by (vertices, faces)
+    under the given transform.  The mesh is ingested on the device (spcu_ingest_mesh: read_ply's normal passes + Mesh's
+    constructor); the triangle records stay in face order, the pre-construction order of a scene whose only bounded
+    primitives are this mesh's (reference base/Scene.h:29-45)."""
+    nu = standin.head["geom"]["n_unbounded"]
+    meta = standin.arrays["geom_meta"].view(np.uint32).reshape(-1)
+    material = int(meta[nu] >> 2)                      # the stand-in mesh's material
+    mesh = ctx.ingest_mesh(np.ascontiguousarray(vertices, dtype=np.float32), np.ascontiguousarray(faces, dtype=np.uint32),
+                           np.asarray(object_to_world, dtype=np.float32), np.asarray(normal_xf, dtype=np.float32), material)
+    k = mesh["prims"].shape[0]
+
+    def cat(key, new, width):
+        top = standin.arrays[key].view(np.uint8).reshape(-1, width)[:nu]
+        return np.concatenate([top, np.ascontiguousarray(new).view(np.uint8).reshape(-1, width)])
+    arrays = dict(standin.arrays)
+    arrays["geom_prims"] = cat("geom_prims", mesh["prims"], 48)
+    arrays["geom_shade"] = cat("geom_shade", mesh["shade"], 48)
+    arrays["geom_meta"] = cat("geom_meta", mesh["meta"], 4)
+    arrays["geom_nodes"] = np.zeros((0, C.sizeof(BvhNode)), dtype=np.uint8)
+    head = dict(standin.head)
+    head["geom"] = {"n_prims": nu + k, "n_unbounded": nu, "n_nodes": 0, "root": ~nu, "root_count": 0, "max_depth": 0}
+    return FlatSceneData(head, arrays)

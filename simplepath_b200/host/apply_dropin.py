@@ -5,6 +5,10 @@ into git): after mkfarm.sh has made <farm> a tree of symlinks into <ref>, this r
   Integrators/Integrator.h    enum IntegratorType gains `Cuda`                               (:18-28)
   Integrators/Integrator.cpp  string_to_integrator_type accepts "cuda[_<inner>]"             (:25-51)
   main_dropin.cpp             = main.cpp with: #include, factory case (:36-49), render() dispatch (:109-130)
+  base/Scene.h                create_acceleration_structure (:27-45) can leave the GEOMETRY accelerator unbuilt — the
+                              top-level list [unbounded..., bounded in pre-construction order] without the BVH over the
+                              bounded part — when sp::CudaIntegrator was selected on the command line: it builds that BVH
+                              on the device (spcu_upload_scene_build), bit-identical to BVHAccelerator(first, part_it)
 
 Each hunk is an insertion next to an anchor line that must occur exactly once; a reference that has moved on fails the
 build loudly instead of silently compiling something else."""
@@ -35,6 +39,27 @@ def main() -> None:
     out = farm / "Integrators/Integrator.cpp"
     out.unlink(missing_ok=True)
     out.write_text(c)
+
+    s = (ref / "base/Scene.h").read_text()
+    s = patch(s, "template <typename Iterator>\n    requires std::random_access_iterator<Iterator>\nListAccelerator create_acceleration_structure(",
+              "// set by sp::CudaIntegrator::select() before the scene is parsed (simplepath_b200/host/cuda_integrator.cpp)\n"
+              "inline bool g_defer_geometry_accelerator = false;\n\n", True, "defer flag")
+    s = patch(s, "    const auto      bounded_accelerator = std::make_shared<BVHAccelerator>(first, part_it);\n",
+              "    if constexpr (std::is_convertible_v<typename std::iterator_traits<Iterator>::value_type,\n"
+              "                                        std::shared_ptr<const GeometricPrimitive>>) {\n"
+              "        if (g_defer_geometry_accelerator) {\n"
+              "            // the order std::partition left behind IS the input of BVHAccelerator(first, part_it): kept as a plain list\n"
+              "            ListAccelerator unbuilt(part_it, last);\n"
+              "            for (auto it = first; it != part_it; ++it) {\n"
+              "                unbuilt.push_back(*it);\n"
+              "            }\n"
+              "            unbuilt.shrink_to_fit();\n"
+              "            return unbuilt;\n"
+              "        }\n"
+              "    }\n", True, "deferred geometry accelerator")
+    out = farm / "base/Scene.h"
+    out.unlink(missing_ok=True)
+    out.write_text(s)
 
     m = (ref / "main.cpp").read_text()
     m = patch(m, "namespace fs = std::filesystem;", '#include "cuda_integrator.h"\n\n', True, "main include")

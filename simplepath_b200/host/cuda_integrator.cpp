@@ -32,6 +32,15 @@ unsigned env_unsigned(const char* name, unsigned fallback)
     return (v && *v) ? static_cast<unsigned>(std::strtoul(v, nullptr, 10)) : fallback;
 }
 
+// Called from string_to_integrator_type while main() reads its arguments, i.e. BEFORE the scene file is parsed: from here on
+// Scene's constructor leaves the geometry accelerator unbuilt (the hunk in base/Scene.h) and render_sum builds it on the device.
+// SPCU_BUILD_ON_DEVICE=0 keeps the reference's own construction; =verify keeps it AND rebuilds on the device to compare.
+void arm_deferred_construction()
+{
+    const char* v = std::getenv("SPCU_BUILD_ON_DEVICE");
+    internal::g_defer_geometry_accelerator = !(v && (*v == '0' || std::string(v) == "verify"));
+}
+
 void leave_now(int status, void*)
 {
     std::fflush(nullptr);
@@ -82,6 +91,7 @@ bool CudaIntegrator::select(std::string_view name)
     name.remove_prefix(prefix.size());
     if (name.empty()) {
         g_selected_inner = "iterative_rrnee";
+        arm_deferred_construction();
         return true;
     }
     if (name.front() != '_') {
@@ -90,6 +100,7 @@ bool CudaIntegrator::select(std::string_view name)
     name.remove_prefix(1);
     integrator_code(std::string(name)); // throws for names without a device path
     g_selected_inner = std::string(name);
+    arm_deferred_construction();
     return true;
 }
 
@@ -121,7 +132,44 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
         for (int i = 0; i < m_options.n_devices; ++i) {
             m_devices.push_back(std::make_unique<Device>(m_options.device + i));
         }
+        if (m_devices.size() > 1) { // one NCCL communicator over the devices: the frame is summed on device 0
+            std::vector<spcu_ctx*> ctxs;
+            for (const auto& d : m_devices) {
+                ctxs.push_back(d->ctx);
+            }
+            if (spcu_comm_init_all(ctxs.data(), static_cast<int>(ctxs.size())) != SPCU_OK) {
+                throw std::runtime_error(std::string("CudaIntegrator: spcu_comm_init_all: ") + spcu_last_error(m_devices[0]->ctx));
+            }
+        }
     }
+    // one host thread per device, for the upload as for the render
+    auto on_every_device = [this](auto&& work) {
+        const auto               n = m_devices.size();
+        std::vector<std::string> errors(n);
+        auto                     guarded = [&](std::size_t k) {
+            try {
+                work(k);
+            } catch (const std::exception& e) {
+                errors[k] = e.what();
+            }
+        };
+        if (n == 1) {
+            guarded(0);
+        } else {
+            std::vector<std::thread> threads;
+            for (std::size_t k = 0; k < n; ++k) {
+                threads.emplace_back(guarded, k);
+            }
+            for (auto& t : threads) {
+                t.join();
+            }
+        }
+        for (const auto& e : errors) {
+            if (!e.empty()) {
+                throw std::runtime_error(e);
+            }
+        }
+    };
     if (m_uploaded_scene != &scene || m_uploaded_spp != spp) {
         const auto t0 = std::chrono::steady_clock::now();
         // The flattened copy only lives for the duration of the upload: nothing of `scene` is retained.
@@ -131,11 +179,21 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
         // (spcu_upload_scene_build).  The flattener lists the bounded primitives in leaf order, and construction from the
         // leaf order is a fixed point of BVHAccelerator::construct (Hoare's partition does not move a partitioned range),
         // so the device must arrive at exactly the tree the reference built: checked, header and primitive order.
-        const bool build_on_device = env_unsigned("SPCU_BUILD_ON_DEVICE", 0) != 0;
-        for (const auto& d : m_devices) {
+        const char* bod             = std::getenv("SPCU_BUILD_ON_DEVICE");
+        const bool  build_on_device = bod && std::string(bod) == "verify";
+        on_every_device([&](std::size_t k) { // the replicas are uploaded concurrently (lucy: 3.4 GB per device)
+            const auto& d = m_devices[k];
+            if (flat.geom_unbuilt) { // the reference never built this tree: BVHAccelerator::construct runs on the device
+                spcu_accel built{};
+                d->check(spcu_upload_scene_build(d->ctx, &flat.view, jitter.data(), spp, flat.geom_bounds.data(), nullptr, &built),
+                         "spcu_upload_scene_build");
+                std::fprintf(stderr, "CudaIntegrator: acceleration structure built on device %d (never on the host): %u primitives, "
+                                     "%u nodes, depth %u\n", d->index, built.n_prims, built.n_nodes, built.max_depth);
+                return;
+            }
             if (!build_on_device) {
                 d->check(spcu_upload_scene(d->ctx, &flat.view, jitter.data(), spp), "spcu_upload_scene");
-                continue;
+                return;
             }
             const spcu_accel&     want = flat.view.geom;
             std::vector<uint32_t> order(want.n_prims - want.n_unbounded);
@@ -152,7 +210,7 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
             }
             std::fprintf(stderr, "CudaIntegrator: acceleration structure built on device %d: %u primitives, %u nodes, depth %u\n",
                          d->index, built.n_prims, built.n_nodes, built.max_depth);
-        }
+        });
         m_uploaded_scene = &scene;
         m_uploaded_spp   = spp;
         m_upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -162,44 +220,17 @@ void CudaIntegrator::render_sum(const Scene& scene, unsigned spp, std::vector<fl
 
     const auto           n_dev = static_cast<std::uint32_t>(m_devices.size());
     const std::uint32_t  code  = integrator_code(m_options.inner);
-    std::vector<spcu_stats>         stats(n_dev);
-    std::vector<std::vector<float>> partial(n_dev);
-    std::vector<std::string>        errors(n_dev);
-    // Tile-interleaved partition (base/TileScheduler.h:66-82 order): device k renders tiles t with t % n == k.
-    // Disjoint pixels, so the per-device sums combine exactly; one host thread drives each device.
-    auto run = [&](std::uint32_t k) {
-        try {
-            std::vector<float>& out = (k == 0) ? rgb_sum : partial[k];
-            if (k != 0) {
-                out.resize(n);
-            }
-            const spcu_partition part{ k, n_dev, 0u, spp, spp, code, m_options.seed };
-            m_devices[k]->check(spcu_render_frame(m_devices[k]->ctx, &part, out.data(), nullptr, &stats[k]), "spcu_render_frame");
-        } catch (const std::exception& e) {
-            errors[k] = e.what();
-        }
-    };
-    if (n_dev == 1) {
-        run(0);
-    } else {
-        std::vector<std::thread> threads;
-        for (std::uint32_t k = 0; k < n_dev; ++k) {
-            threads.emplace_back(run, k);
-        }
-        for (auto& t : threads) {
-            t.join();
-        }
-    }
-    for (const auto& e : errors) {
-        if (!e.empty()) {
-            throw std::runtime_error(e);
-        }
-    }
+    std::vector<spcu_stats> stats(n_dev);
+    // Tile-interleaved partition (base/TileScheduler.h:66-82 order): device k renders tiles t with t % n == k.  Disjoint
+    // pixels, so the sum over devices is exact (every other device contributes +0): the per-device accumulators are summed on
+    // device 0 by ncclReduce over NVLink (spcu_render_frame_reduced) and ONE frame crosses to the host.
+    on_every_device([&](std::size_t k) {
+        const spcu_partition part{ static_cast<std::uint32_t>(k), n_dev, 0u, spp, spp, code, m_options.seed };
+        m_devices[k]->check(spcu_render_frame_reduced(m_devices[k]->ctx, &part, 0, k == 0 ? rgb_sum.data() : nullptr, nullptr, &stats[k]),
+                            "spcu_render_frame_reduced");
+    });
     m_stats = stats[0];
     for (std::uint32_t k = 1; k < n_dev; ++k) {
-        for (std::size_t i = 0; i < n; ++i) {
-            rgb_sum[i] += partial[k][i];
-        }
         m_stats.paths += stats[k].paths;
         m_stats.rays_closest += stats[k].rays_closest;
         m_stats.rays_any += stats[k].rays_any;

@@ -30,6 +30,12 @@ struct FlatScene
     std::vector<spcu_bxdf>     bxdfs;
     std::vector<float>         float_pool;
 
+    // The geometry accelerator was left unbuilt by the patched create_acceleration_structure (apply_dropin.py): geom_prims
+    // hold [unbounded..., bounded in pre-construction order], view.geom only n_prims / n_unbounded, geom_bounds the reference's
+    // own world bounds of the bounded primitives (spheres need them; triangle bounds are recomputed on the device).
+    bool                     geom_unbuilt = false;
+    std::vector<spcu_bounds> geom_bounds;
+
     void finalize();
 };
 

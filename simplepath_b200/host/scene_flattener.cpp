@@ -72,6 +72,7 @@ struct AccelWalker
     std::function<bool(const Hitable*)>  emit;
     uint32_t                             n_prims   = 0;
     uint32_t                             max_depth = 0;
+    std::vector<spcu_bounds>             unbuilt_bounds; // world bounds of the bounded primitives of an UNBUILT list
 
     // Returns the link for this subtree and writes the leaf count word.
     int32_t walk(const BVHAccelerator::NodeBase* node, uint32_t& count_word, uint32_t depth)
@@ -124,14 +125,26 @@ struct AccelWalker
             if (bvh) {
                 throw std::runtime_error("flatten: primitive after the BVH in a top-level list");
             }
+            if (p->is_bounded()) { // only an unbuilt list holds bounded primitives directly: [unbounded..., bounded...]
+                const auto b = p->get_world_bounds();
+                spcu_bounds out{};
+                put3(out.lo, b.get_lower());
+                put3(out.hi, b.get_upper());
+                unbuilt_bounds.push_back(out);
+            } else if (!unbuilt_bounds.empty()) {
+                throw std::runtime_error("flatten: unbounded primitive after a bounded one in an unbuilt list");
+            }
             emit(p.get());
             ++n_prims;
         }
-        a.n_unbounded = n_prims;
+        a.n_unbounded = n_prims - static_cast<uint32_t>(unbuilt_bounds.size());
+        if (bvh && !unbuilt_bounds.empty()) {
+            throw std::runtime_error("flatten: bounded primitives beside a BVH in a top-level list");
+        }
         if (bvh) {
             a.root = walk(bvh->m_root.get(), a.root_count, 0);
         } else {
-            a.root       = ~static_cast<int32_t>(n_prims);
+            a.root       = ~static_cast<int32_t>(a.n_unbounded);
             a.root_count = 0;
         }
         a.n_prims   = n_prims;
@@ -361,7 +374,9 @@ FlatScene flatten_scene(const sp::Scene& scene)
                          fs.geom_meta.push_back(SPCU_MAKE_META(kind, material));
                          return kind != SPCU_PRIM_TRIANGLE;
                      } };
-    fs.view.geom = geom.run(scene.m_accelerator_geometry);
+    fs.view.geom    = geom.run(scene.m_accelerator_geometry);
+    fs.geom_unbuilt = !geom.unbuilt_bounds.empty();
+    fs.geom_bounds  = std::move(geom.unbuilt_bounds);
 
     // ---- lights ----
     std::unordered_map<const sp::Light*, uint32_t> light_id;

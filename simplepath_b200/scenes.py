@@ -341,6 +341,9 @@ def _specs():
         "c3_bunny": (1920, 1080, 256, lambda o: sp_bunny(1920, 1080, _ply(o, "bunny", BUNNY_TRIS, BUNNY_LO, BUNNY_HI))),
         "c4_elf": (1920, 1080, 256, lambda o: sp_elf(1920, 1080, _ply(o, "elf", ELF_TRIS, ELF_LO, ELF_HI))),
         "c5_lucy": (3840, 2160, 256, lambda o: sp_lucy(3840, 2160, _ply(o, "lucy", LUCY_TRIS, LUCY_LO, LUCY_HI))),
+        # lucy.sp's camera / materials / plane / light at the config's resolution over a 40 K-triangle stand-in: what bench.py
+        # flattens through the reference's parser before it swaps in the 28 M-triangle mesh built on the device
+        "c5_lucy_standin": (3840, 2160, 256, lambda o: sp_lucy(3840, 2160, _ply(o, "lucy_small", 40_002, LUCY_LO, LUCY_HI))),
         # reduced sizes of the same scenes for parity tests (oracle finishes in seconds)
         "t_spheres_const": (96, 96, 8, lambda o: sp_material_spheres(96, 96, "const")),
         "t_spheres_ibl": (96, 96, 8, lambda o: sp_material_spheres(96, 96, _pfm(o, 128, 64))),

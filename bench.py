@@ -606,7 +606,7 @@ def run_reference(args) -> None:
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": scene_name, "width": w, "height": h, "spp": spp_full,
-                   "integrator": INTEGRATOR, "spp_sample_per_step": spp},
+                   "integrator": INTEGRATOR},
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -368,7 +368,9 @@ struct Float8
 __device__ __forceinline__ Float8 ldg256(const void* p)
 {
     unsigned long long a, b, c, d; // (four 64-bit registers: cicc 12.9 crashes on eight float outputs in these kernels)
-    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    // volatile: a plain asm is a pure function to the compiler, which then hoists the load out of the branch that guards the
+    // pointer (k_shadow_begin read DAccel::wide == NULL for scenes without internal nodes)
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     Float8 r;
     r.lo = make_float4(__uint_as_float(static_cast<unsigned>(a)), __uint_as_float(static_cast<unsigned>(a >> 32)),
                        __uint_as_float(static_cast<unsigned>(b)), __uint_as_float(static_cast<unsigned>(b >> 32)));

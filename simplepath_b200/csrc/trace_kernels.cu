@@ -8,6 +8,8 @@
 #include "trace.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace spcu {
 namespace {
@@ -149,9 +151,6 @@ constexpr int      kWalkRefillMin  = SPCU_WALK_REFILL_MIN; // ... when the set-u
 // tuning / A-B switches of the walk kernels (make EXTRA=-D...; defaults are what measured best, profiles/r02*)
 #ifndef SPCU_WALK_MIN_BLOCKS
 #define SPCU_WALK_MIN_BLOCKS 8 // resident CTAs per SM the walk kernels are compiled for (register cap = 65536 / (128 * this))
-#endif
-#ifndef SPCU_PAIR_LEAVES
-#define SPCU_PAIR_LEAVES 1 // 0: per-lane leaf loops (round 1's leaf step)
 #endif
 #ifndef SPCU_LEAF_VOTE_NUM
 #define SPCU_LEAF_VOTE_NUM 1
@@ -375,12 +374,23 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_const
             OrderedStack ostack;
             stack.sh = stack_smem + threadIdx.x;
             ostack.attach(stack_smem + threadIdx.x);
-            const RayInv inv = make_inv(r, s.geom.proper_boxes != 0u);
-            if (at_node(walk)) { // the root's two child boxes
-                if (kOrdered) {
-                    closest_node_step_ordered<kCount>(s.geom, r, inv, walk, ostack, &local);
-                } else {
+            const RayInv inv = kOrdered ? make_inv_wide(r, s.geom) : make_inv(r, s.geom.proper_boxes != 0u);
+            if (at_node(walk)) {
+                if (!kOrdered) { // the root's two child boxes; its right child may be left pending
                     closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
+                } else if (!inv.generic) { // the ordered walk starts over at the root: only "does it enter anything" is asked here
+                    if (!wide_root_entered(s.geom, r, inv, walk.t_max)) {
+                        walk.link = kDone;
+                    }
+                } else {
+                    NodeHalf c0, c1;
+                    load_node(s.geom.nodes, walk.link, c0, c1);
+                    bool  h0, h1;
+                    float e0, e1;
+                    slab_pair(s.geom.nodes, walk.link, c0, c1, r, inv, walk.t_max, h0, h1, e0, e1);
+                    if (!h0 && !h1) {
+                        walk.link = kDone;
+                    }
                 }
             } else if (at_leaf(walk)) { // the root is a leaf
                 if (kOrdered) {
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_const
             ex.hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
             done   = walk.link == kDone;
             parked = !done;
-            ex.pad[0] = __int_as_float(park_link(walk.link, (kOrdered ? ostack.n : stack.n) > 0));
+            ex.pad[0] = __int_as_float(park_link(walk.link, !kOrdered && stack.n > 0));
             ex.pad[1] = __uint_as_float(walk.count);
             w.extend[slot] = ex;
             // finished vertices go to the shading stage sorted by material: misses in the last segment
@@ -485,10 +495,14 @@ __device__ __forceinline__ Ray fetch_ray(const Ray& r, int owner)
 
 // the walk's next cursor after a leaf: the pending right child (exact walk, re-tested there) / the nearest deferred child
 template <bool kOrdered, typename StackT>
-__device__ __forceinline__ void leaf_pop(const DAccel& acc, StackT& stack, ClosestWalk& w)
+__device__ __forceinline__ void leaf_pop(const DAccel& acc, StackT& stack, ClosestWalk& w, bool wide_keys)
 {
     if constexpr (kOrdered) {
-        ordered_pop(acc, stack, w);
+        if (wide_keys) {
+            wide_ordered_pop(acc, stack, w);
+        } else {
+            ordered_pop(acc, stack, w);
+        }
     } else {
         if (stack.n > 0) {
             w.link   = stack.pop();
@@ -502,7 +516,7 @@ __device__ __forceinline__ void leaf_pop(const DAccel& acc, StackT& stack, Close
 // All 32 lanes call.  `mine` = this lane holds a ray whose cursor is at a leaf.
 template <bool kCount, bool kOrdered, typename Prims, typename StackT>
 __device__ __forceinline__ void closest_leaf_step_pairs(const DAccel& acc, const Prims& prims, const Ray& r, ClosestWalk& w, StackT& stack,
-                                                        bool mine, uint8_t* tbl, TraceCounters* cnt)
+                                                        bool mine, bool wide_keys, uint8_t* tbl, TraceCounters* cnt)
 {
     const int      lane      = threadIdx.x & 31;
     const uint32_t n         = w.count & SPCU_LEAF_COUNT_MASK;
@@ -547,7 +561,7 @@ __device__ __forceinline__ void closest_leaf_step_pairs(const DAccel& acc, const
             w.gamma = gw;
         }
         if ((p.part_mask >> lane) & 1u) { // participants (also those with an empty leaf) move on
-            leaf_pop<kOrdered>(acc, stack, w);
+            leaf_pop<kOrdered>(acc, stack, w, wide_keys);
         }
     }
     // leaves the pair scheme does not take: mixed or oversized (the per-lane loop, reference order)
@@ -569,7 +583,7 @@ __device__ __forceinline__ void closest_leaf_step_pairs(const DAccel& acc, const
                 w.gamma  = g;
             }
         }
-        leaf_pop<kOrdered>(acc, stack, w);
+        leaf_pop<kOrdered>(acc, stack, w, wide_keys);
     }
 }
 
@@ -590,7 +604,8 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
                                                              const __grid_constant__ SortedQueue sorted,
                                                              unsigned long long* counters, TraceCounters* cnt)
 {
-    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    // exact walk: 24 four-byte levels per thread; ordered walk: 16 eight-byte entries (wide nodes defer up to three per step)
+    __shared__ int32_t stack_smem[(kOrdered ? 2 * kWideSharedOrdered : kStackShared) * kTraceBlock];
     __shared__ uint8_t pair_tbl[kTraceBlock];
     LaneFeed           feed;
     feed.cursor = cursor;
@@ -598,10 +613,13 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
 
     TraceCounters       local{ 0, 0, 0 };
     const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
-    Stack               stack;
-    OrderedStack        ostack;
-    stack.sh = stack_smem + threadIdx.x;
-    ostack.attach(stack_smem + threadIdx.x);
+    using StackS = typename std::conditional<kOrdered, WideOrderedStack, Stack>::type;
+    StackS stack;
+    if constexpr (kOrdered) {
+        stack.attach(stack_smem + threadIdx.x);
+    } else {
+        stack.sh = stack_smem + threadIdx.x;
+    }
     uint8_t*    tbl = pair_tbl + (threadIdx.x & ~31);
     Ray         r{};
     RayInv      inv{};
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
                 const RayRec    rr = w.ray[slot];
                 const ExtendRec ex = w.extend[slot];
                 r                  = Ray{ rr.o.x, rr.o.y, rr.o.z, rr.d.x, rr.d.y, rr.d.z, rr.o.w };
-                inv                = make_inv(r, s.geom.proper_boxes != 0u);
+                inv                = kOrdered ? make_inv_wide(r, s.geom) : make_inv(r, s.geom.proper_boxes != 0u);
                 bool root_pending;
                 walk.link   = unpark_link(__float_as_int(ex.pad[0]), root_pending);
                 walk.count  = __float_as_uint(ex.pad[1]);
@@ -634,19 +652,9 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
                 walk.t_max  = ex.hit.t;
                 walk.beta   = ex.hit.beta;
                 walk.gamma  = ex.hit.gamma;
-                stack.n = ostack.n = 0;
-                if (root_pending) {
-                    if (kOrdered) {
-                        // the root's other child waits with its entry distance: recomputed here (nothing has changed since
-                        // `begin` tested it) instead of travelling through the parked record
-                        NodeHalf c0, c1;
-                        load_node(s.geom.nodes, s.geom.root, c0, c1);
-                        bool  h0, h1;
-                        float e0, e1;
-                        slab_pair(s.geom.nodes, s.geom.root, c0, c1, r, inv, walk.t_max, h0, h1, e0, e1);
-                        const bool right_pending = walk.link == c0.child && walk.count == c0.count;
-                        ostack.push((s.geom.root << 1) | (right_pending ? 1 : 0), right_pending ? e1 : e0);
-                    } else {
+                stack.n     = 0;
+                if constexpr (!kOrdered) {
+                    if (root_pending) {
                         stack.push(s.geom.root);
                     }
                 }
@@ -654,28 +662,18 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
             }
         } else if (n_node + n_leaf == 0) {
             break;
-        } else if (n_node > 0 && (SPCU_PAIR_LEAVES ? !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)
-                                                    : n_node >= n_leaf)) {
+        } else if (n_node > 0 && !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)) {
             if (have && at_node(walk)) {
-                if constexpr (kOrdered) {
-                    closest_node_step_ordered<kCount>(s.geom, r, inv, walk, ostack, &local);
-                } else {
+                if constexpr (!kOrdered) {
                     closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
-                }
-            }
-        } else if (!SPCU_PAIR_LEAVES) {
-            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
-            if (have && at_leaf(walk)) {
-                if constexpr (kOrdered) {
-                    closest_run_ordered<kCount>(s.geom, gp, r, inv, walk, ostack, 1, &local, leaf_mask); // at a leaf: exactly that leaf
+                } else if (!inv.generic) {
+                    closest_wide_step_ordered<kCount>(s.geom, r, inv, walk, stack, &local);
                 } else {
-                    closest_leaf_step<kCount>(gp, r, walk, stack, &local, leaf_mask);
+                    closest_node_step_ordered<kCount>(s.geom, r, inv, walk, stack, &local);
                 }
             }
-        } else if constexpr (kOrdered) {
-            closest_leaf_step_pairs<kCount, true>(s.geom, gp, r, walk, ostack, have && at_leaf(walk), tbl, &local);
         } else {
-            closest_leaf_step_pairs<kCount, false>(s.geom, gp, r, walk, stack, have && at_leaf(walk), tbl, &local);
+            closest_leaf_step_pairs<kCount, kOrdered>(s.geom, gp, r, walk, stack, have && at_leaf(walk), kOrdered && !inv.generic, tbl, &local);
         }
         if (have && walk.link == kDone) {
             w.extend[slot].hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
@@ -728,9 +726,22 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
             stack.sh = stack_smem + threadIdx.x;
             if (!hit) {
                 walk = AnyWalk{ s.geom.root, s.geom.root_count };
-                const RayInv inv = make_inv(r, s.geom.proper_boxes != 0u);
-                if (at_node(walk)) {
-                    any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+                const RayInv inv = make_inv_wide(r, s.geom);
+                if (at_node(walk)) { // the walk starts over at the root: only "does the ray enter anything" is asked here
+                    bool entered;
+                    if (!inv.generic) {
+                        entered = wide_root_entered(s.geom, r, inv, t_max);
+                    } else {
+                        NodeHalf c0, c1;
+                        load_node(s.geom.nodes, walk.link, c0, c1);
+                        bool  h0, h1;
+                        float e0, e1;
+                        slab_pair(s.geom.nodes, walk.link, c0, c1, r, inv, t_max, h0, h1, e0, e1);
+                        entered = h0 || h1;
+                    }
+                    if (!entered) {
+                        walk.link = kDone;
+                    }
                 } else if (at_leaf(walk)) {
                     auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
                         float t, b, g;
@@ -743,7 +754,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
             parked = !hit && walk.link != kDone;
             lit    = !hit && !parked;
             if (parked) {
-                w.extend[slot].pad[0] = __int_as_float(park_link(walk.link, stack.n > 0));
+                w.extend[slot].pad[0] = __int_as_float(park_link(walk.link, false));
                 w.extend[slot].pad[1] = __uint_as_float(walk.count);
             } else if (!q_lit) {
                 w.occluded[slot] = hit ? 1 : 0; // direct lighting reads the flag; the NEE path gets the compacted queue
@@ -765,7 +776,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
 // for the lanes whose leaf holds an accepted primitive (their query is over).
 template <bool kCount, typename Prims>
 __device__ __forceinline__ bool any_leaf_step_pairs(const DAccel& acc, const Prims& prims, const Ray& r, float t_max, AnyWalk& w,
-                                                    Stack& stack, bool mine, uint8_t* tbl, TraceCounters* cnt)
+                                                    WideStack& stack, bool mine, bool wide_keys, uint8_t* tbl, TraceCounters* cnt)
 {
     const int      lane      = threadIdx.x & 31;
     const uint32_t n         = w.count & SPCU_LEAF_COUNT_MASK;
@@ -795,6 +806,8 @@ __device__ __forceinline__ bool any_leaf_step_pairs(const DAccel& acc, const Pri
             found                   = (hits & my_lanes) != 0u;
             if (found) {
                 w.link = kDone;
+            } else if (wide_keys) {
+                wide_any_pop(acc, stack, w);
             } else {
                 any_pop(acc, stack, w);
             }
@@ -807,7 +820,7 @@ __device__ __forceinline__ bool any_leaf_step_pairs(const DAccel& acc, const Pri
             float t, b, g;
             return prims.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
         };
-        found = any_leaf_step(acc, geom_test, w, stack, cnt, other_mask);
+        found = any_leaf_step(acc, geom_test, w, stack, cnt, other_mask, wide_keys);
     }
     return found;
 }
@@ -818,7 +831,7 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
                                                              uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit,
                                                              unsigned long long* counters, TraceCounters* cnt)
 {
-    __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
+    __shared__ int32_t stack_smem[kWideSharedAny * kTraceBlock];
     __shared__ uint8_t pair_tbl[kTraceBlock];
     LaneFeed           feed;
     feed.cursor = cursor;
@@ -826,7 +839,7 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
 
     TraceCounters       local{ 0, 0, 0 };
     const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
-    Stack               stack;
+    WideStack           stack;
     stack.sh = stack_smem + threadIdx.x;
     uint8_t* tbl = pair_tbl + (threadIdx.x & ~31);
     Ray      r{};
@@ -852,36 +865,27 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
                 const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
                 const ExtendRec ex = w.extend[slot];
                 r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
-                inv               = make_inv(r, s.geom.proper_boxes != 0u);
+                inv               = make_inv_wide(r, s.geom);
                 t_max             = lr.wi.w;
                 bool root_pending;
                 walk.link  = unpark_link(__float_as_int(ex.pad[0]), root_pending);
                 walk.count = __float_as_uint(ex.pad[1]);
                 stack.n    = 0;
-                if (root_pending) {
-                    stack.push(s.geom.root);
-                }
                 have = true;
                 hit  = false;
             }
         } else if (n_node + n_leaf == 0) {
             break;
-        } else if (n_node > 0 && (SPCU_PAIR_LEAVES ? !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)
-                                                    : n_node >= n_leaf)) {
+        } else if (n_node > 0 && !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)) {
             if (have && at_node(walk)) {
-                any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
-            }
-        } else if (!SPCU_PAIR_LEAVES) {
-            const unsigned leaf_mask = __ballot_sync(0xffffffffu, have && at_leaf(walk));
-            if (have && at_leaf(walk)) {
-                auto geom_test = [&](uint32_t id, bool mixed, TraceCounters* c) {
-                    float t, b, g;
-                    return gp.template test<kCount>(id, mixed, r, t_max, t, b, g, c);
-                };
-                hit = any_leaf_step(s.geom, geom_test, walk, stack, &local, leaf_mask) || hit;
+                if (!inv.generic) {
+                    any_wide_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+                } else {
+                    any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+                }
             }
         } else {
-            const bool found = any_leaf_step_pairs<kCount>(s.geom, gp, r, t_max, walk, stack, have && at_leaf(walk), tbl, &local);
+            const bool found = any_leaf_step_pairs<kCount>(s.geom, gp, r, t_max, walk, stack, have && at_leaf(walk), !inv.generic, tbl, &local);
             hit              = hit || found;
         }
         if (have && walk.link == kDone) {
@@ -1150,6 +1154,18 @@ void launch_trace_lights(const DScene& s, const spcu_ray* d_rays, uint64_t n, sp
     k_trace_lights<<<grid_for(n), kTraceBlock, 0, st>>>(s, d_rays, n, d_hits);
 }
 
+// SPCU_DEBUG_SYNC=1: synchronise after every traversal launch and name the kernel that failed (stderr)
+static void debug_sync(const Launch& l, const char* what)
+{
+    static const bool on = [] { const char* e = getenv("SPCU_DEBUG_SYNC"); return e && *e == '1'; }();
+    if (on) {
+        const cudaError_t e = cudaStreamSynchronize(l.stream);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "SPCU_DEBUG_SYNC: %s failed: %s\n", what, cudaGetErrorString(e));
+        }
+    }
+}
+
 template <typename K>
 static int trace_ctas_per_sm(K kernel)
 {
@@ -1195,8 +1211,10 @@ static void launch_extend_split(const Launch& l, const DScene& s, const DWave& w
     static const int occ_w = trace_ctas_per_sm(k_extend_walk<kCount, kOrdered, FeatFull>);
     k_extend_begin<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
         s, w, queue, d_n_queue, q_walk, d_n_walk, sorted, d_counters, d_cnt);
+    debug_sync(l, "k_extend_begin");
     k_extend_walk<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
         s, w, q_walk, d_n_walk, d_cursor, sorted, d_counters, d_cnt);
+    debug_sync(l, "k_extend_walk");
 }
 
 int launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
@@ -1245,8 +1263,10 @@ int launch_shadow(const Launch& l, const DScene& s, const DWave& w, const uint32
         static const int occ_w = trace_ctas_per_sm(k_shadow_walk<false, FeatFull>);
         k_shadow_begin<false, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
             s, w, queue, d_n_queue, light_index, q_walk, d_n_walk, q_lit, d_n_lit, d_counters, nullptr);
+        debug_sync(l, "k_shadow_begin");
         k_shadow_walk<false, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
             s, w, q_walk, d_n_walk, light_index, d_cursor, q_lit, d_n_lit, d_counters, nullptr);
+        debug_sync(l, "k_shadow_walk");
         return 2;
     }
     if (d_cnt) {

@@ -175,8 +175,8 @@ def test_stage_batches_fresh_and_ragged(ctx, scene, oracle_port):
 
 
 def test_ordered_extend_stage_mismatches_are_epsilon_ties(ctx, scene, oracle_port):
-    """The render's DEFAULT extend stage (ordered walk + warp-wide leaf steps) against the exact one: same bar as
-    test_ordered_walk_mismatches_are_epsilon_ties, and it must agree with the one-thread-per-ray ordered kernel exactly."""
+    """The render's DEFAULT extend stage (ordered walk over 4-wide nodes + warp-wide leaf steps) against the exact one: same bar
+    as test_ordered_walk_mismatches_are_epsilon_ties."""
     name, flat, vec = scene
     total = differ = 0
     for bname, rays in {**{b: np.ascontiguousarray(vec[f"{b}.rays"]).view(RAY_DTYPE).reshape(-1) for b in batches_of(vec)},
@@ -187,8 +187,13 @@ def test_ordered_extend_stage_mismatches_are_epsilon_ties(ctx, scene, oracle_por
         assert lights.tobytes() == lights2.tobytes()
         shrunk = rays.copy()
         shrunk["t_max"][lights["id"] >= 0] = lights["t"][lights["id"] >= 0]
+        # the one-thread-per-ray ordered kernel walks the binary nodes, the stage kernel their 4-wide copies: two visiting orders
+        # of the same boxes and primitives, so they too may only differ on ties
         per_ray, _ = ctx.trace_closest_fast(shrunk)
-        assert fast.tobytes() == per_ray.tobytes(), f"{name}/{bname}: stage kernel and per-ray ordered kernel disagree"
+        other = fast["id"] != per_ray["id"]
+        assert other.sum() <= max(1, rays.shape[0] // 5_000), f"{name}/{bname}: stage kernel vs per-ray ordered kernel"
+        both_hit = other & (fast["id"] >= 0) & (per_ray["id"] >= 0)
+        assert ulp_diff(fast["t"][both_hit], per_ray["t"][both_hit]).max(initial=0) <= 4
         bad = exact["id"] != fast["id"]
         tied = bad & (exact["id"] >= 0) & (fast["id"] >= 0)
         assert ulp_diff(exact["t"][tied], fast["t"][tied]).max(initial=0) <= 4, f"{name}/{bname}"

@@ -30,8 +30,8 @@ def main() -> None:
     idx = {h: i for i, h in enumerate(rows[0])}
     agg: dict[str, dict[str, float]] = {}
     for r in rows[1:]:
-        name = re.sub(r"<.*", "", re.sub(r".*::", "", re.sub(r"\(.*", "", r[idx["Kernel Name"]])))
-        stage = KERNEL_TO_STAGE.get(name)
+        m = re.search(r"\b(k_[a-z_0-9]+)", r[idx["Kernel Name"]])   # "void spcu::<unnamed>::k_extend_walk<0, 1, spcu::FeatFull>(...)"
+        stage = KERNEL_TO_STAGE.get(m.group(1)) if m else None
         if stage is None:
             continue
         a = agg.setdefault(stage, {"dram_bytes": 0.0, "seconds": 0.0, "launches": 0, "thread_inst": 0.0, "warp_inst": 0.0,

@@ -1038,6 +1038,19 @@ __device__ __forceinline__ void wide_child_of_key(const float4* wide, int32_t ke
     count = __float_as_uint(lc.y);
 }
 
+// The cursor has just become a leaf: start its triangle records on their way to L1 now — the leaf step that tests them runs a few
+// votes later (it waits until enough lanes hold a leaf), and would otherwise begin with a full-latency miss.
+__device__ __forceinline__ void prefetch_leaf(const float4* prims, int32_t link, uint32_t count)
+{
+#ifndef SPCU_NO_LEAF_PREFETCH
+    if (link < 0 && (count & SPCU_LEAF_COUNT_MASK) != 0u) {
+        const float4* p = prims + 3 * static_cast<size_t>(static_cast<uint32_t>(~link));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 3 * ((count & SPCU_LEAF_COUNT_MASK) - 1u) + 2)); // its last 16 bytes
+    }
+#endif
+}
+
 // next deferred child that is still reachable, or kDone (wide keys)
 __device__ __forceinline__ void wide_ordered_pop(const DAccel& acc, WideOrderedStack& stack, ClosestWalk& w)
 {

@@ -668,6 +668,7 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
                     closest_node_step<kCount>(s.geom, r, inv, walk, stack, &local);
                 } else if (!inv.generic) {
                     closest_wide_step_ordered<kCount>(s.geom, r, inv, walk, stack, &local);
+                    prefetch_leaf(s.geom_prims, walk.link, walk.count);
                 } else {
                     closest_node_step_ordered<kCount>(s.geom, r, inv, walk, stack, &local);
                 }
@@ -880,6 +881,7 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
             if (have && at_node(walk)) {
                 if (!inv.generic) {
                     any_wide_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
+                    prefetch_leaf(s.geom_prims, walk.link, walk.count);
                 } else {
                     any_node_step<kCount>(s.geom, r, inv, t_max, walk, stack, &local);
                 }

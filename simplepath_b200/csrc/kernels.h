@@ -35,8 +35,10 @@ int launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const
                   uint32_t max_n, uint32_t light_index, uint32_t* d_cursor, uint32_t* q_lit, uint32_t* d_n_lit, uint32_t* q_walk,
                   uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt);
 // mis: Scene::intersect_lights then, on a light hit, Scene::intersect_p of the BSDF-sampled ray (Integrator.cpp:531-532).
-void launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
-                      const uint32_t* d_n_queue, uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt);
+// d_cursor / q_walk / d_n_walk as for launch_shadow (begin + persistent walk); returns the kernels launched.
+int launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue,
+                     const uint32_t* d_n_queue, uint32_t max_n, uint32_t* d_cursor, uint32_t* q_walk, uint32_t* d_n_walk,
+                     unsigned long long* d_counters, TraceCounters* d_cnt);
 
 // ---- build_kernels.cu: the 4-wide copy of the resident binary nodes (8 x float4 per node, trace.cuh) ------------------------
 void launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int sm_count, cudaStream_t st);

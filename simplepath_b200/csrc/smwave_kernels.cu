@@ -70,6 +70,7 @@ struct SmQueues
     uint32_t live;      // state slots that still carry, or may still draw, a path
     int      preferred; // the stage the CTA ran last
     uint32_t error;     // a bounded wait ran out: every warp leaves, the kernel reports kCntErrors (never a hung GPU)
+    uint32_t idle[32];  // per warp: consecutive empty scans (in shared memory: the kernel has no register to spare for it)
 };
 #ifndef SPCU_SMWAVE_CAPS
 #define SPCU_SMWAVE_CAPS 1 // 0: A/B builds without the bounded waits
@@ -505,8 +506,11 @@ __global__ void __launch_bounds__(kSmBlock, 1)
         q.preferred = kQExtend;
         q.error     = 0u;
     }
+    if (threadIdx.x < 32) {
+        q.idle[threadIdx.x] = 0u;
+    }
     __syncthreads();
-    uint32_t idle = 0;
+    volatile uint32_t* idle = &q.idle[threadIdx.x >> 5];
 
     PathCounters  pc;
     TraceCounters tc{ 0, 0, 0 };
@@ -543,18 +547,21 @@ __global__ void __launch_bounds__(kSmBlock, 1)
                 if (*reinterpret_cast<volatile uint32_t*>(&q.live) == 0u || *reinterpret_cast<volatile uint32_t*>(&q.error) != 0u) {
                     break;
                 }
-                if (SPCU_SMWAVE_CAPS && ++idle > kIdleCap) { // live paths but no queue ever fills again: a protocol fault, not a reason to hang
+                // live paths but no queue ever fills again: a protocol fault, not a reason to hang (the count is the warp's: lane 0 keeps it)
+                if (SPCU_SMWAVE_CAPS && __shfl_sync(0xffffffffu, lane == 0 ? (*idle = *idle + 1u) : 0u, 0) > kIdleCap) {
                     *reinterpret_cast<volatile uint32_t*>(&q.error) = 1u;
                     break;
                 }
                 __nanosleep(64);
                 continue;
             }
+            if (SPCU_SMWAVE_CAPS && lane == 0 && *idle) {
+                *idle = 0u; // work again
+            }
             if (use_affinity && lane == 0) {
                 *reinterpret_cast<volatile int*>(&q.preferred) = stage;
             }
         }
-        idle            = 0;
         const int   idx = q_pop(q, stage, lane);
         const State x{ st, P, static_cast<uint32_t>(max(idx, 0)) * 32u + static_cast<uint32_t>(lane) };
         if (stage == kQExtend) {

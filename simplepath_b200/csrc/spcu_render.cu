@@ -297,7 +297,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
     const bool     whitted     = part->integrator == SPCU_INTEGRATOR_WHITTED;
     const bool     direct      = part->integrator == SPCU_INTEGRATOR_DIRECT_LIGHTING || whitted; // per-light direct term
     const uint32_t n_segments  = std::min<uint32_t>(c->n_materials, kMaxMaterialSegments) + 1u; // + the miss segment
-    const uint32_t counts_need = 1 + max_depth * (4 + 5 * n_lights + n_segments);
+    const uint32_t counts_need = 1 + max_depth * (4 + 7 * n_lights + n_segments);
     CK(c, c->sorted_queue.reserve(static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)));
     if (counts_need > static_cast<uint32_t>(kMaxQueueCounts)) {
         return fail(c, SPCU_ERR_LIMIT, "max_depth x lights needs %u queue counters (limit %d)", counts_need, kMaxQueueCounts);
@@ -376,12 +376,13 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                         launch_nee_bsdf(L, s, c->wave, p, q[kQLit], n_lit, max_n, q[kQMis], n_mis, d_counters);
                         timer.end();
                         timer.begin(kStMisTrace);
-                        launch_mis_trace(L, s, c->wave, q[kQMis], n_mis, max_n, d_counters, d_cnt);
+                        uint32_t* cursor_m = new_count();
+                        launches += launch_mis_trace(L, s, c->wave, q[kQMis], n_mis, max_n, cursor_m, q[kQWalk], new_count(), d_counters, d_cnt);
                         timer.end();
                         timer.begin(kStNeeMisAccumulate);
                         launch_nee_mis_accumulate(L, s, c->wave, q[kQMis], n_mis, max_n, d_counters);
                         timer.end();
-                        launches += 3;
+                        launches += 2;
                     }
                 }
                 if (direct && !whitted) {

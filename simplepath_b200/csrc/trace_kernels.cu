@@ -691,7 +691,10 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
 
 // shadow_begin: the visibility ray's set-up, the unbounded primitives, the lights accelerator (Scene::intersect_p is an
 // OR over both accelerators: base/Scene.h:79-82, so their order is free) and the root's two child boxes.
-template <bool kCount, typename F>
+// kMis: the same two kernels serve the BSDF-strategy ray of the NEE stage (Integrator.cpp:527-532): intersect_lights first,
+// and — only when the ray reaches a light — Scene::intersect_p with the UNSHRUNK limits (t_max stays FLT_MAX: a sphere light
+// therefore occludes itself, as in the reference); the answer goes to MisRec::light / MisRec::occluded.
+template <bool kCount, typename F, bool kMis = false>
 __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                               const uint32_t* queue, const uint32_t* n_queue, uint32_t light_index,
                                                               uint32_t* q_walk, uint32_t* n_walk, uint32_t* q_lit, uint32_t* n_lit,
@@ -699,33 +702,50 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
 {
     __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
     const uint32_t     n = *n_queue;
-    count_items(counters, kStShadow, n);
+    count_items(counters, kMis ? kStMisTrace : kStShadow, n);
     TraceCounters       local{ 0, 0, 0 };
     const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
         const uint32_t i      = base + threadIdx.x;
         const bool     active = i < n;
-        bool           lit = false, parked = false;
+        bool           lit = false, parked = false, traced = !kMis;
         uint32_t       slot = 0;
         if (active) {
-            slot              = queue[i];
-            const float4   p  = w.vertex[slot].p;
-            const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
-            const Ray      r{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
-            const float    t_max = lr.wi.w;
-            bool           hit   = false;
+            slot            = queue[i];
+            const float4 p  = w.vertex[slot].p;
+            float4       d;   // direction xyz; w = t_max (shadow) / t_min (mis)
+            float        t_min, t_max;
+            if (kMis) {
+                d     = w.mis[slot].d;
+                t_min = d.w;
+                t_max = kInfinite;
+            } else {
+                const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
+                d     = lr.wi;
+                t_min = lr.aux.x;
+                t_max = lr.wi.w;
+            }
+            const Ray r{ p.x, p.y, p.z, d.x, d.y, d.z, t_min };
+            bool      hit = false;
+            if (kMis) { // Scene::intersect_lights; without a light the vertex gets nothing from this strategy and no occlusion query
+                float                beta, gamma, t_light = kInfinite;
+                const LightPrimsT<F> lp{ s.lights };
+                const int32_t li = closest_hit<false>(s.lights_accel, lp, r, t_light, beta, gamma, stack_smem + threadIdx.x, nullptr);
+                w.mis[slot].light = li;
+                traced            = li >= 0;
+            }
             // ListAccelerator::intersect_p_impl: unbounded primitives first
-            for (uint32_t k = 0; k < s.geom.n_unbounded && !hit; ++k) {
+            for (uint32_t k = 0; traced && k < s.geom.n_unbounded && !hit; ++k) {
                 float t, b, g;
                 hit = gp.template test<kCount>(k, true, r, t_max, t, b, g, &local);
             }
-            if (!hit) {
+            if (traced && !hit) {
                 hit = lights_any_hit<F>(s, r, t_max, stack_smem + threadIdx.x);
             }
             AnyWalk walk{ kDone, 0 };
             Stack   stack;
             stack.sh = stack_smem + threadIdx.x;
-            if (!hit) {
+            if (traced && !hit) {
                 walk = AnyWalk{ s.geom.root, s.geom.root_count };
                 const RayInv inv = make_inv_wide(r, s.geom);
                 if (at_node(walk)) { // the walk starts over at the root: only "does the ray enter anything" is asked here
@@ -757,15 +777,20 @@ __global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_const
             if (parked) {
                 w.extend[slot].pad[0] = __int_as_float(park_link(walk.link, false));
                 w.extend[slot].pad[1] = __uint_as_float(walk.count);
+            } else if (kMis) {
+                w.mis[slot].occluded = hit ? 1 : 0;
             } else if (!q_lit) {
                 w.occluded[slot] = hit ? 1 : 0; // direct lighting reads the flag; the NEE path gets the compacted queue
             }
         }
-        if (q_lit) { // survivors only go on to the BSDF stages (Integrator.cpp:503-506)
+        if (!kMis && q_lit) { // survivors only go on to the BSDF stages (Integrator.cpp:503-506)
             queue_push(q_lit, n_lit, slot, lit);
         }
         queue_push(q_walk, n_walk, slot, parked);
-        warp_count(counters + kCntRaysAny, active);
+        if (kMis) {
+            warp_count(counters + kCntRaysLights, active);
+        }
+        warp_count(counters + kCntRaysAny, active && traced);
     }
     if (kCount) {
         flush_counters(local, cnt);
@@ -826,7 +851,7 @@ __device__ __forceinline__ bool any_leaf_step_pairs(const DAccel& acc, const Pri
     return found;
 }
 
-template <bool kCount, typename F>
+template <bool kCount, typename F, bool kMis = false>
 __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_walk(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                              const uint32_t* q_walk, const uint32_t* n_walk, uint32_t light_index,
                                                              uint32_t* cursor, uint32_t* q_lit, uint32_t* n_lit,
@@ -861,13 +886,19 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
             const uint32_t i = feed.draw(!have);
             drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
             if (!have && i != 0xffffffffu) {
-                slot              = q_walk[i];
-                const float4   p  = w.vertex[slot].p;
-                const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
+                slot               = q_walk[i];
+                const float4    p  = w.vertex[slot].p;
                 const ExtendRec ex = w.extend[slot];
-                r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
-                inv               = make_inv_wide(r, s.geom);
-                t_max             = lr.wi.w;
+                if (kMis) {
+                    const float4 d = w.mis[slot].d;
+                    r              = Ray{ p.x, p.y, p.z, d.x, d.y, d.z, d.w };
+                    t_max          = kInfinite;
+                } else {
+                    const LightRec lr = w.light[static_cast<size_t>(light_index) * w.capacity + slot];
+                    r                 = Ray{ p.x, p.y, p.z, lr.wi.x, lr.wi.y, lr.wi.z, lr.aux.x };
+                    t_max             = lr.wi.w;
+                }
+                inv = make_inv_wide(r, s.geom);
                 bool root_pending;
                 walk.link  = unpark_link(__float_as_int(ex.pad[0]), root_pending);
                 walk.count = __float_as_uint(ex.pad[1]);
@@ -891,7 +922,9 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
             hit              = hit || found;
         }
         if (have && walk.link == kDone) {
-            if (!q_lit) {
+            if (kMis) {
+                w.mis[slot].occluded = hit ? 1 : 0;
+            } else if (!q_lit) {
                 w.occluded[slot] = hit ? 1 : 0;
             } else if (!hit) {
                 const unsigned act    = __activemask();
@@ -1290,11 +1323,26 @@ static void launch_mis_variant(const Launch& l, const DScene& s, const DWave& w,
         s, w, queue, d_n_queue, d_counters, d_cnt);
 }
 
-void launch_mis_trace(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
-                      uint32_t max_n, unsigned long long* d_counters, TraceCounters* d_cnt)
+int launch_mis_trace(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
+                     uint32_t max_n, uint32_t* d_cursor, uint32_t* q_walk, uint32_t* d_n_walk, unsigned long long* d_counters,
+                     TraceCounters* d_cnt)
 {
-    if (max_n == 0) return;
+    if (max_n == 0) return 0;
     const bool analytic = l.features == FeatAnalytic::id;
+#ifndef SPCU_MIS_SINGLE
+#define SPCU_MIS_SINGLE 0 // 1: A/B builds with round 1's one-thread-per-ray kernel
+#endif
+    if (!analytic && !d_cnt && q_walk && !SPCU_MIS_SINGLE) { // begin + persistent walk, as the shadow stage
+        static const int occ_b = trace_ctas_per_sm(k_shadow_begin<false, FeatFull, true>);
+        static const int occ_w = trace_ctas_per_sm(k_shadow_walk<false, FeatFull, true>);
+        k_shadow_begin<false, FeatFull, true><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, queue, d_n_queue, 0u, q_walk, d_n_walk, nullptr, nullptr, d_counters, nullptr);
+        debug_sync(l, "k_mis_begin");
+        k_shadow_walk<false, FeatFull, true><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, q_walk, d_n_walk, 0u, d_cursor, nullptr, nullptr, d_counters, nullptr);
+        debug_sync(l, "k_mis_walk");
+        return 2;
+    }
     if (d_cnt) {
         analytic ? launch_mis_variant<true, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_counters, d_cnt)
                  : launch_mis_variant<true, FeatFull>(l, s, w, queue, d_n_queue, max_n, d_counters, d_cnt);
@@ -1302,6 +1350,7 @@ void launch_mis_trace(const Launch& l, const DScene& s, const DWave& w, const ui
         analytic ? launch_mis_variant<false, FeatAnalytic>(l, s, w, queue, d_n_queue, max_n, d_counters, nullptr)
                  : launch_mis_variant<false, FeatFull>(l, s, w, queue, d_n_queue, max_n, d_counters, nullptr);
     }
+    return 1;
 }
 
 } // namespace spcu

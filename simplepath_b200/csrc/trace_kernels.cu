@@ -635,7 +635,23 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
             if ((threadIdx.x & 31) == 0) atomicAdd(counters + kCntErrors, 1ull);
             break;
         }
-        if (!drained && (32 - n_node - n_leaf >= kWalkRefillMin || n_node + n_leaf == 0)) {
+        if (n_node + n_leaf == 0 || (!drained && 32 - n_node - n_leaf >= kWalkRefillMin)) {
+            // ---- retire + refill, together.  A finished walk is not written out the moment it ends (one lane, one global atomic
+            // whose round trip stalled the whole warp: 15 % of the kernel's stall samples, ncu r02g) but here, with every other
+            // lane that has finished since the last refill: one aggregated atomic per material segment, issued next to the loads
+            // of the rays that take the freed lanes.
+            const bool finished = have && walk.link == kDone;
+            uint32_t   seg      = 0;
+            if (finished) {
+                w.extend[slot].hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
+                seg = walk.hit_id < 0 ? sorted.n_segments - 1u
+                                      : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + walk.hit_id)), sorted.n_segments - 2u);
+                have = false;
+            }
+            segment_push(sorted, seg, slot, finished);
+            if (drained) {
+                break; // nothing in flight (the other clause needs !drained) and nothing left to draw
+            }
             const uint32_t i = feed.draw(!have);
             drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
             if (!have && i != 0xffffffffu) {
@@ -660,8 +676,6 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
                 }
                 have = true;
             }
-        } else if (n_node + n_leaf == 0) {
-            break;
         } else if (n_node > 0 && !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)) {
             if (have && at_node(walk)) {
                 if constexpr (!kOrdered) {
@@ -675,13 +689,6 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
             }
         } else {
             closest_leaf_step_pairs<kCount, kOrdered>(s.geom, gp, r, walk, stack, have && at_leaf(walk), kOrdered && !inv.generic, tbl, &local);
-        }
-        if (have && walk.link == kDone) {
-            w.extend[slot].hit = HitRec{ walk.hit_id, walk.t_max, walk.beta, walk.gamma };
-            const uint32_t seg = walk.hit_id < 0 ? sorted.n_segments - 1u
-                                                 : min(SPCU_META_MATERIAL(__ldg(s.geom_meta + walk.hit_id)), sorted.n_segments - 2u);
-            segment_push_converged(sorted, seg, slot);
-            have = false;
         }
     }
     if (kCount) {
@@ -882,7 +889,23 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
             if ((threadIdx.x & 31) == 0) atomicAdd(counters + kCntErrors, 1ull);
             break;
         }
-        if (!drained && (32 - n_node - n_leaf >= kWalkRefillMin || n_node + n_leaf == 0)) {
+        if (n_node + n_leaf == 0 || (!drained && 32 - n_node - n_leaf >= kWalkRefillMin)) {
+            // ---- retire + refill, together (see k_extend_walk)
+            const bool finished = have && walk.link == kDone;
+            if (finished) {
+                if (kMis) {
+                    w.mis[slot].occluded = hit ? 1 : 0;
+                } else if (!q_lit) {
+                    w.occluded[slot] = hit ? 1 : 0;
+                }
+                have = false;
+            }
+            if (!kMis && q_lit) { // survivors only go on to the BSDF stages (Integrator.cpp:503-506)
+                queue_push(q_lit, n_lit, slot, finished && !hit);
+            }
+            if (drained) {
+                break;
+            }
             const uint32_t i = feed.draw(!have);
             drained          = __ballot_sync(0xffffffffu, !have && i == 0xffffffffu) != 0u;
             if (!have && i != 0xffffffffu) {
@@ -906,8 +929,6 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
                 have = true;
                 hit  = false;
             }
-        } else if (n_node + n_leaf == 0) {
-            break;
         } else if (n_node > 0 && !vote_leaf_step(n_node, have && at_leaf(walk), walk.count & SPCU_LEAF_COUNT_MASK)) {
             if (have && at_node(walk)) {
                 if (!inv.generic) {
@@ -920,24 +941,6 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_shadow_wa
         } else {
             const bool found = any_leaf_step_pairs<kCount>(s.geom, gp, r, t_max, walk, stack, have && at_leaf(walk), !inv.generic, tbl, &local);
             hit              = hit || found;
-        }
-        if (have && walk.link == kDone) {
-            if (kMis) {
-                w.mis[slot].occluded = hit ? 1 : 0;
-            } else if (!q_lit) {
-                w.occluded[slot] = hit ? 1 : 0;
-            } else if (!hit) {
-                const unsigned act    = __activemask();
-                const int      lane   = threadIdx.x & 31;
-                const int      leader = __ffs(act) - 1;
-                uint32_t       base   = 0;
-                if (lane == leader) {
-                    base = atomicAdd(n_lit, static_cast<uint32_t>(__popc(act)));
-                }
-                base = __shfl_sync(act, base, leader);
-                q_lit[base + __popc(act & ((1u << lane) - 1u))] = slot;
-            }
-            have = false;
         }
     }
     if (kCount) {

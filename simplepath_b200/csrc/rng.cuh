@@ -92,7 +92,11 @@ static __device__ __noinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint
 #endif
 
 // One draw call: returns its pair of words as floats in [0,1) and advances the path's draw counter.
+#ifdef SPCU_RNG_NOINLINE
+__host__ __device__ __noinline__ void rng_next2(Rng& r, float& u0, float& u1)
+#else
 __host__ __device__ __forceinline__ void rng_next2(Rng& r, float& u0, float& u1)
+#endif
 {
 #if defined(SPCU_RNG_WHOLE_BLOCK) && defined(__CUDA_ARCH__) // A/B only (profiles/): round 1's contract, a whole block per draw — NOT what the oracle draws
     {

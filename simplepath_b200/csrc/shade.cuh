@@ -286,6 +286,9 @@ __device__ __forceinline__ float beckmann_D(V3 wh, float ax, float ay)
         return 0.0f;
     }
     const float cos4 = sqr(cos2_theta(wh));
+    if (ax == ay) { // isotropic (every material the .sp parser creates): cos^2 phi + sin^2 phi = 1 up to rounding
+        return expf(-t2 / sqr(ax)) / (kPi * ax * ay * cos4);
+    }
     float       cp, sp;
     cos_sin_phi(wh, cp, sp);
     return expf(-t2 * (sqr(cp) / sqr(ax) + sqr(sp) / sqr(ay))) / (kPi * ax * ay * cos4);
@@ -298,9 +301,12 @@ __device__ __forceinline__ float beckmann_lambda(V3 w, float ax, float ay)
     if (isinf(abs_tan)) {
         return 0.0f;
     }
-    float cp, sp;
-    cos_sin_phi(w, cp, sp);
-    const float alpha = sqrtf(sqr(cp) * sqr(ax) + sqr(sp) * sqr(ay));
+    float alpha = ax;
+    if (ax != ay) { // (isotropic: sqrt(cos^2 phi + sin^2 phi) * ax = ax up to rounding; the azimuth is not needed)
+        float cp, sp;
+        cos_sin_phi(w, cp, sp);
+        alpha = sqrtf(sqr(cp) * sqr(ax) + sqr(sp) * sqr(ay));
+    }
     const float a     = 1.0f / (alpha * abs_tan);
     if (a >= 1.6f) {
         return 0.0f;

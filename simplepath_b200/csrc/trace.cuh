@@ -1130,6 +1130,33 @@ __device__ __forceinline__ void any_wide_step(const DAccel& acc, const Ray& r, c
         wide_any_pop(acc, stack, w);
         return;
     }
+#ifdef SPCU_ANY_SORTED // (A/B: measured slower — elf shadow 11.9 -> 12.7 ms, profiles/r02m_ab_any_hit_order.jsonl — and left off)
+    // Nearest box first, although any order gives the same answer: an occluded ray — half of the shadow rays of a path-traced
+    // frame — usually meets its occluder in the nearer boxes, and the walk ends at the first accepted primitive.
+    const float inf = __int_as_float(0x7f800000);
+    float    k0 = (h & 1u) ? e[0] : inf, k1 = (h & 2u) ? e[1] : inf, k2 = (h & 4u) ? e[2] : inf, k3 = (h & 8u) ? e[3] : inf;
+    unsigned s0 = 0u, s1 = 1u, s2 = 2u, s3 = 3u;
+#define SPCU_CSWAP(ka, sa, kb, sb)        \
+    {                                     \
+        const bool     sw = kb < ka;      \
+        const float    tk = sw ? kb : ka; \
+        const unsigned ts = sw ? sb : sa; \
+        kb                = sw ? ka : kb; \
+        sb                = sw ? sa : sb; \
+        ka                = tk;           \
+        sa                = ts;           \
+    }
+    SPCU_CSWAP(k0, s0, k1, s1)
+    SPCU_CSWAP(k2, s2, k3, s3)
+    SPCU_CSWAP(k0, s0, k2, s2)
+    SPCU_CSWAP(k1, s1, k3, s3)
+    SPCU_CSWAP(k1, s1, k2, s2)
+#undef SPCU_CSWAP
+    if (k3 < inf) stack.push((idx << 2) | static_cast<int32_t>(s3));
+    if (k2 < inf) stack.push((idx << 2) | static_cast<int32_t>(s2));
+    if (k1 < inf) stack.push((idx << 2) | static_cast<int32_t>(s1));
+    wide_child(n, s0, w.link, w.count);
+#else
     const unsigned first = __ffs(h) - 1u;
     h &= h - 1u;
     while (h) {
@@ -1138,6 +1165,7 @@ __device__ __forceinline__ void any_wide_step(const DAccel& acc, const Ray& r, c
         stack.push((idx << 2) | static_cast<int32_t>(k));
     }
     wide_child(n, first, w.link, w.count);
+#endif
 }
 
 __device__ __forceinline__ RayInv make_inv_wide(const Ray& r, const DAccel& acc)

@@ -662,7 +662,11 @@ int device_build(spcu_ctx* c, Scratch& mem, Build& b, spcu_bounds* d_bounds, uin
 // BVHAccelerator(first, last)); bounds, tree and the gather into leaf order all happen on the device, and the context's
 // geometry buffers end up exactly as spcu_upload_scene would have filled them from the flattener's output.
 // ---- 4-wide nodes (trace.cuh): wide node i = the grandchildren of binary node i (a child that is a leaf stands for itself) ----
-__global__ void k_build_wide(const float4* nodes, uint32_t n, float4* wide)
+// Every child is described by ONE packed word (trace.cuh wide_unpack): a walk's stack entry is that word, so a pop finds the
+// child's node or triangles without the dependent load of { link, count } round 2's first wide walk paid.  Leaves of more than
+// kWideSmallLeafMax primitives (the reference makes them where std::partition cannot split: BVHAccelerator.h:195-198) do not
+// fit the word and go through the side table `big` (one { first, count } per such leaf, slots handed out by `n_big`).
+__global__ void k_build_wide(const float4* nodes, uint32_t n, float4* wide, int2* big, uint32_t* n_big)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float    box[4][6];
@@ -696,22 +700,33 @@ __global__ void k_build_wide(const float4* nodes, uint32_t n, float4* wide)
             link[m]  = ~0;
             count[m] = 0u;
         }
+        // one 32-byte sector per child: { lo.xyz, hi.x } { hi.yz, packed child, count }
         float4* o = wide + 8 * static_cast<size_t>(i);
-        o[0] = make_float4(box[0][0], box[0][1], box[0][2], box[0][3]);
-        o[1] = make_float4(box[0][4], box[0][5], box[1][0], box[1][1]);
-        o[2] = make_float4(box[1][2], box[1][3], box[1][4], box[1][5]);
-        o[3] = make_float4(box[2][0], box[2][1], box[2][2], box[2][3]);
-        o[4] = make_float4(box[2][4], box[2][5], box[3][0], box[3][1]);
-        o[5] = make_float4(box[3][2], box[3][3], box[3][4], box[3][5]);
-        o[6] = make_float4(__int_as_float(link[0]), __uint_as_float(count[0]), __int_as_float(link[1]), __uint_as_float(count[1]));
-        o[7] = make_float4(__int_as_float(link[2]), __uint_as_float(count[2]), __int_as_float(link[3]), __uint_as_float(count[3]));
+        for (int k = 0; k < 4; ++k) {
+            int32_t packed = link[k]; // an internal node: its index
+            if (link[k] < 0) {
+                const uint32_t first = static_cast<uint32_t>(~link[k]), cnt = count[k] & SPCU_LEAF_COUNT_MASK;
+                if (cnt <= kWideSmallLeafMax && (first <= kWidePayloadMask || cnt == 0u)) {
+                    packed = static_cast<int32_t>(0x80000000u | ((count[k] & SPCU_LEAF_MIXED_FLAG) >> 1) | (cnt << 27) |
+                                                  (cnt ? first : 0u));
+                } else {
+                    const uint32_t t = atomicAdd(n_big, 1u);
+                    big[t]           = make_int2(link[k], static_cast<int32_t>(count[k]));
+                    packed           = static_cast<int32_t>(0x80000000u | (kWideBigLeafTag << 27) | t);
+                }
+            }
+            o[2 * k + 0] = make_float4(box[k][0], box[k][1], box[k][2], box[k][3]);
+            o[2 * k + 1] = make_float4(box[k][4], box[k][5], __int_as_float(packed), __uint_as_float(count[k]));
+        }
     }
 }
 
-void spcu::launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int sm_count, cudaStream_t st)
+void spcu::launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int2* d_big, uint32_t* d_n_big, int sm_count,
+                             cudaStream_t st)
 {
     if (n) {
-        k_build_wide<<<grid_for(n, sm_count), kBlock, 0, st>>>(d_nodes, n, d_wide);
+        cudaMemsetAsync(d_n_big, 0, sizeof(uint32_t), st);
+        k_build_wide<<<grid_for(n, sm_count), kBlock, 0, st>>>(d_nodes, n, d_wide, d_big, d_n_big);
     }
 }
 

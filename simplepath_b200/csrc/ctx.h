@@ -74,6 +74,7 @@ struct spcu_ctx
     bool         have_scene = false;
     spcu::DScene ds{};
     spcu::DevBuf geom_wide; // 4-wide copy of geom_nodes (built at upload)
+    spcu::DevBuf geom_big;  // its side table of oversized leaves + the slot counter (device_scene.h)
     spcu::DevBuf geom_nodes, geom_prims, geom_shade, geom_meta, light_nodes, lights, light_order, materials, bxdfs, pool,
         jitter;
     uint64_t scene_bytes = 0;

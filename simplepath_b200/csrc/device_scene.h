@@ -9,10 +9,19 @@
 
 namespace spcu {
 
+// Packed child of a 4-wide node (build_kernels.cu k_build_wide, trace.cuh wide_unpack) — what the wide walks keep on their stacks:
+//   bit 31 clear: an internal node, the word is its index;
+//   bit 31 set:   a leaf — bit 30 = SPCU_LEAF_MIXED_FLAG, bits 29..27 = its primitive count (0..kWideSmallLeafMax) and bits
+//                 26..0 = its first primitive, or count bits = kWideBigLeafTag and bits 26..0 = a slot of DAccel::big.
+constexpr uint32_t kWideSmallLeafMax = 6u;
+constexpr uint32_t kWideBigLeafTag   = 7u;
+constexpr uint32_t kWidePayloadMask  = 0x07ffffffu;
+
 struct DAccel
 {
     const float4* nodes; // 4 x float4 per node (spcu_bvh_node)
     const float4* wide;  // 8 x float4 per node: the 4-wide node of binary node i (trace.cuh); NULL without internal nodes
+    const int2*   big;   // { link, count } of the leaves a packed child cannot describe (more than kWideSmallLeafMax primitives)
     int32_t       root;
     uint32_t      root_count;
     uint32_t      n_unbounded;

@@ -41,7 +41,8 @@ int launch_mis_trace(const struct Launch& l, const DScene& s, const DWave& w, co
                      unsigned long long* d_counters, TraceCounters* d_cnt);
 
 // ---- build_kernels.cu: the 4-wide copy of the resident binary nodes (8 x float4 per node, trace.cuh) ------------------------
-void launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int sm_count, cudaStream_t st);
+// d_big: room for n_prims / (kWideSmallLeafMax + 1) + 1 entries; d_n_big: one counter (zeroed here)
+void launch_build_wide(const float4* d_nodes, uint32_t n, float4* d_wide, int2* d_big, uint32_t* d_n_big, int sm_count, cudaStream_t st);
 
 // ---- shade_kernels.cu ------------------------------------------------------------------------------------------
 struct RenderParams

@@ -190,6 +190,7 @@ DAccel device_accel(const spcu_accel& a, const DevBuf& nodes, bool proper_boxes)
 {
     DAccel d;
     d.wide         = nullptr;
+    d.big          = nullptr;
     d.proper_boxes = proper_boxes ? 1u : 0u;
     d.nodes       = nodes.as<const float4>();
     d.root        = a.root;
@@ -261,7 +262,7 @@ void spcu_destroy(spcu_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     spcu_comm_destroy(c);
-    for (DevBuf* b : { &c->geom_wide, &c->geom_nodes, &c->geom_prims, &c->geom_shade, &c->geom_meta, &c->light_nodes, &c->lights,
+    for (DevBuf* b : { &c->geom_wide, &c->geom_big, &c->geom_nodes, &c->geom_prims, &c->geom_shade, &c->geom_meta, &c->light_nodes, &c->lights,
                        &c->light_order, &c->materials, &c->bxdfs, &c->pool, &c->jitter, &c->q_rays, &c->q_out, &c->q_aux,
                        &c->q_cnt, &c->queue_counts, &c->counters, &c->pix_list, &c->host_rgb, &c->host_sq, &c->path_radiance, &c->sorted_queue, &c->packed }) {
         b->release();
@@ -398,11 +399,15 @@ static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitte
     if ((rc = upload(c, c->bxdfs, s->bxdfs, s->n_bxdfs)) != SPCU_OK) return rc;
     if ((rc = upload(c, c->pool, s->float_pool, s->n_pool)) != SPCU_OK) return rc;
     if ((rc = upload(c, c->jitter, jitter, static_cast<size_t>(spp) * 2)) != SPCU_OK) return rc;
-    // the 4-wide copy of the geometry tree for the ordered / any-hit walks (keys are node << 2 | slot: below 2^29 nodes)
-    const bool wide = geom.n_nodes > 0 && geom.n_nodes < (1u << 29) && geom_proper;
+    // the 4-wide copy of the geometry tree for the ordered / any-hit walks (a packed child holds a node index, or a first
+    // primitive / side-table slot in 27 bits: device_scene.h)
+    const bool wide = geom.n_nodes > 0 && geom.n_nodes < (1u << 31) && geom.n_prims <= kWidePayloadMask && geom_proper;
     if (wide) {
+        const size_t big_entries = geom.n_prims / (kWideSmallLeafMax + 1u) + 1u;
         CK(c, c->geom_wide.reserve(static_cast<size_t>(geom.n_nodes) * 128));
-        launch_build_wide(c->geom_nodes.as<const float4>(), geom.n_nodes, c->geom_wide.as<float4>(), c->sm_count, c->stream);
+        CK(c, c->geom_big.reserve(big_entries * sizeof(int2) + sizeof(uint32_t)));
+        launch_build_wide(c->geom_nodes.as<const float4>(), geom.n_nodes, c->geom_wide.as<float4>(), c->geom_big.as<int2>(),
+                          reinterpret_cast<uint32_t*>(c->geom_big.as<int2>() + big_entries), c->sm_count, c->stream);
         CK(c, cudaGetLastError());
     }
     CK(c, cudaStreamSynchronize(c->stream));
@@ -415,6 +420,7 @@ static int upload_impl(spcu_ctx* c, const spcu_flat_scene* s, const float* jitte
     std::memcpy(d.camera, s->camera, sizeof d.camera);
     d.geom         = device_accel(geom, c->geom_nodes, geom_proper);
     d.geom.wide    = wide ? c->geom_wide.as<const float4>() : nullptr;
+    d.geom.big     = wide ? c->geom_big.as<const int2>() : nullptr;
     d.geom_prims   = c->geom_prims.as<const float4>();
     d.geom_shade   = c->geom_shade.as<const float4>();
     d.geom_meta    = c->geom_meta.as<const uint32_t>();

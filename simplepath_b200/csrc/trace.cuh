@@ -949,7 +949,7 @@ __device__ __forceinline__ void any_node_step(const DAccel& acc, const Ray& r, c
 }
 
 // returns true when a primitive of the leaf is hit (the query is over); otherwise the walk moves on
-__device__ __forceinline__ void wide_child_of_key(const float4* wide, int32_t key, int32_t& link, uint32_t& count);
+__device__ __forceinline__ void wide_unpack(const DAccel& acc, int32_t packed, int32_t& link, uint32_t& count);
 
 // (`wide_keys`: the stack holds keys of 4-wide nodes — see "4-wide nodes" below — instead of binary node indices)
 template <typename AnyTest, typename StackS>
@@ -972,7 +972,7 @@ __device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& 
     } else if (!wide_keys) {
         any_pop(acc, stack, w);
     } else if (stack.n > 0) {
-        wide_child_of_key(acc.wide, stack.pop(), w.link, w.count);
+        wide_unpack(acc, stack.pop(), w.link, w.count);
     } else {
         w.link = kDone;
     }
@@ -983,9 +983,13 @@ __device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& 
 // 4-wide nodes: the reference topology with every other level folded away (device_scene.h DAccel::wide, built at upload
 // by k_build_wide, build_kernels.cu).  Wide node i belongs to binary node i and holds the boxes of its GRANDCHILDREN — or of
 // a child where that child is a leaf —, in the reference's left-to-right order:
-//     floats  0..23  four boxes  { lo.xyz hi.xyz }            (an unused slot is a point box at +3e38: never entered)
-//     words  24..31  four { link, count } pairs               (link / count as in spcu_bvh_node; unused: leaf of 0 primitives)
-// 128 bytes = four 256-bit loads.  The walks of the render's traversal stages are bound by the LATENCY of one dependent node
+//     child k = the 32-byte sector k:  { lo.x lo.y lo.z hi.x } { hi.y hi.z packed count }
+//     (an unused slot is a point box at +3e38: never entered; `packed` = the child in one word, device_scene.h; `count` as in
+//     spcu_bvh_node, kept for inspection)
+// 128 bytes = four 256-bit loads.  A stack entry is the child's PACKED word: the pop that follows a leaf or a dead end decodes
+// it in registers and goes straight for the node or the triangles.  (The first wide walk kept (node, slot) keys and paid one
+// dependent 8-byte load per pop — an L1 miss more often than not, the warps of an SM sweep its L1 once per round of steps.)
+// The walks of the render's traversal stages are bound by the LATENCY of one dependent node
 // fetch per step and by the L1's look-up rate for scattered sectors, not by arithmetic (ncu, profiles/r02b_*: long-scoreboard
 // and fixed-latency stalls 7.4 of 11.4 cycles per issued instruction, l1tex at 69 % of peak); a wide step does the work of
 // two binary levels behind ONE fetch, and its four slab tests are independent instruction streams.
@@ -996,8 +1000,14 @@ __device__ __forceinline__ bool any_leaf_step(const DAccel& acc, const AnyTest& 
 // (up to the epsilon ties stated for the ordered walk).  The exact walk stays on the binary nodes.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kWideStackCapacity = 3 * (SPCU_MAX_BVH_DEPTH / 2 + 1) + 2; // up to three deferred children per wide level
-constexpr int kWideSharedAny     = 24;                                    // 4-byte keys: [24][128] = the 12 KB block
-constexpr int kWideSharedOrdered = 16;                                    // 8-byte (key, entry distance): needs [32][128] words
+#ifndef SPCU_WIDE_SHARED_ANY
+#define SPCU_WIDE_SHARED_ANY 24
+#endif
+#ifndef SPCU_WIDE_SHARED_ORDERED
+#define SPCU_WIDE_SHARED_ORDERED 16
+#endif
+constexpr int kWideSharedAny     = SPCU_WIDE_SHARED_ANY;     // 4-byte packed children: [24][128] = the 12 KB block
+constexpr int kWideSharedOrdered = SPCU_WIDE_SHARED_ORDERED; // 8-byte (packed child, entry distance): needs [32][128] words
 using WideStack        = StackT<kWideSharedAny, kWideStackCapacity>;
 using WideOrderedStack = OrderedStackT<kWideSharedOrdered, kWideStackCapacity>;
 
@@ -1013,29 +1023,35 @@ __device__ __forceinline__ WideNode load_wide(const float4* wide, int32_t idx)
 }
 
 // the four slab tests of a wide node (NaN-free form); h = hit mask, e[k] = entry distance of box k (valid where hit)
+__device__ __forceinline__ bool wide_slab(const Float8& q, const Ray& r, const RayInv& inv, float t_max, float& e)
+{
+    return slab_fast(q.lo.x, q.lo.y, q.lo.z, q.lo.w, q.hi.x, q.hi.y, r, inv, t_max, e);
+}
+
 __device__ __forceinline__ unsigned wide_slabs(const WideNode& n, const Ray& r, const RayInv& inv, float t_max, float (&e)[4])
 {
-    const bool h0 = slab_fast(n.q0.lo.x, n.q0.lo.y, n.q0.lo.z, n.q0.lo.w, n.q0.hi.x, n.q0.hi.y, r, inv, t_max, e[0]);
-    const bool h1 = slab_fast(n.q0.hi.z, n.q0.hi.w, n.q1.lo.x, n.q1.lo.y, n.q1.lo.z, n.q1.lo.w, r, inv, t_max, e[1]);
-    const bool h2 = slab_fast(n.q1.hi.x, n.q1.hi.y, n.q1.hi.z, n.q1.hi.w, n.q2.lo.x, n.q2.lo.y, r, inv, t_max, e[2]);
-    const bool h3 = slab_fast(n.q2.lo.z, n.q2.lo.w, n.q2.hi.x, n.q2.hi.y, n.q2.hi.z, n.q2.hi.w, r, inv, t_max, e[3]);
+    const bool h0 = wide_slab(n.q0, r, inv, t_max, e[0]);
+    const bool h1 = wide_slab(n.q1, r, inv, t_max, e[1]);
+    const bool h2 = wide_slab(n.q2, r, inv, t_max, e[2]);
+    const bool h3 = wide_slab(n.q3, r, inv, t_max, e[3]);
     return (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
 }
 
-__device__ __forceinline__ void wide_child(const WideNode& n, unsigned slot, int32_t& link, uint32_t& count)
+// packed child (device_scene.h) -> the cursor's { link, count } (link / count as in spcu_bvh_node)
+__device__ __forceinline__ void wide_unpack(const DAccel& acc, int32_t packed, int32_t& link, uint32_t& count)
 {
-    const float l = slot == 0u ? n.q3.lo.x : slot == 1u ? n.q3.lo.z : slot == 2u ? n.q3.hi.x : n.q3.hi.z;
-    const float c = slot == 0u ? n.q3.lo.y : slot == 1u ? n.q3.lo.w : slot == 2u ? n.q3.hi.y : n.q3.hi.w;
-    link  = __float_as_int(l);
-    count = __float_as_uint(c);
-}
-
-// { link, count } of child `key & 3` of wide node `key >> 2`: one 8-byte load
-__device__ __forceinline__ void wide_child_of_key(const float4* wide, int32_t key, int32_t& link, uint32_t& count)
-{
-    const float2 lc = __ldg(reinterpret_cast<const float2*>(wide + 8 * static_cast<size_t>(key >> 2) + 6) + (key & 3));
-    link  = __float_as_int(lc.x);
-    count = __float_as_uint(lc.y);
+    link = packed;
+    if (packed < 0) {
+        const uint32_t p = static_cast<uint32_t>(packed), tag = (p >> 27) & 7u;
+        if (tag != kWideBigLeafTag) {
+            link  = ~static_cast<int32_t>(p & kWidePayloadMask);
+            count = tag | ((p << 1) & SPCU_LEAF_MIXED_FLAG);
+        } else { // a leaf of more than kWideSmallLeafMax primitives: the side table (rare)
+            const int2 lc = __ldg(acc.big + (p & kWidePayloadMask));
+            link          = lc.x;
+            count         = static_cast<uint32_t>(lc.y);
+        }
+    }
 }
 
 // The cursor has just become a leaf: start its triangle records on their way to L1 now — the leaf step that tests them runs a few
@@ -1058,7 +1074,7 @@ __device__ __forceinline__ void wide_ordered_pop(const DAccel& acc, WideOrderedS
     while (stack.n > 0) {
         const int2 e = stack.pop();
         if (!(__int_as_float(e.y) > w.t_max)) { // entry not beyond the current hit
-            wide_child_of_key(acc.wide, e.x, w.link, w.count);
+            wide_unpack(acc, e.x, w.link, w.count);
             return;
         }
     }
@@ -1067,12 +1083,21 @@ __device__ __forceinline__ void wide_ordered_pop(const DAccel& acc, WideOrderedS
 // One step of the ordered walk at an internal node, over its wide node: the nearest of the (up to four) boxes the ray enters
 // becomes the cursor, the others wait on the stack, farthest first (so the nearest of them is popped first).  Equal entry
 // distances keep the reference's left-to-right order.
+#define SPCU_CSWAP(ka, sa, kb, sb)        \
+    {                                     \
+        const bool    sw = kb < ka;       \
+        const float   tk = sw ? kb : ka;  \
+        const int32_t ts = sw ? sb : sa;  \
+        kb               = sw ? ka : kb;  \
+        sb               = sw ? sa : sb;  \
+        ka               = tk;            \
+        sa               = ts;            \
+    }
 template <bool kCount>
 __device__ __forceinline__ void closest_wide_step_ordered(const DAccel& acc, const Ray& r, const RayInv& inv, ClosestWalk& w,
                                                           WideOrderedStack& stack, TraceCounters* cnt)
 {
-    const int32_t  idx = w.link;
-    const WideNode n   = load_wide(acc.wide, idx);
+    const WideNode n = load_wide(acc.wide, w.link);
     if (kCount) ++cnt->nodes;
     float          e[4];
     const unsigned h = wide_slabs(n, r, inv, w.t_max, e);
@@ -1080,36 +1105,25 @@ __device__ __forceinline__ void closest_wide_step_ordered(const DAccel& acc, con
         wide_ordered_pop(acc, stack, w);
         return;
     }
-    // sort (distance, slot) ascending; a box that is not entered sorts last (+inf)
+    // sort (distance, packed child) ascending; a box that is not entered sorts last (+inf)
     const float inf = __int_as_float(0x7f800000);
-    float    k0 = (h & 1u) ? e[0] : inf, k1 = (h & 2u) ? e[1] : inf, k2 = (h & 4u) ? e[2] : inf, k3 = (h & 8u) ? e[3] : inf;
-    unsigned s0 = 0u, s1 = 1u, s2 = 2u, s3 = 3u;
-#define SPCU_CSWAP(ka, sa, kb, sb)        \
-    {                                     \
-        const bool     sw = kb < ka;      \
-        const float    tk = sw ? kb : ka; \
-        const unsigned ts = sw ? sb : sa; \
-        kb                = sw ? ka : kb; \
-        sb                = sw ? sa : sb; \
-        ka                = tk;           \
-        sa                = ts;           \
-    }
+    float   k0 = (h & 1u) ? e[0] : inf, k1 = (h & 2u) ? e[1] : inf, k2 = (h & 4u) ? e[2] : inf, k3 = (h & 8u) ? e[3] : inf;
+    int32_t s0 = __float_as_int(n.q0.hi.z), s1 = __float_as_int(n.q1.hi.z), s2 = __float_as_int(n.q2.hi.z), s3 = __float_as_int(n.q3.hi.z);
     SPCU_CSWAP(k0, s0, k1, s1)
     SPCU_CSWAP(k2, s2, k3, s3)
     SPCU_CSWAP(k0, s0, k2, s2)
     SPCU_CSWAP(k1, s1, k3, s3)
     SPCU_CSWAP(k1, s1, k2, s2)
-#undef SPCU_CSWAP
-    if (k3 < inf) stack.push((idx << 2) | static_cast<int32_t>(s3), k3);
-    if (k2 < inf) stack.push((idx << 2) | static_cast<int32_t>(s2), k2);
-    if (k1 < inf) stack.push((idx << 2) | static_cast<int32_t>(s1), k1);
-    wide_child(n, s0, w.link, w.count);
+    if (k3 < inf) stack.push(s3, k3);
+    if (k2 < inf) stack.push(s2, k2);
+    if (k1 < inf) stack.push(s1, k1);
+    wide_unpack(acc, s0, w.link, w.count);
 }
 
 __device__ __forceinline__ void wide_any_pop(const DAccel& acc, WideStack& stack, AnyWalk& w)
 {
     if (stack.n > 0) {
-        wide_child_of_key(acc.wide, stack.pop(), w.link, w.count);
+        wide_unpack(acc, stack.pop(), w.link, w.count);
     } else {
         w.link = kDone;
     }
@@ -1121,52 +1135,41 @@ template <bool kCount>
 __device__ __forceinline__ void any_wide_step(const DAccel& acc, const Ray& r, const RayInv& inv, float t_max, AnyWalk& w,
                                               WideStack& stack, TraceCounters* cnt)
 {
-    const int32_t  idx = w.link;
-    const WideNode n   = load_wide(acc.wide, idx);
+    const WideNode n = load_wide(acc.wide, w.link);
     if (kCount) ++cnt->nodes;
-    float    e[4];
-    unsigned h = wide_slabs(n, r, inv, t_max, e);
+    float          e[4];
+    const unsigned h = wide_slabs(n, r, inv, t_max, e);
     if (h == 0u) {
         wide_any_pop(acc, stack, w);
         return;
     }
+    const int32_t s0 = __float_as_int(n.q0.hi.z), s1 = __float_as_int(n.q1.hi.z), s2 = __float_as_int(n.q2.hi.z), s3 = __float_as_int(n.q3.hi.z);
 #ifdef SPCU_ANY_SORTED // (A/B: measured slower — elf shadow 11.9 -> 12.7 ms, profiles/r02m_ab_any_hit_order.jsonl — and left off)
     // Nearest box first, although any order gives the same answer: an occluded ray — half of the shadow rays of a path-traced
     // frame — usually meets its occluder in the nearer boxes, and the walk ends at the first accepted primitive.
     const float inf = __int_as_float(0x7f800000);
-    float    k0 = (h & 1u) ? e[0] : inf, k1 = (h & 2u) ? e[1] : inf, k2 = (h & 4u) ? e[2] : inf, k3 = (h & 8u) ? e[3] : inf;
-    unsigned s0 = 0u, s1 = 1u, s2 = 2u, s3 = 3u;
-#define SPCU_CSWAP(ka, sa, kb, sb)        \
-    {                                     \
-        const bool     sw = kb < ka;      \
-        const float    tk = sw ? kb : ka; \
-        const unsigned ts = sw ? sb : sa; \
-        kb                = sw ? ka : kb; \
-        sb                = sw ? sa : sb; \
-        ka                = tk;           \
-        sa                = ts;           \
-    }
-    SPCU_CSWAP(k0, s0, k1, s1)
-    SPCU_CSWAP(k2, s2, k3, s3)
-    SPCU_CSWAP(k0, s0, k2, s2)
-    SPCU_CSWAP(k1, s1, k3, s3)
-    SPCU_CSWAP(k1, s1, k2, s2)
-#undef SPCU_CSWAP
-    if (k3 < inf) stack.push((idx << 2) | static_cast<int32_t>(s3));
-    if (k2 < inf) stack.push((idx << 2) | static_cast<int32_t>(s2));
-    if (k1 < inf) stack.push((idx << 2) | static_cast<int32_t>(s1));
-    wide_child(n, s0, w.link, w.count);
+    float   k0 = (h & 1u) ? e[0] : inf, k1 = (h & 2u) ? e[1] : inf, k2 = (h & 4u) ? e[2] : inf, k3 = (h & 8u) ? e[3] : inf;
+    int32_t c0 = s0, c1 = s1, c2 = s2, c3 = s3;
+    SPCU_CSWAP(k0, c0, k1, c1)
+    SPCU_CSWAP(k2, c2, k3, c3)
+    SPCU_CSWAP(k0, c0, k2, c2)
+    SPCU_CSWAP(k1, c1, k3, c3)
+    SPCU_CSWAP(k1, c1, k2, c2)
+    if (k3 < inf) stack.push(c3);
+    if (k2 < inf) stack.push(c2);
+    if (k1 < inf) stack.push(c1);
+    wide_unpack(acc, c0, w.link, w.count);
 #else
-    const unsigned first = __ffs(h) - 1u;
-    h &= h - 1u;
-    while (h) {
-        const unsigned k = __ffs(h) - 1u;
-        h &= h - 1u;
-        stack.push((idx << 2) | static_cast<int32_t>(k));
-    }
-    wide_child(n, first, w.link, w.count);
+    // the first entered box (in slot order) becomes the cursor, the others are pushed in slot order
+    const int32_t first = (h & 1u) ? s0 : (h & 2u) ? s1 : (h & 4u) ? s2 : s3;
+    const unsigned rest = h & (h - 1u);
+    if (rest & 2u) stack.push(s1);
+    if (rest & 4u) stack.push(s2);
+    if (rest & 8u) stack.push(s3);
+    wide_unpack(acc, first, w.link, w.count);
 #endif
 }
+#undef SPCU_CSWAP
 
 __device__ __forceinline__ RayInv make_inv_wide(const Ray& r, const DAccel& acc)
 {

@@ -26,9 +26,17 @@ void launch_batch_gather_extend(const DWave& w, uint32_t n, spcu_hit* d_hits, sp
 // extend: Scene::intersect_lights then Scene::intersect for every queued path (Integrator.cpp:558-563).
 // q_walk / d_n_walk: a queue (and its zeroed length) for the two-kernel form — `begin` finishes the rays that end at the root
 // of the BVH and parks the others there for the persistent `walk` kernel; NULL: one kernel.  Returns the kernels launched.
+// adv (only where extend_fuses_advance() says so): `queue` is the previous depth's queue of LIVE vertices and `begin` runs
+// their `advance` stage first (throughput, Russian roulette, next ray) — launch_advance is then not called for that depth.
+struct AdvanceArgs
+{
+    uint64_t seed;
+    uint32_t depth; // of the vertex the path leaves
+};
+bool extend_fuses_advance(const struct Launch& l, const uint32_t* q_walk, const TraceCounters* d_cnt);
 int launch_extend(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
                   uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered, uint32_t* q_walk,
-                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt);
+                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt, const AdvanceArgs* adv = nullptr);
 // shadow: Scene::intersect_p of the light-sample visibility ray (Integrator.cpp:503).
 // Unoccluded entries are compacted into q_lit (may be NULL: then only the per-slot flag is written).
 int launch_shadow(const struct Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,

@@ -335,16 +335,22 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
 
             uint32_t* q_cur  = q[kQCur];
             uint32_t* q_next = q[kQNext];
+            // advance (of depth d) + the set-up of extend (of depth d + 1) as ONE kernel where the extend stage has a `begin`
+            // kernel to put it in; the live queue of depth d then goes to extend directly
+            const bool fuse_advance = !whitted && extend_fuses_advance(L, q[kQWalk], d_cnt);
+            bool       pending_advance = false;
             for (uint32_t depth = 0; depth < max_depth; ++depth) {
                 RenderParams p{ part->seed, part->integrator, depth, 0 };
                 SortedQueue sorted{ c->sorted_queue.as<uint32_t>(), d_counts + next_count, n_segments, capacity };
                 next_count += n_segments;
                 timer.begin(kStExtend);
-                uint32_t* cursor = new_count();
+                uint32_t*         cursor = new_count();
+                const AdvanceArgs adv{ part->seed, depth - 1u };
                 launches += launch_extend(L, s, c->wave, q_cur, n_cur, max_n, cursor, sorted,
                                           // (node counting is DEFINED on the reference-order walk: DESIGN.md byte model)
                                           c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED && !d_cnt, q[kQWalk], new_count(),
-                                          d_counters, d_cnt);
+                                          d_counters, d_cnt, pending_advance ? &adv : nullptr);
+                pending_advance = false;
                 timer.end();
                 uint32_t* n_live   = new_count();
                 uint32_t* n_shadow = d_counts + next_count; // one shadow queue (and counter) per light
@@ -387,6 +393,15 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 }
                 if (direct && !whitted) {
                     break;
+                }
+                if (fuse_advance) {
+                    // the live queue is read by the next depth's extend (and rewritten only by the shade stage after it):
+                    // two buffers in turn, so that this depth's q_live is intact while the next one's is being filled
+                    q_cur           = q[kQLive];
+                    n_cur           = n_live;
+                    pending_advance = true;
+                    std::swap(q[kQLive], q[kQNext]);
+                    continue;
                 }
                 uint32_t* n_next = new_count();
                 timer.begin(kStAdvance);

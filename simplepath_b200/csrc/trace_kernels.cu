@@ -5,6 +5,7 @@
 // Launch shape: one thread per ray, kTraceBlock threads per CTA, grid = ceil(n / kTraceBlock).  The traversal stack's
 // first kStackShared levels live in shared memory ([level][thread], conflict free), the rest spills to local memory.
 #include "kernels.h"
+#include "rng.cuh"
 #include "trace.cuh"
 
 #include <algorithm>
@@ -330,6 +331,38 @@ __global__ void __launch_bounds__(kTraceBlock) k_extend(const __grid_constant__ 
 // Parked cursor: link with bit 30 flipped when the root is on the stack (node and primitive indices stay below 2^30,
 // checked at upload).
 // ---------------------------------------------------------------------------------------------------------------------
+// The `advance` stage of one path (shade_kernels.cu k_advance, Integrator.cpp:601-626) for the fused advance + begin kernel:
+// false when Russian roulette ends the path, otherwise the new throughput and the next segment's ray record are written
+// (and `rr` returns the latter).
+__device__ __forceinline__ bool advance_path(const DScene& s, const DWave& w, const AdvanceArgs& adv, uint32_t slot, RayRec& rr)
+{
+    const SampleRec s0     = w.s0[slot];
+    const VertexRec vx     = w.vertex[slot];
+    const PathRec   pr     = w.path[slot];
+    const float     cosine = fabsf(s0.dir.x * vx.n.x + s0.dir.y * vx.n.y + s0.dir.z * vx.n.z);
+    float           tx = pr.tp.x * (cosine * s0.col.x / s0.dir.w), ty = pr.tp.y * (cosine * s0.col.y / s0.dir.w),
+                    tz = pr.tp.z * (cosine * s0.col.z / s0.dir.w);
+    if (adv.depth >= s.rr_depth) {
+        const float lum = 0.2126f * tx + 0.7152f * ty + 0.0722f * tz; // math/RGB.h:224
+        if (lum < 0.1f) {
+            const float q = (0.05f < lum / 0.1f) ? lum / 0.1f : 0.05f; // probability of continuing
+            Rng rng{ __float_as_uint(pr.tp.w),          __float_as_uint(pr.L.w),           static_cast<uint32_t>(adv.seed),
+                     static_cast<uint32_t>(adv.seed >> 32), rng_stream(adv.depth, kSiteRoulette), 0u };
+            if (!(rng_next1(rng) < q)) {
+                return false;
+            }
+            tx = tx / q;
+            ty = ty / q;
+            tz = tz / q;
+        }
+    }
+    w.path[slot].tp = make_float4(tx, ty, tz, pr.tp.w);
+    rr              = RayRec{ make_float4(vx.p.x, vx.p.y, vx.p.z, cosine == 0.0f ? kRayEpsilon : kRayEpsilon / cosine),
+                              make_float4(s0.dir.x, s0.dir.y, s0.dir.z, kInfinite) };
+    w.ray[slot]     = rr;
+    return true;
+}
+
 constexpr int32_t kPendingBit = 0x40000000;
 __device__ __forceinline__ int32_t park_link(int32_t link, bool root_pending) { return root_pending ? (link ^ kPendingBit) : link; }
 __device__ __forceinline__ int32_t unpark_link(int32_t parked, bool& root_pending)
@@ -338,26 +371,44 @@ __device__ __forceinline__ int32_t unpark_link(int32_t parked, bool& root_pendin
     return root_pending ? (parked ^ kPendingBit) : parked;
 }
 
-template <bool kCount, bool kOrdered, typename F>
-__global__ void __launch_bounds__(kTraceBlock) k_extend_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+// kAdvance: the kernel ALSO is the `advance` stage of the previous vertex (Integrator.cpp:601-626: throughput update, Russian
+// roulette, next segment).  `queue` is then the previous depth's queue of live vertices; a path that survives gets its
+// throughput and its ray record written and goes on into the set-up below with the ray still in registers — one kernel, one
+// pass over the records, instead of advance -> queue -> begin (3.7 + 5.8 % of a bunny frame, ncu launch list r02g).
+#ifndef SPCU_BEGIN_MIN_BLOCKS
+#define SPCU_BEGIN_MIN_BLOCKS 8 // resident CTAs per SM the `begin` kernels are compiled for
+#endif
+template <bool kCount, bool kOrdered, typename F, bool kAdvance = false>
+__global__ void __launch_bounds__(kTraceBlock, SPCU_BEGIN_MIN_BLOCKS) k_extend_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                               const uint32_t* queue, const uint32_t* n_queue,
                                                               uint32_t* q_walk, uint32_t* n_walk,
                                                               const __grid_constant__ SortedQueue sorted,
-                                                              unsigned long long* counters, TraceCounters* cnt)
+                                                              unsigned long long* counters, TraceCounters* cnt,
+                                                              const __grid_constant__ AdvanceArgs adv)
 {
     __shared__ int32_t stack_smem[kStackShared * kTraceBlock];
     const uint32_t     n = *n_queue;
-    count_items(counters, kStExtend, n);
+    count_items(counters, kAdvance ? kStAdvance : kStExtend, n);
     TraceCounters       local{ 0, 0, 0 };
     const GeomPrimsT<F> gp{ s.geom_prims, s.geom_meta };
     for (uint32_t base = blockIdx.x * kTraceBlock; base < n; base += gridDim.x * kTraceBlock) {
         const uint32_t i      = base + threadIdx.x;
-        const bool     active = i < n;
+        bool           active = i < n;
         bool           done = false, parked = false;
         uint32_t       slot = 0, seg = 0;
+        RayRec         rr{};
         if (active) {
-            slot            = queue[i];
-            const RayRec rr = w.ray[slot];
+            slot = queue[i];
+            if constexpr (kAdvance) {
+                active = advance_path(s, w, adv, slot, rr);
+            } else {
+                rr = w.ray[slot];
+            }
+        }
+        if (kAdvance) {
+            warp_count(counters + kNumCounters + kStExtend, active);
+        }
+        if (active) {
             const float4 o = rr.o, d = rr.d;
             const Ray    r{ o.x, o.y, o.z, d.x, d.y, d.z, o.w };
             float        t_max = d.w, beta, gamma;
@@ -702,7 +753,7 @@ __global__ void __launch_bounds__(kTraceBlock, SPCU_WALK_MIN_BLOCKS) k_extend_wa
 // and — only when the ray reaches a light — Scene::intersect_p with the UNSHRUNK limits (t_max stays FLT_MAX: a sphere light
 // therefore occludes itself, as in the reference); the answer goes to MisRec::light / MisRec::occluded.
 template <bool kCount, typename F, bool kMis = false>
-__global__ void __launch_bounds__(kTraceBlock) k_shadow_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
+__global__ void __launch_bounds__(kTraceBlock, SPCU_BEGIN_MIN_BLOCKS) k_shadow_begin(const __grid_constant__ DScene s, const __grid_constant__ DWave w,
                                                               const uint32_t* queue, const uint32_t* n_queue, uint32_t light_index,
                                                               uint32_t* q_walk, uint32_t* n_walk, uint32_t* q_lit, uint32_t* n_lit,
                                                               unsigned long long* counters, TraceCounters* cnt)
@@ -1239,25 +1290,43 @@ static void launch_extend_features(const Launch& l, const DScene& s, const DWave
     }
 }
 
-// begin + walk (scenes with a BVH, exact walk)
+// begin + walk (scenes with a BVH)
 template <bool kCount, bool kOrdered>
 static void launch_extend_split(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
                                 uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, uint32_t* q_walk, uint32_t* d_n_walk,
-                                unsigned long long* d_counters, TraceCounters* d_cnt)
+                                unsigned long long* d_counters, TraceCounters* d_cnt, const AdvanceArgs* adv)
 {
     static const int occ_b = trace_ctas_per_sm(k_extend_begin<kCount, kOrdered, FeatFull>);
     static const int occ_w = trace_ctas_per_sm(k_extend_walk<kCount, kOrdered, FeatFull>);
-    k_extend_begin<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
-        s, w, queue, d_n_queue, q_walk, d_n_walk, sorted, d_counters, d_cnt);
+    if constexpr (!kCount) {
+        if (adv) { // `queue` = the previous depth's live vertices: advance + begin in one kernel
+            static const int occ_a = trace_ctas_per_sm(k_extend_begin<false, kOrdered, FeatFull, true>);
+            k_extend_begin<false, kOrdered, FeatFull, true><<<wavefront_grid(max_n, kTraceBlock, occ_a, l.sm_count), kTraceBlock, 0, l.stream>>>(
+                s, w, queue, d_n_queue, q_walk, d_n_walk, sorted, d_counters, nullptr, *adv);
+        }
+    }
+    if (kCount || !adv) {
+        k_extend_begin<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_b, l.sm_count), kTraceBlock, 0, l.stream>>>(
+            s, w, queue, d_n_queue, q_walk, d_n_walk, sorted, d_counters, d_cnt, AdvanceArgs{});
+    }
     debug_sync(l, "k_extend_begin");
     k_extend_walk<kCount, kOrdered, FeatFull><<<wavefront_grid(max_n, kTraceBlock, occ_w, l.sm_count), kTraceBlock, 0, l.stream>>>(
         s, w, q_walk, d_n_walk, d_cursor, sorted, d_counters, d_cnt);
     debug_sync(l, "k_extend_walk");
 }
 
+bool extend_fuses_advance(const Launch& l, const uint32_t* q_walk, const TraceCounters* d_cnt)
+{
+#ifdef SPCU_NO_FUSED_ADVANCE // (A/B builds)
+    return false;
+#else
+    return l.features != FeatAnalytic::id && q_walk != nullptr && d_cnt == nullptr;
+#endif
+}
+
 int launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32_t* queue, const uint32_t* d_n_queue,
                   uint32_t max_n, uint32_t* d_cursor, const SortedQueue& sorted, bool ordered, uint32_t* q_walk,
-                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt)
+                  uint32_t* d_n_walk, unsigned long long* d_counters, TraceCounters* d_cnt, const AdvanceArgs* adv)
 {
     if (max_n == 0) return 0;
     if (l.features == FeatAnalytic::id) {
@@ -1269,11 +1338,11 @@ int launch_extend(const Launch& l, const DScene& s, const DWave& w, const uint32
         return 1;
     }
     if (d_cnt) {
-        ordered ? launch_extend_split<true, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt)
-                : launch_extend_split<true, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt);
+        ordered ? launch_extend_split<true, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt, nullptr)
+                : launch_extend_split<true, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, d_cnt, nullptr);
     } else {
-        ordered ? launch_extend_split<false, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr)
-                : launch_extend_split<false, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr);
+        ordered ? launch_extend_split<false, true>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr, adv)
+                : launch_extend_split<false, false>(l, s, w, queue, d_n_queue, max_n, d_cursor, sorted, q_walk, d_n_walk, d_counters, nullptr, adv);
     }
     return 2;
 }

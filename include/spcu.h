@@ -349,7 +349,15 @@ int spcu_set_wavefront_size(spcu_ctx* ctx, uint64_t n_paths);
 /*   SPCU_OPT_GENERIC_KERNELS : 1 = always run the kernels compiled for every scene feature (default 0: spcu_upload_scene picks
  *                          the smallest compiled feature set that covers the scene).  Takes effect at the next upload. */
 #define SPCU_OPT_GENERIC_KERNELS 4u
-#define SPCU_OPT_COUNT_ 5u
+/*   SPCU_OPT_BATCH_LANES : how many wavefront batches of one render call are in flight at the same time, each with its own
+ *                          wavefront state on its own CUDA stream (0 = default: 4; 1 = one batch after the other).  The
+ *                          kernels of a batch leave issue slots idle — the walks wait on dependent fetches, every launch
+ *                          has a tail — and the kernels of another batch fill them.  Batches still add their
+ *                          samples to the accumulators in batch order (event-ordered resolve kernels): images are
+ *                          bit-identical for every value.  Only the queue wavefront uses it; per-launch timing and node
+ *                          counting render with one lane. */
+#define SPCU_OPT_BATCH_LANES 5u
+#define SPCU_OPT_COUNT_ 6u
 #define SPCU_TRAVERSAL_EXACT 0u
 #define SPCU_TRAVERSAL_ORDERED 1u
 #define SPCU_PIPELINE_WAVEFRONT 0u

@@ -8,6 +8,7 @@ Per library: spcu_stats.device_ms (CUDA events around the wavefront loop, inside
 warm-up frames, and the per-stage event times of one extra frame."""
 import ctypes as C
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -35,6 +36,9 @@ def run(lib_path, flat, jitter, spp, traversal, frames):
     assert lib.spcu_create(0, C.byref(h)) == 0
     if traversal != "default":
         lib.spcu_set_option(h, 3, 1 if traversal == "ordered" else 0)
+    lanes = int(os.environ.get("SPCU_AB_LANES", "0"))
+    if lanes:
+        lib.spcu_set_option(h, 5, lanes)  # SPCU_OPT_BATCH_LANES (libraries that predate it refuse the option: ignored)
     rc = lib.spcu_upload_scene(h, flat.pointer(), jitter.ctypes.data_as(C.POINTER(C.c_float)), spp)
     assert rc == 0, lib.spcu_last_error(h)
     rgb = np.empty((flat.height, flat.width, 3), dtype=np.float32)
@@ -53,7 +57,7 @@ def run(lib_path, flat, jitter, spp, traversal, frames):
     lib.spcu_stage_times(h, arr, 16, C.byref(n))
     stages = {arr[i].name.decode(): round(arr[i].ms, 2) for i in range(n.value) if arr[i].launches}
     lib.spcu_destroy(h)
-    return {"lib": Path(lib_path).name, "device_ms_mean": float(np.mean(ms)), "device_ms_min": float(np.min(ms)),
+    return {"lib": Path(lib_path).name, "lanes": lanes, "device_ms_mean": float(np.mean(ms)), "device_ms_min": float(np.min(ms)),
             "mpaths_per_s": st.paths / (float(np.min(ms)) * 1e-3) / 1e6, "mean_radiance": float(rgb.mean() / spp), "stages_ms": stages}
 
 

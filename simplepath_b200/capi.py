@@ -117,7 +117,7 @@ EXPORTS = [
     "spcu_reduce_to_root", "spcu_render_frame_reduced",
 ]
 NCCL_ID_BYTES = 128
-OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS = 0, 1, 2, 3, 4
+OPT_COUNT_NODES, OPT_STAGE_TIMING, OPT_PIPELINE, OPT_TRAVERSAL, OPT_GENERIC_KERNELS, OPT_BATCH_LANES = 0, 1, 2, 3, 4, 5
 TRAVERSAL_EXACT, TRAVERSAL_ORDERED = 0, 1
 PIPELINE_WAVEFRONT, PIPELINE_PATHS, PIPELINE_SMWAVE, PIPELINE_AUTO = 0, 1, 2, 3
 IMAGE_PFM, IMAGE_PPM = 0, 1

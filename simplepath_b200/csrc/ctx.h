@@ -55,6 +55,32 @@ constexpr int      kMaxQueueCounts = 4096;     // device queue-length words zero
 constexpr uint64_t kBatchRays      = 1u << 22; // rays per chunk of the batch query entry points
 constexpr uint32_t kMaxMaterialSegments = 15;  // materials beyond share the last segment
 
+constexpr int      kMaxBatchLanes  = 8;        // SPCU_OPT_BATCH_LANES
+constexpr int      kDefaultBatchLanes = 4;
+
+// Wavefront state of one batch in flight beyond the first (whose state lives in the context itself): SPCU_OPT_BATCH_LANES
+struct WaveLane
+{
+    DWave               wave{};
+    std::vector<DevBuf> wave_bufs;
+    DevBuf              queues[kNumQueues];
+    DevBuf              queue_counts;
+    DevBuf              sorted_queue;
+    uint32_t            wave_lights = 0;
+    cudaStream_t        stream   = nullptr;
+    cudaEvent_t         resolved = nullptr; // recorded after each of the lane's resolve kernels
+
+    void release()
+    {
+        for (auto& b : wave_bufs) b.release();
+        wave_bufs.clear();
+        for (auto& q : queues) q.release();
+        queue_counts.release();
+        sorted_queue.release();
+        wave.capacity = 0;
+    }
+};
+
 } // namespace spcu
 
 struct spcu_ctx
@@ -102,6 +128,8 @@ struct spcu_ctx
     uint32_t                  n_materials = 0;
     int                       features    = 0; // feature set of the uploaded scene (features.h)
     uint32_t                  wave_lights = 0; // light planes the wavefront buffers were sized for
+    cudaEvent_t               resolved = nullptr;       // lane 0's "resolve done" event
+    std::vector<spcu::WaveLane> extra_lanes;            // batches in flight beyond the first (SPCU_OPT_BATCH_LANES)
 
     uint32_t                 options[SPCU_OPT_COUNT_] = {};
     std::vector<cudaEvent_t> stage_events; // pairs, when SPCU_OPT_STAGE_TIMING is on

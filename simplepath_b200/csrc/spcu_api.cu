@@ -273,6 +273,13 @@ void spcu_destroy(spcu_ctx* c)
     for (auto& q : c->queues) {
         q.release();
     }
+    for (auto& lane : c->extra_lanes) {
+        if (lane.stream) cudaStreamSynchronize(lane.stream);
+        lane.release();
+        if (lane.resolved) cudaEventDestroy(lane.resolved);
+        if (lane.stream) cudaStreamDestroy(lane.stream);
+    }
+    if (c->resolved) cudaEventDestroy(c->resolved);
     for (auto e : c->stage_events) {
         cudaEventDestroy(e);
     }

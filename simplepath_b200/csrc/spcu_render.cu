@@ -23,47 +23,79 @@ const char* const kStageNames[kNumStages] = { "raygen",   "extend",    "shade", 
 inline bool stage_traverses(int st) { return st == kStExtend || st == kStShadow || st == kStMisTrace; }
 
 template <typename T>
-int wave_array(spcu_ctx* c, T*& ptr, size_t n)
+int wave_array(spcu_ctx* c, std::vector<DevBuf>& bufs, T*& ptr, size_t n)
 {
-    c->wave_bufs.emplace_back();
-    CK(c, c->wave_bufs.back().reserve(std::max<size_t>(n, 1) * sizeof(T)));
-    ptr = c->wave_bufs.back().as<T>();
+    bufs.emplace_back();
+    CK(c, bufs.back().reserve(std::max<size_t>(n, 1) * sizeof(T)));
+    ptr = bufs.back().as<T>();
     return SPCU_OK;
 }
 
-int ensure_wave(spcu_ctx* c, uint32_t capacity)
+// the wavefront state of one batch in flight: records, queues, queue counters
+int ensure_wave_buffers(spcu_ctx* c, DWave& w, std::vector<DevBuf>& bufs, DevBuf* queues, DevBuf& queue_counts, uint32_t& wave_lights,
+                        uint32_t capacity)
 {
-    if (c->wave.capacity == capacity && c->wave_lights == c->ds.n_lights) {
+    if (w.capacity == capacity && wave_lights == c->ds.n_lights) {
         return SPCU_OK; // (capacity is also the stride of the per-light planes, so it must match exactly)
     }
-    c->wave_lights = c->ds.n_lights;
-    for (auto& b : c->wave_bufs) {
+    wave_lights = c->ds.n_lights;
+    for (auto& b : bufs) {
         b.release();
     }
-    c->wave_bufs.clear();
-    c->wave_bufs.reserve(32);
-    c->wave.capacity = 0;
-    DWave& w         = c->wave;
-    int    rc;
+    bufs.clear();
+    bufs.reserve(32);
+    w.capacity = 0;
+    int rc;
 #define WAVE(field) \
-    if ((rc = wave_array(c, w.field, capacity)) != SPCU_OK) return rc
+    if ((rc = wave_array(c, bufs, w.field, capacity)) != SPCU_OK) return rc
     WAVE(path);
     WAVE(ray);
     WAVE(vertex);
     WAVE(extend);
     WAVE(s0);
-    if ((rc = wave_array(c, w.light, static_cast<size_t>(capacity) * std::max(1u, c->ds.n_lights))) != SPCU_OK) return rc;
+    if ((rc = wave_array(c, bufs, w.light, static_cast<size_t>(capacity) * std::max(1u, c->ds.n_lights))) != SPCU_OK) return rc;
     WAVE(mis);
     WAVE(occluded);
 #undef WAVE
     for (int i = 0; i < kNumQueues; ++i) { // the shadow queue has one plane per light
         const size_t planes = (i == kQShadow) ? std::max(1u, c->ds.n_lights) : 1u;
-        CK(c, c->queues[i].reserve(static_cast<size_t>(capacity) * planes * sizeof(uint32_t)));
+        CK(c, queues[i].reserve(static_cast<size_t>(capacity) * planes * sizeof(uint32_t)));
     }
-    CK(c, c->queue_counts.reserve(kMaxQueueCounts * sizeof(uint32_t)));
-    CK(c, c->counters.reserve(kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters)));
+    CK(c, queue_counts.reserve(kMaxQueueCounts * sizeof(uint32_t)));
     w.capacity = capacity;
     return SPCU_OK;
+}
+
+int ensure_wave(spcu_ctx* c, uint32_t capacity)
+{
+    if (int rc = ensure_wave_buffers(c, c->wave, c->wave_bufs, c->queues, c->queue_counts, c->wave_lights, capacity); rc != SPCU_OK) {
+        return rc;
+    }
+    CK(c, c->counters.reserve(kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters)));
+    return SPCU_OK;
+}
+
+// Lane k >= 1 of SPCU_OPT_BATCH_LANES: its own stream, event and wavefront state.  A lane that cannot be allocated is not
+// an error: the render goes on with the lanes it has (the caller shrinks its lane count to what this returns OK for).
+int ensure_extra_lane(spcu_ctx* c, size_t k, uint32_t capacity, size_t sorted_bytes)
+{
+    if (c->extra_lanes.size() <= k) {
+        c->extra_lanes.resize(k + 1);
+    }
+    WaveLane& lane = c->extra_lanes[k];
+    if (!lane.stream) {
+        CK(c, cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&lane.resolved, cudaEventDisableTiming));
+    }
+    int rc = ensure_wave_buffers(c, lane.wave, lane.wave_bufs, lane.queues, lane.queue_counts, lane.wave_lights, capacity);
+    if (rc == SPCU_OK && lane.sorted_queue.reserve(sorted_bytes) != cudaSuccess) {
+        rc = SPCU_ERR_CUDA;
+    }
+    if (rc != SPCU_OK) {
+        cudaGetLastError(); // (out of memory is sticky-free; clear it)
+        lane.release();
+    }
+    return rc;
 }
 
 int ensure_pixel_list(spcu_ctx* c, const spcu_partition& part)
@@ -305,31 +337,68 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
 
     auto*          d_counters = c->counters.as<unsigned long long>();
     TraceCounters* d_cnt      = c->options[SPCU_OPT_COUNT_NODES] ? reinterpret_cast<TraceCounters*>(d_counters + kCounterBlock) : nullptr;
-    uint32_t*      d_counts   = c->queue_counts.as<uint32_t>();
-    uint32_t*      q[kNumQueues];
-    for (int i = 0; i < kNumQueues; ++i) {
-        q[i] = c->queues[i].as<uint32_t>();
-    }
     const uint32_t* d_pix_list = c->pix_list.as<uint32_t>();
-    const Launch    L{ c->sm_count, st, c->features };
     StageTimer      timer{ c, c->options[SPCU_OPT_STAGE_TIMING] != 0, st };
     uint64_t        launches = 0;
 
+    // ---- batches in flight (SPCU_OPT_BATCH_LANES): lane 0 = the context's own wavefront state on the call's stream ----------
+    const uint64_t n_batches = static_cast<uint64_t>((n_pix + pix_per_batch - 1) / pix_per_batch) * ((n_samples + smp_per_batch - 1) / smp_per_batch);
+    uint32_t       want_lanes = c->options[SPCU_OPT_BATCH_LANES] ? c->options[SPCU_OPT_BATCH_LANES] : kDefaultBatchLanes;
+    if (timer.on || d_cnt) {
+        want_lanes = 1; // per-launch events and the node counters describe one batch at a time
+    }
+    want_lanes = static_cast<uint32_t>(std::min<uint64_t>({ want_lanes, kMaxBatchLanes, n_batches }));
+    struct LaneView
+    {
+        DWave        wave;
+        uint32_t*    q[kNumQueues];
+        uint32_t*    d_counts;
+        uint32_t*    sorted;
+        cudaStream_t st;
+        cudaEvent_t  resolved;
+    };
+    std::vector<LaneView> lanes;
+    if (!c->resolved) {
+        CK(c, cudaEventCreateWithFlags(&c->resolved, cudaEventDisableTiming));
+    }
+    {
+        LaneView v{ c->wave, {}, c->queue_counts.as<uint32_t>(), c->sorted_queue.as<uint32_t>(), st, c->resolved };
+        for (int i = 0; i < kNumQueues; ++i) v.q[i] = c->queues[i].as<uint32_t>();
+        lanes.push_back(v);
+    }
+    for (uint32_t k = 1; k < want_lanes; ++k) {
+        if (ensure_extra_lane(c, k - 1, capacity, static_cast<size_t>(n_segments) * capacity * sizeof(uint32_t)) != SPCU_OK) {
+            break; // not enough memory for another lane: render with the ones we have
+        }
+        WaveLane& l = c->extra_lanes[k - 1];
+        LaneView  v{ l.wave, {}, l.queue_counts.as<uint32_t>(), l.sorted_queue.as<uint32_t>(), l.stream, l.resolved };
+        for (int i = 0; i < kNumQueues; ++i) v.q[i] = l.queues[i].as<uint32_t>();
+        lanes.push_back(v);
+    }
+
     CK(c, cudaMemsetAsync(d_counters, 0, kCounterBlock * sizeof(unsigned long long) + sizeof(TraceCounters), st));
     CK(c, cudaEventRecord(c->ev0, st));
+    for (size_t k = 1; k < lanes.size(); ++k) { // the other lanes start after whatever the call's stream held before
+        CK(c, cudaStreamWaitEvent(lanes[k].st, c->ev0, 0));
+    }
 
+    uint64_t batch = 0;
     for (uint32_t pb = 0; pb < n_pix; pb += pix_per_batch) {
         const uint32_t np = std::min(pix_per_batch, n_pix - pb);
         for (uint32_t sb = 0; sb < n_samples; sb += smp_per_batch) {
             const uint32_t ns    = std::min(smp_per_batch, n_samples - sb);
             const uint32_t max_n = np * ns;
-            CK(c, cudaMemsetAsync(d_counts, 0, counts_need * sizeof(uint32_t), st));
+            LaneView&      lane     = lanes[batch % lanes.size()];
+            uint32_t**     q        = lane.q;
+            uint32_t*      d_counts = lane.d_counts;
+            const Launch   L{ c->sm_count, lane.st, c->features };
+            CK(c, cudaMemsetAsync(d_counts, 0, counts_need * sizeof(uint32_t), lane.st));
             uint32_t next_count = 0;
             auto     new_count  = [&]() { return d_counts + next_count++; };
 
             uint32_t* n_cur = new_count();
             timer.begin(kStRaygen);
-            launch_raygen(L, s, c->wave, d_pix_list + pb, np, part->sample_begin + sb, ns, q[kQCur], n_cur, d_counters);
+            launch_raygen(L, s, lane.wave, d_pix_list + pb, np, part->sample_begin + sb, ns, q[kQCur], n_cur, d_counters);
             timer.end();
             ++launches;
 
@@ -341,12 +410,12 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
             bool       pending_advance = false;
             for (uint32_t depth = 0; depth < max_depth; ++depth) {
                 RenderParams p{ part->seed, part->integrator, depth, 0 };
-                SortedQueue sorted{ c->sorted_queue.as<uint32_t>(), d_counts + next_count, n_segments, capacity };
+                SortedQueue sorted{ lane.sorted, d_counts + next_count, n_segments, capacity };
                 next_count += n_segments;
                 timer.begin(kStExtend);
                 uint32_t*         cursor = new_count();
                 const AdvanceArgs adv{ part->seed, depth - 1u };
-                launches += launch_extend(L, s, c->wave, q_cur, n_cur, max_n, cursor, sorted,
+                launches += launch_extend(L, s, lane.wave, q_cur, n_cur, max_n, cursor, sorted,
                                           // (node counting is DEFINED on the reference-order walk: DESIGN.md byte model)
                                           c->options[SPCU_OPT_TRAVERSAL] == SPCU_TRAVERSAL_ORDERED && !d_cnt, q[kQWalk], new_count(),
                                           d_counters, d_cnt, pending_advance ? &adv : nullptr);
@@ -357,7 +426,7 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 next_count += n_lights;
                 uint32_t* q_shadow = (nee || direct) ? q[kQShadow] : nullptr;
                 timer.begin(kStShade);
-                launch_shade(L, s, c->wave, p, sorted, max_n, q[kQLive], n_live, q_shadow, n_shadow, d_counters);
+                launch_shade(L, s, lane.wave, p, sorted, max_n, q[kQLive], n_live, q_shadow, n_shadow, d_counters);
                 timer.end();
                 launches += 1;
                 if (nee || direct) {
@@ -367,26 +436,26 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                         uint32_t* n_lit         = direct ? nullptr : new_count();
                         timer.begin(kStShadow);
                         uint32_t* cursor_l = new_count();
-                        launches += launch_shadow(L, s, c->wave, q_shadow_l, n_shadow + li, max_n, li, cursor_l,
+                        launches += launch_shadow(L, s, lane.wave, q_shadow_l, n_shadow + li, max_n, li, cursor_l,
                                                   direct ? nullptr : q[kQLit], n_lit, q[kQWalk], new_count(), d_counters, d_cnt);
                         timer.end();
                         if (direct) {
                             timer.begin(kStDirectAccumulate);
-                            launch_direct_accumulate(L, s, c->wave, p, q_shadow_l, n_shadow + li, max_n, d_counters);
+                            launch_direct_accumulate(L, s, lane.wave, p, q_shadow_l, n_shadow + li, max_n, d_counters);
                             timer.end();
                             ++launches;
                             continue;
                         }
                         uint32_t* n_mis = new_count();
                         timer.begin(kStNeeBsdf);
-                        launch_nee_bsdf(L, s, c->wave, p, q[kQLit], n_lit, max_n, q[kQMis], n_mis, d_counters);
+                        launch_nee_bsdf(L, s, lane.wave, p, q[kQLit], n_lit, max_n, q[kQMis], n_mis, d_counters);
                         timer.end();
                         timer.begin(kStMisTrace);
                         uint32_t* cursor_m = new_count();
-                        launches += launch_mis_trace(L, s, c->wave, q[kQMis], n_mis, max_n, cursor_m, q[kQWalk], new_count(), d_counters, d_cnt);
+                        launches += launch_mis_trace(L, s, lane.wave, q[kQMis], n_mis, max_n, cursor_m, q[kQWalk], new_count(), d_counters, d_cnt);
                         timer.end();
                         timer.begin(kStNeeMisAccumulate);
-                        launch_nee_mis_accumulate(L, s, c->wave, q[kQMis], n_mis, max_n, d_counters);
+                        launch_nee_mis_accumulate(L, s, lane.wave, q[kQMis], n_mis, max_n, d_counters);
                         timer.end();
                         launches += 2;
                     }
@@ -406,21 +475,33 @@ int render_impl(spcu_ctx* c, const spcu_partition* part, float* d_rgb_sum, float
                 uint32_t* n_next = new_count();
                 timer.begin(kStAdvance);
                 if (whitted) {
-                    launch_whitted_advance(L, s, c->wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
+                    launch_whitted_advance(L, s, lane.wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
                 } else {
-                    launch_advance(L, s, c->wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
+                    launch_advance(L, s, lane.wave, p, q[kQLive], n_live, max_n, q_next, n_next, d_counters);
                 }
                 timer.end();
                 ++launches;
                 std::swap(q_cur, q_next);
                 n_cur = n_next;
             }
+            // batches add their samples to the accumulators in batch order, whichever lane ran them: this resolve waits for the
+            // previous batch's (the float sums, and so the image, do not depend on the number of lanes)
+            if (lanes.size() > 1 && batch > 0) {
+                CK(c, cudaStreamWaitEvent(lane.st, lanes[(batch - 1) % lanes.size()].resolved, 0));
+            }
             timer.begin(kStResolve);
-            launch_resolve(L, &c->wave.path->L, 2, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
+            launch_resolve(L, &lane.wave.path->L, 2, d_pix_list + pb, np, ns, d_rgb_sum, d_lum_sumsq, d_counters);
             timer.end();
             ++launches;
+            if (lanes.size() > 1) {
+                CK(c, cudaEventRecord(lane.resolved, lane.st));
+            }
+            ++batch;
             CK(c, cudaGetLastError());
         }
+    }
+    for (size_t k = 1; k < lanes.size(); ++k) { // join: the call's stream ends after every lane's last resolve
+        CK(c, cudaStreamWaitEvent(st, lanes[k].resolved, 0));
     }
     CK(c, cudaEventRecord(c->ev1, st));
 

@@ -28,6 +28,7 @@ configs  = at N = 1 the other BASELINE configs as short side runs (fewer steps; 
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import re
@@ -298,6 +299,8 @@ def measure(ctx, args, workload: str, spp_total: int, steps: int, warmup: int, w
     issue_peak = sm_count * SM_SCHEDULERS * WARP_LANES * sm_ghz          # G thread-instructions / s
     roof = {"kernel": dominant, "share_of_step": stage_ms[dominant] / kernel_ms if kernel_ms else None,
             "launches": n_launch, "items_per_launch": items / n_launch, "launch_ms": dur_s * 1e3,
+            "timed": "CUDA events around every launch on extra steps right after the timed ones, ONE batch at a time (the timed "
+                     "steps overlap batches on several streams, where a launch has no duration of its own)",
             "algorithmic_gbs": algorithmic_gbs, "algorithmic_frac_of_hbm": algorithmic_gbs / peak,
             "algorithmic_bytes_per_item": bytes_total / max(items, 1), "hbm_peak_gbs": peak, "peak_source": peak_src,
             "ncu_source": ncu_src}
@@ -323,7 +326,7 @@ def measure(ctx, args, workload: str, spp_total: int, steps: int, warmup: int, w
                   f"({paths * 16 / 1e9:.1f} GB) and the accumulators, far above the 126 MB L2 — no explicit flush"
                   if pipeline == "smwave" else
                   "no explicit flush: every batch streams its wavefront state (2^24 slots x 256 B = 4.3 GB) and queues through "
-                  "HBM, far above the 126 MB L2")
+                  "HBM, far above the 126 MB L2; up to 4 batches are in flight at once (SPCU_OPT_BATCH_LANES)")
     return {
         "value": paths * steps / steps_s / 1e6, "unit": "Mpaths/s", "ms_per_step": total_ms / steps, "steps": steps,
         "warmup": warmup,
@@ -331,7 +334,8 @@ def measure(ctx, args, workload: str, spp_total: int, steps: int, warmup: int, w
                    "spp_per_gpu": spp_rank, "integrator": INTEGRATOR, "pipeline": pipeline,
                    "traversal": "exact" if ctx.traversal_exact else "ordered", "max_depth": flat.head["max_depth"],
                    "rr_depth": flat.head["rr_depth"], "primitives": int(flat.n_prims), "paths_per_step": int(paths),
-                   "partition": f"sample ranges x{world} of one frame, scene replicated", "l2": batch_note},
+                   "partition": f"sample ranges x{world} of one frame, scene replicated", "l2": batch_note,
+                   "batch_lanes": 1 if pipeline == "smwave" else (args.batch_lanes or "library default (4 batches in flight, event-ordered resolve)")},
         "mrays_per_s": (rays_closest + rays_any) * steps / steps_s / 1e6,
         "rays": {"closest_per_path": rays_closest / paths, "any_hit_per_path": rays_any / paths,
                  "lights_accel_per_path": rays_lights / paths},
@@ -391,6 +395,7 @@ def run_cuda(args) -> None:
     ctx.set_option(capi.OPT_PIPELINE, {"auto": capi.PIPELINE_AUTO, "smwave": capi.PIPELINE_SMWAVE, "paths": capi.PIPELINE_PATHS,
                                        "wavefront": capi.PIPELINE_WAVEFRONT}[args.pipeline])
     ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_EXACT if ctx.traversal_exact else capi.TRAVERSAL_ORDERED)
+    ctx.set_option(capi.OPT_BATCH_LANES, args.batch_lanes)
     distributed.init_product_comm(ctx)   # libspcu's own NCCL communicator (torch.distributed only carries the unique id)
 
     spp_total = args.spp or WORKLOADS[args.workload][1]
@@ -421,10 +426,12 @@ def run_cuda(args) -> None:
                                 ("c4_elf_1080p_256spp", "elf_1080p_256spp", 256, 2),
                                 ("c5_lucy_4k_8spp_sample_of_256", "lucy_4k_256spp", 8, 2)):
             try:
-                r = measure(ctx, args, wl, spp, k, 3, 1, 0, e2e_steps=1)
+                gc.collect()   # the previous config's host-side scene (lucy: 2.8 GB) goes before the next one is built
+                r = measure(ctx, args, wl, spp, k, 3, 1, 0, e2e_steps=2 if wl == "lucy_4k_256spp" else 1)
                 sflat = r.pop("_flat")
                 if sflat.n_nodes and not ctx.traversal_exact:
                     r["ordered_walk"] = ordered_walk_report(ctx, sflat)
+                del sflat
                 if not args.no_cpu and wl != "lucy_4k_256spp":
                     r["cpu_baseline"] = cpu_baseline(WORKLOADS[wl][0], budget_s=8.0)
                 side[key] = r
@@ -647,6 +654,8 @@ def main() -> None:
                     help="closest-hit walk of the extend stage (SPCU_OPT_TRAVERSAL; the library's default is ordered)")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "smwave", "paths", "wavefront"],
                     help="kernel organisation (SPCU_OPT_PIPELINE); same estimator and random numbers either way")
+    ap.add_argument("--batch-lanes", type=int, default=0,
+                    help="wavefront batches in flight at once (SPCU_OPT_BATCH_LANES; 0 = the library's default, 4)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

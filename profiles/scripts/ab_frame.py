@@ -36,6 +36,9 @@ def run(lib_path, flat, jitter, spp, traversal, frames):
     assert lib.spcu_create(0, C.byref(h)) == 0
     if traversal != "default":
         lib.spcu_set_option(h, 3, 1 if traversal == "ordered" else 0)
+    if os.environ.get("SPCU_AB_WAVEFRONT"):
+        lib.spcu_set_wavefront_size.argtypes = [vp, C.c_uint64]
+        lib.spcu_set_wavefront_size(h, int(os.environ["SPCU_AB_WAVEFRONT"]))
     lanes = int(os.environ.get("SPCU_AB_LANES", "0"))
     if lanes:
         lib.spcu_set_option(h, 5, lanes)  # SPCU_OPT_BATCH_LANES (libraries that predate it refuse the option: ignored)
@@ -57,7 +60,7 @@ def run(lib_path, flat, jitter, spp, traversal, frames):
     lib.spcu_stage_times(h, arr, 16, C.byref(n))
     stages = {arr[i].name.decode(): round(arr[i].ms, 2) for i in range(n.value) if arr[i].launches}
     lib.spcu_destroy(h)
-    return {"lib": Path(lib_path).name, "lanes": lanes, "device_ms_mean": float(np.mean(ms)), "device_ms_min": float(np.min(ms)),
+    return {"lib": Path(lib_path).name, "lanes": lanes, "wavefront": int(os.environ.get("SPCU_AB_WAVEFRONT", "0")), "device_ms_mean": float(np.mean(ms)), "device_ms_min": float(np.min(ms)),
             "mpaths_per_s": st.paths / (float(np.min(ms)) * 1e-3) / 1e6, "mean_radiance": float(rgb.mean() / spp), "stages_ms": stages}
 
 

@@ -158,8 +158,16 @@ def test_partitions_are_exact(ctx, scene):
 
     ctx.set_wavefront_size(777)
     small, small_sq, st = ctx.render(ctx.partition(spp=spp, seed=5))
-    ctx.set_wavefront_size(0)
     assert small.tobytes() == whole.tobytes() and small_sq.tobytes() == whole_sq.tobytes()
+    # ... and however many of those batches are in flight at once (SPCU_OPT_BATCH_LANES: the default is 4): the resolve
+    # kernels are event-ordered, so the per-pixel sums add up in batch order on every lane count
+    for lanes in (1, 2, 3, 8):
+        ctx.set_option(capi.OPT_BATCH_LANES, lanes)
+        laned, laned_sq, st_l = ctx.render(ctx.partition(spp=spp, seed=5))
+        assert laned.tobytes() == whole.tobytes() and laned_sq.tobytes() == whole_sq.tobytes(), f"{lanes} lanes"
+        assert st_l["paths"] == st["paths"] and st_l["rays_closest"] == st["rays_closest"] and st_l["rays_any"] == st["rays_any"]
+    ctx.set_option(capi.OPT_BATCH_LANES, 0)
+    ctx.set_wavefront_size(0)
 
 
 @pytest.mark.parametrize("integrator", INTEGRATORS)

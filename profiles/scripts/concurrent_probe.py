@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Does the GPU do more work per second when two DIFFERENT stages share the SMs?  Two contexts of one process render the two
-halves of a frame's samples at the same time on their own streams (grids sized for half the machine: SPCU_GRID_DIVISOR=2),
-against one context rendering all of them alone (SPCU_GRID_DIVISOR unset -> run this script twice).
+"""Does the GPU do more work per second when the kernels of several batches share it?  N contexts of one process render the N
+parts of a frame's samples at the same time on their own streams, against one context rendering all of them alone: the
+measurement behind SPCU_OPT_BATCH_LANES (records profiles/r02x_*, r02y_*).  (Those records also hold runs with
+every grid sized for 1/2 or 1/3 of the machine — "grid_divisor" — through an environment switch the library had for the
+experiment: half-size grids lost, the switch is gone.)
 
-    [SPCU_GRID_DIVISOR=2] python profiles/scripts/concurrent_probe.py WORKLOAD SPP N_CONTEXTS [frames]
+    python profiles/scripts/concurrent_probe.py WORKLOAD SPP N_CONTEXTS [frames]
 """
 import ctypes as C
 import json

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Render one golden scene with one pipeline (for compute-sanitizer runs):  sanitize_pipelines.py SCENE PIPELINE [integrator]"""
+"""Render one golden scene with one pipeline (for compute-sanitizer runs):
+    [SPCU_SAN_WAVEFRONT=n] sanitize_pipelines.py SCENE PIPELINE [integrator [exact|ordered [extend|shadow]]]"""
 import sys
 from pathlib import Path
 import numpy as np
@@ -25,5 +26,8 @@ if len(sys.argv) > 5:   # only the traversal stages, on the golden camera rays
     else:
         print(name, "shadow_batch ok", int(ctx.shadow_batch(rays).sum()))
     sys.exit(0)
+import os
+if os.environ.get("SPCU_SAN_WAVEFRONT"):   # small batches: several of them in flight on their own streams (SPCU_OPT_BATCH_LANES)
+    ctx.set_wavefront_size(int(os.environ["SPCU_SAN_WAVEFRONT"]))
 rgb, _, st = ctx.render(ctx.partition(integrator=integrator, seed=77))
 print(name, pipeline, integrator, "ok", float(rgb.mean()), st["paths"])

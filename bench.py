@@ -321,6 +321,24 @@ def measure(ctx, args, workload: str, spp_total: int, steps: int, warmup: int, w
         roof.update({"bound": "hbm", "achieved": algorithmic_gbs, "peak": peak, "unit": "GB/s", "frac": algorithmic_gbs / peak,
                      "traffic": None, "note": "no ncu capture for this kernel/workload: frac is the ALGORITHMIC byte model"})
 
+    # ---- the whole frame against the same two peaks: every stage's instructions and DRAM traffic (ncu, per item) x the
+    # items it processed, over the frame's device time — the figure that sees what overlapping the batches buys ----------------
+    frame_inst = frame_bytes = 0.0
+    frame_cover = 0.0
+    for st_name, n_items in stage_items.items():
+        per, _ = ncu_kernel_summary(st_name, workload, pipeline)
+        if per is not None and n_items:
+            frame_inst += per["thread_inst_per_item"] * n_items / stage_steps
+            frame_bytes += per["dram_bytes_per_item"] * n_items / stage_steps
+            frame_cover += stage_ms.get(st_name, 0.0)
+    if frame_inst > 0 and total_ms > 0:
+        frame_s = total_ms / steps / 1e3
+        roof["frame"] = {"thread_inst_per_frame": frame_inst * world, "dram_bytes_per_frame": frame_bytes * world,
+                         "issue_frac": frame_inst / frame_s / 1e9 / issue_peak, "hbm_frac": frame_bytes / frame_s / 1e9 / peak,
+                         "kernels_covered_by_ncu_summaries": frame_cover / kernel_ms if kernel_ms else None,
+                         "what": "all stages' thread instructions / DRAM bytes (ncu per-item figures x this rank's items) over the "
+                                 "timed frame's duration, per GPU: with batches overlapping, the frame — not a launch — is what has a duration"}
+
     steps_s = total_ms / 1e3
     batch_note = ("SM-local wavefront: path state lives in shared memory; every step writes 16 B per path of radiance samples "
                   f"({paths * 16 / 1e9:.1f} GB) and the accumulators, far above the 126 MB L2 — no explicit flush"

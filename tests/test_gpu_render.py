@@ -56,17 +56,21 @@ def test_per_pixel_vs_oracle(ctx, oracle_port, scene, integrator):
     rgb, sq, st = ctx.render(part)
     want, want_sq, want_st = oracle_port.render(flat.pointer(), jitter, part)
     assert st["paths"] == want_st["paths"] == flat.width * flat.height * spp
-    # stated tolerance: a pixel "agrees" when every channel is within 2e-3 * (1 + |oracle|) of the oracle's sum
+    # stated tolerance: a pixel "agrees" when every channel is within 2e-3 * (1 + |oracle|) of the oracle's sum.
+    # The bounds below are 3-4x the worst case measured over all 84 (scene, pipeline, integrator) combinations
+    # (profiles/scripts/parity_margins.py -> profiles/r03t_parity_margins.jsonl: 0.13 % of pixels, 0.035 % of the mean
+    # luminance, 0.24 % of the shade calls, 0.09 % / 0.04 % of the light / any-hit queries, closest-hit counts equal).
     tol = 2e-3 * (1.0 + np.abs(want))
     bad = (np.abs(rgb - want) > tol).any(axis=-1)
-    assert bad.mean() < 0.03, f"{name}/{integrator}: {bad.mean():.2%} of pixels differ from the oracle"
-    assert abs(lum(rgb).mean() - lum(want).mean()) <= 0.01 * lum(want).mean() + 1e-6
+    assert bad.mean() < 0.005, f"{name}/{integrator}: {bad.mean():.2%} of pixels differ from the oracle"
+    assert abs(lum(rgb).mean() - lum(want).mean()) <= 0.002 * lum(want).mean() + 1e-6
     # identical random numbers => identical path structure except for those few paths
     for key in ("rays_closest", "rays_lights"):
-        assert abs(st[key] - want_st[key]) <= 0.01 * want_st[key] + 8, (key, st[key], want_st[key])
-    assert abs(st["shade_calls"] - want_st["shade_calls"]) <= 0.01 * want_st["shade_calls"] + 8
-    # (direct lighting: the reference skips the shadow query when f == 0; the wavefront pipeline traces it anyway)
-    assert abs(st["rays_any"] - want_st["rays_any"]) <= (0.25 if integrator in ("direct_lighting", "whitted") else 0.01) * want_st["rays_any"] + 8
+        assert abs(st[key] - want_st[key]) <= 0.005 * want_st[key] + 8, (key, st[key], want_st[key])
+    assert abs(st["shade_calls"] - want_st["shade_calls"]) <= 0.008 * want_st["shade_calls"] + 8
+    # (direct lighting / whitted: the reference skips the shadow query when f == 0; the wavefront pipeline traces it anyway
+    # — measured: at most 3.7 % more any-hit queries)
+    assert abs(st["rays_any"] - want_st["rays_any"]) <= (0.10 if integrator in ("direct_lighting", "whitted") else 0.005) * want_st["rays_any"] + 8
 
 
 @pytest.mark.parametrize("integrator", INTEGRATORS)

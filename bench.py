@@ -414,6 +414,7 @@ def run_cuda(args) -> None:
                                        "wavefront": capi.PIPELINE_WAVEFRONT}[args.pipeline])
     ctx.set_option(capi.OPT_TRAVERSAL, capi.TRAVERSAL_EXACT if ctx.traversal_exact else capi.TRAVERSAL_ORDERED)
     ctx.set_option(capi.OPT_BATCH_LANES, args.batch_lanes)
+    ctx.set_wavefront_size(args.wavefront_size)
     distributed.init_product_comm(ctx)   # libspcu's own NCCL communicator (torch.distributed only carries the unique id)
 
     spp_total = args.spp or WORKLOADS[args.workload][1]
@@ -674,6 +675,7 @@ def main() -> None:
                     help="kernel organisation (SPCU_OPT_PIPELINE); same estimator and random numbers either way")
     ap.add_argument("--batch-lanes", type=int, default=0,
                     help="wavefront batches in flight at once (SPCU_OPT_BATCH_LANES; 0 = the library's default, 4)")
+    ap.add_argument("--wavefront-size", type=int, default=0, help="slots per wavefront batch (spcu_set_wavefront_size; 0 = default 2^24)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

@@ -367,6 +367,23 @@ class Context:
                                          C.byref(st)), "spcu_render")
         return rgb, sq, st.as_dict()
 
+    def render_passes(self, passes: int, spp: int | None = None, integrator: str = "iterative_rrnee", seed: int = 0,
+                      rank: int = 0, world: int = 1):
+        """Progressive rendering — the multi-pass mode the reference's TileScheduler provides for (`pass` of a ScheduledTile,
+        base/TileScheduler.h:58-86; main.cpp:111 runs it with num_passes = 1): pass p adds samples [p*k, (p+1)*k) of the
+        frame's spp to the same accumulators.  Yields (samples_so_far, rgb_sum, lum_sumsq, stats) after every pass; the
+        arrays are the running SUMS (divide by samples_so_far for the preview), and after the last pass they are, bit for
+        bit, what one spcu_render call of the whole frame returns (sample ranges accumulate in sample order)."""
+        spp = self.spp if spp is None else spp
+        passes = max(1, min(passes, spp))
+        acc = None
+        for p in range(passes):
+            lo, hi = spp * p // passes, spp * (p + 1) // passes
+            part = Partition(rank, world, lo, hi, spp, INTEGRATORS[integrator], seed)
+            rgb, sq, st = self.render(part, into=acc)
+            acc = (rgb, sq)
+            yield hi, rgb, sq, st
+
     def render_frame(self, part: Partition, out=None, want_sumsq: bool = True):
         """Host-buffer render that OVERWRITES its outputs (no accumulator upload, nothing to zero): returns
         (rgb_sum, lum_sumsq | None, stats).  `out` = (rgb, sq) preallocated, e.g. page-locked, arrays to write into."""

@@ -174,6 +174,25 @@ def test_partitions_are_exact(ctx, scene):
     ctx.set_wavefront_size(0)
 
 
+def test_progressive_passes(ctx, scene):
+    """Multi-pass rendering (the reference's TileScheduler hands out (tile, pass); base/TileScheduler.h:58-86): every pass adds
+    its sample range to the same accumulators, each preview is exactly the frame rendered up to that sample, and the last
+    one is the one-call frame bit for bit."""
+    name, flat, vec = scene
+    jitter = vec["jitter"]
+    spp = jitter.shape[0]
+    upload(ctx, flat, jitter)
+    whole, whole_sq, st = ctx.render(ctx.partition(spp=spp, seed=11))
+    seen, paths = [], 0
+    for done, rgb, sq, st_p in ctx.render_passes(3, spp=spp, seed=11):
+        seen.append(done)
+        paths += st_p["paths"]
+        upto, upto_sq, _ = ctx.render(ctx.partition(spp=spp, seed=11, sample_begin=0, sample_end=done))
+        assert rgb.tobytes() == upto.tobytes() and sq.tobytes() == upto_sq.tobytes(), f"{name}: preview after {done} samples"
+    assert seen[-1] == spp and seen == sorted(set(seen)) and paths == st["paths"]
+    assert rgb.tobytes() == whole.tobytes() and sq.tobytes() == whole_sq.tobytes()
+
+
 @pytest.mark.parametrize("integrator", INTEGRATORS)
 def test_feature_specialised_kernels_render_the_same_image(ctx, scene, integrator):
     """spcu_upload_scene picks kernels compiled for the scene's feature set (csrc/features.h: no BVH / triangles /

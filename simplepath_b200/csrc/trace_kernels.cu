@@ -496,6 +496,23 @@ struct PairPlan
 
 __device__ __forceinline__ PairPlan plan_pairs(bool candidate, uint32_t n)
 {
+#ifndef SPCU_PAIR_SCAN_SHUFFLE // (A/B switch: the five-step shuffle scan)
+    // exclusive prefix sum of the leaf sizes (0..kPairLeafMax = 4: three bits) from three ballots — three independent votes
+    // instead of a chain of five dependent shuffles in front of every leaf step
+    static_assert(kPairLeafMax < 8u, "the ballot scan sums three bits");
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+    const uint32_t v  = candidate ? n : 0u;
+    const unsigned b0 = __ballot_sync(0xffffffffu, (v & 1u) != 0u), b1 = __ballot_sync(0xffffffffu, (v & 2u) != 0u),
+                   b2 = __ballot_sync(0xffffffffu, (v & 4u) != 0u);
+    const uint32_t excl = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+    PairPlan       p;
+    const bool     part = candidate && excl + v <= 32u; // a prefix of the candidates, in lane order
+    p.part_mask         = __ballot_sync(0xffffffffu, part);
+    p.my_n              = part ? n : 0u;
+    p.offset            = excl;
+    p.total             = __popc(b0 & p.part_mask) + 2u * __popc(b1 & p.part_mask) + 4u * __popc(b2 & p.part_mask);
+    return p;
+#else
     const int lane = threadIdx.x & 31;
     uint32_t  incl = candidate ? n : 0u;
 #pragma unroll
@@ -512,6 +529,7 @@ __device__ __forceinline__ PairPlan plan_pairs(bool candidate, uint32_t n)
     p.offset        = incl - (candidate ? n : 0u);
     p.total         = p.part_mask ? __shfl_sync(0xffffffffu, incl, 31 - __clz(p.part_mask)) : 0u;
     return p;
+#endif
 }
 
 // owner lane and index within the owner's leaf of the pair this lane runs (lanes >= total: garbage, not used)

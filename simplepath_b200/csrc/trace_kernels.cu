@@ -145,9 +145,13 @@ constexpr uint32_t kChunk          = 64; // queue entries a warp reserves at a t
 #endif
 constexpr int      kRefillMin      = SPCU_REFILL_MIN; // idle lanes that make a refill worth its set-up code
 #ifndef SPCU_WALK_REFILL_MIN
-#define SPCU_WALK_REFILL_MIN 4
+#define SPCU_WALK_REFILL_MIN 12
 #endif
-constexpr int      kWalkRefillMin  = SPCU_WALK_REFILL_MIN; // ... when the set-up is three loads (the begin / walk kernels)
+// ... in the begin / walk kernels, where the phase also retires the finished walks.  4 until the walks stopped paying a
+// global atomic per finished ray; re-swept with four batches in flight: 2 / 4 / 6 / 8 / 12 / 16 / 20 / 24 / 28 give 451 / 466 /
+// 473 / 479 / 482 / 483 / 479 / 475 / 466 Mpaths/s on bunny and 676 / 693 / 697 / 704 / 706-712 / 706 / 700 / 700 / 694 on elf
+// (profiles/r04b_*, r04c_*): a phase at 4 of 32 lanes every few steps costs more than lanes waiting for a fuller one.
+constexpr int      kWalkRefillMin  = SPCU_WALK_REFILL_MIN;
 // phase vote of the walk kernels: a pair leaf step runs when  pairs * NUM > lanes_at_a_node * DEN  (tuned on the GPU: profiles/)
 // tuning / A-B switches of the walk kernels (make EXTRA=-D...; defaults are what measured best, profiles/r02*)
 #ifndef SPCU_WALK_MIN_BLOCKS
